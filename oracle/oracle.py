@@ -1,0 +1,255 @@
+"""ctypes loader for the CPU parity oracle (oracle/picgolf_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, bench.py's cpu_baseline / --impl reference
+legs and __graft_entry__.smoke().  The product package never imports this module.
+Every wrapper mirrors one `oracle_*` C function; see the C file for the reference file:line.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpicgolf_oracle.so")
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64 = C.c_int64
+_d = C.c_double
+_vp = C.c_void_p
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc -O2 -ffp-contract=off)."""
+    src = os.path.join(_HERE, "picgolf_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libpicgolf_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.oracle_jl_mod1.restype = _d
+        L.oracle_jl_mod1.argtypes = [_d]
+        L.oracle_ngp_index.restype = _i64
+        L.oracle_ngp_index.argtypes = [_d, _i64]
+        L.oracle_ngp_index_array.argtypes = [_dp, _i64, _i64, _ip]
+        L.oracle_fft.argtypes = [_dp, _dp, _i64, C.c_int]
+        L.oracle_dft_naive.argtypes = [_dp, _dp, _i64, C.c_int]
+        L.oracle_solve1d.argtypes = [_dp, _i64, _dp]
+        L.oracle_ngp_half_drift.argtypes = [_dp, _dp, _i64, _d]
+        L.oracle_ngp_deposit.argtypes = [_dp, _i64, _i64, _d, _dp]
+        L.oracle_ngp_kick.argtypes = [_dp, _dp, _dp, _i64, _i64, _d]
+        L.oracle_ngp_step.argtypes = [_dp, _dp, _i64, _i64, _d, _d, _dp, _dp, _vp]
+        L.oracle_gauss_stencil.argtypes = [_d, _i64, C.c_int, _ip, _dp]
+        L.oracle_gauss_deposit.argtypes = [_dp, _dp, _i64, _i64, C.c_int, _d, _dp]
+        L.oracle_gauss_gather.restype = _d
+        L.oracle_gauss_gather.argtypes = [_dp, _d, _i64, C.c_int]
+        L.oracle_isapprox.restype = C.c_int
+        L.oracle_isapprox.argtypes = [_dp, _dp, _i64, _d, _d]
+        L.oracle_fixedpoint_step.restype = C.c_int
+        L.oracle_fixedpoint_step.argtypes = [_dp] * 7 + [_i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _vp, _vp]
+        L.oracle_fixedpoint_run.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _i64, _vp, _vp]
+        L.oracle_gauss_leapfrog_step.argtypes = [_dp, _dp, _i64, _i64, C.c_int, _d, _d, _dp, _dp, _vp]
+        L.oracle_quiet_start.argtypes = [_i64, _i64, _i64, _dp, _dp]
+        L.oracle_growth_slope.restype = _d
+        L.oracle_growth_slope.argtypes = [_d]
+        L.oracle_cic_g.argtypes = [_d, _i64, _ip, _dp]
+        L.oracle_boris.argtypes = [_dp, _dp, _dp, _d, _d, _d, _d]
+        L.oracle_cic_deposit.argtypes = [_dp, _dp, _i64, _i64, _i64, _d, _dp]
+        L.oracle_cic_gather.argtypes = [_dp, _dp, _i64, _i64, _dp, _dp, _i64, _dp, _dp]
+        L.oracle_solve2d.argtypes = [_dp, _i64, _i64, _dp, _dp]
+        L.oracle_2d3v_step.argtypes = [_dp] * 5 + [_i64, _i64, _i64, _d, _d, _d, _dp, _dp, _dp, C.c_int]
+        L.oracle_2d3v_diagnostics.argtypes = [_dp, _dp, _i64, _i64, _dp, _dp, _i64, _d, _dp]
+        L.oracle_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+# ---------------------------------------------------------------- Base semantics
+def jl_mod1(x: float) -> float:
+    return lib().oracle_jl_mod1(float(x))
+
+
+def ngp_index(x, N: int) -> np.ndarray:
+    """1-based NGP cell f(x) (NGPFourier.jl:3)."""
+    x = _f64(np.atleast_1d(x))
+    out = np.empty(x.size, dtype=np.int32)
+    lib().oracle_ngp_index_array(x, x.size, N, out)
+    return out
+
+
+def fft(re, im, sign=-1):
+    re, im = _f64(re).copy(), _f64(im).copy()
+    lib().oracle_fft(re, im, re.size, sign)
+    return re, im
+
+
+def dft_naive(re, im, sign=-1):
+    re, im = _f64(re).copy(), _f64(im).copy()
+    lib().oracle_dft_naive(re, im, re.size, sign)
+    return re, im
+
+
+def solve1d(rho) -> np.ndarray:
+    rho = _f64(rho)
+    E = np.empty_like(rho)
+    lib().oracle_solve1d(rho, rho.size, E)
+    return E
+
+
+# ---------------------------------------------------------------- NGP 1D1V
+def ngp_half_drift(x, v, dt):
+    lib().oracle_ngp_half_drift(x, v, x.size, dt)
+
+
+def ngp_deposit(x, N, w) -> np.ndarray:
+    n = np.empty(N)
+    lib().oracle_ngp_deposit(_f64(x), x.size, N, w, n)
+    return n
+
+
+def ngp_kick(x, v, E, dt):
+    lib().oracle_ngp_kick(x, v, _f64(E), x.size, E.size, dt)
+
+
+def ngp_step(x, v, N, dt, w):
+    """In place on x, v.  Returns (rho, E, raw[sumE2, sumv2, sumv])."""
+    rho, E, raw = np.empty(N), np.empty(N), np.empty(3)
+    lib().oracle_ngp_step(x, v, x.size, N, dt, w, rho, E, _ptr(raw))
+    return rho, E, raw
+
+
+# ---------------------------------------------------------------- Gaussian shape
+def gauss_stencil(c: float, N: int, hw: int):
+    idx = np.empty(2 * hw + 1, dtype=np.int32)
+    wt = np.empty(2 * hw + 1)
+    lib().oracle_gauss_stencil(float(c), N, hw, idx, wt)
+    return idx, wt
+
+
+def gauss_deposit(x, y, N, hw, scale) -> np.ndarray:
+    r = np.empty(N)
+    lib().oracle_gauss_deposit(_f64(x), _f64(y), x.size, N, hw, scale, r)
+    return r
+
+
+def gauss_gather(E, c, N, hw) -> np.ndarray:
+    E = _f64(E)
+    c = np.atleast_1d(_f64(c))
+    L = lib()
+    return np.array([L.oracle_gauss_gather(E, float(ci), N, hw) for ci in c])
+
+
+def isapprox(F, E, rtol, atol=0.0) -> bool:
+    return bool(lib().oracle_isapprox(_f64(F), _f64(E), F.size, rtol, atol))
+
+
+class FixedPoint:
+    """State holder mirroring GaussianFixedPoint.jl:1-6 / GaussianFixedPointQuiet.jl:1-7."""
+
+    def __init__(self, x, v, N, dt, W, w=None, hw=6, rtol=1e-8, atol=0.0, max_sweeps=10):
+        self.x, self.v = _f64(x).copy(), _f64(v).copy()
+        self.P, self.N, self.dt, self.W, self.hw = self.x.size, N, dt, W, hw
+        self.w = W / self.P * N if w is None else w
+        self.rtol, self.atol, self.max_sweeps = rtol, atol, max_sweeps
+        self.E, self.F, self.r = np.zeros(N), np.zeros(N), np.zeros(N)
+        self.X, self.V = self.x.copy(), self.v.copy()
+
+    def step(self):
+        """One time step. Returns (D[t,1:4], raw sums, sweeps)."""
+        D4, raw = np.empty(4), np.empty(3)
+        s = lib().oracle_fixedpoint_step(self.x, self.v, self.E, self.X, self.V, self.F, self.r, self.P, self.N,
+                                         self.hw, self.dt, self.W, self.w, self.rtol, self.atol, self.max_sweeps,
+                                         _ptr(D4), _ptr(raw))
+        return D4, raw, s
+
+    def run(self, T):
+        """T steps. Returns (D as T x 4 Fortran-ordered array, sweeps[T])."""
+        D = np.zeros((T, 4), order="F")
+        sw = np.zeros(T, dtype=np.int32)
+        lib().oracle_fixedpoint_run(self.x, self.v, self.E, self.P, self.N, self.hw, self.dt, self.W, self.w,
+                                    self.rtol, self.atol, self.max_sweeps, T, _ptr(D), _ptr(sw))
+        return D, sw
+
+
+def gauss_leapfrog_step(x, v, N, hw, dt, scale):
+    rho, E, raw = np.empty(N), np.empty(N), np.empty(3)
+    lib().oracle_gauss_leapfrog_step(x, v, x.size, N, hw, dt, scale, rho, E, _ptr(raw))
+    return rho, E, raw
+
+
+def quiet_start(P, first=0, count=None):
+    count = P - first if count is None else count
+    x, v = np.empty(count), np.empty(count)
+    lib().oracle_quiet_start(P, first, count, x, v)
+    return x, v
+
+
+def growth_slope(W) -> float:
+    return lib().oracle_growth_slope(W)
+
+
+# ---------------------------------------------------------------- 2D3V
+def cic_g(z, NZ):
+    idx, wt = np.empty(2, dtype=np.int32), np.empty(2)
+    lib().oracle_cic_g(float(z), NZ, idx, wt)
+    return idx, wt
+
+
+def boris(vx, vy, vz, Ex, Ey, dt, B0):
+    a, b, c = np.array([vx], dtype=np.float64), np.array([vy], dtype=np.float64), np.array([vz], dtype=np.float64)
+    lib().oracle_boris(a, b, c, Ex, Ey, dt, B0)
+    return a[0], b[0], c[0]
+
+
+def cic_deposit(x, y, NX, NY, w):
+    rho = np.empty(NX * NY)
+    lib().oracle_cic_deposit(_f64(x), _f64(y), x.size, NX, NY, w, rho)
+    return rho
+
+
+def cic_gather(Ex, Ey, NX, NY, x, y):
+    ex, ey = np.empty(x.size), np.empty(x.size)
+    lib().oracle_cic_gather(_f64(Ex), _f64(Ey), NX, NY, _f64(x), _f64(y), x.size, ex, ey)
+    return ex, ey
+
+
+def solve2d(rho, NX, NY):
+    Ex, Ey = np.empty(NX * NY), np.empty(NX * NY)
+    lib().oracle_solve2d(_f64(rho), NX, NY, Ex, Ey)
+    return Ex, Ey
+
+
+def step_2d3v(x, y, vx, vy, vz, NX, NY, dt, B0, w, Ex, Ey, nthreads=1):
+    """In place on particles and Ex, Ey (flat column-major NX*NY).  Returns rho."""
+    rho = np.empty(NX * NY)
+    lib().oracle_2d3v_step(x, y, vx, vy, vz, x.size, NX, NY, dt, B0, w, Ex, Ey, rho, nthreads)
+    return rho
+
+
+def diagnostics_2d3v(Ex, Ey, NX, NY, vx, vy, w):
+    K = np.empty(5)
+    lib().oracle_2d3v_diagnostics(_f64(Ex), _f64(Ey), NX, NY, _f64(vx), _f64(vy), vx.size, w, K)
+    return K
+
+
+def max_threads() -> int:
+    return lib().oracle_max_threads()

@@ -1,0 +1,468 @@
+"""particleincellcodegolf.jl_b200 -- host-side mirror of libpicgolf.so (include/picgolf.h).
+
+The product is the CUDA library; this module only binds its C ABI with ctypes and keeps the
+reference scripts' parameter surface (N, P, dt, T, W, w, l, stencil half width) so that a run reads
+like the Julia it replaces:
+
+    src/NGPFourier.jl            -> ngp_fourier(...)
+    src/Gaussian.jl              -> gaussian(...)
+    src/GaussianFixedPoint.jl    -> gaussian_fixed_point(...)
+    src/GaussianFixedPointQuiet.jl -> gaussian_fixed_point_quiet(...)
+    src/Electrostatic2D3V.jl     -> electrostatic_2d3v(...)
+
+There is no CPU path: importing works anywhere (so the ABI can be checked), but every compute call
+needs a CUDA device and raises PicGolfError otherwise.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
+HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
+
+NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V = 1, 2, 3, 4
+DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED = 0, 1, 2
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+]
+
+
+class PicGolfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"picgolf error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/picgolf.cu for sm_100a into lib/libpicgolf.so (in-tree, travels with gpurun)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in sorted(os.listdir(src_dir))] + [HEADER_PATH]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(src_dir, "picgolf.cu"), "-ldl"]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Config(C.Structure):
+    """ctypes image of `picgolf_config` (include/picgolf.h)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("scheme", C.c_int32),
+        ("N", C.c_int64), ("NY", C.c_int64), ("P", C.c_int64), ("T", C.c_int64),
+        ("dt", C.c_double), ("W", C.c_double), ("w", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+        ("B0", C.c_double),
+        ("half_width", C.c_int32), ("max_sweeps", C.c_int32), ("diag_every", C.c_int32), ("deposit_mode", C.c_int32),
+        ("deterministic", C.c_int32), ("sort_every", C.c_int32), ("device", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
+        ("local_first", C.c_int64), ("local_count", C.c_int64),
+    ]
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_vp, _i64, _d, _int = C.c_void_p, C.c_int64, C.c_double, C.c_int
+
+# name -> (argtypes) ; every function returns int except picgolf_last_error.  This table is checked
+# against include/picgolf.h by tests/test_abi.py.
+_SIGNATURES = {
+    "picgolf_version": [],
+    "picgolf_device_count": [],
+    "picgolf_config_default": [C.POINTER(Config), _int, _int],
+    "picgolf_create": [C.POINTER(Config), C.POINTER(_vp)],
+    "picgolf_destroy": [_vp],
+    "picgolf_local_range": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "picgolf_set_particles": [_vp, _dp, _dp, _i64],
+    "picgolf_set_particles_2d3v": [_vp, _dp, _dp, _dp, _dp, _dp, _i64],
+    "picgolf_init_quiet": [_vp],
+    "picgolf_init_synthetic": [_vp, C.c_uint64, _d],
+    "picgolf_get_particles": [_vp, _vp, _vp, _i64],
+    "picgolf_get_particles_2d3v": [_vp, _vp, _vp, _vp, _vp, _vp, _i64],
+    "picgolf_step": [_vp, _i64],
+    "picgolf_synchronize": [_vp],
+    "picgolf_steps_done": [_vp, C.POINTER(_i64)],
+    "picgolf_get_fields": [_vp, _vp, _vp],
+    "picgolf_set_field": [_vp, _dp],
+    "picgolf_get_fields_2d": [_vp, _vp, _vp, _vp],
+    "picgolf_get_diagnostics": [_vp, _vp, _i64, _vp, C.POINTER(_i64)],
+    "picgolf_get_raw_diagnostics": [_vp, _vp, _i64, C.POINTER(_i64)],
+    "picgolf_stage_timing": [_vp, _int],
+    "picgolf_stage_times": [_vp, C.POINTER(_d * 5), _int],
+    "picgolf_launch_count": [_vp, C.POINTER(_i64)],
+    "picgolf_get_stream": [_vp, C.POINTER(_vp)],
+    "picgolf_comm_unique_id": [_vp],
+    "picgolf_comm_init": [_vp, _vp, _int, _int],
+    "picgolf_stage_ngp_index": [_dp, _i64, _i64, _ip],
+    "picgolf_stage_mod1": [_dp, _i64, _dp],
+    "picgolf_stage_gauss_stencil": [_dp, _i64, _i64, _int, _ip, _dp],
+    "picgolf_stage_ngp_deposit": [_dp, _i64, _i64, _d, _dp],
+    "picgolf_stage_gauss_deposit": [_dp, _dp, _i64, _i64, _int, _d, _int, _dp],
+    "picgolf_stage_gauss_gather": [_dp, _i64, _int, _dp, _i64, _dp],
+    "picgolf_stage_solve1d": [_dp, _i64, _dp],
+    "picgolf_stage_solve2d": [_dp, _i64, _i64, _dp, _dp],
+    "picgolf_stage_cic_deposit": [_dp, _dp, _i64, _i64, _i64, _d, _dp],
+    "picgolf_stage_cic_gather": [_dp, _dp, _i64, _i64, _dp, _dp, _i64, _dp, _dp],
+    "picgolf_stage_boris": [_dp, _dp, _dp, _dp, _dp, _i64, _d, _d],
+    "picgolf_stage_quiet_start": [_i64, _i64, _i64, _dp, _dp],
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """dlopen libpicgolf.so.  Fails loudly if it was not built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PicGolfError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(nvcc, sm_100a). libpicgolf has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        L.picgolf_last_error.restype = C.c_char_p
+        L.picgolf_last_error.argtypes = []
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PicGolfError(rc, load().picgolf_last_error().decode())
+
+
+def device_count() -> int:
+    return load().picgolf_device_count()
+
+
+def default_config(scheme: int, quiet: bool = False) -> Config:
+    cfg = Config()
+    _check(load().picgolf_config_default(C.byref(cfg), scheme, 1 if quiet else 0))
+    return cfg
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _out_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def shard_range(P: int, rank: int, nranks: int):
+    """Contiguous global index range [first, first+count) of a rank (remainder to the low ranks);
+    the same rule picgolf_create applies when local_first/local_count are -1."""
+    q, r = divmod(P, nranks)
+    first = q * rank + min(rank, r)
+    return first, q + (1 if rank < r else 0)
+
+
+class PIC:
+    """One simulation handle: the state `x, v, E, rho, D` of a reference script living on the GPU."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self._h = _vp()
+        self._lib = load()
+        _check(self._lib.picgolf_create(C.byref(cfg), C.byref(self._h)))
+        f, c = _i64(), _i64()
+        _check(self._lib.picgolf_local_range(self._h, C.byref(f), C.byref(c)))
+        self.first, self.count = f.value, c.value
+        self.is2d = cfg.scheme == CIC_BORIS_2D3V
+        self.ncell = cfg.N * (cfg.NY if self.is2d else 1)
+
+    # -- lifetime
+    def close(self):
+        if self._h:
+            self._lib.picgolf_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- particles
+    def set_particles(self, x, v, y=None, vy=None, vz=None):
+        if self.is2d:
+            arrs = [_f64(a) for a in (x, y, v, vy, vz)]  # x, y, vx, vy, vz
+            _check(self._lib.picgolf_set_particles_2d3v(self._h, *arrs, arrs[0].size))
+        else:
+            x, v = _f64(x), _f64(v)
+            _check(self._lib.picgolf_set_particles(self._h, x, v, x.size))
+
+    def init_quiet(self):
+        _check(self._lib.picgolf_init_quiet(self._h))
+
+    def init_synthetic(self, seed: int = 0, vth: float = 0.0):
+        _check(self._lib.picgolf_init_synthetic(self._h, C.c_uint64(seed), float(vth)))
+
+    def particles(self):
+        """(x, v) or (x, y, vx, vy, vz) of the local shard, in the caller's original order."""
+        n = self.count
+        if self.is2d:
+            out = [np.empty(n) for _ in range(5)]
+            _check(self._lib.picgolf_get_particles_2d3v(self._h, *[_out_ptr(a) for a in out], n))
+            return tuple(out)
+        x, v = np.empty(n), np.empty(n)
+        _check(self._lib.picgolf_get_particles(self._h, _out_ptr(x), _out_ptr(v), n))
+        return x, v
+
+    # -- loop body
+    def step(self, nsteps: int = 1):
+        _check(self._lib.picgolf_step(self._h, int(nsteps)))
+
+    def synchronize(self):
+        _check(self._lib.picgolf_synchronize(self._h))
+
+    @property
+    def steps_done(self) -> int:
+        s = _i64()
+        _check(self._lib.picgolf_steps_done(self._h, C.byref(s)))
+        return s.value
+
+    # -- fields / diagnostics
+    def fields(self):
+        """1D: (rho, E).  2D: (rho, Ex, Ey) as NX x NY Fortran-ordered arrays."""
+        if self.is2d:
+            rho, ex, ey = (np.empty(self.ncell) for _ in range(3))
+            _check(self._lib.picgolf_get_fields_2d(self._h, _out_ptr(rho), _out_ptr(ex), _out_ptr(ey)))
+            shp = (self.cfg.N, self.cfg.NY)
+            return tuple(a.reshape(shp, order="F") for a in (rho, ex, ey))
+        rho, E = np.empty(self.ncell), np.empty(self.ncell)
+        _check(self._lib.picgolf_get_fields(self._h, _out_ptr(rho), _out_ptr(E)))
+        return rho, E
+
+    def set_field(self, E):
+        _check(self._lib.picgolf_set_field(self._h, _f64(E)))
+
+    def diagnostics(self):
+        """(D, sweeps): D is rows x 4 (1D, GaussianFixedPoint.jl:10-11) or rows x 5 (2D K)."""
+        rows = _i64()
+        _check(self._lib.picgolf_get_diagnostics(self._h, None, 0, None, C.byref(rows)))
+        n, ncol = max(rows.value, 1), 5 if self.is2d else 4
+        D = np.zeros((n, ncol), order="F")
+        sw = np.zeros(n, dtype=np.int32)
+        _check(self._lib.picgolf_get_diagnostics(self._h, _out_ptr(D), n, _out_ptr(sw), C.byref(rows)))
+        return D[: rows.value], sw[: rows.value]
+
+    def raw_diagnostics(self):
+        rows = _i64()
+        _check(self._lib.picgolf_get_raw_diagnostics(self._h, None, 0, C.byref(rows)))
+        n = max(rows.value, 1)
+        R = np.zeros((n, 4), order="F")
+        _check(self._lib.picgolf_get_raw_diagnostics(self._h, _out_ptr(R), n, C.byref(rows)))
+        return R[: rows.value]
+
+    # -- instrumentation
+    def stage_timing(self, enable: bool = True):
+        _check(self._lib.picgolf_stage_timing(self._h, 1 if enable else 0))
+
+    def stage_times(self, reset: bool = False):
+        ms = (_d * 5)()
+        _check(self._lib.picgolf_stage_times(self._h, C.byref(ms), 1 if reset else 0))
+        return dict(zip(("particles", "reduction", "solve", "sort", "total"), list(ms)))
+
+    @property
+    def launches(self) -> int:
+        n = _i64()
+        _check(self._lib.picgolf_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def stream(self) -> int:
+        s = _vp()
+        _check(self._lib.picgolf_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    # -- multi-GPU
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(self._lib.picgolf_comm_init(self._h, buf, self.cfg.nranks, self.cfg.rank))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load().picgolf_comm_unique_id(buf))
+    return buf.raw
+
+
+# ------------------------------------------------------------------------------------------------
+# Script-shaped constructors (same literals as line 1 of each reference script)
+# ------------------------------------------------------------------------------------------------
+def _finish(cfg: Config, rank, nranks, device, T, **over) -> PIC:
+    cfg.rank, cfg.nranks, cfg.device = rank, nranks, device
+    if T is not None:
+        cfg.T = T
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return PIC(cfg)
+
+
+def ngp_fourier(N=128, P=None, dt=None, NT=1024, W=200.0, rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/NGPFourier.jl:1  N=128;P=64N;dt=1/4N;NT=1024;W=200;w=W/P*N"""
+    cfg = default_config(NGP_LEAPFROG)
+    cfg.N = N
+    cfg.P = 64 * N if P is None else P
+    cfg.dt = 1 / (4 * N) if dt is None else dt
+    cfg.W = W
+    cfg.w = W / cfg.P * N
+    return _finish(cfg, rank, nranks, device, NT, **over)
+
+
+def gaussian(NX=128, NP=None, dt=None, NT=1024, W=1600.0, rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/Gaussian.jl:2  NX=128; NP=64NX; dt=1/10NX; W=1600; w=W/NP; dx=1/NX (deposit scale w/dx)"""
+    cfg = default_config(GAUSS_LEAPFROG)
+    cfg.N = NX
+    cfg.P = 64 * NX if NP is None else NP
+    cfg.dt = 1 / (10 * NX) if dt is None else dt
+    cfg.W = W
+    cfg.w = W / cfg.P / (1 / NX)
+    return _finish(cfg, rank, nranks, device, NT, **over)
+
+
+def gaussian_fixed_point(N=128, P=None, dt=None, T=1024, W=400.0, l=1e-8, atol=0.0, half_width=6, max_sweeps=10,
+                         rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/GaussianFixedPoint.jl:1-5  N=128;P=32N;dt=1/6N;T=1024;W=400;w=W/P*N;l=1e-8; stencil -6:6"""
+    cfg = default_config(GAUSS_FIXEDPOINT)
+    cfg.N = N
+    cfg.P = 32 * N if P is None else P
+    cfg.dt = 1 / (6 * N) if dt is None else dt
+    cfg.W = W
+    cfg.w = W / cfg.P * N
+    cfg.rtol, cfg.atol, cfg.half_width, cfg.max_sweeps = l, atol, half_width, max_sweeps
+    return _finish(cfg, rank, nranks, device, T, **over)
+
+
+def gaussian_fixed_point_quiet(N=64, P=None, dt=None, T=2 ** 13, W=32 * math.pi ** 2 / 3, l=4 * np.finfo(float).eps,
+                               rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/GaussianFixedPointQuiet.jl:1-6  N=64;P=32N;dt=1/6N;T=2^13;W=32pi^2/3;l=4eps();atol=0; stencil -7:7.
+    Call .init_quiet() for the bit-reversal start (lines 2-3)."""
+    return gaussian_fixed_point(N=N, P=P, dt=dt, T=T, W=W, l=l, atol=0.0, half_width=7, rank=rank, nranks=nranks,
+                                device=device, **over)
+
+
+def electrostatic_2d3v(NX=128, NY=None, P=None, T=2 ** 13, NS=2, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1,
+                       **over) -> PIC:
+    """src/Electrostatic2D3V.jl:23-25  NX=NY=128;P=NX*NY*2^5;NG=sqrt(NX^2+NY^2);n0=4pi^2;vth=sqrt(n0)/NG;
+    dt=1/NG/6vth;B0=sqrt(n0)/4;NS=2;w=n0/P/(dx*dy).  T here is the number of diagnostics rows kept."""
+    cfg = default_config(CIC_BORIS_2D3V)
+    NY = NX if NY is None else NY
+    cfg.N, cfg.NY = NX, NY
+    cfg.P = NX * NY * 32 if P is None else P
+    NG = math.sqrt(NX ** 2 + NY ** 2)
+    vth = math.sqrt(n0) / NG
+    cfg.W = n0
+    cfg.dt = 1 / NG / (6 * vth)
+    cfg.B0 = math.sqrt(n0) / 4
+    cfg.diag_every = NS
+    cfg.w = n0 / cfg.P / ((1 / NX) * (1 / NY))
+    pic = _finish(cfg, rank, nranks, device, T, **over)
+    pic.vth = vth
+    return pic
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage-level calls (one reference expression each; see include/picgolf.h)
+# ------------------------------------------------------------------------------------------------
+def ngp_index(x, N: int) -> np.ndarray:
+    x = _f64(np.atleast_1d(x))
+    out = np.empty(x.size, dtype=np.int32)
+    _check(load().picgolf_stage_ngp_index(x, x.size, N, out))
+    return out
+
+
+def mod1(x) -> np.ndarray:
+    x = _f64(np.atleast_1d(x))
+    out = np.empty_like(x)
+    _check(load().picgolf_stage_mod1(x, x.size, out))
+    return out
+
+
+def gauss_stencil(c, N: int, hw: int = 6):
+    c = _f64(np.atleast_1d(c))
+    nw = 2 * hw + 1
+    idx = np.empty((c.size, nw), dtype=np.int32)
+    wt = np.empty((c.size, nw))
+    _check(load().picgolf_stage_gauss_stencil(c, c.size, N, hw, idx.reshape(-1), wt.reshape(-1)))
+    return idx, wt
+
+
+def ngp_deposit(x, N: int, w: float) -> np.ndarray:
+    x = _f64(x)
+    rho = np.empty(N)
+    _check(load().picgolf_stage_ngp_deposit(x, x.size, N, w, rho))
+    return rho
+
+
+def gauss_deposit(x, y, N: int, hw: int, w: float, mode: int = DEPOSIT_AUTO) -> np.ndarray:
+    x, y = _f64(x), _f64(y)
+    rho = np.empty(N)
+    _check(load().picgolf_stage_gauss_deposit(x, y, x.size, N, hw, w, mode, rho))
+    return rho
+
+
+def gauss_gather(E, c, hw: int = 6) -> np.ndarray:
+    E, c = _f64(E), _f64(np.atleast_1d(c))
+    out = np.empty(c.size)
+    _check(load().picgolf_stage_gauss_gather(E, E.size, hw, c, c.size, out))
+    return out
+
+
+def solve1d(rho) -> np.ndarray:
+    rho = _f64(rho)
+    E = np.empty_like(rho)
+    _check(load().picgolf_stage_solve1d(rho, rho.size, E))
+    return E
+
+
+def solve2d(rho, NX: int, NY: int):
+    rho = _f64(np.asarray(rho).reshape(-1, order="F"))
+    Ex, Ey = np.empty(NX * NY), np.empty(NX * NY)
+    _check(load().picgolf_stage_solve2d(rho, NX, NY, Ex, Ey))
+    return Ex, Ey
+
+
+def cic_deposit(x, y, NX: int, NY: int, w: float) -> np.ndarray:
+    x, y = _f64(x), _f64(y)
+    rho = np.empty(NX * NY)
+    _check(load().picgolf_stage_cic_deposit(x, y, x.size, NX, NY, w, rho))
+    return rho
+
+
+def cic_gather(Ex, Ey, NX: int, NY: int, x, y):
+    x, y = _f64(x), _f64(y)
+    ex, ey = np.empty(x.size), np.empty(x.size)
+    _check(load().picgolf_stage_cic_gather(_f64(Ex).reshape(-1), _f64(Ey).reshape(-1), NX, NY, x, y, x.size, ex, ey))
+    return ex, ey
+
+
+def boris(vx, vy, vz, Ex, Ey, dt: float, B0: float):
+    vx, vy, vz = (_f64(a).copy() for a in (vx, vy, vz))
+    _check(load().picgolf_stage_boris(vx, vy, vz, _f64(Ex), _f64(Ey), vx.size, dt, B0))
+    return vx, vy, vz
+
+
+def quiet_start(P: int, first: int = 0, count: Optional[int] = None):
+    count = P - first if count is None else count
+    x, v = np.empty(count), np.empty(count)
+    _check(load().picgolf_stage_quiet_start(P, first, count, x, v))
+    return x, v

@@ -1,0 +1,87 @@
+// pg_common.cuh -- shared device/host helpers for libpicgolf (sm_100a).
+// Compiled with -fmad=false: every a*b+c below rounds twice exactly like the Julia reference
+// (Julia fuses only under @muladd); fused operations are written as explicit fma().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#define PG_THREADS 256
+#define PG_WARP 32
+
+namespace pg {
+
+// ---- Julia Base semantics -------------------------------------------------------------
+
+// Julia mod(a, 1) for Float64 (base/float.jl): r = rem(a,1); r==0 -> +0; r<0 -> r+1 (may round to
+// exactly 1.0); else r.   src/NGPFourier.jl:2, src/GaussianFixedPoint.jl:9.
+__device__ __forceinline__ double jl_mod1(double a)
+{
+    double r = a - trunc(a); // == fmod(a, 1.0), exact
+    if (r == 0.0) return 0.0;
+    if (r < 0.0) return r + 1.0;
+    return r;
+}
+
+// f(x) = Int(mod1(round(x*N), N)), src/NGPFourier.jl:3 -- returned 0-based (Julia cell - 1).
+// round = ties-to-even (rint); mod1(0,N) = N.
+__device__ __forceinline__ int ngp_cell0(double x, int N)
+{
+    long long r = __double2ll_rn(x * (double)N); // rint, ties to even
+    long long m = (r - 1) % (long long)N;
+    if (m < 0) m += N;
+    return (int)m;
+}
+
+// 0-based wrap of a Julia 1-based stencil index i (any sign): mod1(i,N)-1 == floormod(i-1, N).
+__device__ __forceinline__ int wrap_cell0(int i, int N)
+{
+    int m = (i - 1) % N;
+    return m < 0 ? m + N : m;
+}
+
+// unimod(x, n) = 0 < x <= n ? x : x > n ? x - n : x + n      src/Electrostatic2D3V.jl:83
+__device__ __forceinline__ double unimod(double x, double n) { return (0.0 < x && x <= n) ? x : (x > n ? x - n : x + n); }
+__device__ __forceinline__ int unimod(int x, int n) { return (0 < x && x <= n) ? x : (x > n ? x - n : x + n); }
+
+// ---- reductions -------------------------------------------------------------------------
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0.  scratch: >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double *scratch)
+{
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < nw ? scratch[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// ---- streaming loads/stores (particle arrays are touched once per pass) -------------------
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+
+// splitmix64: counter-based generator for the synthetic starts (NOT Julia's rand).
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ double u01(uint64_t bits) { return (double)(bits >> 11) * (1.0 / 9007199254740992.0); }
+
+} // namespace pg

@@ -1,0 +1,247 @@
+// pg_fft.cuh -- shared-memory radix-2 FFT fused with the spectral Poisson solve.
+//   1D: E = real.(ifft((xi = fft(rho)./ik; xi[1]*=0; xi))),  ik = 2pi*im*vcat(1, 1:N/2, -N/2+1:-1)
+//       src/NGPFourier.jl:3,5; src/GaussianFixedPoint.jl:3,8  (FFTW conventions: forward
+//       sum x[n] e^{-2 pi i nk/N} unnormalised, inverse 1/N).
+//   2D: fft!(phi); phi[1,1]=0; Ex = phi*minvkk*kx; Ey = phi*minvkk*ky; ifft!(Ex); ifft!(Ey)
+//       src/Electrostatic2D3V.jl:70-81,142-157.
+// The forward transform is decimation-in-frequency (natural in, bit-reversed out), the pointwise
+// divide runs on the bit-reversed spectrum, and the inverse is decimation-in-time (bit-reversed in,
+// natural out), so no permutation pass is needed.  cuFFT is not used anywhere.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr double TWO_PI = 6.283185307179586476925286766559; // Julia 2pi
+
+// Device-resident loop control and per-step sums (one per handle).
+struct Ctrl {
+    int final_k;     // fixed point: sweep index whose pass finalises the step (-1: still iterating)
+    int sweeps;      // solves executed in the current step
+    int rows;        // diagnostics rows recorded so far
+    int pad_;
+    long long step;  // steps completed
+    double sumE2;    // sum(E.^2) of the latest solve (2D: sum(Ex^2+Ey^2))
+};
+
+// Batched in-place FFT on shared memory.  Element e of batch b lives at [b*bstride + e*estride].
+// tw[k] = exp(-2 pi i k / twN), k < twN/2, n divides twN.  All threads of the block participate.
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem(double *re, double *im, int n, int batch, int estride, int bstride,
+                                         const double2 *__restrict__ tw, int twN)
+{
+    const int nh = n >> 1;
+    const int total = batch * nh;
+    if (!INVERSE) {
+        for (int half = nh; half >= 1; half >>= 1) {
+            const int tws = twN / (2 * half);
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                int b = t / nh, u = t - b * nh;
+                int pos = u & (half - 1), grp = u / half;
+                int i = b * bstride + (grp * 2 * half + pos) * estride, j = i + half * estride;
+                double2 w = __ldg(&tw[pos * tws]);
+                double ar = re[i], ai = im[i], br = re[j], bi = im[j];
+                re[i] = ar + br; im[i] = ai + bi;
+                double dr = ar - br, di = ai - bi;
+                re[j] = dr * w.x - di * w.y;
+                im[j] = dr * w.y + di * w.x;
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int half = 1; half <= nh; half <<= 1) {
+            const int tws = twN / (2 * half);
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                int b = t / nh, u = t - b * nh;
+                int pos = u & (half - 1), grp = u / half;
+                int i = b * bstride + (grp * 2 * half + pos) * estride, j = i + half * estride;
+                double2 w = __ldg(&tw[pos * tws]); // conjugate below
+                double br = re[j], bi = im[j];
+                double tr = br * w.x + bi * w.y;
+                double ti = bi * w.x - br * w.y;
+                double ar = re[i], ai = im[i];
+                re[j] = ar - tr; im[j] = ai - ti;
+                re[i] = ar + tr; im[i] = ai + ti;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int bitrev(int v, int lg) { return (int)(__brev((unsigned)v) >> (32 - lg)); }
+
+struct Solve1DArgs {
+    double *rho;                    // [N] deposited charge (summed over ranks); zeroed after it is read
+    unsigned long long *counts;     // NGP: integer deposit counts (rho = counts*w); zeroed after read
+    double *rho_last;               // [N] copy kept for picgolf_get_fields
+    double *E;                      // [N] in: previous field (the reference's F), out: new field
+    const double2 *tw;              // twiddles for size N
+    Ctrl *ctrl;
+    double w, rtol, atol;
+    int N, lg, use_counts, fixedpoint, k, max_sweeps;
+};
+
+// One block.  Dynamic shared memory: 2*N doubles + 32.
+__global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
+{
+    extern __shared__ double smem[];
+    double *re = smem, *im = smem + a.N, *scratch = smem + 2 * a.N;
+    if (a.fixedpoint && a.ctrl->final_k >= 0) return; // step already converged: predicated no-op
+    const int N = a.N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double r;
+        if (a.use_counts) { r = (double)a.counts[n] * a.w; a.counts[n] = 0ULL; }
+        else { r = a.rho[n]; a.rho[n] = 0.0; }
+        a.rho_last[n] = r;
+        re[n] = r; im[n] = 0.0;
+    }
+    __syncthreads();
+    fft_smem<false>(re, im, N, 1, 1, 0, a.tw, N);
+    // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        int s = bitrev(p, a.lg); // frequency slot held at position p
+        if (s == 0) { re[p] = 0.0; im[p] = 0.0; }
+        else {
+            double kk = (s <= N / 2) ? (double)s : (double)(s - N);
+            double b = TWO_PI * kk;
+            double zr = re[p], zi = im[p];
+            re[p] = zi / b;
+            im[p] = -zr / b;
+        }
+    }
+    __syncthreads();
+    fft_smem<true>(re, im, N, 1, 1, 0, a.tw, N);
+    double d2 = 0.0, f2 = 0.0, e2 = 0.0;
+    const double dN = (double)N;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double e = re[n] / dN;
+        double f = a.E[n];
+        a.E[n] = e;
+        double d = f - e;
+        d2 = fma(d, d, d2); f2 = fma(f, f, f2); e2 = fma(e, e, e2);
+    }
+    d2 = block_sum(d2, scratch);
+    f2 = block_sum(f2, scratch);
+    e2 = block_sum(e2, scratch);
+    if (threadIdx.x == 0) {
+        a.ctrl->sumE2 = e2;
+        if (a.fixedpoint) {
+            // LinearAlgebra.isapprox(F,E;rtol,atol): norm(F-E) <= max(atol, rtol*max(norm(F),norm(E)))
+            double d = sqrt(d2);
+            double m = fmax(sqrt(f2), sqrt(e2));
+            bool conv = isfinite(d) && d <= fmax(a.atol, a.rtol * m);
+            a.ctrl->sweeps = a.k;
+            if (conv || a.k >= a.max_sweeps) a.ctrl->final_k = a.k;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2D solve: three kernels (x-rows forward, y-columns forward+invert+inverse, x-rows inverse).
+// Z holds the complex spectrum with x in bit-reversed order after pass A.
+// real(ifft(S)) only sees the Hermitian part of S; for real rho that makes Ex on the kx-Nyquist row
+// and Ey on the ky-Nyquist column vanish, after which both spectra are Hermitian and ONE inverse
+// transform of Ex^ + i Ey^ returns Ex in the real part and Ey in the imaginary part.
+// ---------------------------------------------------------------------------------------------
+struct Solve2DArgs {
+    double *rho;        // [NX*NY] column-major; zeroed after read
+    double *rho_last;
+    double2 *Z;         // [NX*NY] complex scratch
+    double2 *E2;        // [NX*NY] (real(Ex), real(Ey)) per cell
+    const double2 *twx, *twy;
+    double *partials;   // per-block partial sums of Ex^2+Ey^2 (pass C)
+    int NX, NY, lgx, lgy;
+};
+
+constexpr int ROWS_PER_BLOCK = 4;
+constexpr int COLS_PER_BLOCK = 8;
+
+// Pass A: forward along x for ROWS_PER_BLOCK rows.  smem: 2*ROWS*NX doubles.
+__global__ void __launch_bounds__(512) solve2d_rows_fwd(Solve2DArgs a)
+{
+    extern __shared__ double smem[];
+    const int NX = a.NX, R = ROWS_PER_BLOCK;
+    double *re = smem, *im = smem + R * NX;
+    const int j0 = blockIdx.x * R;
+    for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
+        int r = t / NX, i = t - r * NX;
+        size_t g = (size_t)i + (size_t)(j0 + r) * NX;
+        double v = a.rho[g];
+        a.rho[g] = 0.0; a.rho_last[g] = v;
+        re[t] = v; im[t] = 0.0;
+    }
+    __syncthreads();
+    fft_smem<false>(re, im, NX, R, 1, NX, a.twx, NX);
+    for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
+        int r = t / NX, i = t - r * NX;
+        a.Z[(size_t)i + (size_t)(j0 + r) * NX] = make_double2(re[t], im[t]);
+    }
+}
+
+// Pass B: for COLS_PER_BLOCK x-positions: forward along y, multiply, inverse along y.
+// smem layout [c][j] with row stride NY+1 to stagger banks.
+__global__ void __launch_bounds__(512) solve2d_cols(Solve2DArgs a)
+{
+    extern __shared__ double smem[];
+    const int NX = a.NX, NY = a.NY, C = COLS_PER_BLOCK, LD = NY + 1;
+    double *re = smem, *im = smem + C * LD;
+    const int p0 = blockIdx.x * C;
+    for (int t = threadIdx.x; t < C * NY; t += blockDim.x) {
+        int j = t / C, c = t - j * C;
+        double2 z = a.Z[(size_t)(p0 + c) + (size_t)j * NX];
+        re[c * LD + j] = z.x; im[c * LD + j] = z.y;
+    }
+    __syncthreads();
+    fft_smem<false>(re, im, NY, C, 1, LD, a.twy, NY);
+    for (int t = threadIdx.x; t < C * NY; t += blockDim.x) {
+        int c = t / NY, q = t - c * NY;
+        int ix = bitrev(p0 + c, a.lgx), iy = bitrev(q, a.lgy); // frequency slots (0-based)
+        double kx = TWO_PI * (double)(ix < NX / 2 ? ix : ix - NX);
+        double ky = TWO_PI * (double)(iy < NY / 2 ? iy : iy - NY);
+        double ar = re[c * LD + q], ai = im[c * LD + q];
+        double zr = 0.0, zi = 0.0;
+        if (ix != 0 || iy != 0) {
+            double m = -1.0 / (kx * kx + ky * ky); // minvkk = (0, m)
+            double tr = -(ai * m), ti = ar * m;    // phi*minvkk
+            double exr = tr * kx, exi = ti * kx, eyr = tr * ky, eyi = ti * ky;
+            if (ix == NX / 2) { exr = 0.0; exi = 0.0; }
+            if (iy == NY / 2) { eyr = 0.0; eyi = 0.0; }
+            zr = exr - eyi; zi = exi + eyr; // Ex^ + i Ey^
+        }
+        re[c * LD + q] = zr; im[c * LD + q] = zi;
+    }
+    __syncthreads();
+    fft_smem<true>(re, im, NY, C, 1, LD, a.twy, NY);
+    for (int t = threadIdx.x; t < C * NY; t += blockDim.x) {
+        int j = t / C, c = t - j * C;
+        a.Z[(size_t)(p0 + c) + (size_t)j * NX] = make_double2(re[c * LD + j], im[c * LD + j]);
+    }
+}
+
+// Pass C: inverse along x; E2 = (re, im)/(NX*NY); per-block partial of sum(Ex^2+Ey^2).
+__global__ void __launch_bounds__(512) solve2d_rows_inv(Solve2DArgs a)
+{
+    extern __shared__ double smem[];
+    const int NX = a.NX, R = ROWS_PER_BLOCK;
+    double *re = smem, *im = smem + R * NX, *scratch = smem + 2 * R * NX;
+    const int j0 = blockIdx.x * R;
+    for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
+        int r = t / NX, i = t - r * NX;
+        double2 z = a.Z[(size_t)i + (size_t)(j0 + r) * NX];
+        re[t] = z.x; im[t] = z.y;
+    }
+    __syncthreads();
+    fft_smem<true>(re, im, NX, R, 1, NX, a.twx, NX);
+    const double inv = (double)NX * (double)a.NY;
+    double e2 = 0.0;
+    for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
+        int r = t / NX, i = t - r * NX;
+        double ex = re[t] / inv, ey = im[t] / inv;
+        a.E2[(size_t)i + (size_t)(j0 + r) * NX] = make_double2(ex, ey);
+        e2 += ex * ex + ey * ey;
+    }
+    e2 = block_sum(e2, scratch);
+    if (threadIdx.x == 0) a.partials[blockIdx.x] = e2;
+}
+
+} // namespace pg

@@ -1,0 +1,1084 @@
+// picgolf.cu -- C ABI of libpicgolf.so (include/picgolf.h).  Host-side orchestration only: every
+// number is produced by the CUDA kernels in pg_*.cuh; there is no CPU compute path and no fallback.
+#include "../../include/picgolf.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "pg_common.cuh"
+#include "pg_fft.cuh"
+#include "pg_gauss.cuh"
+#include "pg_kernels_1d.cuh"
+#include "pg_kernels_2d.cuh"
+
+using namespace pg;
+
+#define PG_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PG_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(PICGOLF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define PG_TRY(expr)            \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+static int ilog2(int64_t n) { int l = 0; while (((int64_t)1 << l) < n) ++l; return l; }
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the process's already-loaded libnccl.so.2 if there is one)
+// ------------------------------------------------------------------------------------------
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;
+typedef void *Comm;
+enum { Sum = 0 };
+enum { Uint64 = 5, Float64 = 8 };
+static void *lib = nullptr;
+static int (*GetUniqueId)(UniqueId *) = nullptr;
+static int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+static int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+static int (*CommDestroy)(Comm) = nullptr;
+static const char *(*GetErrorString)(int) = nullptr;
+
+static int load()
+{
+    if (AllReduce) return 0;
+    const char *env = getenv("PICGOLF_NCCL_LIB");
+    if (env && *env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // share the instance torch loaded
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(PICGOLF_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    GetUniqueId = (int (*)(UniqueId *))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(Comm *, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void *, void *, size_t, int, int, Comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(Comm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+        AllReduce = nullptr;
+        return fail(PICGOLF_ERR_NCCL, "libnccl is missing required symbols");
+    }
+    return 0;
+}
+static int check(int rc, const char *what)
+{
+    if (rc == 0) return 0;
+    return fail(PICGOLF_ERR_NCCL, "%s failed: %s", what, GetErrorString ? GetErrorString(rc) : "?");
+}
+} // namespace nccl
+
+// ------------------------------------------------------------------------------------------
+// stage timers: CUDA events recorded on the handle's stream, resolved lazily (never inside a step)
+// ------------------------------------------------------------------------------------------
+struct StageTimer {
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> open;
+    std::vector<cudaEvent_t> pool;
+    double ms[5] = {0, 0, 0, 0, 0};
+    bool enabled = false;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(int stage, cudaStream_t s)
+    {
+        if (!enabled) return;
+        Span sp{stage, get(), get()};
+        cudaEventRecord(sp.a, s);
+        open.push_back(sp);
+    }
+    void end(cudaStream_t s)
+    {
+        if (!enabled) return;
+        cudaEventRecord(open.back().b, s);
+    }
+    void drain()
+    {
+        for (auto &sp : open) {
+            float t = 0.f;
+            cudaEventSynchronize(sp.b);
+            cudaEventElapsedTime(&t, sp.a, sp.b);
+            ms[sp.stage] += t;
+            pool.push_back(sp.a); pool.push_back(sp.b);
+        }
+        open.clear();
+    }
+    void destroy()
+    {
+        drain();
+        for (auto e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
+enum { ST_PARTICLES = 0, ST_REDUCE = 1, ST_SOLVE = 2, ST_SORT = 3, ST_TOTAL = 4 };
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct picgolf_handle_s {
+    picgolf_config cfg;
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    int64_t first = 0, count = 0;
+    bool is2d = false, fixedpoint = false, ngp = false;
+    // particles (1D: xb/vb ping-pong for the fixed point; leapfrog and 2D use index 0)
+    double *xb[2] = {nullptr, nullptr}, *vb[2] = {nullptr, nullptr};
+    double *y = nullptr, *vy = nullptr, *vz = nullptr; // 2D: x=xb[0], vx=vb[0]
+    int par = 0;
+    // grids
+    double *rho = nullptr, *rho_last = nullptr, *E = nullptr;
+    unsigned long long *counts = nullptr;
+    double2 *tw = nullptr, *twy = nullptr, *Z = nullptr, *E2 = nullptr;
+    double *epartials = nullptr;
+    int64_t ncell = 0;
+    // control / diagnostics
+    Ctrl *ctrl = nullptr;
+    double *partials = nullptr, *raw = nullptr;
+    int64_t T = 1;
+    int nblocks = 1, npart = 2;
+    size_t smem_pass = 0;
+    bool have_particles = false;
+    int64_t steps = 0, launches = 0;
+    nccl::Comm comm = nullptr;
+    int nranks = 1, rank = 0;
+    StageTimer timer;
+};
+
+static int use_device(picgolf_handle h) { PG_CUDA(cudaSetDevice(h->device)); return 0; }
+
+template <typename T>
+static int dalloc(T **p, size_t n)
+{
+    PG_CUDA(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+static int make_twiddles(double2 **dst, int n)
+{
+    std::vector<double2> t(std::max(n / 2, 1));
+    for (int k = 0; k < n / 2; ++k) {
+        long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        t[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    PG_TRY(dalloc(dst, t.size()));
+    PG_CUDA(cudaMemcpy(*dst, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <typename K>
+static int occupancy_blocks(K kernel, int threads, size_t smem, int sms, int64_t work, int *out)
+{
+    int per_sm = 0;
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(PICGOLF_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", smem);
+    int64_t want = (work + threads - 1) / threads;
+    int64_t cap = (int64_t)per_sm * sms;
+    *out = (int)std::max<int64_t>(1, std::min(want, cap));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+PG_API int picgolf_version(void) { return PICGOLF_VERSION; }
+PG_API const char *picgolf_last_error(void) { return g_err; }
+PG_API int picgolf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
+{
+    if (!c) return fail(PICGOLF_ERR_ARG, "cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(*c);
+    c->scheme = scheme;
+    c->half_width = 6; c->max_sweeps = 10; c->diag_every = 1;
+    c->device = -1; c->rank = 0; c->nranks = 1; c->local_first = -1; c->local_count = -1;
+    const double pi = 3.14159265358979323846;
+    switch (scheme) {
+    case PICGOLF_NGP_LEAPFROG: // NGPFourier.jl:1
+        c->N = 128; c->P = 64 * c->N; c->dt = 1.0 / (4 * c->N); c->T = 1024; c->W = 200;
+        c->w = c->W / (double)c->P * (double)c->N;
+        break;
+    case PICGOLF_GAUSS_LEAPFROG: // Gaussian.jl:2   (deposit scale w/dx)
+        c->N = 128; c->P = 64 * c->N; c->dt = 1.0 / (10 * c->N); c->T = 1024; c->W = 1600;
+        c->w = c->W / (double)c->P / (1.0 / (double)c->N);
+        break;
+    case PICGOLF_GAUSS_FIXEDPOINT:
+        if (!quiet) { // GaussianFixedPoint.jl:1-5
+            c->N = 128; c->P = 32 * c->N; c->dt = 1.0 / (6 * c->N); c->T = 1024; c->W = 400;
+            c->rtol = 1e-8; c->atol = 0; c->half_width = 6;
+        } else { // GaussianFixedPointQuiet.jl:1-6
+            c->N = 64; c->P = 32 * c->N; c->dt = 1.0 / (6 * c->N); c->T = 1 << 13; c->W = 32 * pi * pi / 3;
+            c->rtol = 4 * 2.220446049250313e-16; c->atol = 0; c->half_width = 7;
+        }
+        c->w = c->W / (double)c->P * (double)c->N;
+        break;
+    case PICGOLF_CIC_BORIS_2D3V: { // Electrostatic2D3V.jl:23-25
+        c->N = 128; c->NY = 128; c->P = c->N * c->NY * 32; c->T = 1 << 13;
+        double NG = sqrt((double)(c->N * c->N + c->NY * c->NY));
+        double n0 = 4 * pi * pi, vth = sqrt(n0) / NG;
+        c->W = n0; c->dt = 1 / NG / (6 * vth); c->B0 = sqrt(n0) / 4; c->diag_every = 2;
+        c->w = n0 / (double)c->P / ((1.0 / (double)c->N) * (1.0 / (double)c->NY));
+        break;
+    }
+    default:
+        return fail(PICGOLF_ERR_ARG, "unknown scheme %d", scheme);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+static int destroy_impl(picgolf_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->timer.destroy();
+    if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
+    void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->y, h->vy, h->vz, h->rho, h->rho_last, h->E, h->counts,
+                    h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+PG_API int picgolf_destroy(picgolf_handle h) { return destroy_impl(h); }
+
+static int create_impl(const picgolf_config *cfg, picgolf_handle h)
+{
+    const picgolf_config &c = h->cfg;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(PICGOLF_ERR_CUDA, "no CUDA device: libpicgolf has no CPU path");
+    }
+    if (c.device >= 0) h->device = c.device; else PG_CUDA(cudaGetDevice(&h->device));
+    if (h->device >= ndev) return fail(PICGOLF_ERR_ARG, "device %d out of range (%d visible)", h->device, ndev);
+    PG_CUDA(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    PG_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    h->sms = prop.multiProcessorCount;
+    PG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    h->is2d = c.scheme == PICGOLF_CIC_BORIS_2D3V;
+    h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT;
+    h->ngp = c.scheme == PICGOLF_NGP_LEAPFROG;
+    h->nranks = std::max(1, c.nranks);
+    h->rank = c.rank;
+    if (h->rank < 0 || h->rank >= h->nranks) return fail(PICGOLF_ERR_ARG, "rank %d outside [0,%d)", h->rank, h->nranks);
+    if (c.local_first >= 0 && c.local_count >= 0) { h->first = c.local_first; h->count = c.local_count; }
+    else { // even split, remainder to the low ranks
+        int64_t q = c.P / h->nranks, r = c.P % h->nranks;
+        h->first = q * h->rank + std::min<int64_t>(h->rank, r);
+        h->count = q + (h->rank < r ? 1 : 0);
+    }
+    if (h->first < 0 || h->first + h->count > c.P) return fail(PICGOLF_ERR_ARG, "local shard outside [0,P)");
+    h->T = std::max<int64_t>(1, c.T);
+
+    const size_t n = (size_t)h->count;
+    if (!h->is2d) {
+        const int N = (int)c.N;
+        h->ncell = N;
+        PG_TRY(dalloc(&h->xb[0], n)); PG_TRY(dalloc(&h->vb[0], n));
+        if (h->fixedpoint) { PG_TRY(dalloc(&h->xb[1], n)); PG_TRY(dalloc(&h->vb[1], n)); }
+        PG_TRY(dalloc(&h->rho, N)); PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, N));
+        PG_TRY(dalloc(&h->counts, N));
+        PG_CUDA(cudaMemset(h->rho, 0, N * sizeof(double)));
+        PG_CUDA(cudaMemset(h->rho_last, 0, N * sizeof(double)));
+        PG_CUDA(cudaMemset(h->E, 0, N * sizeof(double)));
+        PG_CUDA(cudaMemset(h->counts, 0, N * sizeof(unsigned long long)));
+        PG_TRY(make_twiddles(&h->tw, N));
+        h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
+        h->npart = 2;
+        PG_TRY(set_smem(solve1d_kernel, h->smem_pass));
+        if (h->fixedpoint) {
+            PG_TRY(set_smem(fp_pass_atomic<true>, h->smem_pass));
+            PG_TRY(set_smem(fp_pass_atomic<false>, h->smem_pass));
+            PG_TRY(occupancy_blocks(fp_pass_atomic<false>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+        } else if (h->ngp) {
+            PG_TRY(set_smem(lf_pass<0>, h->smem_pass));
+            PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+        } else {
+            PG_TRY(set_smem(lf_pass<1>, h->smem_pass));
+            PG_TRY(occupancy_blocks(lf_pass<1>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+        }
+    } else {
+        const int NX = (int)c.N, NY = (int)c.NY;
+        h->ncell = (int64_t)NX * NY;
+        PG_TRY(dalloc(&h->xb[0], n)); PG_TRY(dalloc(&h->vb[0], n));
+        PG_TRY(dalloc(&h->y, n)); PG_TRY(dalloc(&h->vy, n)); PG_TRY(dalloc(&h->vz, n));
+        PG_TRY(dalloc(&h->rho, h->ncell)); PG_TRY(dalloc(&h->rho_last, h->ncell));
+        PG_TRY(dalloc(&h->Z, h->ncell)); PG_TRY(dalloc(&h->E2, h->ncell));
+        PG_TRY(dalloc(&h->epartials, NY / ROWS_PER_BLOCK));
+        PG_CUDA(cudaMemset(h->rho, 0, h->ncell * sizeof(double)));
+        PG_CUDA(cudaMemset(h->rho_last, 0, h->ncell * sizeof(double)));
+        PG_CUDA(cudaMemset(h->E2, 0, h->ncell * sizeof(double2)));
+        PG_TRY(make_twiddles(&h->tw, NX)); PG_TRY(make_twiddles(&h->twy, NY));
+        PG_TRY(set_smem(solve2d_rows_fwd, (size_t)2 * ROWS_PER_BLOCK * NX * 8));
+        PG_TRY(set_smem(solve2d_rows_inv, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8));
+        PG_TRY(set_smem(solve2d_cols, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8));
+        h->npart = 3;
+        PG_TRY(occupancy_blocks(particles_2d3v_kernel, PG_THREADS, 0, h->sms, h->count, &h->nblocks));
+    }
+    PG_TRY(dalloc(&h->ctrl, 1));
+    Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
+    PG_CUDA(cudaMemcpy(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice));
+    PG_TRY(dalloc(&h->partials, (size_t)3 * h->nblocks));
+    PG_CUDA(cudaMemset(h->partials, 0, (size_t)3 * h->nblocks * sizeof(double)));
+    PG_TRY(dalloc(&h->raw, (size_t)4 * h->T));
+    PG_CUDA(cudaMemset(h->raw, 0, (size_t)4 * h->T * sizeof(double)));
+    (void)cfg;
+    return 0;
+}
+
+PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
+{
+    if (!cfg || !out) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (cfg->struct_size != (int32_t)sizeof(picgolf_config))
+        return fail(PICGOLF_ERR_ARG, "struct_size %d != %zu (header/library mismatch)", cfg->struct_size, sizeof(picgolf_config));
+    const picgolf_config &c = *cfg;
+    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_CIC_BORIS_2D3V) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.P < 1) return fail(PICGOLF_ERR_ARG, "P must be >= 1");
+    if (!(c.dt > 0) || !isfinite(c.dt)) return fail(PICGOLF_ERR_ARG, "dt must be positive and finite");
+    if (!isfinite(c.w)) return fail(PICGOLF_ERR_ARG, "w must be finite");
+    if (c.scheme == PICGOLF_CIC_BORIS_2D3V) {
+        if (c.N < 16 || c.NY < 16 || c.N > 1024 || c.NY > 1024) return fail(PICGOLF_ERR_ARG, "2D grid must be 16..1024 per side");
+        if (!is_pow2(c.N) || !is_pow2(c.NY))
+            return fail(PICGOLF_ERR_UNSUPPORTED, "NX=%lld NY=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N, (long long)c.NY);
+    } else {
+        if (c.N < 16 || c.N > 8192) return fail(PICGOLF_ERR_ARG, "N must be in 16..8192");
+        if (!is_pow2(c.N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N);
+        if (c.scheme != PICGOLF_NGP_LEAPFROG && c.half_width != 6 && c.half_width != 7)
+            return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
+        if (c.scheme == PICGOLF_GAUSS_FIXEDPOINT && (c.max_sweeps < 1 || c.max_sweeps > 64))
+            return fail(PICGOLF_ERR_ARG, "max_sweeps must be in 1..64");
+    }
+    picgolf_handle h = new picgolf_handle_s();
+    h->cfg = c;
+    if (h->cfg.diag_every < 1) h->cfg.diag_every = 1;
+    int rc = create_impl(cfg, h);
+    if (rc != 0) { char keep[512]; memcpy(keep, g_err, sizeof(keep)); destroy_impl(h); memcpy(g_err, keep, sizeof(keep)); return rc; }
+    *out = h;
+    return 0;
+}
+
+PG_API int picgolf_local_range(picgolf_handle h, int64_t *first, int64_t *count)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (first) *first = h->first;
+    if (count) *count = h->count;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// particle state
+// ------------------------------------------------------------------------------------------
+static int reset_run_state(picgolf_handle h)
+{
+    Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
+    PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemsetAsync(h->rho, 0, h->ncell * sizeof(double), h->stream));
+    PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
+    if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
+    else {
+        PG_CUDA(cudaMemsetAsync(h->E, 0, h->ncell * sizeof(double), h->stream));
+        PG_CUDA(cudaMemsetAsync(h->counts, 0, h->ncell * sizeof(unsigned long long), h->stream));
+    }
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    h->par = 0; h->steps = 0; h->have_particles = true;
+    return 0;
+}
+
+PG_API int picgolf_set_particles(picgolf_handle h, const double *x, const double *v, int64_t count)
+{
+    if (!h || !x || !v) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "use picgolf_set_particles_2d3v for the 2D3V scheme");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaMemcpyAsync(h->xb[0], x, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vb[0], v, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return reset_run_state(h);
+}
+
+PG_API int picgolf_set_particles_2d3v(picgolf_handle h, const double *x, const double *y, const double *vx,
+                                      const double *vy, const double *vz, int64_t count)
+{
+    if (!h || !x || !y || !vx || !vy || !vz) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (!h->is2d) return fail(PICGOLF_ERR_ARG, "handle is not a 2D3V scheme");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    const size_t b = count * sizeof(double);
+    PG_CUDA(cudaMemcpyAsync(h->xb[0], x, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->y, y, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vb[0], vx, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vy, vy, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vz, vz, b, cudaMemcpyHostToDevice, h->stream));
+    return reset_run_state(h);
+}
+
+static int init_grid(picgolf_handle h) { return (int)std::max<int64_t>(1, std::min<int64_t>((h->count + 255) / 256, (int64_t)h->sms * 8)); }
+
+PG_API int picgolf_init_quiet(picgolf_handle h)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "quiet start is a 1D1V initialisation (GaussianFixedPointQuiet.jl:2-3)");
+    PG_TRY(use_device(h));
+    quiet_start_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P);
+    h->launches++;
+    PG_CUDA(cudaGetLastError());
+    return reset_run_state(h);
+}
+
+PG_API int picgolf_init_synthetic(picgolf_handle h, uint64_t seed, double vth)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    PG_TRY(use_device(h));
+    if (h->is2d)
+        synthetic_2d3v_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->y, h->vb[0], h->vy, h->vz, h->count, h->first, seed, vth);
+    else
+        synthetic_1d_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P, seed);
+    h->launches++;
+    PG_CUDA(cudaGetLastError());
+    return reset_run_state(h);
+}
+
+PG_API int picgolf_synchronize(picgolf_handle h)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+PG_API int picgolf_get_particles(picgolf_handle h, double *x, double *v, int64_t count)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "use picgolf_get_particles_2d3v for the 2D3V scheme");
+    if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "particles were never set");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    if (x) PG_CUDA(cudaMemcpyAsync(x, h->xb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (v) PG_CUDA(cudaMemcpyAsync(v, h->vb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, double *vx, double *vy, double *vz,
+                                      int64_t count)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (!h->is2d) return fail(PICGOLF_ERR_ARG, "handle is not a 2D3V scheme");
+    if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "particles were never set");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    const size_t b = count * sizeof(double);
+    double *src[5] = {h->xb[0], h->y, h->vb[0], h->vy, h->vz};
+    double *dst[5] = {x, y, vx, vy, vz};
+    for (int i = 0; i < 5; ++i)
+        if (dst[i]) PG_CUDA(cudaMemcpyAsync(dst[i], src[i], b, cudaMemcpyDeviceToHost, h->stream));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// the loop body
+// ------------------------------------------------------------------------------------------
+static int allreduce_grid(picgolf_handle h)
+{
+    if (!h->comm) return 0;
+    h->timer.begin(ST_REDUCE, h->stream);
+    int rc;
+    if (h->ngp) rc = nccl::AllReduce(h->counts, h->counts, (size_t)h->ncell, nccl::Uint64, nccl::Sum, h->comm, h->stream);
+    else rc = nccl::AllReduce(h->rho, h->rho, (size_t)h->ncell, nccl::Float64, nccl::Sum, h->comm, h->stream);
+    h->timer.end(h->stream);
+    return nccl::check(rc, "ncclAllReduce(rho)");
+}
+
+static int launch_solve1d(picgolf_handle h, int k)
+{
+    const picgolf_config &c = h->cfg;
+    Solve1DArgs a;
+    a.rho = h->rho; a.counts = h->counts; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
+    a.w = c.w; a.rtol = c.rtol; a.atol = c.atol;
+    a.N = (int)c.N; a.lg = ilog2(c.N); a.use_counts = h->ngp ? 1 : 0; a.fixedpoint = h->fixedpoint ? 1 : 0;
+    a.k = k; a.max_sweeps = c.max_sweeps;
+    int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
+    h->timer.begin(ST_SOLVE, h->stream);
+    solve1d_kernel<<<1, threads, h->smem_pass, h->stream>>>(a);
+    h->timer.end(h->stream);
+    h->launches++;
+    return 0;
+}
+
+static int launch_step_end(picgolf_handle h, bool record)
+{
+    StepEndArgs a;
+    a.partials = h->partials; a.epartials = h->is2d ? h->epartials : nullptr; a.raw = h->raw; a.ctrl = h->ctrl;
+    a.nblocks = h->nblocks; a.npart = h->npart; a.neblocks = h->is2d ? (int)(h->cfg.NY / ROWS_PER_BLOCK) : 0;
+    a.T = (int)h->T; a.record = record ? 1 : 0; a.is2d = h->is2d ? 1 : 0;
+    step_end_kernel<<<1, 256, 0, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+
+static int step_fixedpoint(picgolf_handle h)
+{
+    const picgolf_config &c = h->cfg;
+    FPArgs a;
+    a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
+    a.E = h->E; a.rho = h->rho; a.partials = h->partials; a.ctrl = h->ctrl;
+    a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.k = 0;
+    h->timer.begin(ST_PARTICLES, h->stream);
+    fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    h->timer.end(h->stream);
+    h->launches++;
+    for (int k = 1; k <= c.max_sweeps; ++k) {
+        PG_TRY(allreduce_grid(h));
+        PG_TRY(launch_solve1d(h, k));
+        a.k = k;
+        h->timer.begin(ST_PARTICLES, h->stream);
+        fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+        h->timer.end(h->stream);
+        h->launches++;
+    }
+    PG_TRY(launch_step_end(h, true));
+    h->par ^= 1;
+    return 0;
+}
+
+static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
+{
+    const picgolf_config &c = h->cfg;
+    LFArgs a;
+    a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho; a.counts = h->counts; a.partials = h->partials;
+    a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
+    h->timer.begin(ST_PARTICLES, h->stream);
+    if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    h->timer.end(h->stream);
+    h->launches++;
+    return 0;
+}
+
+static int launch_solve2d(picgolf_handle h)
+{
+    const picgolf_config &c = h->cfg;
+    Solve2DArgs a;
+    a.rho = h->rho; a.rho_last = h->rho_last; a.Z = h->Z; a.E2 = h->E2; a.twx = h->tw; a.twy = h->twy;
+    a.partials = h->epartials; a.NX = (int)c.N; a.NY = (int)c.NY; a.lgx = ilog2(c.N); a.lgy = ilog2(c.NY);
+    const int NX = a.NX, NY = a.NY;
+    h->timer.begin(ST_SOLVE, h->stream);
+    solve2d_rows_fwd<<<NY / ROWS_PER_BLOCK, 512, (size_t)2 * ROWS_PER_BLOCK * NX * 8, h->stream>>>(a);
+    solve2d_cols<<<NX / COLS_PER_BLOCK, 512, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8, h->stream>>>(a);
+    solve2d_rows_inv<<<NY / ROWS_PER_BLOCK, 512, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8, h->stream>>>(a);
+    h->timer.end(h->stream);
+    h->launches += 3;
+    return 0;
+}
+
+static int step_2d3v(picgolf_handle h)
+{
+    const picgolf_config &c = h->cfg;
+    P2DArgs a;
+    a.x = h->xb[0]; a.y = h->y; a.vx = h->vb[0]; a.vy = h->vy; a.vz = h->vz; a.E2 = h->E2; a.rho = h->rho;
+    a.partials = h->partials; a.P = h->count; a.dt = c.dt; a.w = c.w;
+    a.t1 = c.B0 * c.dt / 2;                       // tvec[1]   Electrostatic2D3V.jl:32
+    a.tscale = 2 / (1 + (a.t1 * a.t1 + 0.0 + 0.0)); // :33
+    a.NX = (int)c.N; a.NY = (int)c.NY;
+    h->timer.begin(ST_PARTICLES, h->stream);
+    particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);
+    h->timer.end(h->stream);
+    h->launches++;
+    PG_TRY(allreduce_grid(h));
+    PG_TRY(launch_solve2d(h));
+    bool record = ((h->steps + 1) % c.diag_every) == 0; // if t % NS == 0   :164
+    PG_TRY(launch_step_end(h, record));
+    return 0;
+}
+
+PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (nsteps < 0) return fail(PICGOLF_ERR_ARG, "nsteps < 0");
+    if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "set or initialise particles before stepping");
+    if (nsteps == 0) return 0;
+    PG_TRY(use_device(h));
+    h->timer.begin(ST_TOTAL, h->stream);
+    int rc = 0;
+    if (h->fixedpoint) {
+        for (int64_t s = 0; s < nsteps && rc == 0; ++s) { rc = step_fixedpoint(h); h->steps++; }
+    } else if (h->is2d) {
+        for (int64_t s = 0; s < nsteps && rc == 0; ++s) { rc = step_2d3v(h); h->steps++; }
+    } else {
+        rc = lf_launch(h, 0, 1); // u(); deposit of the first step
+        for (int64_t s = 0; s < nsteps && rc == 0; ++s) {
+            rc = allreduce_grid(h);
+            if (rc == 0) rc = launch_solve1d(h, 1);
+            if (rc == 0) rc = lf_launch(h, 1, s + 1 < nsteps ? 1 : 0); // u(); kick [; u(); deposit of the next step]
+            if (rc == 0) rc = launch_step_end(h, true);
+            h->steps++;
+        }
+    }
+    h->timer.end(h->stream);
+    if (rc != 0) return rc;
+    PG_CUDA(cudaGetLastError());
+    if (h->timer.enabled && h->timer.open.size() > 4096) h->timer.drain();
+    return 0;
+}
+
+PG_API int picgolf_steps_done(picgolf_handle h, int64_t *steps)
+{
+    if (!h || !steps) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    *steps = h->steps;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// fields and diagnostics
+// ------------------------------------------------------------------------------------------
+PG_API int picgolf_get_fields(picgolf_handle h, double *rho, double *E)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "use picgolf_get_fields_2d for the 2D3V scheme");
+    PG_TRY(use_device(h));
+    const size_t b = (size_t)h->ncell * sizeof(double);
+    if (rho) PG_CUDA(cudaMemcpyAsync(rho, h->rho_last, b, cudaMemcpyDeviceToHost, h->stream));
+    if (E) PG_CUDA(cudaMemcpyAsync(E, h->E, b, cudaMemcpyDeviceToHost, h->stream));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+PG_API int picgolf_set_field(picgolf_handle h, const double *E)
+{
+    if (!h || !E) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "picgolf_set_field is 1D only");
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaMemcpyAsync(h->E, E, (size_t)h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+PG_API int picgolf_get_fields_2d(picgolf_handle h, double *rho, double *Ex, double *Ey)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (!h->is2d) return fail(PICGOLF_ERR_ARG, "handle is not a 2D3V scheme");
+    PG_TRY(use_device(h));
+    const size_t b = (size_t)h->ncell * sizeof(double);
+    if (rho) PG_CUDA(cudaMemcpyAsync(rho, h->rho_last, b, cudaMemcpyDeviceToHost, h->stream));
+    if (Ex || Ey) {
+        double *tmp = nullptr;
+        PG_TRY(dalloc(&tmp, (size_t)2 * h->ncell));
+        split_E2_kernel<<<(unsigned)((h->ncell + 255) / 256), 256, 0, h->stream>>>(h->E2, h->ncell, tmp, tmp + h->ncell);
+        h->launches++;
+        if (Ex) PG_CUDA(cudaMemcpyAsync(Ex, tmp, b, cudaMemcpyDeviceToHost, h->stream));
+        if (Ey) PG_CUDA(cudaMemcpyAsync(Ey, tmp + h->ncell, b, cudaMemcpyDeviceToHost, h->stream));
+        PG_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(tmp);
+    }
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+struct DevTmp {
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { PG_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 8))); return 0; }
+};
+
+// Fetch raw rows to the host; particle-derived columns are summed over ranks (collective call).
+static int fetch_raw(picgolf_handle h, std::vector<double> &raw, int64_t *rows)
+{
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    Ctrl c;
+    PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
+    *rows = c.rows;
+    raw.resize((size_t)4 * h->T);
+    PG_CUDA(cudaMemcpy(raw.data(), h->raw, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h->comm) {
+        // columns 1,2 (and 3 in 2D) hold local-shard sums: all-reduce them out of place.
+        const size_t ncol = h->is2d ? 3 : 2, cnt = ncol * (size_t)h->T;
+        DevTmp tmp;
+        PG_TRY(tmp.alloc(cnt * sizeof(double)));
+        PG_TRY(nccl::check(nccl::AllReduce(h->raw + h->T, tmp.p, cnt, nccl::Float64, nccl::Sum, h->comm, h->stream),
+                           "ncclAllReduce(diagnostics)"));
+        PG_CUDA(cudaStreamSynchronize(h->stream));
+        PG_CUDA(cudaMemcpy(raw.data() + h->T, tmp.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+PG_API int picgolf_get_raw_diagnostics(picgolf_handle h, double *raw, int64_t ld, int64_t *rows_out)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    std::vector<double> r;
+    int64_t rows = 0;
+    PG_TRY(fetch_raw(h, r, &rows));
+    if (rows_out) *rows_out = rows;
+    if (raw) {
+        if (ld < rows) return fail(PICGOLF_ERR_ARG, "ld %lld < rows %lld", (long long)ld, (long long)rows);
+        for (int c = 0; c < 4; ++c)
+            for (int64_t t = 0; t < rows; ++t) raw[c * ld + t] = r[c * h->T + t];
+    }
+    return 0;
+}
+
+PG_API int picgolf_get_diagnostics(picgolf_handle h, double *D, int64_t ld, int32_t *sweeps, int64_t *rows_out)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    std::vector<double> r;
+    int64_t rows = 0;
+    PG_TRY(fetch_raw(h, r, &rows));
+    if (rows_out) *rows_out = rows;
+    if (D && ld < rows) return fail(PICGOLF_ERR_ARG, "ld %lld < rows %lld", (long long)ld, (long long)rows);
+    const picgolf_config &c = h->cfg;
+    const int64_t T = h->T;
+    for (int64_t t = 0; t < rows; ++t) {
+        double se = r[t], s1 = r[T + t], s2 = r[2 * T + t], s3 = r[3 * T + t];
+        if (!h->is2d) {
+            if (D) {
+                // D[t,1:2].=(sum(E.^2)/N,sum(v.^2)*W/P)./2; D[t,3:4].=sum.((D[t,1:2],v/P)); D[t,1:3].*=2/W
+                double d1 = (se / (double)c.N) / 2, d2 = (s1 * c.W / (double)c.P) / 2;
+                double d3 = d1 + d2, sc = 2 / c.W;
+                D[t] = d1 * sc; D[ld + t] = d2 * sc; D[2 * ld + t] = d3 * sc; D[3 * ld + t] = s2 / (double)c.P;
+            }
+            if (sweeps) sweeps[t] = (int32_t)s3;
+        } else {
+            if (D) {
+                // K[ti,1]=mean(Ex^2+Ey^2); K2=sum((vx^2+vy^2)*w); K3=K1+K2; K4=sum(vx)/P; K5=sum(vy)/P   :166-170
+                double k1 = se / (double)(c.N * c.NY), k2 = s1 * c.w;
+                D[t] = k1; D[ld + t] = k2; D[2 * ld + t] = k1 + k2; D[3 * ld + t] = s2 / (double)c.P; D[4 * ld + t] = s3 / (double)c.P;
+            }
+            if (sweeps) sweeps[t] = 1;
+        }
+    }
+    return 0;
+}
+
+PG_API int picgolf_stage_timing(picgolf_handle h, int enable)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    PG_TRY(use_device(h));
+    if (!enable) h->timer.drain();
+    h->timer.enabled = enable != 0;
+    return 0;
+}
+
+PG_API int picgolf_stage_times(picgolf_handle h, double ms[5], int reset)
+{
+    if (!h || !ms) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    h->timer.drain();
+    for (int i = 0; i < 5; ++i) ms[i] = h->timer.ms[i];
+    if (reset) for (int i = 0; i < 5; ++i) h->timer.ms[i] = 0;
+    return 0;
+}
+
+PG_API int picgolf_launch_count(picgolf_handle h, int64_t *launches)
+{
+    if (!h || !launches) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    *launches = h->launches;
+    return 0;
+}
+
+PG_API int picgolf_get_stream(picgolf_handle h, void **stream)
+{
+    if (!h || !stream) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    *stream = (void *)h->stream;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------------
+PG_API int picgolf_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    PG_TRY(nccl::load());
+    nccl::UniqueId id;
+    PG_TRY(nccl::check(nccl::GetUniqueId(&id), "ncclGetUniqueId"));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+PG_API int picgolf_comm_init(picgolf_handle h, const void *id128, int nranks, int rank)
+{
+    if (!h || !id128) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (nranks != h->nranks || rank != h->rank)
+        return fail(PICGOLF_ERR_ARG, "comm (rank %d of %d) does not match the handle's shard (rank %d of %d)", rank, nranks, h->rank, h->nranks);
+    if (nranks == 1) return 0;
+    PG_TRY(use_device(h));
+    PG_TRY(nccl::load());
+    nccl::UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    PG_TRY(nccl::check(nccl::CommInitRank(&h->comm, nranks, id, rank), "ncclCommInitRank"));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage-level entry points
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { PG_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 8))); return 0; }
+    int upload(const void *src, size_t bytes) { PG_TRY(alloc(bytes)); PG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+    int zero(size_t bytes) { PG_TRY(alloc(bytes)); PG_CUDA(cudaMemset(p, 0, bytes)); return 0; }
+    int download(void *dst, size_t bytes) { PG_CUDA(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost)); return 0; }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+static int stage_ready()
+{
+    if (picgolf_device_count() < 1) return fail(PICGOLF_ERR_CUDA, "no CUDA device: libpicgolf has no CPU path");
+    return 0;
+}
+static unsigned grid1(int64_t n) { return (unsigned)std::max<int64_t>(1, (n + 255) / 256); }
+static int finish() { PG_CUDA(cudaGetLastError()); PG_CUDA(cudaDeviceSynchronize()); return 0; }
+static int check_grid1d(int64_t N)
+{
+    if (N < 16 || N > 8192) return fail(PICGOLF_ERR_ARG, "N must be in 16..8192");
+    if (!is_pow2(N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built", (long long)N);
+    return 0;
+}
+
+PG_API int picgolf_stage_ngp_index(const double *x, int64_t count, int64_t N, int32_t *idx1)
+{
+    if (!x || !idx1 || count < 0 || N < 1) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf dx, di;
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(di.alloc(count * 4));
+    stage_ngp_index_kernel<<<grid1(count), 256>>>(dx.as<double>(), count, (int)N, di.as<int>());
+    PG_TRY(finish());
+    return di.download(idx1, count * 4);
+}
+
+PG_API int picgolf_stage_mod1(const double *x, int64_t count, double *out)
+{
+    if (!x || !out || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf dx, dout;
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(dout.alloc(count * 8));
+    stage_mod1_kernel<<<grid1(count), 256>>>(dx.as<double>(), count, dout.as<double>());
+    PG_TRY(finish());
+    return dout.download(out, count * 8);
+}
+
+PG_API int picgolf_stage_gauss_stencil(const double *c, int64_t count, int64_t N, int hw, int32_t *idx1, double *wt)
+{
+    if (!c || !idx1 || !wt || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    if (hw != 6 && hw != 7) return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
+    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    const size_t nw = 2 * hw + 1;
+    DevBuf dc, di, dw;
+    PG_TRY(dc.upload(c, count * 8)); PG_TRY(di.alloc(count * nw * 4)); PG_TRY(dw.alloc(count * nw * 8));
+    stage_gauss_stencil_kernel<<<grid1(count), 256>>>(dc.as<double>(), count, (int)N, hw, di.as<int>(), dw.as<double>());
+    PG_TRY(finish());
+    PG_TRY(di.download(idx1, count * nw * 4));
+    return dw.download(wt, count * nw * 8);
+}
+
+PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, double w, double *rho)
+{
+    if (!x || !rho || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    // Runs the production pass (deposit half only) and the production solve's count->rho conversion.
+    DevBuf dx, dv, dcnt, dpart;
+    std::vector<double> zeros((size_t)count, 0.0);
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(dv.upload(zeros.data(), count * 8));
+    PG_TRY(dcnt.zero(N * 8)); PG_TRY(dpart.zero(2 * 1024 * 8));
+    size_t smem = (size_t)(2 * N + 32) * 8;
+    PG_TRY(set_smem(lf_pass<0>, smem));
+    LFArgs a;
+    a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = nullptr; a.counts = dcnt.as<unsigned long long>();
+    a.partials = dpart.as<double>(); a.P = count; a.dt = 0.0; a.w = w; a.N = (int)N; a.do_kick = 0; a.do_deposit = 1;
+    // with v = 0 and dt = 0 the half drift is x = mod(x + 0, 1): positions in [0,1) are unchanged
+    lf_pass<0><<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(a);
+    PG_TRY(finish());
+    std::vector<unsigned long long> cnt((size_t)N);
+    PG_TRY(dcnt.download(cnt.data(), N * 8));
+    for (int64_t n = 0; n < N; ++n) rho[n] = (double)cnt[n] * w; // same expression as solve1d_kernel
+    return 0;
+}
+
+PG_API int picgolf_stage_gauss_deposit(const double *x, const double *y, int64_t count, int64_t N, int hw, double w,
+                                       int mode, double *rho)
+{
+    if (!x || !y || !rho || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    if (hw != 6 && hw != 7) return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
+    (void)mode;
+    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    DevBuf dx, dy, dr;
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(dy.upload(y, count * 8)); PG_TRY(dr.zero(N * 8));
+    size_t smem = (size_t)N * 8;
+    PG_TRY(set_smem(stage_gauss_deposit_kernel, smem));
+    stage_gauss_deposit_kernel<<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(
+        dx.as<double>(), dy.as<double>(), count, (int)N, w, dr.as<double>());
+    PG_TRY(finish());
+    return dr.download(rho, N * 8);
+}
+
+PG_API int picgolf_stage_gauss_gather(const double *E, int64_t N, int hw, const double *c, int64_t count, double *out)
+{
+    if (!E || !c || !out || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    if (hw != 6 && hw != 7) return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
+    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    DevBuf dE, dc, dout;
+    PG_TRY(dE.upload(E, N * 8)); PG_TRY(dc.upload(c, count * 8)); PG_TRY(dout.alloc(count * 8));
+    stage_gauss_gather_kernel<<<grid1(count), 256>>>(dE.as<double>(), (int)N, dc.as<double>(), count, dout.as<double>());
+    PG_TRY(finish());
+    return dout.download(out, count * 8);
+}
+
+PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
+{
+    if (!rho || !E) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    DevBuf dr, dl, dE, dctrl;
+    double2 *tw = nullptr;
+    PG_TRY(dr.upload(rho, N * 8)); PG_TRY(dl.alloc(N * 8)); PG_TRY(dE.zero(N * 8)); PG_TRY(dctrl.zero(sizeof(Ctrl)));
+    PG_TRY(make_twiddles(&tw, (int)N));
+    Solve1DArgs a;
+    a.rho = dr.as<double>(); a.counts = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
+    a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N); a.use_counts = 0;
+    a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1;
+    size_t smem = (size_t)(2 * N + 32) * 8;
+    int rc = set_smem(solve1d_kernel, smem);
+    if (rc == 0) {
+        solve1d_kernel<<<1, (int)std::min<int64_t>(1024, std::max<int64_t>(32, N / 2)), smem>>>(a);
+        rc = finish();
+    }
+    if (rc == 0) rc = dE.download(E, N * 8);
+    cudaFree(tw);
+    return rc;
+}
+
+PG_API int picgolf_stage_solve2d(const double *rho, int64_t NX, int64_t NY, double *Ex, double *Ey)
+{
+    if (!rho || !Ex || !Ey) return fail(PICGOLF_ERR_ARG, "bad argument");
+    if (NX < 16 || NY < 16 || NX > 1024 || NY > 1024) return fail(PICGOLF_ERR_ARG, "2D grid must be 16..1024 per side");
+    if (!is_pow2(NX) || !is_pow2(NY)) return fail(PICGOLF_ERR_UNSUPPORTED, "only power-of-two grids are built");
+    PG_TRY(stage_ready());
+    const size_t n = (size_t)NX * NY;
+    DevBuf dr, dl, dZ, dE2, dp, dsplit;
+    double2 *twx = nullptr, *twy = nullptr;
+    PG_TRY(dr.upload(rho, n * 8)); PG_TRY(dl.alloc(n * 8)); PG_TRY(dZ.alloc(n * 16)); PG_TRY(dE2.alloc(n * 16));
+    PG_TRY(dp.alloc((NY / ROWS_PER_BLOCK) * 8)); PG_TRY(dsplit.alloc(2 * n * 8));
+    PG_TRY(make_twiddles(&twx, (int)NX));
+    int rc = make_twiddles(&twy, (int)NY);
+    Solve2DArgs a;
+    a.rho = dr.as<double>(); a.rho_last = dl.as<double>(); a.Z = dZ.as<double2>(); a.E2 = dE2.as<double2>();
+    a.twx = twx; a.twy = twy; a.partials = dp.as<double>(); a.NX = (int)NX; a.NY = (int)NY; a.lgx = ilog2(NX); a.lgy = ilog2(NY);
+    if (rc == 0) rc = set_smem(solve2d_rows_fwd, (size_t)2 * ROWS_PER_BLOCK * NX * 8);
+    if (rc == 0) rc = set_smem(solve2d_rows_inv, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8);
+    if (rc == 0) rc = set_smem(solve2d_cols, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8);
+    if (rc == 0) {
+        solve2d_rows_fwd<<<(unsigned)(NY / ROWS_PER_BLOCK), 512, (size_t)2 * ROWS_PER_BLOCK * NX * 8>>>(a);
+        solve2d_cols<<<(unsigned)(NX / COLS_PER_BLOCK), 512, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8>>>(a);
+        solve2d_rows_inv<<<(unsigned)(NY / ROWS_PER_BLOCK), 512, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8>>>(a);
+        split_E2_kernel<<<grid1((int64_t)n), 256>>>(dE2.as<double2>(), (long long)n, dsplit.as<double>(), dsplit.as<double>() + n);
+        rc = finish();
+    }
+    if (rc == 0) rc = dsplit.download(Ex, n * 8);
+    if (rc == 0) PG_CUDA(cudaMemcpy(Ey, dsplit.as<double>() + n, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(twx); cudaFree(twy);
+    return rc;
+}
+
+PG_API int picgolf_stage_cic_deposit(const double *x, const double *y, int64_t count, int64_t NX, int64_t NY, double w,
+                                     double *rho)
+{
+    if (!x || !y || !rho || count < 0 || NX < 1 || NY < 1) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf dx, dy, dr;
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(dy.upload(y, count * 8)); PG_TRY(dr.zero(NX * NY * 8));
+    stage_cic_deposit_kernel<<<grid1(count), 256>>>(dx.as<double>(), dy.as<double>(), count, (int)NX, (int)NY, w, dr.as<double>());
+    PG_TRY(finish());
+    return dr.download(rho, NX * NY * 8);
+}
+
+PG_API int picgolf_stage_cic_gather(const double *Ex, const double *Ey, int64_t NX, int64_t NY, const double *x,
+                                    const double *y, int64_t count, double *ex, double *ey)
+{
+    if (!Ex || !Ey || !x || !y || !ex || !ey || count < 0 || NX < 1 || NY < 1) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf dEx, dEy, dx, dy, dex, dey;
+    PG_TRY(dEx.upload(Ex, NX * NY * 8)); PG_TRY(dEy.upload(Ey, NX * NY * 8));
+    PG_TRY(dx.upload(x, count * 8)); PG_TRY(dy.upload(y, count * 8));
+    PG_TRY(dex.alloc(count * 8)); PG_TRY(dey.alloc(count * 8));
+    stage_cic_gather_kernel<<<grid1(count), 256>>>(dEx.as<double>(), dEy.as<double>(), (int)NX, (int)NY, dx.as<double>(),
+                                                   dy.as<double>(), count, dex.as<double>(), dey.as<double>());
+    PG_TRY(finish());
+    PG_TRY(dex.download(ex, count * 8));
+    return dey.download(ey, count * 8);
+}
+
+PG_API int picgolf_stage_boris(double *vx, double *vy, double *vz, const double *Ex, const double *Ey, int64_t count,
+                               double dt, double B0)
+{
+    if (!vx || !vy || !vz || !Ex || !Ey || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf a, b, c, e1, e2;
+    PG_TRY(a.upload(vx, count * 8)); PG_TRY(b.upload(vy, count * 8)); PG_TRY(c.upload(vz, count * 8));
+    PG_TRY(e1.upload(Ex, count * 8)); PG_TRY(e2.upload(Ey, count * 8));
+    double t1 = B0 * dt / 2, tscale = 2 / (1 + (t1 * t1 + 0.0 + 0.0));
+    stage_boris_kernel<<<grid1(count), 256>>>(a.as<double>(), b.as<double>(), c.as<double>(), e1.as<double>(), e2.as<double>(),
+                                             count, dt, t1, tscale);
+    PG_TRY(finish());
+    PG_TRY(a.download(vx, count * 8)); PG_TRY(b.download(vy, count * 8));
+    return c.download(vz, count * 8);
+}
+
+PG_API int picgolf_stage_quiet_start(int64_t P, int64_t first, int64_t count, double *x, double *v)
+{
+    if (!x || !v || count < 0 || first < 0 || first + count > P) return fail(PICGOLF_ERR_ARG, "bad argument");
+    PG_TRY(stage_ready());
+    DevBuf dx, dv;
+    PG_TRY(dx.alloc(count * 8)); PG_TRY(dv.alloc(count * 8));
+    quiet_start_kernel<<<(unsigned)std::min<int64_t>(grid1(count), 4096), 256>>>(dx.as<double>(), dv.as<double>(), count, first, P);
+    PG_TRY(finish());
+    PG_TRY(dx.download(x, count * 8));
+    return dv.download(v, count * 8);
+}

@@ -1,0 +1,350 @@
+"""Parity of the CUDA path (through the C ABI of libpicgolf.so) against the CPU oracle and the
+committed golden fixtures.  Bars (BASELINE.json north_star):
+  * NGP cell indices f(x), Julia mod, quiet start, NGP rho with dyadic w: BIT-EXACT;
+  * rho, E, x, v after a step: |delta| <= 1e-12 * max|.| (norm-wise; SURVEY.md 7.4 explains why
+    element-wise rtol is meaningless at zero crossings);
+  * diagnostics traces within 1e-9 relative over the short horizon before two-stream chaos diverges;
+  * long horizon: growth rate of log10 D[:,1] within 1% of the analytic 2*gamma line."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import golden, relnorm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+# =============================================================================================
+# stage level
+# =============================================================================================
+def test_ngp_index_bit_exact(pg, oracle):
+    N = 128
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(100000), (np.arange(2 * N + 1) * 0.5) / N,  # every tie k+1/2 and integer
+                        np.nextafter((np.arange(N) + 0.5) / N, 0), np.nextafter((np.arange(N) + 0.5) / N, 1),
+                        [0.0, 1.0, 1e-300, 1 - 2 ** -53, -1e-20, 1.0000001]])
+    for n in (64, 128, 4096):
+        assert np.array_equal(pg.ngp_index(x, n), oracle.ngp_index(x, n))
+    g = golden("c1_ngp")
+    assert np.array_equal(pg.ngp_index(g["x0"], int(g["N"])), g["idx1"])
+
+
+def test_float_mod_bit_exact(pg, oracle):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.random(10000) * 4 - 2, [-1e-20, -1e-300, 0.0, -0.0, 1.0, -1.0, 2.0, 1 - 2 ** -53,
+                                                   -2 ** -54, 1.25, -0.25, 1e15 + 0.5]])
+    got = pg.mod1(x)
+    want = np.array([oracle.jl_mod1(v) for v in x])
+    assert np.array_equal(got, want)
+    assert got[10000] == 1.0  # mod(-1e-20, 1) == 1.0 exactly
+
+
+def test_quiet_start_bit_exact(pg, oracle):
+    for P, first, count in ((2048, 0, 2048), (2 ** 20, 12345, 4097), (2 ** 30, 2 ** 29 - 5, 1000)):
+        x, v = pg.quiet_start(P, first, count)
+        xo, vo = oracle.quiet_start(P, first, count)
+        assert np.array_equal(x, xo) and np.array_equal(v, vo)
+    x, _ = pg.quiet_start(2048)
+    assert np.array_equal(x[:8], [0.5, 0.0, 0.75, 0.25, 0.625, 0.125, 0.875, 0.375])
+
+
+def test_gauss_stencil_parity(pg, oracle):
+    """Indices bit-exact; weights within 2.3e-16 absolute (2 ulp of 1/2 -- the reference's own erf/2
+    quantisation) of the literal 2-erf evaluation, from the committed fixture."""
+    g = golden("stencils")
+    for N, hw in ((64, 7), (128, 6), (4096, 6), (4096, 7)):
+        c = g[f"c_{N}_{hw}"]
+        idx, wt = pg.gauss_stencil(c, N, hw)
+        assert np.array_equal(idx, g[f"idx_{N}_{hw}"])
+        assert np.abs(wt - g[f"wt_{N}_{hw}"]).max() < 2.3e-16
+        assert np.abs(wt.sum(axis=1) - 1).max() < 3e-16
+        if hw == 7:
+            assert np.all(wt[:, 0] == 0) and np.all(wt[:, -1] == 0)
+
+
+def test_ngp_deposit_bit_exact(pg, oracle):
+    g = golden("c1_ngp")
+    N, w = int(g["N"]), float(g["w"])
+    rho = pg.ngp_deposit(g["x0"], N, w)
+    assert np.array_equal(rho, oracle.ngp_deposit(g["x0"], N, w))  # dyadic w: exact and order independent
+    rng = np.random.default_rng(2)
+    x = rng.random(1 << 20)
+    assert np.array_equal(pg.ngp_deposit(x, 4096, 0.5), oracle.ngp_deposit(x, 4096, 0.5))
+    # ragged / degenerate inputs
+    assert np.array_equal(pg.ngp_deposit(np.full(1000, 0.5), 128, 2.0), oracle.ngp_deposit(np.full(1000, 0.5), 128, 2.0))
+    assert np.array_equal(pg.ngp_deposit(np.array([0.25]), 128, 1.0), oracle.ngp_deposit(np.array([0.25]), 128, 1.0))
+    assert np.array_equal(pg.ngp_deposit(np.zeros(0), 128, 1.0), np.zeros(128))
+
+
+@pytest.mark.parametrize("N,hw,P", [(128, 6, 4096), (64, 7, 2048), (4096, 6, 1 << 18), (4096, 7, 33333)])
+def test_gauss_deposit_parity(pg, oracle, N, hw, P):
+    rng = np.random.default_rng(3)
+    x = rng.random(P) * 1.02 - 0.01  # slightly outside [0,1]: x is not wrapped during sweeps
+    y = rng.random(P)
+    w = 400.0 / P * N
+    got = pg.gauss_deposit(x, y, N, hw, w)
+    want = oracle.gauss_deposit(x, y, N, hw, w)
+    assert relnorm(got, want) < TOL
+    assert abs(got.sum() / (P * w) - 1) < 1e-13  # charge conservation
+    # collisions: every particle in one cell
+    xs = np.full(5000, 0.4321)
+    assert relnorm(pg.gauss_deposit(xs, xs, N, hw, w), oracle.gauss_deposit(xs, xs, N, hw, w)) < TOL
+
+
+def test_gauss_gather_parity(pg, oracle):
+    rng = np.random.default_rng(4)
+    for N, hw in ((128, 6), (64, 7), (4096, 6)):
+        E = rng.standard_normal(N)
+        c = np.concatenate([rng.random(2000), [-0.004, 1.003, 0.0, 1.0]])
+        assert relnorm(pg.gauss_gather(E, c, hw), oracle.gauss_gather(E, c, N, hw)) < TOL
+
+
+@pytest.mark.parametrize("N", [16, 64, 128, 1024, 4096, 8192])
+def test_solve1d_parity(pg, oracle, N):
+    rng = np.random.default_rng(5)
+    rho = 200 + rng.standard_normal(N)
+    assert relnorm(pg.solve1d(rho), oracle.solve1d(rho)) < TOL
+    xs = np.arange(1, N + 1) / N
+    E = pg.solve1d(200 + 0.7 * np.cos(2 * np.pi * 3 * xs))
+    assert np.abs(E - 0.7 * np.sin(2 * np.pi * 3 * xs) / (2 * np.pi * 3)).max() < 1e-15 * N
+    assert np.abs(pg.solve1d(200 + np.cos(2 * np.pi * (N // 2) * xs))).max() < 1e-13  # Nyquist -> 0
+    assert np.abs(pg.solve1d(np.full(N, 5.0))).max() == 0.0                            # xi[1] *= 0
+    # linearity (size-independent property)
+    a, b = rng.standard_normal(N), rng.standard_normal(N)
+    assert relnorm(pg.solve1d(a + 2 * b), pg.solve1d(a) + 2 * pg.solve1d(b)) < 1e-13
+
+
+def test_unsupported_grid_is_an_error(pg):
+    with pytest.raises(pg.PicGolfError) as e:
+        pg.solve1d(np.ones(100))
+    assert e.value.code == -5
+
+
+def test_2d_stage_parity(pg, oracle):
+    rng = np.random.default_rng(6)
+    for NX, NY in ((32, 32), (64, 128), (256, 256)):
+        rho = 39.0 + rng.standard_normal(NX * NY)
+        Ex, Ey = pg.solve2d(rho, NX, NY)
+        Exo, Eyo = oracle.solve2d(rho, NX, NY)
+        assert relnorm(Ex, Exo) < TOL and relnorm(Ey, Eyo) < TOL
+        P = 20000
+        x, y = 1 - rng.random(P), 1 - rng.random(P)
+        x[:4] = [1.0, 1e-12, 0.5, 1.0 / NX]  # grid points: r == 0 (the reference would @assert; weights (1,0))
+        w = 39.0 / P * NX * NY
+        assert relnorm(pg.cic_deposit(x, y, NX, NY, w), oracle.cic_deposit(x, y, NX, NY, w)) < TOL
+        ex, ey = pg.cic_gather(Exo, Eyo, NX, NY, x, y)
+        exo, eyo = oracle.cic_gather(Exo, Eyo, NX, NY, x, y)
+        assert relnorm(ex, exo) < TOL and relnorm(ey, eyo) < TOL
+    v = rng.standard_normal((3, 1000))
+    E = rng.standard_normal((2, 1000))
+    got = pg.boris(v[0], v[1], v[2], E[0], E[1], 0.013, 1.57)
+    want = np.array([oracle.boris(v[0, i], v[1, i], v[2, i], E[0, i], E[1, i], 0.013, 1.57) for i in range(1000)]).T
+    assert np.array_equal(np.array(got), want)  # same expression order -> bit-exact
+
+
+# =============================================================================================
+# full steps
+# =============================================================================================
+def test_c1_ngp_steps(pg, oracle):
+    """Config 1 (src/NGPFourier.jl): rho bit-exact (dyadic w); E, x, v within 1e-12 per step."""
+    g = golden("c1_ngp")
+    N = int(g["N"])
+    sim = pg.ngp_fourier(N=N, NT=64)
+    assert sim.cfg.P == int(g["P"]) and sim.cfg.dt == float(g["dt"]) and sim.cfg.w == float(g["w"])
+    sim.set_particles(g["x0"], g["v0"])
+    x, v = g["x0"].copy(), g["v0"].copy()
+    for t in range(8):
+        sim.step(1)
+        rho, E = sim.fields()
+        ro, Eo, raw = oracle.ngp_step(x, v, N, sim.cfg.dt, sim.cfg.w)
+        assert np.array_equal(rho, ro) and np.array_equal(rho, g["rho"][t])
+        assert relnorm(E, Eo) < TOL and relnorm(E, g["E"][t]) < TOL
+        xg, vg = sim.particles()
+        assert relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
+        assert np.array_equal(pg.ngp_index(xg, N), oracle.ngp_index(x, N))
+    R = sim.raw_diagnostics()
+    assert R.shape == (8, 4) and relnorm(R[:, :3], g["raw"]) < 1e-11
+    # stepping 8 at once (fused kick + next deposit passes) gives the same state as 8 single steps
+    sim2 = pg.ngp_fourier(N=N, NT=64)
+    sim2.set_particles(g["x0"], g["v0"])
+    sim2.step(8)
+    x2, v2 = sim2.particles()
+    assert np.array_equal(x2, xg) and np.array_equal(v2, vg)
+    assert relnorm(x2, g["x"]) < TOL and relnorm(v2, g["v"]) < TOL
+
+
+def test_explicit_gaussian_steps(pg, oracle):
+    """src/Gaussian.jl: leapfrog with the erf shape."""
+    g = golden("gauss_explicit")
+    sim = pg.gaussian(NX=int(g["N"]), NT=16)
+    assert sim.cfg.w == float(g["scale"])
+    sim.set_particles(g["x0"], g["v0"])
+    for t in range(8):
+        sim.step(1)
+        rho, E = sim.fields()
+        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-11
+    x, v = sim.particles()
+    assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
+    assert relnorm(sim.raw_diagnostics()[:, :3], g["raw"]) < 1e-10
+
+
+def test_c2_fixed_point_steps(pg, oracle):
+    """Config 2 (src/GaussianFixedPoint.jl): sweeps/step == 4; rho, E, x, v within 1e-12 after one
+    step; diagnostics D within 1e-10 over 16 steps."""
+    g = golden("c2_fixedpoint")
+    sim = pg.gaussian_fixed_point(T=64)
+    assert (sim.cfg.N, sim.cfg.P) == (int(g["N"]), int(g["P"]))
+    sim.set_particles(g["x0"], g["v0"])
+    sim.step(1)
+    rho, E = sim.fields()
+    x, v = sim.particles()
+    assert relnorm(rho, g["rho"][0]) < TOL and relnorm(E, g["E"][0]) < TOL
+    assert relnorm(x, g["x1"]) < TOL and relnorm(v, g["v1"]) < TOL
+    assert 0 <= x.min() and x.max() <= 1
+    sim.step(15)
+    D, sw = sim.diagnostics()
+    assert D.shape == (16, 4) and np.array_equal(sw, g["sweeps"]) and np.all(sw == 4)
+    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    assert np.abs(D[:, 3] - g["D"][:, 3]).max() < 1e-13
+    x, v = sim.particles()
+    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10  # 16 steps of error growth
+    rho, E = sim.fields()
+    assert relnorm(E, g["E"][15]) < 1e-10
+
+
+def test_c2_against_live_oracle_other_seed(pg, oracle):
+    rng = np.random.default_rng(99)
+    N, P = 128, 4096
+    x0, v0 = rng.random(P), rng.choice([-1.0, 1.0], P)
+    sim = pg.gaussian_fixed_point(T=8)
+    sim.set_particles(x0, v0)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, sim.cfg.W, hw=6, rtol=1e-8)
+    for t in range(3):
+        sim.step(1)
+        D4, raw, s = fp.step()
+        x, v = sim.particles()
+        rho, E = sim.fields()
+        assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(E, fp.E) < 1e-11
+        assert relnorm(rho, fp.r) < TOL
+    D, sw = sim.diagnostics()
+    assert list(sw) == [4, 4, 4]
+
+
+def test_c3_quiet_short_horizon(pg, oracle):
+    """Config 3 (src/GaussianFixedPointQuiet.jl), first 16 steps.  E is pure round-off here (max|E| ~
+    1e-16), so E is compared with atol = 1e-12*max|rho|/(2 pi); x, v to 1e-12."""
+    g = golden("c3_quiet")
+    sim = pg.gaussian_fixed_point_quiet(T=64)
+    sim.init_quiet()
+    x0, v0 = sim.particles()
+    xo, vo = oracle.quiet_start(int(g["P"]))
+    assert np.array_equal(x0, xo) and np.array_equal(v0, vo)
+    sim.step(16)
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    assert relnorm(x, g["x16"]) < TOL and relnorm(v, g["v16"]) < TOL
+    assert np.abs(E - g["E16"]).max() < 1e-12 * np.abs(rho).max() / (2 * np.pi)
+    D, sw = sim.diagnostics()
+    assert np.abs(D[:, 1] - g["D"][:16, 1]).max() < 1e-13 and np.abs(D[:, 2] - 1).max() < 1e-13
+    assert np.abs(D[:, 3]).max() < 1e-15
+    assert sw.min() >= 2 and sw.max() <= 10
+
+
+def test_c3_growth_rate_long_horizon(pg, oracle):
+    """The acceptance test of the reference (GaussianFixedPointQuiet.jl:16-20): over the full T=2^13
+    run the field energy grows ~30 decades along the analytic 2*gamma line; momentum stays at
+    round-off and the energy error bounded (README.md:46-47,76).  Compared with the oracle's trace."""
+    g = golden("c3_quiet")
+    T, dt, W = int(g["T"]), float(g["dt"]), float(g["W"])
+    sim = pg.gaussian_fixed_point_quiet()
+    sim.init_quiet()
+    sim.step(T)
+    D, sw = sim.diagnostics()
+    assert D.shape == (T, 4)
+    t = np.arange(1, T + 1) * dt
+    sel = (t > 1) & (t < 8)
+    slope = np.polyfit(t[sel], np.log10(D[sel, 0]), 1)[0]
+    pred = oracle.growth_slope(W)
+    assert abs(pred - 3.1509) < 1e-4
+    assert abs(slope / pred - 1) < 0.01
+    slope_o = np.polyfit(t[sel], np.log10(g["D"][sel, 0]), 1)[0]
+    assert abs(slope - slope_o) < 0.02
+    assert np.abs(D[:, 3]).max() < 1e-13
+    assert np.abs(1 - D[:, 2]).max() < 1e-2 and np.abs(1 - D[: T // 5, 2]).max() < 1e-13
+    assert abs(np.log10(D[:, 0]).max() - np.log10(g["D"][:, 0]).max()) < 0.05
+    assert abs(np.log10(D[T // 8 - 1, 0]) - np.log10(g["D"][T // 8 - 1, 0])) < 1.0  # round-off seeded: same decade
+    assert sw.min() >= 2 and sw.max() <= 10
+
+
+def test_c5_2d3v_steps(pg, oracle):
+    g = golden("c5_2d3v")
+    NX, NY = int(g["NX"]), int(g["NY"])
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=int(g["P"]), T=16, NS=1)
+    assert sim.cfg.dt == float(g["dt"]) and sim.cfg.w == float(g["w"]) and sim.cfg.B0 == float(g["B0"])
+    sim.set_particles(g["x0"], g["vx0"], y=g["y0"], vy=g["vy0"], vz=g["vz0"])
+    for t in range(4):
+        sim.step(1)
+        rho, Ex, Ey = sim.fields()
+        assert relnorm(rho.reshape(-1, order="F"), g["rho"][t]) < TOL
+        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < 1e-11 and relnorm(Ey.reshape(-1, order="F"), g["Ey"][t]) < 1e-11
+    x, y, vx, vy, vz = sim.particles()
+    for a, k in ((x, "x"), (y, "y"), (vx, "vx"), (vy, "vy"), (vz, "vz")):
+        assert relnorm(a, g[k]) < 1e-11
+    assert x.min() > 0 and x.max() <= 1 and y.min() > 0 and y.max() <= 1
+    K, _ = sim.diagnostics()
+    assert K.shape == (4, 5) and relnorm(K[:, :3], g["K"][:, :3]) < 1e-10
+    assert np.abs(K[:, 3:] - g["K"][:, 3:]).max() < 1e-14
+
+
+# =============================================================================================
+# size-independent properties at BASELINE sizes
+# =============================================================================================
+def test_scaled_config4_properties(pg, oracle):
+    """Config 4 shape (N=4096, Gaussian fixed point) at 2^22 particles: the oracle checks a sampled
+    deposit; conservation laws check the rest."""
+    N, P = 4096, 1 << 22
+    sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=400.0)
+    sim.init_quiet()
+    sim.step(2)
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    D, sw = sim.diagnostics()
+    assert abs(rho.mean() / 400.0 - 1) < 1e-12           # charge conservation: mean rho == W
+    assert abs(E.sum()) < 1e-9 * np.abs(E).max() * N + 1e-20  # xi[1]=0: zero-mean field
+    assert np.abs(D[:, 3]).max() < 1e-14                 # momentum
+    assert np.abs(D[:, 2] - 1).max() < 1e-12
+    assert 0 <= x.min() and x.max() <= 1
+    # seeded-uniform start, one step vs the oracle on the full population (seconds on CPU at 2^18)
+    P2 = 1 << 18
+    rng = np.random.default_rng(12)
+    x0, v0 = rng.random(P2), np.where(np.arange(P2) >= P2 // 2, 1.0, -1.0)
+    sim = pg.gaussian_fixed_point(N=N, P=P2, T=8, W=400.0)
+    sim.set_particles(x0, v0)
+    sim.step(1)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, 400.0, hw=6, rtol=1e-8)
+    _, _, s = fp.step()
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    _, sw = sim.diagnostics()
+    assert sw[0] == s
+    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-11
+    assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL
+
+
+def test_scaled_ngp_properties(pg, oracle):
+    """Config-1-scaled NGP (N=4096): rho is an exact histogram whatever the size."""
+    N, P = 4096, 1 << 22
+    sim = pg.ngp_fourier(N=N, P=P, NT=8, W=256.0)  # w = 256/2^22*4096 = 0.25 dyadic
+    sim.init_synthetic(seed=7)
+    x0, v0 = sim.particles()
+    sim.step(1)
+    rho, E = sim.fields()
+    xh = x0.copy()
+    oracle.ngp_half_drift(xh, v0, sim.cfg.dt)
+    assert np.array_equal(rho, oracle.ngp_deposit(xh, N, sim.cfg.w))
+    assert rho.sum() == P * sim.cfg.w
+    x, v = sim.particles()
+    ro, Eo, _ = oracle.ngp_step(x0, v0, N, sim.cfg.dt, sim.cfg.w)  # in place on x0, v0
+    assert relnorm(E, Eo) < TOL and relnorm(x, x0) < TOL and relnorm(v, v0) < TOL

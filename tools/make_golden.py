@@ -1,0 +1,148 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz with the CPU oracle (oracle/picgolf_oracle.c).
+
+The reference has no tests or golden vectors and Julia cannot run here, so these fixtures are
+outputs of the oracle restatement on seeded inputs (inputs are stored too, so the fixtures do not
+depend on numpy's RNG stream).  They pin (a) the oracle against accidental drift and (b) the CUDA
+path on the GPU box, where neither /root/reference nor a long CPU run is available.
+
+Run:  python tools/make_golden.py [--skip-c3]
+"""
+import argparse
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as o  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def c1_ngp(steps=8):
+    """Config 1: src/NGPFourier.jl  N=128, P=64N, dt=1/4N, W=200 (w=3.125 dyadic)."""
+    N, P = 128, 64 * 128
+    dt, W = 1 / (4 * N), 200.0
+    w = W / P * N
+    rng = np.random.default_rng(0)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(1, P + 1) > P / 2, 1.0, -1.0)
+    x, v = x0.copy(), v0.copy()
+    rhos, Es, raws = [], [], []
+    for _ in range(steps):
+        rho, E, raw = o.ngp_step(x, v, N, dt, w)
+        rhos.append(rho); Es.append(E); raws.append(raw)
+    save("c1_ngp", N=N, P=P, dt=dt, W=W, w=w, x0=x0, v0=v0, x=x, v=v, rho=np.array(rhos), E=np.array(Es),
+         raw=np.array(raws), idx1=o.ngp_index(x0, N))
+
+
+def gauss_explicit(steps=8):
+    """src/Gaussian.jl  NX=128, NP=64NX, dt=1/10NX, W=1600, w=W/NP, deposit scale w/dx."""
+    N, P = 128, 64 * 128
+    dt, W = 1 / (10 * N), 1600.0
+    scale = W / P / (1 / N)
+    rng = np.random.default_rng(1)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(1, P + 1) > P / 2, 1.0, -1.0)
+    x, v = x0.copy(), v0.copy()
+    rhos, Es, raws = [], [], []
+    for _ in range(steps):
+        rho, E, raw = o.gauss_leapfrog_step(x, v, N, 6, dt, scale)
+        rhos.append(rho); Es.append(E); raws.append(raw)
+    save("gauss_explicit", N=N, P=P, dt=dt, W=W, scale=scale, x0=x0, v0=v0, x=x, v=v, rho=np.array(rhos),
+         E=np.array(Es), raw=np.array(raws))
+
+
+def c2_fixedpoint(steps=16):
+    """Config 2: src/GaussianFixedPoint.jl  N=128, P=32N, dt=1/6N, W=400, +-6, l=1e-8."""
+    N, P = 128, 32 * 128
+    dt, W = 1 / (6 * N), 400.0
+    rng = np.random.default_rng(2)
+    x0 = rng.random(P)
+    v0 = rng.choice([-1.0, 1.0], P)
+    fp = o.FixedPoint(x0, v0, N, dt, W, hw=6, rtol=1e-8, atol=0.0)
+    Ds, sws, Es, rhos = [], [], [], []
+    x1 = v1 = None
+    for t in range(steps):
+        D4, raw, s = fp.step()
+        Ds.append(D4); sws.append(s); Es.append(fp.E.copy()); rhos.append(fp.r.copy())
+        if t == 0:
+            x1, v1 = fp.x.copy(), fp.v.copy()
+    save("c2_fixedpoint", N=N, P=P, dt=dt, W=W, w=fp.w, x0=x0, v0=v0, x1=x1, v1=v1, x=fp.x, v=fp.v, D=np.array(Ds),
+         sweeps=np.array(sws, dtype=np.int32), E=np.array(Es), rho=np.array(rhos))
+
+
+def c3_quiet(T=2 ** 13):
+    """Config 3: src/GaussianFixedPointQuiet.jl  N=64, P=2048, T=2^13, W=32pi^2/3, +-7, l=4eps, quiet start."""
+    N, P = 64, 2048
+    dt, W = 1 / (6 * N), 32 * math.pi ** 2 / 3
+    x0, v0 = o.quiet_start(P)
+    fp = o.FixedPoint(x0, v0, N, dt, W, hw=7, rtol=4 * np.finfo(float).eps, atol=0.0)
+    # first 16 steps one by one (state snapshots), then the rest in one call
+    D, sw = np.zeros((T, 4)), np.zeros(T, dtype=np.int32)
+    x16 = v16 = E16 = None
+    for t in range(16):
+        D[t], _, sw[t] = fp.step()
+    x16, v16, E16 = fp.x.copy(), fp.v.copy(), fp.E.copy()
+    Drest, swrest = fp.run(T - 16)
+    D[16:], sw[16:] = Drest, swrest
+    save("c3_quiet", N=N, P=P, dt=dt, W=W, w=fp.w, T=T, D=D, sweeps=sw, x16=x16, v16=v16, E16=E16,
+         slope_pred=o.growth_slope(W))
+
+
+def c5_2d3v(steps=4):
+    """Config 5 shape at test size: src/Electrostatic2D3V.jl with NX=NY=32, P=NX*NY*8."""
+    NX = NY = 32
+    P = NX * NY * 8
+    NG = math.sqrt(NX ** 2 + NY ** 2)
+    n0 = 4 * math.pi ** 2
+    vth = math.sqrt(n0) / NG
+    dt = 1 / NG / (6 * vth)
+    B0 = math.sqrt(n0) / 4
+    w = n0 / P / ((1 / NX) * (1 / NY))
+    rng = np.random.default_rng(5)
+    x0, y0 = 1.0 - rng.random(P), 1.0 - rng.random(P)  # (0,1]
+    vx0, vy0, vz0 = (rng.standard_normal(P) * vth / math.sqrt(2) for _ in range(3))
+    x, y, vx, vy, vz = (a.copy() for a in (x0, y0, vx0, vy0, vz0))
+    Ex, Ey = np.zeros(NX * NY), np.zeros(NX * NY)
+    rhos, Exs, Eys, Ks = [], [], [], []
+    for _ in range(steps):
+        rho = o.step_2d3v(x, y, vx, vy, vz, NX, NY, dt, B0, w, Ex, Ey, nthreads=1)
+        rhos.append(rho); Exs.append(Ex.copy()); Eys.append(Ey.copy())
+        Ks.append(o.diagnostics_2d3v(Ex, Ey, NX, NY, vx, vy, w))
+    save("c5_2d3v", NX=NX, NY=NY, P=P, dt=dt, B0=B0, w=w, n0=n0, vth=vth, x0=x0, y0=y0, vx0=vx0, vy0=vy0, vz0=vz0,
+         x=x, y=y, vx=vx, vy=vy, vz=vz, rho=np.array(rhos), Ex=np.array(Exs), Ey=np.array(Eys), K=np.array(Ks))
+
+
+def stencils():
+    """Stage-level vectors: Gaussian stencils at awkward centres for N = 64, 128, 4096."""
+    rng = np.random.default_rng(7)
+    out = {}
+    for N, hw in ((64, 7), (128, 6), (4096, 6), (4096, 7)):
+        c = np.concatenate([rng.random(256), rng.random(32) * 0.02 - 0.01, 1 + rng.random(32) * 0.02 - 0.01,
+                            (np.arange(8) + 0.5) / N, [0.0, 1.0, 0.5, 1e-300, -1e-300]])
+        idx = np.zeros((c.size, 2 * hw + 1), dtype=np.int32)
+        wt = np.zeros((c.size, 2 * hw + 1))
+        for j, cj in enumerate(c):
+            idx[j], wt[j] = o.gauss_stencil(cj, N, hw)
+        out[f"c_{N}_{hw}"], out[f"idx_{N}_{hw}"], out[f"wt_{N}_{hw}"] = c, idx, wt
+    save("stencils", **out)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-c3", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils()
+    if not args.skip_c3:
+        c3_quiet()
