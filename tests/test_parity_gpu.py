@@ -59,7 +59,7 @@ def test_gauss_stencil_parity(pg, oracle):
         idx, wt = pg.gauss_stencil(c, N, hw)
         assert np.array_equal(idx, g[f"idx_{N}_{hw}"])
         assert np.abs(wt - g[f"wt_{N}_{hw}"]).max() < 2.3e-16
-        assert np.abs(wt.sum(axis=1) - 1).max() < 3e-16
+        assert np.abs(wt.sum(axis=1) - 1).max() < 5e-16
         if hw == 7:
             assert np.all(wt[:, 0] == 0) and np.all(wt[:, -1] == 0)
 
