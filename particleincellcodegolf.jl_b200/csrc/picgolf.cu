@@ -97,7 +97,7 @@ static int check(int rc, const char *what)
 // stage timers: CUDA events recorded on the handle's stream, resolved lazily (never inside a step)
 // ------------------------------------------------------------------------------------------
 struct StageTimer {
-    struct Span { int stage; cudaEvent_t a, b; };
+    struct Span { int stage; cudaEvent_t a, b; bool done; };
     std::vector<Span> open;
     std::vector<cudaEvent_t> pool;
     double ms[5] = {0, 0, 0, 0, 0};
@@ -107,25 +107,29 @@ struct StageTimer {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
-    void begin(int stage, cudaStream_t s)
+    // begin() returns a span id for end(); spans may nest (ST_TOTAL encloses the stage spans).
+    int begin(int stage, cudaStream_t s)
     {
-        if (!enabled) return;
-        Span sp{stage, get(), get()};
+        if (!enabled) return -1;
+        Span sp{stage, get(), get(), false};
         cudaEventRecord(sp.a, s);
         open.push_back(sp);
+        return (int)open.size() - 1;
     }
-    void end(cudaStream_t s)
+    void end(int id, cudaStream_t s)
     {
-        if (!enabled) return;
-        cudaEventRecord(open.back().b, s);
+        if (id < 0 || id >= (int)open.size()) return;
+        cudaEventRecord(open[id].b, s);
+        open[id].done = true;
     }
     void drain()
     {
         for (auto &sp : open) {
             float t = 0.f;
-            cudaEventSynchronize(sp.b);
-            cudaEventElapsedTime(&t, sp.a, sp.b);
-            ms[sp.stage] += t;
+            if (sp.done && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess)
+                ms[sp.stage] += t;
+            else
+                cudaGetLastError();
             pool.push_back(sp.a); pool.push_back(sp.b);
         }
         open.clear();
@@ -527,11 +531,11 @@ PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, do
 static int allreduce_grid(picgolf_handle h)
 {
     if (!h->comm) return 0;
-    h->timer.begin(ST_REDUCE, h->stream);
+    const int sp1_ = h->timer.begin(ST_REDUCE, h->stream);
     int rc;
     if (h->ngp) rc = nccl::AllReduce(h->counts, h->counts, (size_t)h->ncell, nccl::Uint64, nccl::Sum, h->comm, h->stream);
     else rc = nccl::AllReduce(h->rho, h->rho, (size_t)h->ncell, nccl::Float64, nccl::Sum, h->comm, h->stream);
-    h->timer.end(h->stream);
+    h->timer.end(sp1_, h->stream);
     return nccl::check(rc, "ncclAllReduce(rho)");
 }
 
@@ -544,9 +548,9 @@ static int launch_solve1d(picgolf_handle h, int k)
     a.N = (int)c.N; a.lg = ilog2(c.N); a.use_counts = h->ngp ? 1 : 0; a.fixedpoint = h->fixedpoint ? 1 : 0;
     a.k = k; a.max_sweeps = c.max_sweeps;
     int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
-    h->timer.begin(ST_SOLVE, h->stream);
+    const int sp2_ = h->timer.begin(ST_SOLVE, h->stream);
     solve1d_kernel<<<1, threads, h->smem_pass, h->stream>>>(a);
-    h->timer.end(h->stream);
+    h->timer.end(sp2_, h->stream);
     h->launches++;
     return 0;
 }
@@ -569,17 +573,17 @@ static int step_fixedpoint(picgolf_handle h)
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
     a.E = h->E; a.rho = h->rho; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.k = 0;
-    h->timer.begin(ST_PARTICLES, h->stream);
+    const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
     fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-    h->timer.end(h->stream);
+    h->timer.end(sp3_, h->stream);
     h->launches++;
     for (int k = 1; k <= c.max_sweeps; ++k) {
         PG_TRY(allreduce_grid(h));
         PG_TRY(launch_solve1d(h, k));
         a.k = k;
-        h->timer.begin(ST_PARTICLES, h->stream);
+        const int sp4_ = h->timer.begin(ST_PARTICLES, h->stream);
         fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-        h->timer.end(h->stream);
+        h->timer.end(sp4_, h->stream);
         h->launches++;
     }
     PG_TRY(launch_step_end(h, true));
@@ -593,10 +597,10 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
     LFArgs a;
     a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho; a.counts = h->counts; a.partials = h->partials;
     a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
-    h->timer.begin(ST_PARTICLES, h->stream);
+    const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
     if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
     else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-    h->timer.end(h->stream);
+    h->timer.end(sp5_, h->stream);
     h->launches++;
     return 0;
 }
@@ -608,11 +612,11 @@ static int launch_solve2d(picgolf_handle h)
     a.rho = h->rho; a.rho_last = h->rho_last; a.Z = h->Z; a.E2 = h->E2; a.twx = h->tw; a.twy = h->twy;
     a.partials = h->epartials; a.NX = (int)c.N; a.NY = (int)c.NY; a.lgx = ilog2(c.N); a.lgy = ilog2(c.NY);
     const int NX = a.NX, NY = a.NY;
-    h->timer.begin(ST_SOLVE, h->stream);
+    const int sp6_ = h->timer.begin(ST_SOLVE, h->stream);
     solve2d_rows_fwd<<<NY / ROWS_PER_BLOCK, 512, (size_t)2 * ROWS_PER_BLOCK * NX * 8, h->stream>>>(a);
     solve2d_cols<<<NX / COLS_PER_BLOCK, 512, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8, h->stream>>>(a);
     solve2d_rows_inv<<<NY / ROWS_PER_BLOCK, 512, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8, h->stream>>>(a);
-    h->timer.end(h->stream);
+    h->timer.end(sp6_, h->stream);
     h->launches += 3;
     return 0;
 }
@@ -626,9 +630,9 @@ static int step_2d3v(picgolf_handle h)
     a.t1 = c.B0 * c.dt / 2;                       // tvec[1]   Electrostatic2D3V.jl:32
     a.tscale = 2 / (1 + (a.t1 * a.t1 + 0.0 + 0.0)); // :33
     a.NX = (int)c.N; a.NY = (int)c.NY;
-    h->timer.begin(ST_PARTICLES, h->stream);
+    const int sp7_ = h->timer.begin(ST_PARTICLES, h->stream);
     particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);
-    h->timer.end(h->stream);
+    h->timer.end(sp7_, h->stream);
     h->launches++;
     PG_TRY(allreduce_grid(h));
     PG_TRY(launch_solve2d(h));
@@ -644,7 +648,7 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
     if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "set or initialise particles before stepping");
     if (nsteps == 0) return 0;
     PG_TRY(use_device(h));
-    h->timer.begin(ST_TOTAL, h->stream);
+    const int sp8_ = h->timer.begin(ST_TOTAL, h->stream);
     int rc = 0;
     if (h->fixedpoint) {
         for (int64_t s = 0; s < nsteps && rc == 0; ++s) { rc = step_fixedpoint(h); h->steps++; }
@@ -660,7 +664,7 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
             h->steps++;
         }
     }
-    h->timer.end(h->stream);
+    h->timer.end(sp8_, h->stream);
     if (rc != 0) return rc;
     PG_CUDA(cudaGetLastError());
     if (h->timer.enabled && h->timer.open.size() > 4096) h->timer.drain();
