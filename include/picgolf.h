@@ -172,6 +172,9 @@ int picgolf_stage_timing(picgolf_handle h, int enable);
 int picgolf_stage_times(picgolf_handle h, double ms[5], int reset);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int picgolf_launch_count(picgolf_handle h, int64_t *launches);
+/* Cell-sorted mode bookkeeping: number of sorts so far and number of particle deposits that fell
+ * outside their warp's shared-memory window (slow path) -- a stale-sort indicator. */
+int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_particles);
 /* The cudaStream_t the handle enqueues on (for CUDA-event timing by the caller). */
 int picgolf_get_stream(picgolf_handle h, void **stream);
 

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "picgolf_stage_timing": [_vp, _int],
     "picgolf_stage_times": [_vp, C.POINTER(_d * 5), _int],
     "picgolf_launch_count": [_vp, C.POINTER(_i64)],
+    "picgolf_sort_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "picgolf_get_stream": [_vp, C.POINTER(_vp)],
     "picgolf_comm_unique_id": [_vp],
     "picgolf_comm_init": [_vp, _vp, _int, _int],
@@ -286,6 +287,12 @@ class PIC:
         n = _i64()
         _check(self._lib.picgolf_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def sort_stats(self):
+        """(number of cell sorts, particle deposits that took the out-of-window slow path)."""
+        a, b = _i64(), _i64()
+        _check(self._lib.picgolf_sort_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def stream(self) -> int:

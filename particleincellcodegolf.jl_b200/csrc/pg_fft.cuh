@@ -71,14 +71,15 @@ __device__ __forceinline__ void fft_smem(double *re, double *im, int n, int batc
 __device__ __forceinline__ int bitrev(int v, int lg) { return (int)(__brev((unsigned)v) >> (32 - lg)); }
 
 struct Solve1DArgs {
-    double *rho;                    // [N] deposited charge (summed over ranks); zeroed after it is read
-    unsigned long long *counts;     // NGP: integer deposit counts (rho = counts*w); zeroed after read
+    const double *rho_in;           // stage entry only: fp64 charge density given by the caller
+    unsigned long long *rho_fx;     // [N] integer deposit grid summed over ranks (NGP counts or Gaussian fixed
+                                    // point): rho = fx * fx_inv * w; zeroed after it is read
     double *rho_last;               // [N] copy kept for picgolf_get_fields
     double *E;                      // [N] in: previous field (the reference's F), out: new field
     const double2 *tw;              // twiddles for size N
     Ctrl *ctrl;
-    double w, rtol, atol;
-    int N, lg, use_counts, fixedpoint, k, max_sweeps;
+    double w, fx_inv, rtol, atol;   // fx_inv = 2^-frac
+    int N, lg, fixedpoint, k, max_sweeps;
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     const int N = a.N;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double r;
-        if (a.use_counts) { r = (double)a.counts[n] * a.w; a.counts[n] = 0ULL; }
-        else { r = a.rho[n]; a.rho[n] = 0.0; }
+        if (a.rho_in) r = a.rho_in[n];
+        else { r = (double)(long long)a.rho_fx[n] * a.fx_inv * a.w; a.rho_fx[n] = 0ULL; }
         a.rho_last[n] = r;
         re[n] = r; im[n] = 0.0;
     }

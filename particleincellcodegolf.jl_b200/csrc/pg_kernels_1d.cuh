@@ -15,19 +15,31 @@ namespace pg {
 // ------------------------------------------------------------------------------------------
 // deposit primitives on a block-private shared-memory grid
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gauss_deposit_atomic(double *rs, int ibase, const double (&W)[GAUSS_NW], double scale,
+// All Gaussian deposits accumulate in 64-bit FIXED POINT: value = round(weight * 2^frac) with
+// frac = 62 - ceil(log2(P+1)) so that even all P particles in one cell cannot overflow (picgolf.cu).
+// Integer addition is
+// associative, so the grid is bit-identical whatever the order of the atomics, the particle order or the
+// number of GPUs -- in particular two sweeps with identical particle positions give identical rho, which
+// is what lets the fixed point stop after 2 sweeps while the field is still round-off (as the sequential
+// reference does).  In cell-sorted mode only whole chunk sums are quantised (relative error ~1e-14 at
+// P = 2^28, N = 4096, below the ~1e-13 rounding error of a sequential fp64 running sum of 2^16 terms).
+// rho = fixed * 2^-frac * w is formed by the solve.
+typedef unsigned long long fx_t;
+__device__ __forceinline__ fx_t to_fx(double v, double fx_scale) { return (fx_t)__double2ll_rn(v * fx_scale); }
+
+__device__ __forceinline__ void gauss_deposit_atomic(fx_t *rs, int ibase, const double (&W)[GAUSS_NW], double fx_scale,
                                                      int Nmask)
 {
-    // r[k[1]] += k[2]*w      src/GaussianFixedPoint.jl:6
+    // r[k[1]] += k[2]*w      src/GaussianFixedPoint.jl:6   (the factor w is applied by the solve)
 #pragma unroll
-    for (int k = 0; k < GAUSS_NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], W[k] * scale);
+    for (int k = 0; k < GAUSS_NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale));
 }
 
-__device__ __forceinline__ void flush_grid(const double *rs, double *rho, int N)
+__device__ __forceinline__ void flush_grid(const fx_t *rs, fx_t *rho, int N)
 {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        double r = rs[n];
-        if (r != 0.0) atomicAdd(&rho[n], r);
+        fx_t r = rs[n];
+        if (r) atomicAdd(&rho[n], r);
     }
 }
 
@@ -45,19 +57,22 @@ struct FPArgs {
     double *v;           // working velocity v_k (in place)
     double *xout;        // wrapped end-of-step position
     const double *E;     // field of solve k
-    double *rho;         // global deposit grid (zeroed by the solve that consumed it)
+    fx_t *rho;           // global fixed-point deposit grid (zeroed by the solve that consumed it)
     double *partials;    // [2*gridDim.x] per-block (sum v^2, sum v)
     Ctrl *ctrl;
+    unsigned long long *slow_count; // sorted mode: particles that fell outside their warp's window
     long long P;
-    double dt, w;
+    double dt, fx_scale; // fx_scale = 2^frac
     int N, k;
+    int K;               // sorted mode: batches of 32 particles per warp chunk
 };
 
 template <bool FIRST>
 __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 {
     extern __shared__ double smem[];
-    double *Es = smem, *rs = smem + a.N, *scratch = smem + 2 * a.N;
+    double *Es = smem, *scratch = smem + 2 * a.N;
+    fx_t *rs = reinterpret_cast<fx_t *>(smem + a.N);
     const int fk = a.ctrl->final_k;
     if (!FIRST && fk >= 0 && a.k > fk) return;
     const bool final = !FIRST && fk == a.k;
@@ -65,7 +80,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
     const double dN = (double)N, dt = a.dt;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         if (!FIRST) Es[n] = a.E[n];
-        rs[n] = 0.0;
+        rs[n] = 0ULL;
     }
     __syncthreads();
     double sv2 = 0.0, sv = 0.0;
@@ -90,7 +105,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
             xj = Xj + (vj + Vj) / 2 * dt;
         }
         gauss_weights((xj + Xj) / 2, dN, ibase, W);
-        gauss_deposit_atomic(rs, ibase, W, a.w, Nmask);
+        gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
     }
     __syncthreads();
     if (final) {
@@ -103,6 +118,198 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Sorted variant of the fixed-point pass.  Particles are kept in cell order (pg_sort.cuh), so the 32*K
+// consecutive particles a warp processes ("chunk") touch only a few neighbouring cells.  Each warp owns
+// a WIN_ROWS-cell window of the grid in shared memory with one private column per lane:
+//     acc[row][lane]  (row stride 33 doubles -> conflict-free both for the per-lane read-modify-write
+//                      and for the row sums of the flush)
+// so the 13 deposits of a particle are plain LDS/DADD/STS -- no atomics, no warp divergence; the
+// SORTED_NP particles a lane evaluates together are summed in registers first when they share a window row.  At the
+// end of the chunk lane r sums row r and issues ONE global fp64 RED per window cell.  The 32-cell slice
+// of E the chunk needs is staged the same way (Ew), so the gather is 13 broadcast-friendly LDS.
+// A particle whose stencil leaves the window (stale sort, sparse cells) takes the slow path: global
+// atomics for the deposit, global loads for the gather; it is counted in slow_count.
+// Window rows are Julia (1-based, unwrapped) indices base..base+31; wrap is applied at load/flush.
+// ------------------------------------------------------------------------------------------
+constexpr int WIN_ROWS = 32;                    // grid cells covered by a warp's window
+constexpr int WIN_ALLOC = WIN_ROWS + GAUSS_NW;  // + 13 trash rows: where out-of-window stencils land harmlessly
+constexpr int WIN_LD = 33;
+constexpr int WIN_LO = 6;                       // rows kept below the smallest centre of the first batch
+constexpr int WIN_MAXOFF = WIN_ROWS - GAUSS_NW; // largest row a stencil may start at
+constexpr int WIN_WARP_DOUBLES = WIN_ALLOC * WIN_LD + WIN_ROWS;
+constexpr int SORTED_NP = 2;                    // particles evaluated together per lane
+
+// Rare path: stencil outside the warp window.  Kept out of line so the hot loop stays small.
+__device__ __noinline__ double slow_gather(const double *E, double c, int N)
+{
+    int ibase; double W[GAUSS_NW];
+    gauss_weights(c, (double)N, ibase, W);
+    double g = 0.0;
+    for (int q = 0; q < GAUSS_NW; ++q) g = fma(__ldg(&E[(ibase + q - 1) & (N - 1)]), W[q], g);
+    return g;
+}
+__device__ __noinline__ void slow_deposit(fx_t *rho, double c, int N, double fx_scale)
+{
+    int ibase; double W[GAUSS_NW];
+    gauss_weights(c, (double)N, ibase, W);
+    for (int q = 0; q < GAUSS_NW; ++q) atomicAdd(&rho[(ibase + q - 1) & (N - 1)], to_fx(W[q], fx_scale));
+}
+
+template <bool FIRST, int NP>
+__global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
+{
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    const int fk = a.ctrl->final_k;
+    if (!FIRST && fk >= 0 && a.k > fk) return;
+    const bool final = !FIRST && fk == a.k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *acc = smem + warp * WIN_WARP_DOUBLES; // [WIN_ALLOC][WIN_LD]
+    double *Ew = acc + WIN_ALLOC * WIN_LD;        // [WIN_ROWS]
+    const int N = a.N, Nmask = N - 1;
+    const double dN = (double)N, dt = a.dt;
+    const long long CH = 32LL * a.K; // a.K is a multiple of NP
+    const long long nchunks = (a.P + CH - 1) / CH;
+    double sv2 = 0.0, sv = 0.0;
+    unsigned int nslow = 0;
+    for (long long ch = (long long)blockIdx.x * wpb + warp; ch < nchunks; ch += (long long)gridDim.x * wpb) {
+        const long long j0 = ch * CH;
+        // window base: smallest cell centre among the first batch of the chunk (same in all lanes)
+        int base;
+        {
+            long long jf = j0 + lane < a.P ? j0 + lane : j0;
+            int c0 = (int)rint(a.X[jf] * dN);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+            base = c0 - 6 - WIN_LO;
+        }
+        if (!FIRST) Ew[lane] = a.E[(base + lane - 1) & Nmask];
+        if (!final)
+#pragma unroll 4
+            for (int r = 0; r < WIN_ROWS; ++r) acc[r * WIN_LD + lane] = 0.0;
+        __syncwarp();
+        for (int kb = 0; kb < a.K; kb += NP) {
+            long long j[NP];
+            bool live[NP];
+            double Xj[NP], Vj[NP], vj[NP], xj[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                j[q] = j0 + 32LL * (kb + q) + lane;
+                live[q] = j[q] < a.P;
+                Xj[q] = live[q] ? ld_stream(a.X + j[q]) : 0.0;
+                Vj[q] = live[q] ? ld_stream(a.V + j[q]) : 0.0;
+                vj[q] = FIRST ? Vj[q] : (live[q] ? ld_stream(a.v + j[q]) : 0.0);
+            }
+            if (!live[0]) break;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) / 2 * dt; // x.=X.+(v.+V)/2*dt
+            if (!FIRST) {
+                double d[NP], g[NP], mid[NP];
+                const double *e[NP];
+                bool ok[NP];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    int ibase;
+                    mid[q] = (xj[q] + Xj[q]) / 2;
+                    gauss_centre(mid[q], dN, ibase, d[q]);
+                    const int off = (ibase - base) & Nmask; // periodic: Julia indices 0 and N are the same cell
+                    ok[q] = off <= WIN_MAXOFF;
+                    e[q] = Ew + (ok[q] ? off : 0) + 6;
+                    g[q] = 0.0;
+                }
+                gauss_stream<NP>(
+                    d,
+                    [&](auto m, const double(&wp)[NP], const double(&wm)[NP]) {
+                        constexpr int M = decltype(m)::value;
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) { g[q] = fma(e[q][M], wp[q], g[q]); g[q] = fma(e[q][-M], wm[q], g[q]); }
+                    },
+                    [&](const double(&w0)[NP]) {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) g[q] = fma(e[q][0], w0[q], g[q]);
+                    });
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (!ok[q] && live[q]) g[q] = slow_gather(a.E, mid[q], N);
+                    vj[q] = Vj[q] + g[q] * dt; // v[j]=V[j]+sum(...)*dt
+                    if (live[q]) st_stream(a.v + j[q], vj[q]);
+                }
+                if (final) {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q)
+                        if (live[q]) {
+                            st_stream(a.xout + j[q], jl_mod1(xj[q])); // x.=mod.(x,1)
+                            sv2 = fma(vj[q], vj[q], sv2);
+                            sv += vj[q];
+                        }
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) / 2 * dt;
+            }
+            // deposit at (x+X)/2 into the lane-private window column
+            double d[NP], mid[NP];
+            double *col[NP];
+            bool ok[NP], merged[NP]; // merged[q]: particle q shares particle 0's window rows -> summed in registers
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                int ibase;
+                mid[q] = (xj[q] + Xj[q]) / 2;
+                gauss_centre(mid[q], dN, ibase, d[q]);
+                const int o = (ibase - base) & Nmask;
+                ok[q] = live[q] && o <= WIN_MAXOFF;
+                col[q] = acc + ((ok[q] ? o : WIN_ROWS) + 6) * WIN_LD + lane; // trash rows when outside
+                merged[q] = col[q] == col[0];
+            }
+            // One stencil evaluation for all NP particles; no divergent code paths: particles in the same
+            // rows as particle 0 (the usual case in cell order) cost one read-modify-write per cell together,
+            // the others a predicated extra one.
+            gauss_stream<NP>(
+                d,
+                [&](auto m, const double(&wp)[NP], const double(&wm)[NP]) {
+                    constexpr int M = decltype(m)::value;
+                    double sp = wp[0], sm = wm[0];
+#pragma unroll
+                    for (int q = 1; q < NP; ++q) { sp += merged[q] ? wp[q] : 0.0; sm += merged[q] ? wm[q] : 0.0; }
+                    col[0][M * WIN_LD] += sp;
+                    col[0][-M * WIN_LD] += sm;
+#pragma unroll
+                    for (int q = 1; q < NP; ++q)
+                        if (!merged[q]) { col[q][M * WIN_LD] += wp[q]; col[q][-M * WIN_LD] += wm[q]; }
+                },
+                [&](const double(&w0)[NP]) {
+                    double s0 = w0[0];
+#pragma unroll
+                    for (int q = 1; q < NP; ++q) s0 += merged[q] ? w0[q] : 0.0;
+                    col[0][0] += s0;
+#pragma unroll
+                    for (int q = 1; q < NP; ++q)
+                        if (!merged[q]) col[q][0] += w0[q];
+                });
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (live[q] && !ok[q]) { ++nslow; slow_deposit(a.rho, mid[q], N, a.fx_scale); }
+        }
+        __syncwarp();
+        if (!final) {
+            double s = 0.0;
+            const double *row = acc + lane * WIN_LD;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) s += row[c];
+            if (s != 0.0) atomicAdd(&a.rho[(base + lane - 1) & Nmask], to_fx(s, a.fx_scale)); // one integer RED per window cell
+        }
+        __syncwarp();
+    }
+    if (final) {
+        sv2 = block_sum(sv2, scratch);
+        sv = block_sum(sv, scratch);
+        if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
+    } else if (nslow && a.slow_count) {
+        atomicAdd(a.slow_count, (unsigned long long)nslow);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Leapfrog passes (NGP and explicit Gaussian).  One pass = [second half drift + kick of step t]
 // followed by [first half drift + deposit of step t+1]; either half can be switched off so the
 // state handed back to the caller is always an end-of-step state.
@@ -110,16 +317,16 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 //   kick: v += E[f.(x)]*dt                 NGPFourier.jl:6 ;  Gaussian.jl:10
 //   deposit: n[f(j)] += w                  NGPFourier.jl:5 ;  Gaussian.jl:7
 // NGP deposits are exact integer counts (shared-memory u32, global u64); rho = count*w is formed by
-// the solve kernel, so NGP charge is bit-reproducible and independent of particle order.
+// the solve kernel, so NGP charge is bit-reproducible and independent of particle order.  The explicit
+// Gaussian deposits in fixed point like the fixed-point scheme above.
 // ------------------------------------------------------------------------------------------
 struct LFArgs {
     double *x, *v;
     const double *E;
-    double *rho;                 // Gaussian
-    unsigned long long *counts;  // NGP
+    fx_t *rho;                   // integer deposit grid: NGP counts (frac = 0) or Gaussian fixed point
     double *partials;            // [2*gridDim.x]
     long long P;
-    double dt, w;
+    double dt, fx_scale;
     int N, do_kick, do_deposit;
 };
 
@@ -127,13 +334,14 @@ template <int SHAPE> // 0 = NGP, 1 = Gaussian
 __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
 {
     extern __shared__ double smem[];
-    double *Es = smem, *rs = smem + a.N, *scratch = smem + 2 * a.N;
+    double *Es = smem, *scratch = smem + 2 * a.N;
+    fx_t *rs = reinterpret_cast<fx_t *>(smem + a.N);
     unsigned int *cs = reinterpret_cast<unsigned int *>(rs);
     const int N = a.N, Nmask = N - 1;
     const double dN = (double)N, dt = a.dt;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         if (a.do_kick) Es[n] = a.E[n];
-        if (SHAPE == 0) cs[n] = 0u; else rs[n] = 0.0;
+        if (SHAPE == 0) cs[n] = 0u; else rs[n] = 0ULL;
     }
     __syncthreads();
     double sv2 = 0.0, sv = 0.0;
@@ -159,7 +367,7 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
             else {
                 int ibase; double W[GAUSS_NW];
                 gauss_weights(xj, dN, ibase, W);
-                gauss_deposit_atomic(rs, ibase, W, a.w, Nmask);
+                gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
             }
         }
         st_stream(a.x + j, xj);
@@ -170,7 +378,7 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
         if (SHAPE == 0) {
             for (int n = threadIdx.x; n < N; n += blockDim.x) {
                 unsigned int c = cs[n];
-                if (c) atomicAdd(&a.counts[n], (unsigned long long)c);
+                if (c) atomicAdd(&a.rho[n], (fx_t)c);
             }
         } else flush_grid(rs, a.rho, N);
     }
@@ -280,11 +488,11 @@ __global__ void stage_gauss_stencil_kernel(const double *c, long long count, int
 }
 
 __global__ void __launch_bounds__(PG_THREADS) stage_gauss_deposit_kernel(const double *x, const double *y, long long count,
-                                                                        int N, double scale, double *rho)
+                                                                        int N, double scale, fx_t *rho)
 {
     extern __shared__ double smem[];
-    double *rs = smem;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) rs[n] = 0.0;
+    fx_t *rs = reinterpret_cast<fx_t *>(smem);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) rs[n] = 0ULL;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {

@@ -1,0 +1,130 @@
+// pg_sort.cuh -- counting sort of the particle arrays by grid cell (1D) or tile (2D).
+// The reference sorts too (sortparticles!, src/Electrostatic2D3V.jl:57-62,159-161; src/PIC2D3V.jl:210-215)
+// for cache locality; here cell order is what lets a warp accumulate its deposit in a private
+// window without atomics (pg_kernels_1d.cuh).  A permutation array `pid` remembers each particle's
+// original slot so picgolf_get_particles returns the caller's order.
+//   1. sort_hist_kernel    per-block shared histogram -> global bin counts
+//   2. sort_scan_kernel    exclusive scan of the bins (one block)
+//   3. sort_scatter_kernel per-block histogram, one global reservation per (block, bin), local ranks
+//                          from shared-memory atomics, payload scatter
+// Summation order inside a bin is not reproducible (atomic ranks); the deterministic mode does not
+// use this path.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16; // particles per thread in a scatter tile
+constexpr int SORT_MAX_ARR = 5;
+
+struct SortArgs {
+    const double *in[SORT_MAX_ARR];
+    double *out[SORT_MAX_ARR];
+    const unsigned int *pid_in; // NULL: identity
+    unsigned int *pid_out;
+    unsigned int *bin_count;  // [nbins]
+    unsigned int *bin_cursor; // [nbins] running start offsets
+    long long P;
+    int narr, nbins;
+    int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1])
+    int N, NY;  // grid
+    int tshift; // 2D: log2(tile edge in cells)
+};
+
+__device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
+{
+    if (a.mode == 0) {
+        int c = (int)rint(a.in[0][j] * (double)a.N); // the stencil centre Int(round(x*N)): a bin shares its window rows
+        return c & (a.N - 1);
+    }
+    int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
+    int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);
+    return (cy >> a.tshift) * (a.N >> a.tshift) + (cx >> a.tshift);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortArgs a)
+{
+    extern __shared__ unsigned int sh[];
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) atomicAdd(&sh[sort_key(a, j)], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+        unsigned int c = sh[b];
+        if (c) atomicAdd(&a.bin_count[b], c);
+    }
+}
+
+// One block of 1024 threads; bins <= 65536.
+__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count, unsigned int *bin_cursor, int nbins)
+{
+    __shared__ unsigned int part[1024];
+    const int per = (nbins + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, nbins);
+    unsigned int s = 0;
+    for (int b = lo; b < hi; ++b) s += bin_count[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan
+        unsigned int t = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned int run = part[threadIdx.x] - s; // exclusive
+    for (int b = lo; b < hi; ++b) {
+        unsigned int c = bin_count[b];
+        bin_cursor[b] = run;
+        bin_count[b] = 0u; // ready for the next sort
+        run += c;
+    }
+}
+
+// Dynamic shared memory: 2*nbins u32.
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
+{
+    extern __shared__ unsigned int sh[];
+    unsigned int *cnt = sh, *base = sh + a.nbins;
+    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
+    const long long ntiles = (a.P + tile - 1) / tile;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) cnt[b] = 0u;
+        __syncthreads();
+        const long long j0 = t * tile;
+        int key[SORT_ITEMS];
+        unsigned int rank[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
+            key[i] = -1;
+            if (j < a.P) { key[i] = sort_key(a, j); rank[i] = atomicAdd(&cnt[key[i]], 1u); }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+            unsigned int c = cnt[b];
+            if (c) base[b] = atomicAdd(&a.bin_cursor[b], c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
+            if (key[i] >= 0) {
+                long long d = (long long)base[key[i]] + rank[i];
+                for (int q = 0; q < a.narr; ++q) a.out[q][d] = a.in[q][j];
+                a.pid_out[d] = a.pid_in ? a.pid_in[j] : (unsigned int)j;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// out[pid[i]] = in[i]: back to the caller's particle order.
+__global__ void unsort_kernel(const double *in, const unsigned int *pid, double *out, long long P)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) out[pid[i]] = in[i];
+}
+
+} // namespace pg

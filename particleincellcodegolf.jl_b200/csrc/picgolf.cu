@@ -16,6 +16,7 @@
 #include "pg_gauss.cuh"
 #include "pg_kernels_1d.cuh"
 #include "pg_kernels_2d.cuh"
+#include "pg_sort.cuh"
 
 using namespace pg;
 
@@ -58,7 +59,7 @@ namespace nccl {
 typedef struct { char internal[128]; } UniqueId;
 typedef void *Comm;
 enum { Sum = 0 };
-enum { Uint64 = 5, Float64 = 8 };
+enum { Int64 = 4, Uint64 = 5, Float64 = 8 };
 static void *lib = nullptr;
 static int (*GetUniqueId)(UniqueId *) = nullptr;
 static int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
@@ -157,8 +158,9 @@ struct picgolf_handle_s {
     double *y = nullptr, *vy = nullptr, *vz = nullptr; // 2D: x=xb[0], vx=vb[0]
     int par = 0;
     // grids
-    double *rho = nullptr, *rho_last = nullptr, *E = nullptr;
-    unsigned long long *counts = nullptr;
+    double *rho = nullptr, *rho_last = nullptr, *E = nullptr; // rho: 2D fp64 deposit grid
+    unsigned long long *rho_fx = nullptr;                     // 1D integer deposit grid (NGP counts / fixed point)
+    double fx_scale = 1.0, fx_inv = 1.0;                      // 2^frac, 2^-frac
     double2 *tw = nullptr, *twy = nullptr, *Z = nullptr, *E2 = nullptr;
     double *epartials = nullptr;
     int64_t ncell = 0;
@@ -173,6 +175,15 @@ struct picgolf_handle_s {
     nccl::Comm comm = nullptr;
     int nranks = 1, rank = 0;
     StageTimer timer;
+    // cell-sorted mode
+    bool sorted = false, pid_valid = false;
+    unsigned int *pid[2] = {nullptr, nullptr};
+    int pidpar = 0;
+    unsigned int *bin_count = nullptr, *bin_cursor = nullptr;
+    unsigned long long *slow_count = nullptr;
+    int nbins = 0, K = 1, sort_every = 1, nblocks_sorted = 1;
+    int64_t since_sort = 0, sorts = 0;
+    size_t smem_sorted = 0;
 };
 
 static int use_device(picgolf_handle h) { PG_CUDA(cudaSetDevice(h->device)); return 0; }
@@ -279,8 +290,9 @@ static int destroy_impl(picgolf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->timer.destroy();
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
-    void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->y, h->vy, h->vz, h->rho, h->rho_last, h->E, h->counts,
-                    h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw};
+    void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->y, h->vy, h->vz, h->rho, h->rho_last, h->E, h->rho_fx,
+                    h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
+                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -326,12 +338,17 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->ncell = N;
         PG_TRY(dalloc(&h->xb[0], n)); PG_TRY(dalloc(&h->vb[0], n));
         if (h->fixedpoint) { PG_TRY(dalloc(&h->xb[1], n)); PG_TRY(dalloc(&h->vb[1], n)); }
-        PG_TRY(dalloc(&h->rho, N)); PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, N));
-        PG_TRY(dalloc(&h->counts, N));
-        PG_CUDA(cudaMemset(h->rho, 0, N * sizeof(double)));
+        PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, N));
+        PG_TRY(dalloc(&h->rho_fx, N));
         PG_CUDA(cudaMemset(h->rho_last, 0, N * sizeof(double)));
         PG_CUDA(cudaMemset(h->E, 0, N * sizeof(double)));
-        PG_CUDA(cudaMemset(h->counts, 0, N * sizeof(unsigned long long)));
+        PG_CUDA(cudaMemset(h->rho_fx, 0, N * sizeof(unsigned long long)));
+        if (!h->ngp) {
+            // fixed-point format of the Gaussian deposit grid: weights are <= 1 and sum to 1 per particle, so
+            // no cell can exceed P (all ranks) -> 62 - ceil(log2(P+1)) fractional bits can never overflow.
+            int frac = std::max(8, std::min(60, 62 - ilog2(c.P + 1)));
+            h->fx_scale = ldexp(1.0, frac); h->fx_inv = ldexp(1.0, -frac);
+        }
         PG_TRY(make_twiddles(&h->tw, N));
         h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
         h->npart = 2;
@@ -340,6 +357,30 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             PG_TRY(set_smem(fp_pass_atomic<true>, h->smem_pass));
             PG_TRY(set_smem(fp_pass_atomic<false>, h->smem_pass));
             PG_TRY(occupancy_blocks(fp_pass_atomic<false>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+            const int64_t ppc = h->count / N;
+            if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
+            else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 18) && ppc >= 64;
+            if (h->sorted) {
+                h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
+                h->K = (h->K + SORTED_NP - 1) / SORTED_NP * SORTED_NP; // whole groups of SORTED_NP batches
+                h->nbins = N;
+                // re-sort before the slowest/fastest particles (|v| ~ 3) have drifted ~5 cells from their bin
+                double cells_per_step = 3.0 * c.dt * (double)N;
+                h->sort_every = c.sort_every > 0 ? c.sort_every : (int)std::max(1.0, std::min(1000.0, floor(5.0 / cells_per_step)));
+                h->smem_sorted = (size_t)(PG_THREADS / 32) * WIN_WARP_DOUBLES * sizeof(double);
+                PG_TRY(set_smem(fp_pass_sorted<true, SORTED_NP>, h->smem_sorted));
+                PG_TRY(set_smem(fp_pass_sorted<false, SORTED_NP>, h->smem_sorted));
+                int64_t warps = (h->count + 32LL * h->K - 1) / (32LL * h->K);
+                PG_TRY(occupancy_blocks(fp_pass_sorted<false, SORTED_NP>, PG_THREADS, h->smem_sorted, h->sms, warps * 32, &h->nblocks_sorted));
+                h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
+                PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
+                PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
+                PG_CUDA(cudaMemset(h->bin_count, 0, h->nbins * sizeof(unsigned int)));
+                PG_TRY(dalloc(&h->slow_count, 1));
+                PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
+                PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
+                PG_TRY(set_smem(sort_scatter_kernel, (size_t)h->nbins * 8));
+            }
         } else if (h->ngp) {
             PG_TRY(set_smem(lf_pass<0>, h->smem_pass));
             PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
@@ -422,15 +463,17 @@ static int reset_run_state(picgolf_handle h)
 {
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
-    PG_CUDA(cudaMemsetAsync(h->rho, 0, h->ncell * sizeof(double), h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
-    if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
-    else {
+    if (h->is2d) {
+        PG_CUDA(cudaMemsetAsync(h->rho, 0, h->ncell * sizeof(double), h->stream));
+        PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
+    } else {
         PG_CUDA(cudaMemsetAsync(h->E, 0, h->ncell * sizeof(double), h->stream));
-        PG_CUDA(cudaMemsetAsync(h->counts, 0, h->ncell * sizeof(unsigned long long), h->stream));
+        PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, h->ncell * sizeof(unsigned long long), h->stream));
     }
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
+    h->pid_valid = false; h->pidpar = 0; h->since_sort = 0;
     return 0;
 }
 
@@ -502,6 +545,20 @@ PG_API int picgolf_get_particles(picgolf_handle h, double *x, double *v, int64_t
     if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "particles were never set");
     if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
     PG_TRY(use_device(h));
+    if (h->sorted && h->pid_valid) {
+        // back to the caller's order through the free ping-pong buffer
+        double *tmp = h->xb[1 - h->par];
+        const double *src[2] = {h->xb[h->par], h->vb[h->par]};
+        double *dst[2] = {x, v};
+        for (int q = 0; q < 2; ++q) {
+            if (!dst[q]) continue;
+            unsort_kernel<<<h->sms * 8, 256, 0, h->stream>>>(src[q], h->pid[h->pidpar], tmp, h->count);
+            h->launches++;
+            PG_CUDA(cudaMemcpyAsync(dst[q], tmp, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        PG_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     if (x) PG_CUDA(cudaMemcpyAsync(x, h->xb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (v) PG_CUDA(cudaMemcpyAsync(v, h->vb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
@@ -533,7 +590,8 @@ static int allreduce_grid(picgolf_handle h)
     if (!h->comm) return 0;
     const int sp1_ = h->timer.begin(ST_REDUCE, h->stream);
     int rc;
-    if (h->ngp) rc = nccl::AllReduce(h->counts, h->counts, (size_t)h->ncell, nccl::Uint64, nccl::Sum, h->comm, h->stream);
+    // 1D: integer grid (two's-complement sums are exact and order independent); 2D: fp64 grid
+    if (!h->is2d) rc = nccl::AllReduce(h->rho_fx, h->rho_fx, (size_t)h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
     else rc = nccl::AllReduce(h->rho, h->rho, (size_t)h->ncell, nccl::Float64, nccl::Sum, h->comm, h->stream);
     h->timer.end(sp1_, h->stream);
     return nccl::check(rc, "ncclAllReduce(rho)");
@@ -543,9 +601,9 @@ static int launch_solve1d(picgolf_handle h, int k)
 {
     const picgolf_config &c = h->cfg;
     Solve1DArgs a;
-    a.rho = h->rho; a.counts = h->counts; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
-    a.w = c.w; a.rtol = c.rtol; a.atol = c.atol;
-    a.N = (int)c.N; a.lg = ilog2(c.N); a.use_counts = h->ngp ? 1 : 0; a.fixedpoint = h->fixedpoint ? 1 : 0;
+    a.rho_in = nullptr; a.rho_fx = h->rho_fx; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
+    a.w = c.w; a.fx_inv = h->fx_inv; a.rtol = c.rtol; a.atol = c.atol;
+    a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = h->fixedpoint ? 1 : 0;
     a.k = k; a.max_sweeps = c.max_sweeps;
     int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
     const int sp2_ = h->timer.begin(ST_SOLVE, h->stream);
@@ -566,15 +624,42 @@ static int launch_step_end(picgolf_handle h, bool record)
     return 0;
 }
 
+// Counting sort of the step-start state (xb[par], vb[par]) by cell into the other ping-pong buffers.
+static int sort_particles_1d(picgolf_handle h)
+{
+    const int sp = h->timer.begin(ST_SORT, h->stream);
+    SortArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in[0] = h->xb[h->par]; a.in[1] = h->vb[h->par];
+    a.out[0] = h->xb[1 - h->par]; a.out[1] = h->vb[1 - h->par];
+    a.pid_in = h->pid_valid ? h->pid[h->pidpar] : nullptr;
+    a.pid_out = h->pid[1 - h->pidpar];
+    a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor;
+    a.P = h->count; a.narr = 2; a.nbins = h->nbins; a.mode = 0; a.N = (int)h->cfg.N; a.NY = 1; a.tshift = 0;
+    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
+    int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
+    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
+    sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
+    sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->nbins);
+    sort_scatter_kernel<<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    h->launches += 3;
+    h->timer.end(sp, h->stream);
+    h->par ^= 1; h->pidpar ^= 1; h->pid_valid = true; h->since_sort = 0; h->sorts++;
+    return 0;
+}
+
 static int step_fixedpoint(picgolf_handle h)
 {
+    if (h->sorted && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_1d(h));
     const picgolf_config &c = h->cfg;
     FPArgs a;
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
-    a.E = h->E; a.rho = h->rho; a.partials = h->partials; a.ctrl = h->ctrl;
-    a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.k = 0;
+    a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
+    a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
+    a.slow_count = h->slow_count; a.K = h->K;
     const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
-    fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    if (h->sorted) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
+    else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
     h->timer.end(sp3_, h->stream);
     h->launches++;
     for (int k = 1; k <= c.max_sweeps; ++k) {
@@ -582,12 +667,14 @@ static int step_fixedpoint(picgolf_handle h)
         PG_TRY(launch_solve1d(h, k));
         a.k = k;
         const int sp4_ = h->timer.begin(ST_PARTICLES, h->stream);
-        fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+        if (h->sorted) fp_pass_sorted<false, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
+        else fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
         h->timer.end(sp4_, h->stream);
         h->launches++;
     }
     PG_TRY(launch_step_end(h, true));
     h->par ^= 1;
+    h->since_sort++;
     return 0;
 }
 
@@ -595,8 +682,8 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
 {
     const picgolf_config &c = h->cfg;
     LFArgs a;
-    a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho; a.counts = h->counts; a.partials = h->partials;
-    a.P = h->count; a.dt = c.dt; a.w = c.w; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
+    a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
+    a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
     const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
     if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
     else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
@@ -827,6 +914,22 @@ PG_API int picgolf_launch_count(picgolf_handle h, int64_t *launches)
     return 0;
 }
 
+PG_API int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_particles)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    PG_TRY(use_device(h));
+    if (sorts) *sorts = h->sorts;
+    if (slow_particles) {
+        unsigned long long n = 0;
+        if (h->slow_count) {
+            PG_CUDA(cudaStreamSynchronize(h->stream));
+            PG_CUDA(cudaMemcpy(&n, h->slow_count, sizeof(n), cudaMemcpyDeviceToHost));
+        }
+        *slow_particles = (int64_t)n;
+    }
+    return 0;
+}
+
 PG_API int picgolf_get_stream(picgolf_handle h, void **stream)
 {
     if (!h || !stream) return fail(PICGOLF_ERR_ARG, "NULL argument");
@@ -936,8 +1039,8 @@ PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, 
     size_t smem = (size_t)(2 * N + 32) * 8;
     PG_TRY(set_smem(lf_pass<0>, smem));
     LFArgs a;
-    a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = nullptr; a.counts = dcnt.as<unsigned long long>();
-    a.partials = dpart.as<double>(); a.P = count; a.dt = 0.0; a.w = w; a.N = (int)N; a.do_kick = 0; a.do_deposit = 1;
+    a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = dcnt.as<unsigned long long>();
+    a.partials = dpart.as<double>(); a.P = count; a.dt = 0.0; a.fx_scale = 1.0; a.N = (int)N; a.do_kick = 0; a.do_deposit = 1;
     // with v = 0 and dt = 0 the half drift is x = mod(x + 0, 1): positions in [0,1) are unchanged
     lf_pass<0><<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(a);
     PG_TRY(finish());
@@ -958,10 +1061,15 @@ PG_API int picgolf_stage_gauss_deposit(const double *x, const double *y, int64_t
     PG_TRY(dx.upload(x, count * 8)); PG_TRY(dy.upload(y, count * 8)); PG_TRY(dr.zero(N * 8));
     size_t smem = (size_t)N * 8;
     PG_TRY(set_smem(stage_gauss_deposit_kernel, smem));
+    // same fixed-point format rule as picgolf_create
+    int frac = std::max(8, std::min(60, 62 - ilog2(count + 1)));
     stage_gauss_deposit_kernel<<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(
-        dx.as<double>(), dy.as<double>(), count, (int)N, w, dr.as<double>());
+        dx.as<double>(), dy.as<double>(), count, (int)N, ldexp(1.0, frac), dr.as<unsigned long long>());
     PG_TRY(finish());
-    return dr.download(rho, N * 8);
+    std::vector<long long> fx((size_t)N);
+    PG_TRY(dr.download(fx.data(), N * 8));
+    for (int64_t n = 0; n < N; ++n) rho[n] = (double)fx[n] * ldexp(1.0, -frac) * w; // same expression as solve1d_kernel
+    return 0;
 }
 
 PG_API int picgolf_stage_gauss_gather(const double *E, int64_t N, int hw, const double *c, int64_t count, double *out)
@@ -985,8 +1093,8 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     PG_TRY(dr.upload(rho, N * 8)); PG_TRY(dl.alloc(N * 8)); PG_TRY(dE.zero(N * 8)); PG_TRY(dctrl.zero(sizeof(Ctrl)));
     PG_TRY(make_twiddles(&tw, (int)N));
     Solve1DArgs a;
-    a.rho = dr.as<double>(); a.counts = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
-    a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N); a.use_counts = 0;
+    a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
+    a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.fx_inv = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N);
     a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1;
     size_t smem = (size_t)(2 * N + 32) * 8;
     int rc = set_smem(solve1d_kernel, smem);

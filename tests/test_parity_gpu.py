@@ -348,3 +348,68 @@ def test_scaled_ngp_properties(pg, oracle):
     x, v = sim.particles()
     ro, Eo, _ = oracle.ngp_step(x0, v0, N, sim.cfg.dt, sim.cfg.w)  # in place on x0, v0
     assert relnorm(E, Eo) < TOL and relnorm(x, x0) < TOL and relnorm(v, v0) < TOL
+
+
+# =============================================================================================
+# cell-sorted deposit mode (pg_sort.cuh + fp_pass_sorted): same results, caller's particle order
+# =============================================================================================
+def test_sorted_mode_c2_golden(pg, oracle):
+    g = golden("c2_fixedpoint")
+    sim = pg.gaussian_fixed_point(T=64, deposit_mode=pg.DEPOSIT_SORTED, sort_every=3)
+    sim.set_particles(g["x0"], g["v0"])
+    sim.step(1)
+    rho, E = sim.fields()
+    x, v = sim.particles()  # unsorted back to the caller's order
+    assert relnorm(rho, g["rho"][0]) < TOL and relnorm(E, g["E"][0]) < TOL
+    assert relnorm(x, g["x1"]) < TOL and relnorm(v, g["v1"]) < TOL
+    sim.step(15)
+    D, sw = sim.diagnostics()
+    assert np.array_equal(sw, g["sweeps"])
+    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    x, v = sim.particles()
+    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10
+    sorts, slow = sim.sort_stats()
+    assert sorts == 6  # steps 0,3,6,9,12,15
+
+
+@pytest.mark.parametrize("start", ["uniform", "quiet"])
+def test_sorted_mode_matches_atomic_mode(pg, oracle, start):
+    """N=4096, 2^20 particles (256 per cell): AUTO picks the sorted path; 12 steps with re-sorts must
+    agree with the order-agnostic atomic path to round-off, and with the oracle after one step."""
+    N, P = 4096, 1 << 20
+    rng = np.random.default_rng(21)
+    sims = []
+    for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, deposit_mode=mode, sort_every=4)
+        if start == "quiet":
+            sim.init_quiet()
+        else:
+            x0 = rng.random(P) if not sims else x0  # noqa: F821
+            v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0)
+            sim.set_particles(x0, v0)
+        sims.append(sim)
+    a, s = sims
+    x0, v0 = a.particles()
+    xs0, vs0 = s.particles()
+    assert np.array_equal(x0, xs0) and np.array_equal(v0, vs0)
+    a.step(1); s.step(1)
+    fp = oracle.FixedPoint(x0, v0, N, a.cfg.dt, 400.0, hw=6, rtol=1e-8)
+    _, _, so = fp.step()
+    for sim in (a, s):
+        x, v = sim.particles()
+        rho, E = sim.fields()
+        assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL and relnorm(rho, fp.r) < TOL
+        # quiet start: E is pure round-off, compare on the scale of rho (SURVEY.md 7.3)
+        assert np.abs(E - fp.E).max() < max(1e-11 * np.abs(fp.E).max(), 1e-12 * np.abs(fp.r).max() / (2 * np.pi))
+        assert sim.diagnostics()[1][0] == so
+    a.step(11); s.step(11)
+    xa, va = a.particles()
+    xs, vs = s.particles()
+    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    Da, swa = a.diagnostics()
+    Ds, sws = s.diagnostics()
+    if start == "uniform":
+        assert np.array_equal(swa, sws)
+    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    sorts, slow = s.sort_stats()
+    assert sorts == 3 and slow < P // 100  # steps 0,4,8; almost everything stays inside its window
