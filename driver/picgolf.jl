@@ -1,0 +1,124 @@
+# picgolf.jl -- Julia-side binding of libpicgolf.so (include/picgolf.h).
+#
+# A reference script keeps its parameter / initialisation lines and replaces the body of its
+# `for t` loop by `step!`.  Example, src/GaussianFixedPointQuiet.jl with the loop on the GPU:
+#
+#     include("driver/picgolf.jl"); using .PicGolf
+#     N=64;P=32N;dt=1/6N;T=2^13;W=32π^2/3;w=W/P*N
+#     x=(bitreverse.(0:P-1).+2.0^63)/2.0^64; v=collect(1:P.>P/2).*2 .-1.
+#     sim = PicGolf.Sim(scheme=PicGolf.GAUSS_FIXEDPOINT, N=N, P=P, dt=dt, T=T, W=W, w=w,
+#                       rtol=4eps(), atol=0.0, half_width=7)
+#     PicGolf.set_particles!(sim, x, v)          # or PicGolf.init_quiet!(sim)
+#     PicGolf.step!(sim, T)                      # replaces lines 8-15 (minus the plotting)
+#     D, sweeps = PicGolf.diagnostics(sim)       # D[t,1:4] exactly as line 11/13 forms it
+#     x, v = PicGolf.particles(sim); r, E = PicGolf.fields(sim)
+#     # ... the plotting lines 16-21 run unchanged on D
+#
+# NOTE: Julia is not installed in the build container, so this file is shipped untested; the same
+# ABI is exercised through Python ctypes (particleincellcodegolf.jl_b200/__init__.py, tests/).
+module PicGolf
+
+const LIB = get(ENV, "PICGOLF_LIB", joinpath(@__DIR__, "..", "particleincellcodegolf.jl_b200", "lib", "libpicgolf.so"))
+
+const NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V = Int32(1), Int32(2), Int32(3), Int32(4)
+
+# Mirror of `picgolf_config` (include/picgolf.h) -- field order and types must match.
+Base.@kwdef mutable struct Config
+    struct_size::Int32 = 0
+    scheme::Int32 = GAUSS_FIXEDPOINT
+    N::Int64 = 128
+    NY::Int64 = 0
+    P::Int64 = 4096
+    T::Int64 = 1024
+    dt::Float64 = 1 / 768
+    W::Float64 = 400.0
+    w::Float64 = 12.5
+    rtol::Float64 = 1e-8
+    atol::Float64 = 0.0
+    B0::Float64 = 0.0
+    half_width::Int32 = 6
+    max_sweeps::Int32 = 10
+    diag_every::Int32 = 1
+    deposit_mode::Int32 = 0
+    deterministic::Int32 = 0
+    sort_every::Int32 = 0
+    device::Int32 = -1
+    rank::Int32 = 0
+    nranks::Int32 = 1
+    reserved_::Int32 = 0
+    local_first::Int64 = -1
+    local_count::Int64 = -1
+end
+
+struct PicGolfError <: Exception
+    code::Int
+    msg::String
+end
+
+lasterror() = unsafe_string(ccall((:picgolf_last_error, LIB), Cstring, ()))
+check(rc) = rc == 0 ? nothing : throw(PicGolfError(rc, lasterror()))
+
+mutable struct Sim
+    h::Ptr{Cvoid}
+    cfg::Config
+    count::Int64
+    function Sim(; kw...)
+        cfg = Config(; kw...)
+        cfg.struct_size = Int32(sizeof(Config))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:picgolf_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h))
+        first, count = Ref{Int64}(0), Ref{Int64}(0)
+        check(ccall((:picgolf_local_range, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), h[], first, count))
+        s = new(h[], cfg, count[])
+        finalizer(s -> ccall((:picgolf_destroy, LIB), Cint, (Ptr{Cvoid},), s.h), s)
+        return s
+    end
+end
+
+function set_particles!(s::Sim, x::Vector{Float64}, v::Vector{Float64})
+    GC.@preserve x v check(ccall((:picgolf_set_particles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64),
+                                 s.h, x, v, length(x)))
+end
+
+function set_particles!(s::Sim, x, y, vx, vy, vz)   # src/Electrostatic2D3V.jl:45-55
+    GC.@preserve x y vx vy vz check(ccall((:picgolf_set_particles_2d3v, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+        s.h, x, y, vx, vy, vz, length(x)))
+end
+
+init_quiet!(s::Sim) = check(ccall((:picgolf_init_quiet, LIB), Cint, (Ptr{Cvoid},), s.h))
+step!(s::Sim, n::Integer=1) = check(ccall((:picgolf_step, LIB), Cint, (Ptr{Cvoid}, Int64), s.h, n))
+synchronize(s::Sim) = check(ccall((:picgolf_synchronize, LIB), Cint, (Ptr{Cvoid},), s.h))
+
+function particles(s::Sim)
+    x, v = Vector{Float64}(undef, s.count), Vector{Float64}(undef, s.count)
+    check(ccall((:picgolf_get_particles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), s.h, x, v, s.count))
+    return x, v
+end
+
+function fields(s::Sim)
+    r, E = Vector{Float64}(undef, s.cfg.N), Vector{Float64}(undef, s.cfg.N)
+    check(ccall((:picgolf_get_fields, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s.h, r, E))
+    return r, E
+end
+
+function fields2d(s::Sim)
+    n = s.cfg.N * s.cfg.NY
+    r, Ex, Ey = (Vector{Float64}(undef, n) for _ in 1:3)
+    check(ccall((:picgolf_get_fields_2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s.h, r, Ex, Ey))
+    return (reshape(a, s.cfg.N, s.cfg.NY) for a in (r, Ex, Ey))   # column-major, same as Julia
+end
+
+function diagnostics(s::Sim)
+    rows = Ref{Int64}(0)
+    check(ccall((:picgolf_get_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Ref{Int64}),
+                s.h, C_NULL, 0, C_NULL, rows))
+    ncol = s.cfg.scheme == CIC_BORIS_2D3V ? 5 : 4
+    D = zeros(max(rows[], 1), ncol)                 # column-major T x ncol: the ABI's layout IS Julia's
+    sw = zeros(Int32, max(rows[], 1))
+    check(ccall((:picgolf_get_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Ref{Int64}),
+                s.h, D, size(D, 1), sw, rows))
+    return D[1:rows[], :], sw[1:rows[]]
+end
+
+end # module
