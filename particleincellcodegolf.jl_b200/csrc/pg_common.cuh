@@ -45,6 +45,12 @@ __device__ __forceinline__ int wrap_cell0(int i, int N)
 __device__ __forceinline__ double unimod(double x, double n) { return (0.0 < x && x <= n) ? x : (x > n ? x - n : x + n); }
 __device__ __forceinline__ int unimod(int x, int n) { return (0 < x && x <= n) ? x : (x > n ? x - n : x + n); }
 
+// ---- fixed-point charge accumulation ------------------------------------------------------
+// Deposits accumulate as round(weight * 2^frac) in 64-bit integers: integer addition is associative, so
+// the grid is bit-identical whatever the order of the atomics (see pg_kernels_1d.cuh).
+typedef unsigned long long fx_t;
+__device__ __forceinline__ fx_t to_fx(double v, double fx_scale) { return (fx_t)__double2ll_rn(v * fx_scale); }
+
 // ---- reductions -------------------------------------------------------------------------
 
 __device__ __forceinline__ double warp_sum(double v)

@@ -145,12 +145,14 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
 // transform of Ex^ + i Ey^ returns Ex in the real part and Ey in the imaginary part.
 // ---------------------------------------------------------------------------------------------
 struct Solve2DArgs {
-    double *rho;        // [NX*NY] column-major; zeroed after read
+    const double *rho_in; // stage entry only: fp64 charge density given by the caller
+    fx_t *rho_fx;       // [NX*NY] column-major fixed-point deposit grid; rho = fx*fx_inv*w; zeroed after read
     double *rho_last;
     double2 *Z;         // [NX*NY] complex scratch
     double2 *E2;        // [NX*NY] (real(Ex), real(Ey)) per cell
     const double2 *twx, *twy;
     double *partials;   // per-block partial sums of Ex^2+Ey^2 (pass C)
+    double w, fx_inv;
     int NX, NY, lgx, lgy;
 };
 
@@ -167,8 +169,10 @@ __global__ void __launch_bounds__(512) solve2d_rows_fwd(Solve2DArgs a)
     for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
         int r = t / NX, i = t - r * NX;
         size_t g = (size_t)i + (size_t)(j0 + r) * NX;
-        double v = a.rho[g];
-        a.rho[g] = 0.0; a.rho_last[g] = v;
+        double v;
+        if (a.rho_in) v = a.rho_in[g];
+        else { v = (double)(long long)a.rho_fx[g] * a.fx_inv * a.w; a.rho_fx[g] = 0ULL; }
+        a.rho_last[g] = v;
         re[t] = v; im[t] = 0.0;
     }
     __syncthreads();

@@ -24,9 +24,6 @@ namespace pg {
 // reference does).  In cell-sorted mode only whole chunk sums are quantised (relative error ~1e-14 at
 // P = 2^28, N = 4096, below the ~1e-13 rounding error of a sequential fp64 running sum of 2^16 terms).
 // rho = fixed * 2^-frac * w is formed by the solve.
-typedef unsigned long long fx_t;
-__device__ __forceinline__ fx_t to_fx(double v, double fx_scale) { return (fx_t)__double2ll_rn(v * fx_scale); }
-
 __device__ __forceinline__ void gauss_deposit_atomic(fx_t *rs, int ibase, const double (&W)[GAUSS_NW], double fx_scale,
                                                      int Nmask)
 {
@@ -330,15 +327,51 @@ struct LFArgs {
     int N, do_kick, do_deposit;
 };
 
+// One particle of a leapfrog pass (shared by the vectorised and the scalar loops).
+template <int SHAPE>
+__device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, fx_t *rs, unsigned int *cs, double &xj, double &vj,
+                                            double &sv2, double &sv)
+{
+    const int N = a.N, Nmask = N - 1;
+    const double dN = (double)N, dt = a.dt;
+    if (a.do_kick) {
+        xj = jl_mod1(xj + vj / 2 * dt);
+        double e;
+        if (SHAPE == 0) e = Es[ngp_cell0(xj, N)];
+        else {
+            int ibase; double W[GAUSS_NW];
+            gauss_weights(xj, dN, ibase, W);
+            e = gauss_gather(Es, ibase, W, Nmask);
+        }
+        vj = vj + e * dt;
+        sv2 = fma(vj, vj, sv2);
+        sv += vj;
+    }
+    if (a.do_deposit) {
+        xj = jl_mod1(xj + vj / 2 * dt);
+        if (SHAPE == 0) atomicAdd(&cs[ngp_cell0(xj, N)], 1u);
+        else {
+            int ibase; double W[GAUSS_NW];
+            gauss_weights(xj, dN, ibase, W);
+            gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
+        }
+    }
+}
+
+// Shared memory: Es[N] doubles, then the block-private deposit grid (NGP: N u32 counts; Gaussian: N
+// int64 fixed point), then 32 doubles of reduction scratch.  NGP streams the particle arrays with 128-bit
+// loads/stores, two pairs (4 particles) in flight per thread.
+__host__ __device__ inline size_t lf_smem_bytes(int shape, int N) { return (size_t)N * 8 + (size_t)N * (shape == 0 ? 4 : 8) + 256; }
+
 template <int SHAPE> // 0 = NGP, 1 = Gaussian
 __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
 {
     extern __shared__ double smem[];
-    double *Es = smem, *scratch = smem + 2 * a.N;
+    double *Es = smem;
     fx_t *rs = reinterpret_cast<fx_t *>(smem + a.N);
-    unsigned int *cs = reinterpret_cast<unsigned int *>(rs);
-    const int N = a.N, Nmask = N - 1;
-    const double dN = (double)N, dt = a.dt;
+    unsigned int *cs = reinterpret_cast<unsigned int *>(smem + a.N);
+    double *scratch = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + lf_smem_bytes(SHAPE, a.N) - 256);
+    const int N = a.N;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         if (a.do_kick) Es[n] = a.E[n];
         if (SHAPE == 0) cs[n] = 0u; else rs[n] = 0ULL;
@@ -346,32 +379,37 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
     __syncthreads();
     double sv2 = 0.0, sv = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
-        double xj = ld_stream(a.x + j), vj = ld_stream(a.v + j);
-        if (a.do_kick) {
-            xj = jl_mod1(xj + vj / 2 * dt);
-            double e;
-            if (SHAPE == 0) e = Es[ngp_cell0(xj, N)];
-            else {
-                int ibase; double W[GAUSS_NW];
-                gauss_weights(xj, dN, ibase, W);
-                e = gauss_gather(Es, ibase, W, Nmask);
-            }
-            vj = vj + e * dt;
-            sv2 = fma(vj, vj, sv2);
-            sv += vj;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (SHAPE == 0) {
+        const long long npair = a.P >> 1;
+        double2 *x2 = reinterpret_cast<double2 *>(a.x), *v2 = reinterpret_cast<double2 *>(a.v);
+        long long p = tid;
+        for (; p + stride < npair; p += 2 * stride) { // two 128-bit loads per array in flight
+            double2 xa = __ldcs(x2 + p), va = __ldcs(v2 + p), xb = __ldcs(x2 + p + stride), vb = __ldcs(v2 + p + stride);
+            lf_particle<SHAPE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
+            lf_particle<SHAPE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
+            lf_particle<SHAPE>(a, Es, rs, cs, xb.x, vb.x, sv2, sv);
+            lf_particle<SHAPE>(a, Es, rs, cs, xb.y, vb.y, sv2, sv);
+            __stcs(x2 + p, xa); __stcs(v2 + p, va); __stcs(x2 + p + stride, xb); __stcs(v2 + p + stride, vb);
         }
-        if (a.do_deposit) {
-            xj = jl_mod1(xj + vj / 2 * dt);
-            if (SHAPE == 0) atomicAdd(&cs[ngp_cell0(xj, N)], 1u);
-            else {
-                int ibase; double W[GAUSS_NW];
-                gauss_weights(xj, dN, ibase, W);
-                gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
-            }
+        for (; p < npair; p += stride) {
+            double2 xa = __ldcs(x2 + p), va = __ldcs(v2 + p);
+            lf_particle<SHAPE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
+            lf_particle<SHAPE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
+            __stcs(x2 + p, xa); __stcs(v2 + p, va);
         }
-        st_stream(a.x + j, xj);
-        st_stream(a.v + j, vj);
+        if ((a.P & 1) && tid == 0) { // odd tail
+            double xj = a.x[a.P - 1], vj = a.v[a.P - 1];
+            lf_particle<SHAPE>(a, Es, rs, cs, xj, vj, sv2, sv);
+            a.x[a.P - 1] = xj; a.v[a.P - 1] = vj;
+        }
+    } else {
+        for (long long j = tid; j < a.P; j += stride) {
+            double xj = ld_stream(a.x + j), vj = ld_stream(a.v + j);
+            lf_particle<SHAPE>(a, Es, rs, cs, xj, vj, sv2, sv);
+            st_stream(a.x + j, xj);
+            st_stream(a.v + j, vj);
+        }
     }
     __syncthreads();
     if (a.do_deposit) {

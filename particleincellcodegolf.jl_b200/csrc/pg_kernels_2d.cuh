@@ -2,7 +2,8 @@
 //   gather E at the old position (eval :94-103) -> boris (:35-41) -> move + unimod (:131-132)
 //   -> CIC deposit at the new position (depositcharge! :105-109).
 // Five fp64 SoA streams in, five out (80 B per particle-step).  The field is kept as one
-// (Ex,Ey) double2 per cell so a CIC corner is a single 16-byte load.
+// (Ex,Ey) double2 per cell so a CIC corner is a single 16-byte load.  Charge accumulates in 64-bit fixed
+// point (order-independent, bit-reproducible; see pg_kernels_1d.cuh).
 #pragma once
 #include "pg_common.cuh"
 
@@ -34,13 +35,30 @@ __device__ __forceinline__ void boris(double &vx, double &vy, double &vz, double
 struct P2DArgs {
     double *x, *y, *vx, *vy, *vz;
     const double2 *E2;   // (real(Ex), real(Ey)) per cell, column-major NX x NY
-    double *rho;         // global deposit grid (fp64 atomics)
+    fx_t *rho;           // global fixed-point deposit grid (sum of wx*wy; the factor w is applied by the solve)
     double *partials;    // [3*gridDim.x] per-block (sum vx^2+vy^2, sum vx, sum vy)
     long long P;
-    double dt, w, t1, tscale;
+    double dt, t1, tscale;
+    double fx_scale;     // 2^frac of the global grid
     int NX, NY;
+    // tile-sorted mode
+    const unsigned int *tile_start, *tile_end; // particle range of each tile in the sorted arrays
+    const unsigned int *item_off;              // [ntiles+1] prefix of ceil(count/T2_CHUNK): work items per tile
+    unsigned long long *slow_count;
+    double fxw_scale;    // 2^frac of the shared-memory window (finer than the global grid)
+    int fx_shift;        // window -> global: rounded right shift
+    int ntx, ntiles;
 };
 
+// One particle: gather at the old position -> boris -> move -> CIC corners/weights at the new position.
+struct Cic4 { int ix[2], iy[2]; double wx[2], wy[2]; };
+__device__ __forceinline__ void cic4(double x, double y, int NX, int NY, Cic4 &c)
+{
+    cic_g(x, NX, c.ix[0], c.wx[0], c.ix[1], c.wx[1]);
+    cic_g(y, NY, c.iy[0], c.wy[0], c.iy[1], c.wy[1]);
+}
+
+// Any particle order: E2 from global memory (L1/L2), deposit with 64-bit integer REDs to the global grid.
 __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_kernel(P2DArgs a)
 {
     __shared__ double scratch[32];
@@ -50,30 +68,27 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_kernel(P2DArgs a)
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += stride) {
         double x = ld_stream(a.x + p), y = ld_stream(a.y + p);
         double vx = ld_stream(a.vx + p), vy = ld_stream(a.vy + p), vz = ld_stream(a.vz + p);
-        int ix[2], iy[2];
-        double wx[2], wy[2];
-        cic_g(x, NX, ix[0], wx[0], ix[1], wx[1]);
-        cic_g(y, NY, iy[0], wy[0], iy[1], wy[1]);
+        Cic4 c;
+        cic4(x, y, NX, NY, c);
         double ex = 0.0, ey = 0.0;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
-                double wxy = wx[ii] * wy[jj];
-                double2 f = __ldg(&a.E2[(ix[ii] - 1) + (size_t)(iy[jj] - 1) * NX]);
+                double wxy = c.wx[ii] * c.wy[jj];
+                double2 f = __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
                 ex = fma(f.x, wxy, ex); // @muladd F1o += real(F1[i,j]) * wxy
                 ey = fma(f.y, wxy, ey);
             }
         boris(vx, vy, vz, ex, ey, a.dt, a.t1, a.tscale);
         x = unimod(x + vx * a.dt, 1.0);
         y = unimod(y + vy * a.dt, 1.0);
-        cic_g(x, NX, ix[0], wx[0], ix[1], wx[1]);
-        cic_g(y, NY, iy[0], wy[0], iy[1], wy[1]);
+        cic4(x, y, NX, NY, c);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-            for (int ii = 0; ii < 2; ++ii)
-                atomicAdd(&a.rho[(ix[ii] - 1) + (size_t)(iy[jj] - 1) * NX], wx[ii] * wy[jj] * a.w); // F[i,j] += wx*wy*w
+            for (int ii = 0; ii < 2; ++ii) // F[i,j] += wx*wy*w
+                atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
         st_stream(a.x + p, x); st_stream(a.y + p, y);
         st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
         s0 += vx * vx + vy * vy; s1 += vx; s2 += vy;
@@ -84,6 +99,142 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_kernel(P2DArgs a)
     if (threadIdx.x == 0) {
         a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile-sorted variant.  Particles are kept sorted by T2_TS x T2_TS-cell tile (pg_sort.cuh, mode 1).  A work
+// item is up to T2_CHUNK consecutive particles of ONE tile; the block stages the (T2_TS+2*T2_R)^2 window of
+// E2 around the tile in shared memory and accumulates the deposit into a fixed-point window of the same size
+// (shared-memory 64-bit atomics), flushed once per item with integer REDs.  So the random-access traffic
+// (4 field corners + 4 deposits per particle) never leaves the SM; HBM sees only the 80 B/particle streams.
+// Particles that drifted more than T2_R cells out of their tile since the last sort use global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_TS = 16, T2_SHIFT = 4, T2_R = 8, T2_WS = T2_TS + 2 * T2_R, T2_CHUNK = 8192;
+
+// item_off[t] = sum_{u<t} ceil(count_u / T2_CHUNK); one block of 1024 threads, ntiles <= 4096.
+__global__ void __launch_bounds__(1024) tile_worklist_kernel(const unsigned int *tile_start, const unsigned int *tile_end,
+                                                            unsigned int *item_off, int ntiles)
+{
+    __shared__ unsigned int part[1024];
+    const int per = (ntiles + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, ntiles);
+    unsigned int s = 0;
+    for (int t = lo; t < hi; ++t) s += (tile_end[t] - tile_start[t] + T2_CHUNK - 1) / T2_CHUNK;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned int run = part[threadIdx.x] - s;
+    for (int t = lo; t < hi; ++t) {
+        item_off[t] = run;
+        run += (tile_end[t] - tile_start[t] + T2_CHUNK - 1) / T2_CHUNK;
+    }
+    if (threadIdx.x == 1023) item_off[ntiles] = part[1023];
+}
+
+__global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
+{
+    __shared__ double2 Ew[T2_WS * T2_WS];
+    __shared__ fx_t rw[T2_WS * T2_WS];
+    __shared__ double scratch[32];
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    unsigned int nslow = 0;
+    const unsigned int nitems = a.item_off[a.ntiles];
+    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int lo = 0, hi = a.ntiles; // tile of this item: last t with item_off[t] <= item
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int tile = lo;
+        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
+        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
+        const int ox = (tile % a.ntx) * T2_TS - T2_R, oy = (tile / a.ntx) * T2_TS - T2_R; // window origin (0-based cells)
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
+            Ew[c] = a.E2[gx + (size_t)gy * NX];
+            rw[c] = 0ULL;
+        }
+        __syncthreads();
+        for (long long p = start + threadIdx.x; p < end; p += blockDim.x) {
+            double x = ld_stream(a.x + p), y = ld_stream(a.y + p);
+            double vx = ld_stream(a.vx + p), vy = ld_stream(a.vy + p), vz = ld_stream(a.vz + p);
+            Cic4 c;
+            cic4(x, y, NX, NY, c);
+            double ex = 0.0, ey = 0.0;
+            {
+                const int rx = (c.ix[0] - 1 - ox) & mx, ry = (c.iy[0] - 1 - oy) & my;
+                if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
+                    const double2 *e = Ew + rx + ry * T2_WS;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            double wxy = c.wx[ii] * c.wy[jj];
+                            double2 f = e[ii + jj * T2_WS];
+                            ex = fma(f.x, wxy, ex);
+                            ey = fma(f.y, wxy, ey);
+                        }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            double wxy = c.wx[ii] * c.wy[jj];
+                            double2 f = __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
+                            ex = fma(f.x, wxy, ex);
+                            ey = fma(f.y, wxy, ey);
+                        }
+                }
+            }
+            boris(vx, vy, vz, ex, ey, a.dt, a.t1, a.tscale);
+            x = unimod(x + vx * a.dt, 1.0);
+            y = unimod(y + vy * a.dt, 1.0);
+            cic4(x, y, NX, NY, c);
+            {
+                const int rx = (c.ix[0] - 1 - ox) & mx, ry = (c.iy[0] - 1 - oy) & my;
+                if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
+                    fx_t *r = rw + rx + ry * T2_WS;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) atomicAdd(&r[ii + jj * T2_WS], to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale));
+                } else {
+                    ++nslow;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii)
+                            atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
+                }
+            }
+            st_stream(a.x + p, x); st_stream(a.y + p, y);
+            st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
+            s0 += vx * vx + vy * vy; s1 += vx; s2 += vy;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            long long v = (long long)rw[c];
+            if (v) {
+                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift; // rounded: weights are >= 0
+                int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
+                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)v);
+            }
+        }
+        __syncthreads();
+    }
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+        a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
+    }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
 }
 
 // x,y ~ U(0,1]; v Maxwellian (Box-Muller on splitmix64 draws) with per-component std vth/sqrt(2),
@@ -106,8 +257,8 @@ __global__ void synthetic_2d3v_kernel(double *x, double *y, double *vx, double *
 }
 
 // ---- stage kernels -------------------------------------------------------------------------
-__global__ void stage_cic_deposit_kernel(const double *x, const double *y, long long count, int NX, int NY, double w,
-                                         double *rho)
+__global__ void stage_cic_deposit_kernel(const double *x, const double *y, long long count, int NX, int NY, double fx_scale,
+                                         fx_t *rho)
 {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
@@ -116,7 +267,7 @@ __global__ void stage_cic_deposit_kernel(const double *x, const double *y, long 
     cic_g(y[p], NY, iy[0], wy[0], iy[1], wy[1]);
     for (int jj = 0; jj < 2; ++jj)
         for (int ii = 0; ii < 2; ++ii)
-            atomicAdd(&rho[(ix[ii] - 1) + (size_t)(iy[jj] - 1) * NX], wx[ii] * wy[jj] * w);
+            atomicAdd(&rho[(ix[ii] - 1) + (size_t)(iy[jj] - 1) * NX], to_fx(wx[ii] * wy[jj], fx_scale));
 }
 
 __global__ void stage_cic_gather_kernel(const double *Ex, const double *Ey, int NX, int NY, const double *x,

@@ -24,7 +24,8 @@ struct SortArgs {
     const unsigned int *pid_in; // NULL: identity
     unsigned int *pid_out;
     unsigned int *bin_count;  // [nbins]
-    unsigned int *bin_cursor; // [nbins] running start offsets
+    unsigned int *bin_cursor; // [nbins] running start offsets (== end offsets once the scatter is done)
+    unsigned int *bin_start;  // [nbins] start offsets (kept for the tiled 2D kernel); may be NULL
     long long P;
     int narr, nbins;
     int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1])
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortArgs a)
 }
 
 // One block of 1024 threads; bins <= 65536.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count, unsigned int *bin_cursor, int nbins)
+__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count, unsigned int *bin_cursor,
+                                                        unsigned int *bin_start, int nbins)
 {
     __shared__ unsigned int part[1024];
     const int per = (nbins + 1023) / 1024;
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count
     for (int b = lo; b < hi; ++b) {
         unsigned int c = bin_count[b];
         bin_cursor[b] = run;
+        if (bin_start) bin_start[b] = run;
         bin_count[b] = 0u; // ready for the next sort
         run += c;
     }

@@ -155,11 +155,11 @@ struct picgolf_handle_s {
     bool is2d = false, fixedpoint = false, ngp = false;
     // particles (1D: xb/vb ping-pong for the fixed point; leapfrog and 2D use index 0)
     double *xb[2] = {nullptr, nullptr}, *vb[2] = {nullptr, nullptr};
-    double *y = nullptr, *vy = nullptr, *vz = nullptr; // 2D: x=xb[0], vx=vb[0]
+    double *p2[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}}; // 2D: x,y,vx,vy,vz ping-pong
     int par = 0;
     // grids
-    double *rho = nullptr, *rho_last = nullptr, *E = nullptr; // rho: 2D fp64 deposit grid
-    unsigned long long *rho_fx = nullptr;                     // 1D integer deposit grid (NGP counts / fixed point)
+    double *rho_last = nullptr, *E = nullptr;
+    unsigned long long *rho_fx = nullptr;                     // integer deposit grid (NGP counts / fixed point), 1D and 2D
     double fx_scale = 1.0, fx_inv = 1.0;                      // 2^frac, 2^-frac
     double2 *tw = nullptr, *twy = nullptr, *Z = nullptr, *E2 = nullptr;
     double *epartials = nullptr;
@@ -169,7 +169,7 @@ struct picgolf_handle_s {
     double *partials = nullptr, *raw = nullptr;
     int64_t T = 1;
     int nblocks = 1, npart = 2;
-    size_t smem_pass = 0;
+    size_t smem_pass = 0, smem_lf = 0;
     bool have_particles = false;
     int64_t steps = 0, launches = 0;
     nccl::Comm comm = nullptr;
@@ -179,7 +179,8 @@ struct picgolf_handle_s {
     bool sorted = false, pid_valid = false;
     unsigned int *pid[2] = {nullptr, nullptr};
     int pidpar = 0;
-    unsigned int *bin_count = nullptr, *bin_cursor = nullptr;
+    unsigned int *bin_count = nullptr, *bin_cursor = nullptr, *bin_start = nullptr, *item_off = nullptr;
+    double fxw_scale = 1.0; int fx_shift = 0; // 2D tiled: shared-memory window format
     unsigned long long *slow_count = nullptr;
     int nbins = 0, K = 1, sort_every = 1, nblocks_sorted = 1;
     int64_t since_sort = 0, sorts = 0;
@@ -290,7 +291,9 @@ static int destroy_impl(picgolf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->timer.destroy();
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
-    void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->y, h->vy, h->vz, h->rho, h->rho_last, h->E, h->rho_fx,
+    void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
+                    h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off,
+                    h->rho_last, h->E, h->rho_fx,
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
                     h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -382,21 +385,22 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 PG_TRY(set_smem(sort_scatter_kernel, (size_t)h->nbins * 8));
             }
         } else if (h->ngp) {
-            PG_TRY(set_smem(lf_pass<0>, h->smem_pass));
-            PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+            h->smem_lf = lf_smem_bytes(0, N);
+            PG_TRY(set_smem(lf_pass<0>, h->smem_lf));
+            PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_lf, h->sms, (h->count + 3) / 4, &h->nblocks));
         } else {
-            PG_TRY(set_smem(lf_pass<1>, h->smem_pass));
-            PG_TRY(occupancy_blocks(lf_pass<1>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
+            h->smem_lf = lf_smem_bytes(1, N);
+            PG_TRY(set_smem(lf_pass<1>, h->smem_lf));
+            PG_TRY(occupancy_blocks(lf_pass<1>, PG_THREADS, h->smem_lf, h->sms, h->count, &h->nblocks));
         }
     } else {
         const int NX = (int)c.N, NY = (int)c.NY;
         h->ncell = (int64_t)NX * NY;
-        PG_TRY(dalloc(&h->xb[0], n)); PG_TRY(dalloc(&h->vb[0], n));
-        PG_TRY(dalloc(&h->y, n)); PG_TRY(dalloc(&h->vy, n)); PG_TRY(dalloc(&h->vz, n));
-        PG_TRY(dalloc(&h->rho, h->ncell)); PG_TRY(dalloc(&h->rho_last, h->ncell));
+        for (int q = 0; q < 5; ++q) PG_TRY(dalloc(&h->p2[0][q], n));
+        PG_TRY(dalloc(&h->rho_fx, h->ncell)); PG_TRY(dalloc(&h->rho_last, h->ncell));
         PG_TRY(dalloc(&h->Z, h->ncell)); PG_TRY(dalloc(&h->E2, h->ncell));
         PG_TRY(dalloc(&h->epartials, NY / ROWS_PER_BLOCK));
-        PG_CUDA(cudaMemset(h->rho, 0, h->ncell * sizeof(double)));
+        PG_CUDA(cudaMemset(h->rho_fx, 0, h->ncell * sizeof(unsigned long long)));
         PG_CUDA(cudaMemset(h->rho_last, 0, h->ncell * sizeof(double)));
         PG_CUDA(cudaMemset(h->E2, 0, h->ncell * sizeof(double2)));
         PG_TRY(make_twiddles(&h->tw, NX)); PG_TRY(make_twiddles(&h->twy, NY));
@@ -405,6 +409,32 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         PG_TRY(set_smem(solve2d_cols, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8));
         h->npart = 3;
         PG_TRY(occupancy_blocks(particles_2d3v_kernel, PG_THREADS, 0, h->sms, h->count, &h->nblocks));
+        {   // fixed-point formats: CIC weights are <= 1 and sum to 1 per particle (no overflow possible)
+            int frac = std::max(8, std::min(60, 62 - ilog2(c.P + 1)));
+            h->fx_scale = ldexp(1.0, frac); h->fx_inv = ldexp(1.0, -frac);
+            int fracw = std::max(frac, 62 - ilog2((int64_t)T2_CHUNK + 1)); // a window only sees T2_CHUNK particles
+            h->fxw_scale = ldexp(1.0, fracw); h->fx_shift = fracw - frac;
+        }
+        const int64_t ppc = h->count / h->ncell;
+        if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
+        else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 20) && ppc >= 8;
+        if (h->sorted) {
+            const int ntx = std::max(1, NX >> T2_SHIFT), nty = std::max(1, NY >> T2_SHIFT);
+            h->nbins = ntx * nty;
+            h->sort_every = c.sort_every > 0 ? c.sort_every : 12;
+            for (int q = 0; q < 5; ++q) PG_TRY(dalloc(&h->p2[1][q], n));
+            PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
+            PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
+            PG_TRY(dalloc(&h->bin_start, h->nbins)); PG_TRY(dalloc(&h->item_off, h->nbins + 1));
+            PG_CUDA(cudaMemset(h->bin_count, 0, h->nbins * sizeof(unsigned int)));
+            PG_TRY(dalloc(&h->slow_count, 1));
+            PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
+            PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
+            PG_TRY(set_smem(sort_scatter_kernel, (size_t)h->nbins * 8));
+            int64_t items = h->count / T2_CHUNK + h->nbins;
+            PG_TRY(occupancy_blocks(particles_2d3v_tiled, PG_THREADS, 0, h->sms, items * PG_THREADS, &h->nblocks_sorted));
+            h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
+        }
     }
     PG_TRY(dalloc(&h->ctrl, 1));
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
@@ -464,13 +494,9 @@ static int reset_run_state(picgolf_handle h)
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
-    if (h->is2d) {
-        PG_CUDA(cudaMemsetAsync(h->rho, 0, h->ncell * sizeof(double), h->stream));
-        PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
-    } else {
-        PG_CUDA(cudaMemsetAsync(h->E, 0, h->ncell * sizeof(double), h->stream));
-        PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, h->ncell * sizeof(unsigned long long), h->stream));
-    }
+    PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
+    else PG_CUDA(cudaMemsetAsync(h->E, 0, h->ncell * sizeof(double), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0;
@@ -496,11 +522,8 @@ PG_API int picgolf_set_particles_2d3v(picgolf_handle h, const double *x, const d
     if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
     PG_TRY(use_device(h));
     const size_t b = count * sizeof(double);
-    PG_CUDA(cudaMemcpyAsync(h->xb[0], x, b, cudaMemcpyHostToDevice, h->stream));
-    PG_CUDA(cudaMemcpyAsync(h->y, y, b, cudaMemcpyHostToDevice, h->stream));
-    PG_CUDA(cudaMemcpyAsync(h->vb[0], vx, b, cudaMemcpyHostToDevice, h->stream));
-    PG_CUDA(cudaMemcpyAsync(h->vy, vy, b, cudaMemcpyHostToDevice, h->stream));
-    PG_CUDA(cudaMemcpyAsync(h->vz, vz, b, cudaMemcpyHostToDevice, h->stream));
+    const double *src[5] = {x, y, vx, vy, vz};
+    for (int q = 0; q < 5; ++q) PG_CUDA(cudaMemcpyAsync(h->p2[0][q], src[q], b, cudaMemcpyHostToDevice, h->stream));
     return reset_run_state(h);
 }
 
@@ -522,7 +545,8 @@ PG_API int picgolf_init_synthetic(picgolf_handle h, uint64_t seed, double vth)
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
     PG_TRY(use_device(h));
     if (h->is2d)
-        synthetic_2d3v_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->y, h->vb[0], h->vy, h->vz, h->count, h->first, seed, vth);
+        synthetic_2d3v_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4], h->count,
+                                                                   h->first, seed, vth);
     else
         synthetic_1d_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P, seed);
     h->launches++;
@@ -574,10 +598,18 @@ PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, do
     if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
     PG_TRY(use_device(h));
     const size_t b = count * sizeof(double);
-    double *src[5] = {h->xb[0], h->y, h->vb[0], h->vy, h->vz};
     double *dst[5] = {x, y, vx, vy, vz};
-    for (int i = 0; i < 5; ++i)
-        if (dst[i]) PG_CUDA(cudaMemcpyAsync(dst[i], src[i], b, cudaMemcpyDeviceToHost, h->stream));
+    for (int i = 0; i < 5; ++i) {
+        if (!dst[i]) continue;
+        const double *src = h->p2[h->par][i];
+        if (h->sorted && h->pid_valid) { // back to the caller's order through a free ping-pong buffer
+            double *tmp = h->p2[1 - h->par][0];
+            unsort_kernel<<<h->sms * 8, 256, 0, h->stream>>>(src, h->pid[h->pidpar], tmp, h->count);
+            h->launches++;
+            src = tmp;
+        }
+        PG_CUDA(cudaMemcpyAsync(dst[i], src, b, cudaMemcpyDeviceToHost, h->stream));
+    }
     PG_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -590,9 +622,8 @@ static int allreduce_grid(picgolf_handle h)
     if (!h->comm) return 0;
     const int sp1_ = h->timer.begin(ST_REDUCE, h->stream);
     int rc;
-    // 1D: integer grid (two's-complement sums are exact and order independent); 2D: fp64 grid
-    if (!h->is2d) rc = nccl::AllReduce(h->rho_fx, h->rho_fx, (size_t)h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
-    else rc = nccl::AllReduce(h->rho, h->rho, (size_t)h->ncell, nccl::Float64, nccl::Sum, h->comm, h->stream);
+    // integer grid: two's-complement sums are exact and order independent
+    rc = nccl::AllReduce(h->rho_fx, h->rho_fx, (size_t)h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
     h->timer.end(sp1_, h->stream);
     return nccl::check(rc, "ncclAllReduce(rho)");
 }
@@ -640,7 +671,7 @@ static int sort_particles_1d(picgolf_handle h)
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
     int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
     sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
-    sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->nbins);
+    sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
     sort_scatter_kernel<<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
     h->launches += 3;
     h->timer.end(sp, h->stream);
@@ -685,8 +716,8 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
     a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
     const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
-    if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-    else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+    else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
     h->timer.end(sp5_, h->stream);
     h->launches++;
     return 0;
@@ -696,7 +727,8 @@ static int launch_solve2d(picgolf_handle h)
 {
     const picgolf_config &c = h->cfg;
     Solve2DArgs a;
-    a.rho = h->rho; a.rho_last = h->rho_last; a.Z = h->Z; a.E2 = h->E2; a.twx = h->tw; a.twy = h->twy;
+    a.rho_in = nullptr; a.rho_fx = h->rho_fx; a.w = c.w; a.fx_inv = h->fx_inv;
+    a.rho_last = h->rho_last; a.Z = h->Z; a.E2 = h->E2; a.twx = h->tw; a.twy = h->twy;
     a.partials = h->epartials; a.NX = (int)c.N; a.NY = (int)c.NY; a.lgx = ilog2(c.N); a.lgy = ilog2(c.NY);
     const int NX = a.NX, NY = a.NY;
     const int sp6_ = h->timer.begin(ST_SOLVE, h->stream);
@@ -708,23 +740,57 @@ static int launch_solve2d(picgolf_handle h)
     return 0;
 }
 
+// Counting sort of the 2D particle arrays by 16x16-cell tile + the per-tile work list.
+static int sort_particles_2d(picgolf_handle h)
+{
+    const int sp = h->timer.begin(ST_SORT, h->stream);
+    SortArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int q = 0; q < 5; ++q) { a.in[q] = h->p2[h->par][q]; a.out[q] = h->p2[1 - h->par][q]; }
+    a.pid_in = h->pid_valid ? h->pid[h->pidpar] : nullptr;
+    a.pid_out = h->pid[1 - h->pidpar];
+    a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor; a.bin_start = h->bin_start;
+    a.P = h->count; a.narr = 5; a.nbins = h->nbins; a.mode = 1; a.N = (int)h->cfg.N; a.NY = (int)h->cfg.NY; a.tshift = T2_SHIFT;
+    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
+    int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
+    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
+    sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
+    sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->bin_start, h->nbins);
+    sort_scatter_kernel<<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    tile_worklist_kernel<<<1, 1024, 0, h->stream>>>(h->bin_start, h->bin_cursor, h->item_off, h->nbins);
+    h->launches += 4;
+    h->timer.end(sp, h->stream);
+    h->par ^= 1; h->pidpar ^= 1; h->pid_valid = true; h->since_sort = 0; h->sorts++;
+    return 0;
+}
+
 static int step_2d3v(picgolf_handle h)
 {
     const picgolf_config &c = h->cfg;
+    if (h->sorted && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_2d(h));
     P2DArgs a;
-    a.x = h->xb[0]; a.y = h->y; a.vx = h->vb[0]; a.vy = h->vy; a.vz = h->vz; a.E2 = h->E2; a.rho = h->rho;
-    a.partials = h->partials; a.P = h->count; a.dt = c.dt; a.w = c.w;
+    memset(&a, 0, sizeof(a));
+    double **p = h->p2[h->par];
+    a.x = p[0]; a.y = p[1]; a.vx = p[2]; a.vy = p[3]; a.vz = p[4]; a.E2 = h->E2; a.rho = h->rho_fx;
+    a.partials = h->partials; a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale;
     a.t1 = c.B0 * c.dt / 2;                       // tvec[1]   Electrostatic2D3V.jl:32
     a.tscale = 2 / (1 + (a.t1 * a.t1 + 0.0 + 0.0)); // :33
     a.NX = (int)c.N; a.NY = (int)c.NY;
     const int sp7_ = h->timer.begin(ST_PARTICLES, h->stream);
-    particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);
+    if (h->sorted) {
+        a.tile_start = h->bin_start; a.tile_end = h->bin_cursor; a.item_off = h->item_off; a.slow_count = h->slow_count;
+        a.fxw_scale = h->fxw_scale; a.fx_shift = h->fx_shift; a.ntx = std::max(1, a.NX >> T2_SHIFT); a.ntiles = h->nbins;
+        particles_2d3v_tiled<<<h->nblocks_sorted, PG_THREADS, 0, h->stream>>>(a);
+    } else {
+        particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);
+    }
     h->timer.end(sp7_, h->stream);
     h->launches++;
     PG_TRY(allreduce_grid(h));
     PG_TRY(launch_solve2d(h));
     bool record = ((h->steps + 1) % c.diag_every) == 0; // if t % NS == 0   :164
     PG_TRY(launch_step_end(h, record));
+    h->since_sort++;
     return 0;
 }
 
@@ -1036,7 +1102,7 @@ PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, 
     std::vector<double> zeros((size_t)count, 0.0);
     PG_TRY(dx.upload(x, count * 8)); PG_TRY(dv.upload(zeros.data(), count * 8));
     PG_TRY(dcnt.zero(N * 8)); PG_TRY(dpart.zero(2 * 1024 * 8));
-    size_t smem = (size_t)(2 * N + 32) * 8;
+    size_t smem = lf_smem_bytes(0, (int)N);
     PG_TRY(set_smem(lf_pass<0>, smem));
     LFArgs a;
     a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = dcnt.as<unsigned long long>();
@@ -1121,7 +1187,8 @@ PG_API int picgolf_stage_solve2d(const double *rho, int64_t NX, int64_t NY, doub
     PG_TRY(make_twiddles(&twx, (int)NX));
     int rc = make_twiddles(&twy, (int)NY);
     Solve2DArgs a;
-    a.rho = dr.as<double>(); a.rho_last = dl.as<double>(); a.Z = dZ.as<double2>(); a.E2 = dE2.as<double2>();
+    a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.w = 1.0; a.fx_inv = 1.0;
+    a.rho_last = dl.as<double>(); a.Z = dZ.as<double2>(); a.E2 = dE2.as<double2>();
     a.twx = twx; a.twy = twy; a.partials = dp.as<double>(); a.NX = (int)NX; a.NY = (int)NY; a.lgx = ilog2(NX); a.lgy = ilog2(NY);
     if (rc == 0) rc = set_smem(solve2d_rows_fwd, (size_t)2 * ROWS_PER_BLOCK * NX * 8);
     if (rc == 0) rc = set_smem(solve2d_rows_inv, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8);
@@ -1146,9 +1213,14 @@ PG_API int picgolf_stage_cic_deposit(const double *x, const double *y, int64_t c
     PG_TRY(stage_ready());
     DevBuf dx, dy, dr;
     PG_TRY(dx.upload(x, count * 8)); PG_TRY(dy.upload(y, count * 8)); PG_TRY(dr.zero(NX * NY * 8));
-    stage_cic_deposit_kernel<<<grid1(count), 256>>>(dx.as<double>(), dy.as<double>(), count, (int)NX, (int)NY, w, dr.as<double>());
+    int frac = std::max(8, std::min(60, 62 - ilog2(count + 1))); // same format rule as picgolf_create
+    stage_cic_deposit_kernel<<<grid1(count), 256>>>(dx.as<double>(), dy.as<double>(), count, (int)NX, (int)NY, ldexp(1.0, frac),
+                                                    dr.as<unsigned long long>());
     PG_TRY(finish());
-    return dr.download(rho, NX * NY * 8);
+    std::vector<long long> fx((size_t)(NX * NY));
+    PG_TRY(dr.download(fx.data(), NX * NY * 8));
+    for (int64_t n = 0; n < NX * NY; ++n) rho[n] = (double)fx[n] * ldexp(1.0, -frac) * w; // as solve2d_rows_fwd
+    return 0;
 }
 
 PG_API int picgolf_stage_cic_gather(const double *Ex, const double *Ey, int64_t NX, int64_t NY, const double *x,

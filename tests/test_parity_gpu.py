@@ -413,3 +413,69 @@ def test_sorted_mode_matches_atomic_mode(pg, oracle, start):
     assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
     sorts, slow = s.sort_stats()
     assert sorts == 3 and slow < P // 100  # steps 0,4,8; almost everything stays inside its window
+
+
+def test_2d3v_tile_sorted_mode(pg, oracle):
+    """Tile-sorted 2D path (pg_sort mode 1 + particles_2d3v_tiled): golden fixture with frequent re-sorts,
+    then a 128x128 run against the any-order path."""
+    g = golden("c5_2d3v")
+    NX, NY = int(g["NX"]), int(g["NY"])
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=int(g["P"]), T=16, NS=1, deposit_mode=pg.DEPOSIT_SORTED, sort_every=2)
+    sim.set_particles(g["x0"], g["vx0"], y=g["y0"], vy=g["vy0"], vz=g["vz0"])
+    for t in range(4):
+        sim.step(1)
+        rho, Ex, Ey = sim.fields()
+        assert relnorm(rho.reshape(-1, order="F"), g["rho"][t]) < TOL
+        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < 1e-11
+    got = sim.particles()  # caller's order
+    for a, k in zip(got, ("x", "y", "vx", "vy", "vz")):
+        assert relnorm(a, g[k]) < 1e-11
+    K, _ = sim.diagnostics()
+    assert relnorm(K[:, :3], g["K"][:, :3]) < 1e-10
+    assert sim.sort_stats()[0] == 2
+    # larger: sorted (AUTO) vs any-order
+    NX = NY = 128
+    P = 1 << 20
+    rng = np.random.default_rng(31)
+    sims = [pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=16, NS=1, deposit_mode=m, sort_every=5)
+            for m in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO)]
+    st = [1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * sims[0].vth / np.sqrt(2) for _ in range(3)]
+    for s in sims:
+        s.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
+        s.step(12)
+    pa, ps = sims[0].particles(), sims[1].particles()
+    for a, b in zip(ps, pa):
+        assert relnorm(a, b) < 1e-10
+    fa, fs = sims[0].fields(), sims[1].fields()
+    assert np.array_equal(fa[0], fs[0]) or relnorm(fs[0], fa[0]) < 1e-13  # integer accumulation: (almost) order free
+    assert relnorm(fs[1], fa[1]) < 1e-10
+    sorts, slow = sims[1].sort_stats()
+    assert sorts == 3 and slow < P // 1000
+    # one step vs the oracle
+    so = [a.copy() for a in st]
+    Ex, Ey = np.zeros(NX * NY), np.zeros(NX * NY)
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=4, NS=1)
+    sim.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
+    sim.step(1)
+    ro = oracle.step_2d3v(*so, NX, NY, sim.cfg.dt, sim.cfg.B0, sim.cfg.w, Ex, Ey, nthreads=4)
+    rho, ex, ey = sim.fields()
+    assert relnorm(rho.reshape(-1, order="F"), ro) < TOL and relnorm(ex.reshape(-1, order="F"), Ex) < 1e-11
+    got = sim.particles()
+    assert relnorm(got[0], so[0]) < TOL and relnorm(got[2], so[2]) < TOL
+
+
+def test_ngp_odd_particle_count(pg, oracle):
+    """The NGP pass streams particle pairs with 128-bit accesses; an odd P exercises the tail."""
+    N, P = 128, 8191
+    rng = np.random.default_rng(41)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0)
+    sim = pg.ngp_fourier(N=N, P=P, NT=8, W=200.0)
+    sim.set_particles(x0, v0)
+    sim.step(3)
+    x, v = x0.copy(), v0.copy()
+    for _ in range(3):
+        ro, Eo, _ = oracle.ngp_step(x, v, N, sim.cfg.dt, sim.cfg.w)
+    rho, E = sim.fields()
+    xg, vg = sim.particles()
+    assert relnorm(rho, ro) < 1e-13 and relnorm(E, Eo) < 1e-11 and relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
