@@ -138,6 +138,7 @@ def run_gpu(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    sorts0 = sim.sort_stats()[0]
     l0 = sim.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -147,6 +148,7 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = sim.launches - l0
+    sorts_timed = sim.sort_stats()[0] - sorts0
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -160,7 +162,8 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel (the particle pass), timed live with CUDA events ------
     sim.stage_timing(True)
     sim.stage_times(reset=True)
-    nroof = min(K, 5)
+    nroof = 12  # long enough to contain a re-sort of the (nearly sorted) particle arrays
+    s0 = sim.sort_stats()[0]
     sim.step(nroof)
     st = sim.stage_times(reset=True)
     sim.stage_timing(False)
@@ -168,21 +171,22 @@ def run_gpu(args):
     if args.workload == "gauss_fp":
         passes = float((sw2[Wm + K:Wm + K + nroof] + 1).sum())  # S solves -> S+1 particle passes per step
         alg_bytes_launch = 32.0 * per_gpu
-        kernel = "fp_pass_atomic (gather+implicit-midpoint update+deposit)"
+        kernel = "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)"
     elif args.workload == "ngp":
         passes = float(nroof + 1)
         alg_bytes_launch = 32.0 * per_gpu
-        kernel = "lf_pass<NGP> (drift+kick+drift+deposit)"
+        kernel = "lf_pass<0> (drift + kick + drift + NGP deposit)"
     else:
         passes = float(nroof)
         alg_bytes_launch = 80.0 * per_gpu
-        kernel = "particles_2d3v_kernel (gather+boris+move+deposit)"
+        kernel = "particles_2d3v_tiled (gather + boris + move + CIC deposit)"
     launch_ms = st["particles"] / passes
     peak, peak_src = peaks()
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_bytes_launch,
-                "stage_ms_per_step": {k: v / nroof for k, v in st.items()}}
+                "stage_ms_per_step": {k: v / nroof for k, v in st.items()},
+                "resorts_in_stage_window": sim.sort_stats()[0] - s0, "stage_window_steps": nroof}
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None
@@ -244,6 +248,7 @@ def run_gpu(args):
             "algorithmic_bytes_per_particle_step": bpu,
             "hbm_roofline_frac_step": (value / world) * bpu / (peak * 1e9),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "sorts_in_timed_region": int(sorts_timed), "sort_stats_total": list(sim.sort_stats()),
         }
         print(json.dumps(line), flush=True)
     sim.close()
@@ -323,7 +328,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gauss_fp", choices=["gauss_fp", "ngp", "2d3v"])

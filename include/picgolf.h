@@ -77,7 +77,10 @@ typedef struct picgolf_config {
     int32_t max_sweeps;      /* fixed point: 10 (`for _ in 0:9`) */
     int32_t diag_every;      /* record a diagnostics row every diag_every steps (2D: NS=2, :25); 1D: 1 */
     int32_t deposit_mode;    /* picgolf_deposit_mode */
-    int32_t deterministic;   /* 1: bit-reproducible deposits (cell-sorted order + fixed reduction tree) */
+    int32_t deterministic;   /* 1: bit-reproducible charge for ANY particle order, run and GPU count: every deposit is
+                              * quantised to 64-bit fixed point and summed with integer atomics (order-free kernel).
+                              * 0: the faster cell-sorted path may be used; it is reproducible between sweeps of a step
+                              * but its summation order changes from run to run at round-off level. */
     int32_t sort_every;      /* re-sort particles by cell every this many steps (0 = library default) */
     int32_t device;          /* CUDA device ordinal; -1 = current device */
     int32_t rank, nranks;    /* particle sharding: this handle owns global indices [first, first+count) */

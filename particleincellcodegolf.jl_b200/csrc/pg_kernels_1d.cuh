@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 // Window rows are Julia (1-based, unwrapped) indices base..base+31; wrap is applied at load/flush.
 // ------------------------------------------------------------------------------------------
 constexpr int WIN_ROWS = 32;                    // grid cells covered by a warp's window
-constexpr int WIN_ALLOC = WIN_ROWS + GAUSS_NW;  // + 13 trash rows: where out-of-window stencils land harmlessly
+constexpr int WIN_ALLOC = WIN_ROWS;             // out-of-window stencils are predicated off (slow path instead)
 constexpr int WIN_LD = 33;
 constexpr int WIN_LO = 6;                       // rows kept below the smallest centre of the first batch
 constexpr int WIN_MAXOFF = WIN_ROWS - GAUSS_NW; // largest row a stencil may start at
@@ -152,8 +152,11 @@ __device__ __noinline__ void slow_deposit(fx_t *rho, double c, int N, double fx_
     for (int q = 0; q < GAUSS_NW; ++q) atomicAdd(&rho[(ibase + q - 1) & (N - 1)], to_fx(W[q], fx_scale));
 }
 
+#ifndef PG_SORTED_MINBLOCKS
+#define PG_SORTED_MINBLOCKS 2
+#endif
 template <bool FIRST, int NP>
-__global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
+__global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorted(FPArgs a)
 {
     extern __shared__ double smem[];
     __shared__ double scratch[32];
@@ -185,6 +188,16 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
 #pragma unroll 4
             for (int r = 0; r < WIN_ROWS; ++r) acc[r * WIN_LD + lane] = 0.0;
         __syncwarp();
+        // software pipeline: the loads of the next group are issued before the current group is evaluated
+        double Xn[NP], Vn[NP], vn[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const long long jn = j0 + 32LL * q + lane;
+            const bool ln = jn < a.P;
+            Xn[q] = ln ? ld_stream(a.X + jn) : 0.0;
+            Vn[q] = ln ? ld_stream(a.V + jn) : 0.0;
+            vn[q] = FIRST ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
+        }
         for (int kb = 0; kb < a.K; kb += NP) {
             long long j[NP];
             bool live[NP];
@@ -193,11 +206,19 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
             for (int q = 0; q < NP; ++q) {
                 j[q] = j0 + 32LL * (kb + q) + lane;
                 live[q] = j[q] < a.P;
-                Xj[q] = live[q] ? ld_stream(a.X + j[q]) : 0.0;
-                Vj[q] = live[q] ? ld_stream(a.V + j[q]) : 0.0;
-                vj[q] = FIRST ? Vj[q] : (live[q] ? ld_stream(a.v + j[q]) : 0.0);
+                Xj[q] = Xn[q]; Vj[q] = Vn[q]; vj[q] = vn[q];
             }
             if (!live[0]) break;
+            if (kb + NP < a.K) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const long long jn = j[q] + 32LL * NP;
+                    const bool ln = jn < a.P;
+                    Xn[q] = ln ? ld_stream(a.X + jn) : 0.0;
+                    Vn[q] = ln ? ld_stream(a.V + jn) : 0.0;
+                    vn[q] = FIRST ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < NP; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) / 2 * dt; // x.=X.+(v.+V)/2*dt
             if (!FIRST) {
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
             // deposit at (x+X)/2 into the lane-private window column
             double d[NP], mid[NP];
             double *col[NP];
-            bool ok[NP], merged[NP]; // merged[q]: particle q shares particle 0's window rows -> summed in registers
+            bool ok[NP], merged[NP], own[NP]; // merged[q]: summed into particle 0's rows in registers; own[q]: own RMW
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 int ibase;
@@ -255,12 +276,13 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
                 gauss_centre(mid[q], dN, ibase, d[q]);
                 const int o = (ibase - base) & Nmask;
                 ok[q] = live[q] && o <= WIN_MAXOFF;
-                col[q] = acc + ((ok[q] ? o : WIN_ROWS) + 6) * WIN_LD + lane; // trash rows when outside
-                merged[q] = col[q] == col[0];
+                col[q] = acc + ((ok[q] ? o : 0) + 6) * WIN_LD + lane;
+                merged[q] = q > 0 && ok[q] && ok[0] && col[q] == col[0];
+                own[q] = ok[q] && !merged[q];
             }
-            // One stencil evaluation for all NP particles; no divergent code paths: particles in the same
-            // rows as particle 0 (the usual case in cell order) cost one read-modify-write per cell together,
-            // the others a predicated extra one.
+            // One stencil evaluation for all NP particles, no divergent code paths: particles in the same rows as
+            // particle 0 (the usual case in cell order) share one read-modify-write per cell; the others get a
+            // predicated one of their own; out-of-window particles are predicated off and handled below.
             gauss_stream<NP>(
                 d,
                 [&](auto m, const double(&wp)[NP], const double(&wm)[NP]) {
@@ -268,20 +290,19 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_sorted(FPArgs a)
                     double sp = wp[0], sm = wm[0];
 #pragma unroll
                     for (int q = 1; q < NP; ++q) { sp += merged[q] ? wp[q] : 0.0; sm += merged[q] ? wm[q] : 0.0; }
-                    col[0][M * WIN_LD] += sp;
-                    col[0][-M * WIN_LD] += sm;
+                    if (own[0]) { col[0][M * WIN_LD] += sp; col[0][-M * WIN_LD] += sm; }
 #pragma unroll
                     for (int q = 1; q < NP; ++q)
-                        if (!merged[q]) { col[q][M * WIN_LD] += wp[q]; col[q][-M * WIN_LD] += wm[q]; }
+                        if (own[q]) { col[q][M * WIN_LD] += wp[q]; col[q][-M * WIN_LD] += wm[q]; }
                 },
                 [&](const double(&w0)[NP]) {
                     double s0 = w0[0];
 #pragma unroll
                     for (int q = 1; q < NP; ++q) s0 += merged[q] ? w0[q] : 0.0;
-                    col[0][0] += s0;
+                    if (own[0]) col[0][0] += s0;
 #pragma unroll
                     for (int q = 1; q < NP; ++q)
-                        if (!merged[q]) col[q][0] += w0[q];
+                        if (own[q]) col[q][0] += w0[q];
                 });
 #pragma unroll
             for (int q = 0; q < NP; ++q)

@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(1024) tile_worklist_kernel(const unsigned int 
 __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
 {
     __shared__ double2 Ew[T2_WS * T2_WS];
-    __shared__ fx_t rw[T2_WS * T2_WS];
+    // fixed-point deposit window as two 32-bit limbs: 64-bit shared atomics are CAS loops on sm_100a
+    // (ATOMS.CAST.SPIN.64), 32-bit adds are native; the carry out of the low limb is recovered from the
+    // value the low-limb atomic returns.  hi cannot overflow: a cell receives at most T2_CHUNK units of weight.
+    __shared__ unsigned int rlo[T2_WS * T2_WS], rhi[T2_WS * T2_WS];
     __shared__ double scratch[32];
     const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
         for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
             int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
             Ew[c] = a.E2[gx + (size_t)gy * NX];
-            rw[c] = 0ULL;
+            rlo[c] = 0u; rhi[c] = 0u;
         }
         __syncthreads();
         for (long long p = start + threadIdx.x; p < end; p += blockDim.x) {
@@ -199,11 +202,27 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
             {
                 const int rx = (c.ix[0] - 1 - ox) & mx, ry = (c.iy[0] - 1 - oy) & my;
                 if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
-                    fx_t *r = rw + rx + ry * T2_WS;
+                    const int r0 = rx + ry * T2_WS;
+                    unsigned int lo[4], old[4];
+                    fx_t v[4];
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) atomicAdd(&r[ii + jj * T2_WS], to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale));
+                        for (int ii = 0; ii < 2; ++ii) {
+                            const int k = ii + 2 * jj;
+                            v[k] = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale);
+                            lo[k] = (unsigned int)v[k];
+                            old[k] = atomicAdd(&rlo[r0 + ii + jj * T2_WS], lo[k]);
+                        }
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            const int k = ii + 2 * jj;
+                            const unsigned int carry = (old[k] + lo[k]) < old[k] ? 1u : 0u;
+                            const unsigned int hi = (unsigned int)(v[k] >> 32) + carry;
+                            if (hi) atomicAdd(&rhi[r0 + ii + jj * T2_WS], hi);
+                        }
                 } else {
                     ++nslow;
 #pragma unroll
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
         }
         __syncthreads();
         for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            long long v = (long long)rw[c];
+            long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
             if (v) {
                 if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift; // rounded: weights are >= 0
                 int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;

@@ -15,7 +15,7 @@
 namespace pg {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16; // particles per thread in a scatter tile
+constexpr int SORT_ITEMS = 8;  // particles per thread in a scatter tile
 constexpr int SORT_MAX_ARR = 5;
 
 struct SortArgs {
@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count
     }
 }
 
-// Dynamic shared memory: 2*nbins u32.
+// Dynamic shared memory: 2*nbins u32.  NARR is a template parameter so that the payload loads of a particle
+// (and of the SORT_ITEMS particles of a thread) are independent and all in flight together.
+template <int NARR>
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
 {
     extern __shared__ unsigned int sh[];
@@ -101,9 +103,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; ++i) {
             long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
-            key[i] = -1;
-            if (j < a.P) { key[i] = sort_key(a, j); rank[i] = atomicAdd(&cnt[key[i]], 1u); }
+            key[i] = j < a.P ? sort_key(a, j) : -1;
         }
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i)
+            if (key[i] >= 0) rank[i] = atomicAdd(&cnt[key[i]], 1u);
         __syncthreads();
         for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
             unsigned int c = cnt[b];
@@ -111,12 +115,26 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; ++i) {
-            long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
-            if (key[i] >= 0) {
-                long long d = (long long)base[key[i]] + rank[i];
-                for (int q = 0; q < a.narr; ++q) a.out[q][d] = a.in[q][j];
-                a.pid_out[d] = a.pid_in ? a.pid_in[j] : (unsigned int)j;
+        for (int i0 = 0; i0 < SORT_ITEMS; i0 += 4) {
+            double val[4][NARR];
+            unsigned int id[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                long long j = j0 + (long long)(i0 + u) * SORT_THREADS + threadIdx.x;
+                if (key[i0 + u] >= 0) {
+#pragma unroll
+                    for (int q = 0; q < NARR; ++q) val[u][q] = __ldcs(a.in[q] + j);
+                    id[u] = a.pid_in ? __ldcs(a.pid_in + j) : (unsigned int)j;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (key[i0 + u] >= 0) {
+                    long long d = (long long)base[key[i0 + u]] + rank[i0 + u];
+#pragma unroll
+                    for (int q = 0; q < NARR; ++q) a.out[q][d] = val[u][q];
+                    a.pid_out[d] = id[u];
+                }
             }
         }
         __syncthreads();

@@ -361,7 +361,10 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             PG_TRY(set_smem(fp_pass_atomic<false>, h->smem_pass));
             PG_TRY(occupancy_blocks(fp_pass_atomic<false>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
             const int64_t ppc = h->count / N;
-            if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
+            // deterministic: per-deposit fixed point in the order-free atomic kernel (bit-identical for any
+            // particle order, run and GPU count); the sorted path is reproducible only between sweeps.
+            if (c.deterministic) h->sorted = false;
+            else if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
             else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 18) && ppc >= 64;
             if (h->sorted) {
                 h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
@@ -382,7 +385,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 PG_TRY(dalloc(&h->slow_count, 1));
                 PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
                 PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
-                PG_TRY(set_smem(sort_scatter_kernel, (size_t)h->nbins * 8));
+                PG_TRY(set_smem(sort_scatter_kernel<2>, (size_t)h->nbins * 8));
             }
         } else if (h->ngp) {
             h->smem_lf = lf_smem_bytes(0, N);
@@ -416,12 +419,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             h->fxw_scale = ldexp(1.0, fracw); h->fx_shift = fracw - frac;
         }
         const int64_t ppc = h->count / h->ncell;
-        if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
+        if (c.deterministic) h->sorted = false;
+        else if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
         else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 20) && ppc >= 8;
         if (h->sorted) {
             const int ntx = std::max(1, NX >> T2_SHIFT), nty = std::max(1, NY >> T2_SHIFT);
             h->nbins = ntx * nty;
-            h->sort_every = c.sort_every > 0 ? c.sort_every : 12;
+            h->sort_every = c.sort_every > 0 ? c.sort_every : 16; // 4-sigma thermal drift ~0.33 cells/step vs the 8-cell window margin
             for (int q = 0; q < 5; ++q) PG_TRY(dalloc(&h->p2[1][q], n));
             PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
             PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
@@ -430,7 +434,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             PG_TRY(dalloc(&h->slow_count, 1));
             PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
             PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
-            PG_TRY(set_smem(sort_scatter_kernel, (size_t)h->nbins * 8));
+            PG_TRY(set_smem(sort_scatter_kernel<5>, (size_t)h->nbins * 8));
             int64_t items = h->count / T2_CHUNK + h->nbins;
             PG_TRY(occupancy_blocks(particles_2d3v_tiled, PG_THREADS, 0, h->sms, items * PG_THREADS, &h->nblocks_sorted));
             h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
@@ -669,10 +673,10 @@ static int sort_particles_1d(picgolf_handle h)
     a.P = h->count; a.narr = 2; a.nbins = h->nbins; a.mode = 0; a.N = (int)h->cfg.N; a.NY = 1; a.tshift = 0;
     const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
-    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
+    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 8));
     sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
     sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
-    sort_scatter_kernel<<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    sort_scatter_kernel<2><<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
     h->launches += 3;
     h->timer.end(sp, h->stream);
     h->par ^= 1; h->pidpar ^= 1; h->pid_valid = true; h->since_sort = 0; h->sorts++;
@@ -756,7 +760,7 @@ static int sort_particles_2d(picgolf_handle h)
     int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
     sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
     sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->bin_start, h->nbins);
-    sort_scatter_kernel<<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    sort_scatter_kernel<5><<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
     tile_worklist_kernel<<<1, 1024, 0, h->stream>>>(h->bin_start, h->bin_cursor, h->item_off, h->nbins);
     h->launches += 4;
     h->timer.end(sp, h->stream);

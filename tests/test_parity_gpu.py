@@ -447,7 +447,7 @@ def test_2d3v_tile_sorted_mode(pg, oracle):
     for a, b in zip(ps, pa):
         assert relnorm(a, b) < 1e-10
     fa, fs = sims[0].fields(), sims[1].fields()
-    assert np.array_equal(fa[0], fs[0]) or relnorm(fs[0], fa[0]) < 1e-13  # integer accumulation: (almost) order free
+    assert relnorm(fs[0], fa[0]) < TOL  # both fixed point; the tiled path quantises per work item, not per deposit
     assert relnorm(fs[1], fa[1]) < 1e-10
     sorts, slow = sims[1].sort_stats()
     assert sorts == 3 and slow < P // 1000
