@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 // Sorted variant of the fixed-point pass.  Particles are kept in cell order (pg_sort.cuh), so the 32*K
 // consecutive particles a warp processes ("chunk") touch only a few neighbouring cells.  Each warp owns
 // a WIN_ROWS-cell window of the grid in shared memory with one private column per lane:
-//     acc[row][lane]  (row stride 33 doubles -> conflict-free both for the per-lane read-modify-write
-//                      and for the row sums of the flush)
+//     acc[row][lane]  (row stride 32 doubles: a lane always hits its own bank whatever row it uses;
+//                      the row sums of the flush read skewed columns, also conflict-free)
 // so the 13 deposits of a particle are plain LDS/DADD/STS -- no atomics, no warp divergence; the
 // SORTED_NP particles a lane evaluates together are summed in registers first when they share a window row.  At the
 // end of the chunk lane r sums row r and issues ONE global fp64 RED per window cell.  The 32-cell slice
@@ -130,11 +130,14 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
 // ------------------------------------------------------------------------------------------
 constexpr int WIN_ROWS = 32;                    // grid cells covered by a warp's window
 constexpr int WIN_ALLOC = WIN_ROWS;             // out-of-window stencils are predicated off (slow path instead)
-constexpr int WIN_LD = 33;
+constexpr int WIN_LD = 32;                      // row stride: bank = lane for every row -> conflict-free whatever rows the lanes use
 constexpr int WIN_LO = 6;                       // rows kept below the smallest centre of the first batch
 constexpr int WIN_MAXOFF = WIN_ROWS - GAUSS_NW; // largest row a stencil may start at
 constexpr int WIN_WARP_DOUBLES = WIN_ALLOC * WIN_LD + WIN_ROWS;
-constexpr int SORTED_NP = 2;                    // particles evaluated together per lane
+#ifndef PG_SORTED_NP
+#define PG_SORTED_NP 2
+#endif
+constexpr int SORTED_NP = PG_SORTED_NP;         // particles evaluated together per lane
 
 // Rare path: stencil outside the warp window.  Kept out of line so the hot loop stays small.
 __device__ __noinline__ double slow_gather(const double *E, double c, int N)
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
             double s = 0.0;
             const double *row = acc + lane * WIN_LD;
 #pragma unroll 8
-            for (int c = 0; c < 32; ++c) s += row[c];
+            for (int c = 0; c < 32; ++c) s += row[(c + lane) & 31]; // skewed: lane r starts at column r (distinct banks)
             if (s != 0.0) atomicAdd(&a.rho[(base + lane - 1) & Nmask], to_fx(s, a.fx_scale)); // one integer RED per window cell
         }
         __syncwarp();
