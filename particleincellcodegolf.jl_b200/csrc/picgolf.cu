@@ -185,6 +185,10 @@ struct picgolf_handle_s {
     int nbins = 0, K = 1, sort_every = 1, nblocks_sorted = 1;
     int64_t since_sort = 0, sorts = 0;
     size_t smem_sorted = 0;
+    // CUDA graphs of one fixed-point step, one per ping-pong parity
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+    int64_t graph_launches = 0;
+    bool graph_failed = false;
 };
 
 static int use_device(picgolf_handle h) { PG_CUDA(cudaSetDevice(h->device)); return 0; }
@@ -290,6 +294,7 @@ static int destroy_impl(picgolf_handle h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->timer.destroy();
+    for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off,
@@ -683,9 +688,8 @@ static int sort_particles_1d(picgolf_handle h)
     return 0;
 }
 
-static int step_fixedpoint(picgolf_handle h)
+static int enqueue_fixedpoint_step(picgolf_handle h)
 {
-    if (h->sorted && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_1d(h));
     const picgolf_config &c = h->cfg;
     FPArgs a;
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
@@ -708,6 +712,45 @@ static int step_fixedpoint(picgolf_handle h)
         h->launches++;
     }
     PG_TRY(launch_step_end(h, true));
+    return 0;
+}
+
+// One fixed-point step = 2*max_sweeps + 2 launches, most of them predicated no-ops.  For small problems the
+// step is launch-bound, so the whole sequence is captured once per ping-pong parity into a CUDA graph and
+// replayed (single GPU, stage timers off; NCCL calls and timing events stay out of graphs).
+static int step_fixedpoint(picgolf_handle h)
+{
+    if (h->sorted && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_1d(h));
+    const bool use_graph = !h->comm && !h->timer.enabled && h->count <= (1 << 22) && !h->graph_failed;
+    if (!use_graph) {
+        PG_TRY(enqueue_fixedpoint_step(h));
+    } else {
+        cudaGraphExec_t &exec = h->step_graph[h->par];
+        if (!exec) {
+            const int64_t l0 = h->launches;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            int rc = 0;
+            if (e == cudaSuccess) {
+                rc = enqueue_fixedpoint_step(h);
+                e = cudaStreamEndCapture(h->stream, &g);
+            }
+            if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            h->graph_launches = h->launches - l0;
+            h->launches = l0;
+            if (e != cudaSuccess || rc != 0 || !exec) { // fall back to plain launches for good
+                cudaGetLastError();
+                exec = nullptr;
+                h->graph_failed = true;
+                PG_TRY(enqueue_fixedpoint_step(h));
+                h->par ^= 1; h->since_sort++;
+                return 0;
+            }
+        }
+        PG_CUDA(cudaGraphLaunch(exec, h->stream));
+        h->launches += h->graph_launches;
+    }
     h->par ^= 1;
     h->since_sort++;
     return 0;
