@@ -188,6 +188,16 @@ def run_gpu(args):
                 "stage_ms_per_step": {k: v / nroof for k, v in st.items()},
                 "resorts_in_stage_window": sim.sort_stats()[0] - s0, "stage_window_steps": nroof}
 
+    # ---- FP64 pipe view of the same kernel (the binding limit of the erf-shape passes) ----------
+    fp64 = None
+    if args.workload == "gauss_fp":
+        peak_tf = pg.fp64_peak_tflops()
+        # FP64 instructions per particle-pass measured with ncu (profiles/): first 136, middle 267, final 137
+        fp64_inst = float(sum(136 + 267 * (int(s_) - 1) + 137 for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
+        ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
+        fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
+                "note": "FP64 lane-instructions of the pass kernels x2 / kernel time; this, not HBM, bounds the erf-shape path"}
+
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -247,7 +257,7 @@ def run_gpu(args):
             "mean_sweeps_per_step": mean_sweeps, "particle_sweeps_per_s": value * mean_sweeps,
             "algorithmic_bytes_per_particle_step": bpu,
             "hbm_roofline_frac_step": (value / world) * bpu / (peak * 1e9),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "fp64_pipe": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "sorts_in_timed_region": int(sorts_timed), "sort_stats_total": list(sim.sort_stats()),
         }
         print(json.dumps(line), flush=True)

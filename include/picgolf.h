@@ -215,6 +215,9 @@ int picgolf_stage_cic_gather(const double *Ex, const double *Ey, int64_t NX, int
 /* boris() (Electrostatic2D3V.jl:32-41) on arrays, in place. */
 int picgolf_stage_boris(double *vx, double *vy, double *vz, const double *Ex, const double *Ey, int64_t count,
                         double dt, double B0);
+/* Measured FP64 FMA peak of the device (TFLOP/s, 2 flops per lane-FMA): the physically binding roofline of the
+ * erf-shape kernels; MEASURED_PEAKS.json carries no fp64 figure. */
+int picgolf_stage_fp64_peak(double *tflops);
 /* Quiet start for global indices [first, first+count) of P (GaussianFixedPointQuiet.jl:2-3). */
 int picgolf_stage_quiet_start(int64_t P, int64_t first, int64_t count, double *x, double *v);
 

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "picgolf_stage_cic_deposit": [_dp, _dp, _i64, _i64, _i64, _d, _dp],
     "picgolf_stage_cic_gather": [_dp, _dp, _i64, _i64, _dp, _dp, _i64, _dp, _dp],
     "picgolf_stage_boris": [_dp, _dp, _dp, _dp, _dp, _i64, _d, _d],
+    "picgolf_stage_fp64_peak": [C.POINTER(_d)],
     "picgolf_stage_quiet_start": [_i64, _i64, _i64, _dp, _dp],
 }
 
@@ -466,6 +467,13 @@ def boris(vx, vy, vz, Ex, Ey, dt: float, B0: float):
     vx, vy, vz = (_f64(a).copy() for a in (vx, vy, vz))
     _check(load().picgolf_stage_boris(vx, vy, vz, _f64(Ex), _f64(Ey), vx.size, dt, B0))
     return vx, vy, vz
+
+
+def fp64_peak_tflops() -> float:
+    """Measured FP64 FMA peak of the current device (TFLOP/s)."""
+    t = _d()
+    _check(load().picgolf_stage_fp64_peak(C.byref(t)))
+    return t.value
 
 
 def quiet_start(P: int, first: int = 0, count: Optional[int] = None):

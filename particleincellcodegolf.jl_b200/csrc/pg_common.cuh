@@ -80,6 +80,19 @@ __device__ __forceinline__ double block_sum(double v, double *scratch)
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
+// FP64 pipe peak: 8 independent DFMA chains per thread (the denominator for the erf-shape kernels, which are
+// bound by the FP64 pipe rather than by HBM; MEASURED_PEAKS.json has no fp64 figure).
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    double s = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s; // never true; keeps the chains alive
+}
+
 // splitmix64: counter-based generator for the synthetic starts (NOT Julia's rand).
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z)
 {

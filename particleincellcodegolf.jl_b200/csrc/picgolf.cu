@@ -1302,6 +1302,35 @@ PG_API int picgolf_stage_boris(double *vx, double *vy, double *vz, const double 
     return c.download(vz, count * 8);
 }
 
+PG_API int picgolf_stage_fp64_peak(double *tflops)
+{
+    if (!tflops) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    PG_TRY(stage_ready());
+    int dev = 0, sms = 0;
+    PG_CUDA(cudaGetDevice(&dev));
+    PG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DevBuf out;
+    const int blocks = sms * 8, iters = 8192;
+    PG_TRY(out.alloc((size_t)blocks * 256 * 8));
+    cudaEvent_t e0, e1;
+    PG_CUDA(cudaEventCreate(&e0)); PG_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        PG_CUDA(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, 256>>>(out.as<double>(), iters, 0.999999, 1e-9);
+        PG_CUDA(cudaEventRecord(e1));
+        PG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    PG_TRY(finish());
+    *tflops = best;
+    return 0;
+}
+
 PG_API int picgolf_stage_quiet_start(int64_t P, int64_t first, int64_t count, double *x, double *v)
 {
     if (!x || !v || count < 0 || first < 0 || first + count > P) return fail(PICGOLF_ERR_ARG, "bad argument");
