@@ -183,8 +183,15 @@ def run_gpu(args):
     launch_ms = st["particles"] / passes
     peak, peak_src = peaks()
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # per-launch DRAM bytes of the same kernel from the committed ncu --set full capture (only valid at 2^28/GPU)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[args.workload]
+        if per_gpu == 1 << 28:
+            traffic = tj["traffic_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "peak_source": peak_src, "traffic": traffic, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "stage_ms_per_step": {k: v / nroof for k, v in st.items()},
                 "resorts_in_stage_window": sim.sort_stats()[0] - s0, "stage_window_steps": nroof}
 
@@ -192,8 +199,8 @@ def run_gpu(args):
     fp64 = None
     if args.workload == "gauss_fp":
         peak_tf = pg.fp64_peak_tflops()
-        # FP64 instructions per particle-pass measured with ncu (profiles/): first 136, middle 267, final 137
-        fp64_inst = float(sum(136 + 267 * (int(s_) - 1) + 137 for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
+        # FP64 instructions per particle-pass measured with ncu (profiles/): first 130, middle 255, final 131
+        fp64_inst = float(sum(130 + 255 * (int(s_) - 1) + 131 for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
         ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
         fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
                 "note": "FP64 lane-instructions of the pass kernels x2 / kernel time; this, not HBM, bounds the erf-shape path"}
@@ -246,6 +253,38 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.workload, args.cpu_log2_particles, args.cpu_steps)
 
+    # ---- the other two scoped workloads, briefly (device-resident, same timing rules) ----------------------
+    others = None
+    if args.others and args.workload == "gauss_fp":
+        sim.close()
+        others = {}
+        for wl in ("ngp", "2d3v"):
+            s2, name2, bpu2 = make_sim(pg, wl, per_gpu, rank, world, local, T=64)
+            if world > 1:
+                pgd.connect(s2)
+            init_sim(s2, wl)
+            st2 = torch.cuda.ExternalStream(s2.stream, device=torch.device("cuda", local))
+            s2.step(4)
+            s2.synchronize(); torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            Ko = 16
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(st2)
+            s2.step(Ko)
+            g1.record(st2)
+            s2.synchronize(); torch.cuda.synchronize()
+            mso = g0.elapsed_time(g1)
+            if world > 1:
+                t = torch.tensor([mso], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                mso = float(t.item())
+            vo = s2.cfg.P * Ko / (mso * 1e-3)
+            others[wl] = {"workload": name2, "value": vo, "unit": UNIT, "steps": Ko, "ms_per_step": mso / Ko,
+                          "algorithmic_bytes_per_particle_step": bpu2, "hbm_roofline_frac_step": (vo / world) * bpu2 / (peak * 1e9),
+                          "sorts_total_incl_warmup": s2.sort_stats()[0]}
+            s2.close()
+
     if rank == 0:
         if args.workload == "gauss_fp":
             bpu = 32.0 * (mean_sweeps + 1)
@@ -258,11 +297,12 @@ def run_gpu(args):
             "algorithmic_bytes_per_particle_step": bpu,
             "hbm_roofline_frac_step": (value / world) * bpu / (peak * 1e9),
             "roofline": roofline, "fp64_pipe": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "sorts_in_timed_region": int(sorts_timed), "sort_stats_total": list(sim.sort_stats()),
+            "sorts_in_timed_region": int(sorts_timed), "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -346,6 +386,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", dest="others", action="store_false", help="skip the brief NGP and 2D3V runs")
     ap.add_argument("--cpu-log2-particles", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3)
     args = ap.parse_args()
