@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
     const int fk = a.ctrl->final_k;
     if (!FIRST && fk >= 0 && a.k > fk) return;
     const bool final = !FIRST && fk == a.k;
+    const bool v0_is_V = FIRST || a.k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
     const int N = a.N, Nmask = N - 1;
     const double dN = (double)N, dt = a.dt;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
         const double Xj = ld_stream(a.X + j), Vj = ld_stream(a.V + j);
-        double vj = FIRST ? Vj : ld_stream(a.v + j);
+        double vj = v0_is_V ? Vj : ld_stream(a.v + j);
         double xj = Xj + (vj + Vj) / 2 * dt; // x.=X.+(v.+V)/2*dt
         int ibase;
         double W[GAUSS_NW];
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
     const int fk = a.ctrl->final_k;
     if (!FIRST && fk >= 0 && a.k > fk) return;
     const bool final = !FIRST && fk == a.k;
+    const bool v0_is_V = FIRST || a.k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *acc = smem + warp * WIN_WARP_DOUBLES; // [WIN_ALLOC][WIN_LD]
     double *Ew = acc + WIN_ALLOC * WIN_LD;        // [WIN_ROWS]
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
             const bool ln = jn < a.P;
             Xn[q] = ln ? ld_stream(a.X + jn) : 0.0;
             Vn[q] = ln ? ld_stream(a.V + jn) : 0.0;
-            vn[q] = FIRST ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
+            vn[q] = v0_is_V ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
         }
         for (int kb = 0; kb < a.K; kb += NP) {
             long long j[NP];
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
                     const bool ln = jn < a.P;
                     Xn[q] = ln ? ld_stream(a.X + jn) : 0.0;
                     Vn[q] = ln ? ld_stream(a.V + jn) : 0.0;
-                    vn[q] = FIRST ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
+                    vn[q] = v0_is_V ? Vn[q] : (ln ? ld_stream(a.v + jn) : 0.0);
                 }
             }
 #pragma unroll

@@ -479,3 +479,141 @@ def test_ngp_odd_particle_count(pg, oracle):
     rho, E = sim.fields()
     xg, vg = sim.particles()
     assert relnorm(rho, ro) < 1e-13 and relnorm(E, Eo) < 1e-11 and relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
+
+
+# =============================================================================================
+# edge cases: ragged sizes, extreme grids, sweep cap, checkpoint/resume, trace capacity
+# =============================================================================================
+@pytest.mark.parametrize("P", [1, 33, 1000])
+def test_ragged_particle_counts_atomic(pg, oracle, P):
+    N = 64
+    rng = np.random.default_rng(P)
+    x0, v0 = rng.random(P), rng.choice([-1.0, 1.0], P)
+    sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=50.0)
+    sim.set_particles(x0, v0)
+    sim.step(3)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, 50.0, hw=6, rtol=1e-8)
+    sw_o = [fp.step()[2] for _ in range(3)]
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    D, sw = sim.diagnostics()
+    assert list(sw) == sw_o
+    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10
+
+
+def test_ragged_particle_count_sorted(pg, oracle):
+    """Sorted path with a particle count that is not a multiple of the warp chunk (tail groups, dead lanes)."""
+    N, P = 1024, (1 << 18) + 37
+    rng = np.random.default_rng(77)
+    x0, v0 = rng.random(P), np.where(np.arange(P) % 2 == 0, 1.0, -1.0)
+    sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=100.0, deposit_mode=pg.DEPOSIT_SORTED)
+    sim.set_particles(x0, v0)
+    sim.step(2)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, 100.0, hw=6, rtol=1e-8)
+    sw_o = [fp.step()[2] for _ in range(2)]
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    assert list(sim.diagnostics()[1]) == sw_o
+    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10
+
+
+@pytest.mark.parametrize("N", [16, 8192])
+def test_extreme_grid_sizes(pg, oracle, N):
+    P = 4 * N if N == 8192 else 4096
+    rng = np.random.default_rng(N)
+    x0, v0 = rng.random(P), rng.choice([-1.0, 1.0], P)
+    sim = pg.gaussian_fixed_point(N=N, P=P, T=4, W=20.0)
+    sim.set_particles(x0, v0)
+    sim.step(1)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, 20.0, hw=6, rtol=1e-8)
+    _, _, s = fp.step()
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    assert sim.diagnostics()[1][0] == s
+    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10 and relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11
+    ng = pg.ngp_fourier(N=N, P=P, NT=4, W=float(N))  # w = N*N/P dyadic
+    ng.set_particles(x0, v0)
+    ng.step(2)
+    xo, vo = x0.copy(), v0.copy()
+    for _ in range(2):
+        ro, Eo, _ = oracle.ngp_step(xo, vo, N, ng.cfg.dt, ng.cfg.w)
+    rho, E = ng.fields()
+    xg, vg = ng.particles()
+    assert np.array_equal(rho, ro) and relnorm(E, Eo) < 1e-10 and relnorm(xg, xo) < TOL and relnorm(vg, vo) < TOL
+
+
+def test_sweep_cap_is_not_an_error(pg, oracle):
+    """rtol=0, atol=0 never converges on noisy data: the reference silently proceeds after 10 sweeps."""
+    N, P = 128, 4096
+    rng = np.random.default_rng(5)
+    x0, v0 = rng.random(P), rng.choice([-1.0, 1.0], P)
+    sim = pg.gaussian_fixed_point(T=4, l=0.0)
+    sim.set_particles(x0, v0)
+    sim.step(2)
+    fp = oracle.FixedPoint(x0, v0, N, sim.cfg.dt, 400.0, hw=6, rtol=0.0)
+    sw_o = [fp.step()[2] for _ in range(2)]
+    D, sw = sim.diagnostics()
+    x, v = sim.particles()
+    assert list(sw) == sw_o
+    assert sw.max() <= 10
+    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11
+    few = pg.gaussian_fixed_point(T=4, max_sweeps=2)
+    few.set_particles(x0, v0)
+    few.step(1)
+    assert few.diagnostics()[1][0] == 2
+
+
+def test_checkpoint_resume_bit_exact(pg):
+    """State is (x, v, E): get -> new handle -> set_particles + set_field continues bit-identically
+    (order-free fixed-point deposits)."""
+    rng = np.random.default_rng(8)
+    x0, v0 = rng.random(4096), rng.choice([-1.0, 1.0], 4096)
+    a = pg.gaussian_fixed_point(T=16)
+    a.set_particles(x0, v0)
+    a.step(6)
+    xa, va = a.particles()
+    b = pg.gaussian_fixed_point(T=16)
+    b.set_particles(x0, v0)
+    b.step(3)
+    xm, vm = b.particles()
+    _, Em = b.fields()
+    c = pg.gaussian_fixed_point(T=16)
+    c.set_particles(xm, vm)
+    c.set_field(Em)
+    c.step(3)
+    xc, vc = c.particles()
+    assert np.array_equal(xc, xa) and np.array_equal(vc, va)
+    assert np.array_equal(c.fields()[1], a.fields()[1])
+    assert c.steps_done == 3 and a.steps_done == 6
+
+
+def test_trace_capacity_and_diag_every(pg):
+    sim = pg.gaussian_fixed_point(T=4)
+    sim.init_synthetic(seed=3)
+    sim.step(7)  # more steps than rows: recording stops, stepping does not
+    D, sw = sim.diagnostics()
+    assert D.shape == (4, 4) and sim.steps_done == 7
+    s2 = pg.electrostatic_2d3v(NX=32, NY=32, P=8192, T=8, NS=2)
+    s2.init_synthetic(seed=4, vth=s2.vth)
+    s2.step(7)
+    K, _ = s2.diagnostics()
+    assert K.shape == (3, 5)  # rows at t = 2, 4, 6  (Electrostatic2D3V.jl:164 `if t % NS == 0`)
+    assert np.all(K[:, 1] > 0) and np.all(np.isfinite(K))
+
+
+def test_deterministic_flag_bit_reproducible(pg):
+    """deterministic=1: charge does not depend on particle order or on the run."""
+    N, P = 4096, 1 << 19
+    rng = np.random.default_rng(9)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0)
+    perm = rng.permutation(P)
+    res = []
+    for xs, vs in ((x0, v0), (x0[perm], v0[perm]), (x0, v0)):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=4, W=400.0, deterministic=1)
+        sim.set_particles(xs, vs)
+        sim.step(2)
+        res.append((sim.fields(), sim.particles()))
+    assert np.array_equal(res[0][0][0], res[1][0][0]) and np.array_equal(res[0][0][1], res[1][0][1])  # order free
+    assert np.array_equal(res[0][1][0], res[2][1][0]) and np.array_equal(res[0][1][1], res[2][1][1])  # run to run
+    assert np.array_equal(res[1][1][0], res[0][1][0][perm])
