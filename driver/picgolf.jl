@@ -20,7 +20,7 @@ module PicGolf
 
 const LIB = get(ENV, "PICGOLF_LIB", joinpath(@__DIR__, "..", "particleincellcodegolf.jl_b200", "lib", "libpicgolf.so"))
 
-const NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V = Int32(1), Int32(2), Int32(3), Int32(4)
+const NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13 = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 
 # Mirror of `picgolf_config` (include/picgolf.h) -- field order and types must match.
 Base.@kwdef mutable struct Config

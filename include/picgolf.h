@@ -45,7 +45,8 @@ typedef enum picgolf_scheme {
     PICGOLF_NGP_LEAPFROG = 1,     /* src/NGPFourier.jl:4-7 (+ NGPFourierWithDiagnostics.jl:6-7) */
     PICGOLF_GAUSS_LEAPFROG = 2,   /* src/Gaussian.jl:8-12 */
     PICGOLF_GAUSS_FIXEDPOINT = 3, /* src/GaussianFixedPoint.jl:7-12, src/GaussianFixedPointQuiet.jl:8-15 */
-    PICGOLF_CIC_BORIS_2D3V = 4    /* src/Electrostatic2D3V.jl:120-176 */
+    PICGOLF_CIC_BORIS_2D3V = 4,   /* src/Electrostatic2D3V.jl:120-176 */
+    PICGOLF_GAUSS_SIMPSON13 = 5   /* src/GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 quadrature of E, 3 solves/sweep) */
 } picgolf_scheme;
 
 /* Deposit accumulation mode. */
@@ -103,7 +104,8 @@ int picgolf_device_count(void);
  * scheme GAUSS_LEAPFROG -> Gaussian.jl:2     (NX=128,NP=64NX,dt=1/10NX,NT=1024,W=1600,w=W/NP/dx)
  * scheme GAUSS_FIXEDPOINT, quiet=0 -> GaussianFixedPoint.jl:1-5 (N=128,P=32N,dt=1/6N,T=1024,W=400,hw 6,l=1e-8)
  * scheme GAUSS_FIXEDPOINT, quiet=1 -> GaussianFixedPointQuiet.jl:1-6 (N=64,P=32N,T=2^13,W=32pi^2/3,hw 7,l=4eps)
- * scheme CIC_BORIS_2D3V -> Electrostatic2D3V.jl:23-25 (NX=NY=128,P=NX*NY*2^5,T=2^13,n0=4pi^2,...) */
+ * scheme CIC_BORIS_2D3V -> Electrostatic2D3V.jl:23-25 (NX=NY=128,P=NX*NY*2^5,T=2^13,n0=4pi^2,...)
+ * scheme GAUSS_SIMPSON13 -> GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point) */
 int picgolf_config_default(picgolf_config *cfg, int scheme, int quiet);
 
 /* ---- lifetime --------------------------------------------------------------------------- */
@@ -141,6 +143,7 @@ int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, double *v
  *   GAUSS_LEAPFROG   Gaussian.jl:9-10
  *   GAUSS_FIXEDPOINT GaussianFixedPoint.jl:7-10 (<= max_sweeps sweeps, 2-norm isapprox test on device)
  *   CIC_BORIS_2D3V   Electrostatic2D3V.jl:121-157
+ *   GAUSS_SIMPSON13  GaussianFixedPointQuietSimpson13.jl:8-17 (fields: rho = rho(x,x), E = E[end,:])
  * and append one diagnostics row per recorded step.  Asynchronous: returns after enqueueing;
  * any getter or picgolf_synchronize() waits. */
 int picgolf_step(picgolf_handle h, int64_t nsteps);

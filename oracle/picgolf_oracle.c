@@ -336,6 +336,62 @@ ORACLE_API void oracle_fixedpoint_run(double *x, double *v, double *E, int64_t P
     free(X);
 }
 
+/* One step of GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 time quadrature of E: three field
+ * solves per sweep).  E is 3 x N stored row by row here (E1 | E2 | E3), F likewise; the convergence test is the
+ * Frobenius-norm isapprox over the whole 3 x N matrix.  Returns sweeps; D4 as in the plain fixed point but with
+ * sum(E[end,:].^2) (line 18). */
+ORACLE_API int oracle_simpson_step(double *x, double *v, double *E3N, double *X, double *V, double *F3N, double *r,
+                                   int64_t P, int64_t N, int hw, double dt, double W, double w, double rtol, double atol,
+                                   int max_sweeps, double *D4)
+{
+    int sweeps = 0;
+    double *E1 = E3N, *E2 = E3N + N, *E3 = E3N + 2 * N;
+    memcpy(X, x, sizeof(double) * (size_t)P);
+    memcpy(V, v, sizeof(double) * (size_t)P);
+    for (int64_t i = 0; i < 3 * N; ++i) F3N[i] = NAN;                         /* F.*=NaN */
+    oracle_gauss_deposit(X, X, P, N, hw, w, r);                               /* E[1,:] = solve(rho(X,X))  :9 */
+    oracle_solve1d(r, N, E1);
+    for (int it = 0; it < max_sweeps; ++it) {                                 /* :10 */
+        if (oracle_isapprox(F3N, E3N, 3 * N, rtol, atol)) break;
+        memcpy(F3N, E3N, sizeof(double) * (size_t)(3 * N));
+        for (int64_t j = 0; j < P; ++j) x[j] = X[j] + (v[j] + V[j]) / 2 * dt; /* :11 */
+        for (int64_t j = 0; j < P; ++j)                                       /* :12  ...*dt/6 */
+            v[j] = V[j] + oracle_gauss_gather(E1, (X[j] + X[j]) / 2, N, hw) * dt / 6;
+        oracle_gauss_deposit(X, x, P, N, hw, w, r);                           /* :13 */
+        oracle_solve1d(r, N, E2);
+        for (int64_t j = 0; j < P; ++j)                                       /* :14  ...*4dt/6 */
+            v[j] = v[j] + oracle_gauss_gather(E2, (X[j] + x[j]) / 2, N, hw) * (4 * dt) / 6;
+        oracle_gauss_deposit(x, x, P, N, hw, w, r);                           /* :15 */
+        oracle_solve1d(r, N, E3);
+        for (int64_t j = 0; j < P; ++j)                                       /* :16 */
+            v[j] = v[j] + oracle_gauss_gather(E3, (x[j] + x[j]) / 2, N, hw) * dt / 6;
+        ++sweeps;
+    }
+    for (int64_t j = 0; j < P; ++j) x[j] = oracle_jl_mod1(x[j]);              /* :17 */
+    double se = 0, sv2 = 0, svp = 0;
+    for (int64_t i = 0; i < N; ++i) se += E3[i] * E3[i];                      /* sum(E[end,:].^2)  :18 */
+    for (int64_t j = 0; j < P; ++j) { sv2 += v[j] * v[j]; svp += v[j] / (double)P; }
+    if (D4) {
+        double d1 = (se / (double)N) / 2, d2 = (sv2 * W / (double)P) / 2, s = 2 / W;
+        D4[0] = d1 * s; D4[1] = d2 * s; D4[2] = (d1 + d2) * s; D4[3] = svp;
+    }
+    return sweeps;
+}
+
+ORACLE_API void oracle_simpson_run(double *x, double *v, double *E3N, int64_t P, int64_t N, int hw, double dt, double W,
+                                   double w, double rtol, double atol, int max_sweeps, int64_t T, double *D, int32_t *sweeps)
+{
+    double *X = (double *)malloc(sizeof(double) * (size_t)(2 * P + 4 * N));
+    double *V = X + P, *F = V + P, *r = F + 3 * N;
+    for (int64_t t = 0; t < T; ++t) {
+        double d4[4];
+        int s = oracle_simpson_step(x, v, E3N, X, V, F, r, P, N, hw, dt, W, w, rtol, atol, max_sweeps, d4);
+        if (D) for (int c = 0; c < 4; ++c) D[c * T + t] = d4[c];
+        if (sweeps) sweeps[t] = s;
+    }
+    free(X);
+}
+
 /* Explicit Gaussian leapfrog: Gaussian.jl:8-11.  scale = w/dx (Gaussian.jl:7), hw = 6. */
 ORACLE_API void oracle_gauss_leapfrog_step(double *x, double *v, int64_t P, int64_t N, int hw, double dt,
                                            double scale, double *rho, double *E, double *raw)

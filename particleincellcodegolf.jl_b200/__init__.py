@@ -28,7 +28,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
 
-NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V = 1, 2, 3, 4
+NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13 = 1, 2, 3, 4, 5
 DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED = 0, 1, 2
 
 NVCC_FLAGS = [
@@ -366,6 +366,20 @@ def gaussian_fixed_point_quiet(N=64, P=None, dt=None, T=2 ** 13, W=32 * math.pi 
     Call .init_quiet() for the bit-reversal start (lines 2-3)."""
     return gaussian_fixed_point(N=N, P=P, dt=dt, T=T, W=W, l=l, atol=0.0, half_width=7, rank=rank, nranks=nranks,
                                 device=device, **over)
+
+
+def gaussian_fixed_point_quiet_simpson13(N=64, P=None, dt=None, T=2 ** 13, W=32 * math.pi ** 2 / 3, l=4 * np.finfo(float).eps,
+                                         half_width=7, max_sweeps=10, rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point); Simpson-1/3 time
+    quadrature of E with three field solves per sweep (lines 8-18).  fields() returns (rho(x,x), E[end,:])."""
+    cfg = default_config(GAUSS_SIMPSON13)
+    cfg.N = N
+    cfg.P = 32 * N if P is None else P
+    cfg.dt = 1 / (6 * N) if dt is None else dt
+    cfg.W = W
+    cfg.w = W / cfg.P * N
+    cfg.rtol, cfg.atol, cfg.half_width, cfg.max_sweeps = l, 0.0, half_width, max_sweeps
+    return _finish(cfg, rank, nranks, device, T, **over)
 
 
 def electrostatic_2d3v(NX=128, NY=None, P=None, T=2 ** 13, NS=2, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1,

@@ -22,6 +22,10 @@ struct Ctrl {
     int pad_;
     long long step;  // steps completed
     double sumE2;    // sum(E.^2) of the latest solve (2D: sum(Ex^2+Ey^2))
+    // Simpson-1/3 variant: ||E1||^2 of the step, per-row norm partials of the E2/E3 solve, arrival counter
+    double normE1sq;
+    double sp_acc[6];
+    unsigned int sp_arrive, pad2_;
 };
 
 // Batched in-place FFT on shared memory.  Element e of batch b lives at [b*bstride + e*estride].
@@ -80,6 +84,7 @@ struct Solve1DArgs {
     Ctrl *ctrl;
     double w, fx_inv, rtol, atol;   // fx_inv = 2^-frac
     int N, lg, fixedpoint, k, max_sweeps;
+    int store_normE1; // Simpson variant: this is the E1 solve of the step
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -126,6 +131,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     e2 = block_sum(e2, scratch);
     if (threadIdx.x == 0) {
         a.ctrl->sumE2 = e2;
+        if (a.store_normE1) a.ctrl->normE1sq = e2;
         if (a.fixedpoint) {
             // LinearAlgebra.isapprox(F,E;rtol,atol): norm(F-E) <= max(atol, rtol*max(norm(F),norm(E)))
             double d = sqrt(d2);

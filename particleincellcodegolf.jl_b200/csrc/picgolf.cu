@@ -17,6 +17,7 @@
 #include "pg_kernels_1d.cuh"
 #include "pg_kernels_2d.cuh"
 #include "pg_sort.cuh"
+#include "pg_kernels_simpson.cuh"
 
 using namespace pg;
 
@@ -152,7 +153,8 @@ struct picgolf_handle_s {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     int64_t first = 0, count = 0;
-    bool is2d = false, fixedpoint = false, ngp = false;
+    bool is2d = false, fixedpoint = false, ngp = false, simpson = false;
+    size_t smem_sp1 = 0, smem_spk = 0;
     // particles (1D: xb/vb ping-pong for the fixed point; leapfrog and 2D use index 0)
     double *xb[2] = {nullptr, nullptr}, *vb[2] = {nullptr, nullptr};
     double *p2[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}}; // 2D: x,y,vx,vy,vz ping-pong
@@ -164,6 +166,7 @@ struct picgolf_handle_s {
     double2 *tw = nullptr, *twy = nullptr, *Z = nullptr, *E2 = nullptr;
     double *epartials = nullptr;
     int64_t ncell = 0;
+    int grid_rows = 1;
     // control / diagnostics
     Ctrl *ctrl = nullptr;
     double *partials = nullptr, *raw = nullptr;
@@ -261,6 +264,9 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
         c->N = 128; c->P = 64 * c->N; c->dt = 1.0 / (10 * c->N); c->T = 1024; c->W = 1600;
         c->w = c->W / (double)c->P / (1.0 / (double)c->N);
         break;
+    case PICGOLF_GAUSS_SIMPSON13: // GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point)
+        quiet = 1;
+        /* fall through */
     case PICGOLF_GAUSS_FIXEDPOINT:
         if (!quiet) { // GaussianFixedPoint.jl:1-5
             c->N = 128; c->P = 32 * c->N; c->dt = 1.0 / (6 * c->N); c->T = 1024; c->W = 400;
@@ -326,7 +332,8 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     PG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
     h->is2d = c.scheme == PICGOLF_CIC_BORIS_2D3V;
-    h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT;
+    h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13;
+    h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT || h->simpson;
     h->ngp = c.scheme == PICGOLF_NGP_LEAPFROG;
     h->nranks = std::max(1, c.nranks);
     h->rank = c.rank;
@@ -346,11 +353,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->ncell = N;
         PG_TRY(dalloc(&h->xb[0], n)); PG_TRY(dalloc(&h->vb[0], n));
         if (h->fixedpoint) { PG_TRY(dalloc(&h->xb[1], n)); PG_TRY(dalloc(&h->vb[1], n)); }
-        PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, N));
-        PG_TRY(dalloc(&h->rho_fx, N));
+        const int rows = h->simpson ? 3 : 1; // Simpson-1/3: E1|E2|E3 and rho1|rho2|rho3
+        h->grid_rows = rows;
+        PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, (size_t)rows * N));
+        PG_TRY(dalloc(&h->rho_fx, (size_t)rows * N));
         PG_CUDA(cudaMemset(h->rho_last, 0, N * sizeof(double)));
-        PG_CUDA(cudaMemset(h->E, 0, N * sizeof(double)));
-        PG_CUDA(cudaMemset(h->rho_fx, 0, N * sizeof(unsigned long long)));
+        PG_CUDA(cudaMemset(h->E, 0, (size_t)rows * N * sizeof(double)));
+        PG_CUDA(cudaMemset(h->rho_fx, 0, (size_t)rows * N * sizeof(unsigned long long)));
         if (!h->ngp) {
             // fixed-point format of the Gaussian deposit grid: weights are <= 1 and sum to 1 per particle, so
             // no cell can exceed P (all ranks) -> 62 - ceil(log2(P+1)) fractional bits can never overflow.
@@ -361,7 +370,15 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
         h->npart = 2;
         PG_TRY(set_smem(solve1d_kernel, h->smem_pass));
-        if (h->fixedpoint) {
+        if (h->simpson) {
+            h->smem_sp1 = (size_t)3 * N * 8;
+            h->smem_spk = (size_t)(4 * N + 32) * 8;
+            PG_TRY(set_smem(sp_pass0, (size_t)N * 8));
+            PG_TRY(set_smem(sp_pass1, h->smem_sp1));
+            PG_TRY(set_smem(sp_passk, h->smem_spk));
+            PG_TRY(set_smem(solve_simpson23_kernel, h->smem_pass));
+            PG_TRY(occupancy_blocks(sp_passk, PG_THREADS, h->smem_spk, h->sms, h->count, &h->nblocks));
+        } else if (h->fixedpoint) {
             PG_TRY(set_smem(fp_pass_atomic<true>, h->smem_pass));
             PG_TRY(set_smem(fp_pass_atomic<false>, h->smem_pass));
             PG_TRY(occupancy_blocks(fp_pass_atomic<false>, PG_THREADS, h->smem_pass, h->sms, h->count, &h->nblocks));
@@ -462,7 +479,7 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
     if (cfg->struct_size != (int32_t)sizeof(picgolf_config))
         return fail(PICGOLF_ERR_ARG, "struct_size %d != %zu (header/library mismatch)", cfg->struct_size, sizeof(picgolf_config));
     const picgolf_config &c = *cfg;
-    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_CIC_BORIS_2D3V) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_GAUSS_SIMPSON13) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
     if (c.P < 1) return fail(PICGOLF_ERR_ARG, "P must be >= 1");
     if (!(c.dt > 0) || !isfinite(c.dt)) return fail(PICGOLF_ERR_ARG, "dt must be positive and finite");
     if (!isfinite(c.w)) return fail(PICGOLF_ERR_ARG, "w must be finite");
@@ -475,7 +492,8 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
         if (!is_pow2(c.N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N);
         if (c.scheme != PICGOLF_NGP_LEAPFROG && c.half_width != 6 && c.half_width != 7)
             return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
-        if (c.scheme == PICGOLF_GAUSS_FIXEDPOINT && (c.max_sweeps < 1 || c.max_sweeps > 64))
+        if (c.scheme == PICGOLF_GAUSS_SIMPSON13 && c.N > 4096) return fail(PICGOLF_ERR_ARG, "Simpson-1/3 scheme: N must be <= 4096");
+        if ((c.scheme == PICGOLF_GAUSS_FIXEDPOINT || c.scheme == PICGOLF_GAUSS_SIMPSON13) && (c.max_sweeps < 1 || c.max_sweeps > 64))
             return fail(PICGOLF_ERR_ARG, "max_sweeps must be in 1..64");
     }
     picgolf_handle h = new picgolf_handle_s();
@@ -503,9 +521,9 @@ static int reset_run_state(picgolf_handle h)
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
-    PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, h->ncell * sizeof(unsigned long long), h->stream));
+    PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, (size_t)h->grid_rows * h->ncell * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
-    else PG_CUDA(cudaMemsetAsync(h->E, 0, h->ncell * sizeof(double), h->stream));
+    else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0;
@@ -626,25 +644,26 @@ PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, do
 // ------------------------------------------------------------------------------------------
 // the loop body
 // ------------------------------------------------------------------------------------------
-static int allreduce_grid(picgolf_handle h)
+static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
 {
     if (!h->comm) return 0;
     const int sp1_ = h->timer.begin(ST_REDUCE, h->stream);
     int rc;
     // integer grid: two's-complement sums are exact and order independent
-    rc = nccl::AllReduce(h->rho_fx, h->rho_fx, (size_t)h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
+    unsigned long long *g = h->rho_fx + (size_t)row0 * h->ncell;
+    rc = nccl::AllReduce(g, g, (size_t)nrows * h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
     h->timer.end(sp1_, h->stream);
     return nccl::check(rc, "ncclAllReduce(rho)");
 }
 
-static int launch_solve1d(picgolf_handle h, int k)
+static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
 {
     const picgolf_config &c = h->cfg;
     Solve1DArgs a;
     a.rho_in = nullptr; a.rho_fx = h->rho_fx; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
     a.w = c.w; a.fx_inv = h->fx_inv; a.rtol = c.rtol; a.atol = c.atol;
-    a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = h->fixedpoint ? 1 : 0;
-    a.k = k; a.max_sweeps = c.max_sweeps;
+    a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = (h->fixedpoint && !simpson_e1) ? 1 : 0;
+    a.k = k; a.max_sweeps = c.max_sweeps; a.store_normE1 = simpson_e1 ? 1 : 0;
     int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
     const int sp2_ = h->timer.begin(ST_SOLVE, h->stream);
     solve1d_kernel<<<1, threads, h->smem_pass, h->stream>>>(a);
@@ -715,15 +734,54 @@ static int enqueue_fixedpoint_step(picgolf_handle h)
     return 0;
 }
 
+static int enqueue_simpson_step(picgolf_handle h)
+{
+    const picgolf_config &c = h->cfg;
+    const int N = (int)c.N;
+    SPArgs a;
+    a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
+    a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
+    a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = N; a.k = 0;
+    int sp = h->timer.begin(ST_PARTICLES, h->stream);
+    sp_pass0<<<h->nblocks, PG_THREADS, (size_t)N * 8, h->stream>>>(a);
+    h->timer.end(sp, h->stream);
+    h->launches++;
+    PG_TRY(allreduce_grid(h, 0, 1));
+    PG_TRY(launch_solve1d(h, 0, true)); // E[1,:] = solve(rho(X,X))
+    sp = h->timer.begin(ST_PARTICLES, h->stream);
+    sp_pass1<<<h->nblocks, PG_THREADS, h->smem_sp1, h->stream>>>(a);
+    h->timer.end(sp, h->stream);
+    h->launches++;
+    SolveSPArgs s;
+    s.rho_fx = h->rho_fx; s.rho_last = h->rho_last; s.E = h->E; s.tw = h->tw; s.ctrl = h->ctrl;
+    s.w = c.w; s.fx_inv = h->fx_inv; s.rtol = c.rtol; s.atol = c.atol; s.N = N; s.lg = ilog2(c.N); s.max_sweeps = c.max_sweeps;
+    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
+    for (int k = 1; k <= c.max_sweeps; ++k) {
+        PG_TRY(allreduce_grid(h, 1, 2));
+        s.k = k;
+        sp = h->timer.begin(ST_SOLVE, h->stream);
+        solve_simpson23_kernel<<<2, threads, h->smem_pass, h->stream>>>(s);
+        h->timer.end(sp, h->stream);
+        a.k = k;
+        sp = h->timer.begin(ST_PARTICLES, h->stream);
+        sp_passk<<<h->nblocks, PG_THREADS, h->smem_spk, h->stream>>>(a);
+        h->timer.end(sp, h->stream);
+        h->launches += 2;
+    }
+    PG_TRY(launch_step_end(h, true));
+    return 0;
+}
+
 // One fixed-point step = 2*max_sweeps + 2 launches, most of them predicated no-ops.  For small problems the
 // step is launch-bound, so the whole sequence is captured once per ping-pong parity into a CUDA graph and
 // replayed (single GPU, stage timers off; NCCL calls and timing events stay out of graphs).
 static int step_fixedpoint(picgolf_handle h)
 {
     if (h->sorted && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_1d(h));
+    int (*enqueue)(picgolf_handle) = h->simpson ? enqueue_simpson_step : enqueue_fixedpoint_step;
     const bool use_graph = !h->comm && !h->timer.enabled && h->count <= (1 << 22) && !h->graph_failed;
     if (!use_graph) {
-        PG_TRY(enqueue_fixedpoint_step(h));
+        PG_TRY(enqueue(h));
     } else {
         cudaGraphExec_t &exec = h->step_graph[h->par];
         if (!exec) {
@@ -732,7 +790,7 @@ static int step_fixedpoint(picgolf_handle h)
             cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
             int rc = 0;
             if (e == cudaSuccess) {
-                rc = enqueue_fixedpoint_step(h);
+                rc = enqueue(h);
                 e = cudaStreamEndCapture(h->stream, &g);
             }
             if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&exec, g, 0);
@@ -743,7 +801,7 @@ static int step_fixedpoint(picgolf_handle h)
                 cudaGetLastError();
                 exec = nullptr;
                 h->graph_failed = true;
-                PG_TRY(enqueue_fixedpoint_step(h));
+                PG_TRY(enqueue(h));
                 h->par ^= 1; h->since_sort++;
                 return 0;
             }
@@ -888,7 +946,7 @@ PG_API int picgolf_get_fields(picgolf_handle h, double *rho, double *E)
     PG_TRY(use_device(h));
     const size_t b = (size_t)h->ncell * sizeof(double);
     if (rho) PG_CUDA(cudaMemcpyAsync(rho, h->rho_last, b, cudaMemcpyDeviceToHost, h->stream));
-    if (E) PG_CUDA(cudaMemcpyAsync(E, h->E, b, cudaMemcpyDeviceToHost, h->stream));
+    if (E) PG_CUDA(cudaMemcpyAsync(E, h->E + (size_t)(h->grid_rows - 1) * h->ncell, b, cudaMemcpyDeviceToHost, h->stream)); // E[end,:]
     PG_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -898,7 +956,7 @@ PG_API int picgolf_set_field(picgolf_handle h, const double *E)
     if (!h || !E) return fail(PICGOLF_ERR_ARG, "NULL argument");
     if (h->is2d) return fail(PICGOLF_ERR_ARG, "picgolf_set_field is 1D only");
     PG_TRY(use_device(h));
-    PG_CUDA(cudaMemcpyAsync(h->E, E, (size_t)h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->E + (size_t)(h->grid_rows - 1) * h->ncell, E, (size_t)h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1208,7 +1266,7 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     Solve1DArgs a;
     a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
     a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.fx_inv = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N);
-    a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1;
+    a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1; a.store_normE1 = 0;
     size_t smem = (size_t)(2 * N + 32) * 8;
     int rc = set_smem(solve1d_kernel, smem);
     if (rc == 0) {

@@ -50,6 +50,8 @@ def test_config_struct_layout(pg):
     assert g.dt == 1 / 1280 and g.w == 1600 / 8192 * 128
     e = pg.default_config(pg.CIC_BORIS_2D3V)  # src/Electrostatic2D3V.jl:23-25
     assert (e.N, e.NY, e.P, e.diag_every) == (128, 128, 128 * 128 * 32, 2)
+    sp = pg.default_config(pg.GAUSS_SIMPSON13)  # src/GaussianFixedPointQuietSimpson13.jl:1-6
+    assert (sp.N, sp.P, sp.T, sp.half_width, sp.scheme) == (64, 2048, 8192, 7, 5) and sp.rtol == 4 * np.finfo(float).eps
 
 
 def test_argument_errors_are_codes_not_crashes(pg):

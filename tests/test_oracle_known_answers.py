@@ -237,3 +237,25 @@ def test_2d3v_golden_and_thread_chunks(oracle):
     rho4 = oracle.step_2d3v(*st4, *args, Ex4, Ey4, nthreads=4)
     assert relnorm(rho4, rho) < 1e-14 and relnorm(Ex4, Ex) < 1e-12
     assert np.array_equal(st4[0], st[0])  # particles do not depend on the reduction order within a step
+
+
+def test_simpson13_known_answers(oracle):
+    """src/GaussianFixedPointQuietSimpson13.jl.  Same analytic growth-rate acceptance
+    (:26-27); the Simpson-1/3 quadrature conserves energy to ~1e-14 in the linear phase."""
+    g = golden("simpson13")
+    N, P, T, dt, W = int(g["N"]), int(g["P"]), int(g["T"]), float(g["dt"]), float(g["W"])
+    D, sw = g["D"], g["sweeps"]
+    t = np.arange(1, T + 1) * dt
+    sel = (t > 1) & (t < 5)
+    slope = np.polyfit(t[sel], np.log10(D[sel, 0]), 1)[0]
+    assert abs(slope / oracle.growth_slope(W) - 1) < 0.01
+    assert np.abs(D[:, 3]).max() < 1e-14 and np.abs(1 - D[:, 2]).max() < 1e-12
+    assert sw.min() >= 2 and sw.max() <= 10
+    x0, v0 = oracle.quiet_start(P)
+    s = oracle.Simpson13(x0, v0, N, dt, W)
+    Dh, swh = s.run(64)
+    assert np.array_equal(Dh, D[:64]) and np.array_equal(swh, sw[:64])
+    n = oracle.Simpson13(g["xr"], g["vr"], 128, 1 / (6 * 128), 400.0, hw=6, rtol=1e-8)
+    for k in range(2):
+        d, _, it = n.step()
+        assert it == g["swn"][k] and np.array_equal(d, g["Dn"][k])

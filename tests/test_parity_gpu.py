@@ -617,3 +617,53 @@ def test_deterministic_flag_bit_reproducible(pg):
     assert np.array_equal(res[0][0][0], res[1][0][0]) and np.array_equal(res[0][0][1], res[1][0][1])  # order free
     assert np.array_equal(res[0][1][0], res[2][1][0]) and np.array_equal(res[0][1][1], res[2][1][1])  # run to run
     assert np.array_equal(res[1][1][0], res[0][1][0][perm])
+
+
+# =============================================================================================
+# Simpson-1/3 fixed point (src/GaussianFixedPointQuietSimpson13.jl)
+# =============================================================================================
+def test_simpson13_steps(pg, oracle):
+    g = golden("simpson13")
+    # noisy start, N=128, +-6, l=1e-8: sweeps equal, state within 1e-11 after 8 steps
+    sim = pg.gaussian_fixed_point_quiet_simpson13(N=128, P=4096, T=16, W=400.0, l=1e-8, half_width=6)
+    sim.set_particles(g["xr"], g["vr"])
+    sim.step(8)
+    D, sw = sim.diagnostics()
+    x, v = sim.particles()
+    rho, E = sim.fields()  # rho(x,x) and E[end,:]
+    assert np.array_equal(sw, g["swn"])
+    assert relnorm(D[:, :3], g["Dn"][:, :3]) < 1e-10 and np.abs(D[:, 3] - g["Dn"][:, 3]).max() < 1e-13
+    assert relnorm(x, g["xn"]) < 1e-10 and relnorm(v, g["vn"]) < 1e-10
+    assert relnorm(rho, g["rn"]) < 1e-10 and relnorm(E, g["En"][2 * 128:]) < 1e-10
+    # one step against the live oracle at 1e-12
+    one = pg.gaussian_fixed_point_quiet_simpson13(N=128, P=4096, T=4, W=400.0, l=1e-8, half_width=6)
+    one.set_particles(g["xr"], g["vr"])
+    one.step(1)
+    o1 = oracle.Simpson13(g["xr"], g["vr"], 128, one.cfg.dt, 400.0, hw=6, rtol=1e-8)
+    _, _, s = o1.step()
+    x, v = one.particles()
+    rho, E = one.fields()
+    assert one.diagnostics()[1][0] == s
+    assert relnorm(x, o1.x) < TOL and relnorm(v, o1.v) < TOL and relnorm(rho, o1.r) < TOL and relnorm(E, o1.E[256:]) < 1e-11
+
+
+def test_simpson13_quiet_growth(pg, oracle):
+    """The script's own configuration (N=64, P=2048, +-7, l=4eps, quiet start) over its first 2048 steps:
+    growth rate on the analytic line, energy conserved to round-off, state after 16 steps equal to the oracle's."""
+    g = golden("simpson13")
+    T, dt, W = int(g["T"]), float(g["dt"]), float(g["W"])
+    sim = pg.gaussian_fixed_point_quiet_simpson13(T=T)
+    assert (sim.cfg.N, sim.cfg.P, sim.cfg.half_width) == (64, 2048, 7) and sim.cfg.rtol == 4 * np.finfo(float).eps
+    sim.init_quiet()
+    sim.step(16)
+    x, v = sim.particles()
+    assert relnorm(x, g["x16"]) < TOL and relnorm(v, g["v16"]) < TOL
+    sim.step(T - 16)
+    D, sw = sim.diagnostics()
+    t = np.arange(1, T + 1) * dt
+    sel = (t > 1) & (t < 5)
+    slope = np.polyfit(t[sel], np.log10(D[sel, 0]), 1)[0]
+    assert abs(slope / oracle.growth_slope(W) - 1) < 0.01
+    assert abs(slope - np.polyfit(t[sel], np.log10(g["D"][sel, 0]), 1)[0]) < 0.02
+    assert np.abs(D[:, 3]).max() < 1e-13 and np.abs(1 - D[:, 2]).max() < 1e-12
+    assert sw.min() >= 2 and sw.max() <= 10

@@ -99,6 +99,30 @@ def c3_quiet(T=2 ** 13):
          slope_pred=o.growth_slope(W))
 
 
+def simpson13(T=2048):
+    """src/GaussianFixedPointQuietSimpson13.jl (N=64, P=2048, +-7, l=4eps, quiet start), first
+    2048 of its 2^13 steps, plus a noisy-start case (N=128, P=4096, +-6, l=1e-8) for step-level parity."""
+    N, P = 64, 2048
+    dt, W = 1 / (6 * N), 32 * math.pi ** 2 / 3
+    x0, v0 = o.quiet_start(P)
+    s = o.Simpson13(x0, v0, N, dt, W)
+    D, sw = np.zeros((T, 4)), np.zeros(T, dtype=np.int32)
+    for t in range(16):
+        D[t], _, sw[t] = s.step()
+    x16, v16, E16 = s.x.copy(), s.v.copy(), s.E.copy()
+    Dr, swr = s.run(T - 16)
+    D[16:], sw[16:] = Dr, swr
+    rng = np.random.default_rng(13)
+    xr, vr = rng.random(4096), rng.choice([-1.0, 1.0], 4096)
+    n = o.Simpson13(xr, vr, 128, 1 / (6 * 128), 400.0, hw=6, rtol=1e-8)
+    Dn, swn = [], []
+    for t in range(8):
+        d, _, k = n.step()
+        Dn.append(d); swn.append(k)
+    save("simpson13", N=N, P=P, dt=dt, W=W, T=T, D=D, sweeps=sw, x16=x16, v16=v16, E16=E16,
+         xr=xr, vr=vr, xn=n.x, vn=n.v, En=n.E, rn=n.r, Dn=np.array(Dn), swn=np.array(swn, dtype=np.int32))
+
+
 def c5_2d3v(steps=4):
     """Config 5 shape at test size: src/Electrostatic2D3V.jl with NX=NY=32, P=NX*NY*8."""
     NX = NY = 32
@@ -141,8 +165,13 @@ def stencils():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--only", default=None, help="generate a single fixture, e.g. simpson13")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
+    if args.only:
+        globals()[args.only]()
+        sys.exit(0)
     c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils()
     if not args.skip_c3:
         c3_quiet()
+        simpson13()
