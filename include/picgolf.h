@@ -46,7 +46,8 @@ typedef enum picgolf_scheme {
     PICGOLF_GAUSS_LEAPFROG = 2,   /* src/Gaussian.jl:8-12 */
     PICGOLF_GAUSS_FIXEDPOINT = 3, /* src/GaussianFixedPoint.jl:7-12, src/GaussianFixedPointQuiet.jl:8-15 */
     PICGOLF_CIC_BORIS_2D3V = 4,   /* src/Electrostatic2D3V.jl:120-176 */
-    PICGOLF_GAUSS_SIMPSON13 = 5   /* src/GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 quadrature of E, 3 solves/sweep) */
+    PICGOLF_GAUSS_SIMPSON13 = 5,  /* src/GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 quadrature of E, 3 solves/sweep) */
+    PICGOLF_AREA_SIMPSON13 = 6    /* src/AreaFixedPointQuietSimpson13.jl:7-17 (same schedule, 2-cell "area" shape d(y) of line 5) */
 } picgolf_scheme;
 
 /* Deposit accumulation mode. */

@@ -60,8 +60,9 @@ def lib() -> C.CDLL:
         L.oracle_fixedpoint_step.argtypes = [_dp] * 7 + [_i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _vp, _vp]
         L.oracle_fixedpoint_run.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _i64, _vp, _vp]
         L.oracle_simpson_step.restype = C.c_int
-        L.oracle_simpson_step.argtypes = [_dp] * 7 + [_i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _vp]
-        L.oracle_simpson_run.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _i64, _vp, _vp]
+        L.oracle_simpson_step.argtypes = [_dp] * 7 + [_i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _vp, C.c_int]
+        L.oracle_area_stencil.argtypes = [_d, _i64, _ip, _dp]
+        L.oracle_simpson_run.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _i64, _vp, _vp, C.c_int]
         L.oracle_gauss_leapfrog_step.argtypes = [_dp, _dp, _i64, _i64, C.c_int, _d, _d, _dp, _dp, _vp]
         L.oracle_quiet_start.argtypes = [_i64, _i64, _i64, _dp, _dp]
         L.oracle_growth_slope.restype = _d
@@ -196,22 +197,30 @@ class FixedPoint:
 class Simpson13(FixedPoint):
     """GaussianFixedPointQuietSimpson13.jl: E is 3 x N (rows E1 | E2 | E3 stored consecutively)."""
 
-    def __init__(self, x, v, N, dt, W, w=None, hw=7, rtol=4 * np.finfo(float).eps, atol=0.0, max_sweeps=10):
+    def __init__(self, x, v, N, dt, W, w=None, hw=7, rtol=4 * np.finfo(float).eps, atol=0.0, max_sweeps=10, shape=0):
+        """shape 0: Gaussian (GaussianFixedPointQuietSimpson13.jl); shape 1: area d(y) (AreaFixedPointQuietSimpson13.jl, l=1e-14)."""
         super().__init__(x, v, N, dt, W, w=w, hw=hw, rtol=rtol, atol=atol, max_sweeps=max_sweeps)
         self.E, self.F = np.zeros(3 * N), np.zeros(3 * N)
+        self.shape = shape
 
     def step(self):
         D4 = np.empty(4)
         s = lib().oracle_simpson_step(self.x, self.v, self.E, self.X, self.V, self.F, self.r, self.P, self.N, self.hw,
-                                      self.dt, self.W, self.w, self.rtol, self.atol, self.max_sweeps, _ptr(D4))
+                                      self.dt, self.W, self.w, self.rtol, self.atol, self.max_sweeps, _ptr(D4), self.shape)
         return D4, None, s
 
     def run(self, T):
         D = np.zeros((T, 4), order="F")
         sw = np.zeros(T, dtype=np.int32)
         lib().oracle_simpson_run(self.x, self.v, self.E, self.P, self.N, self.hw, self.dt, self.W, self.w, self.rtol,
-                                 self.atol, self.max_sweeps, T, _ptr(D), _ptr(sw))
+                                 self.atol, self.max_sweeps, T, _ptr(D), _ptr(sw), self.shape)
         return D, sw
+
+
+def area_stencil(y, N):
+    idx, wt = np.empty(2, dtype=np.int32), np.empty(2)
+    lib().oracle_area_stencil(float(y), N, idx, wt)
+    return idx, wt
 
 
 def gauss_leapfrog_step(x, v, N, hw, dt, scale):

@@ -336,35 +336,68 @@ ORACLE_API void oracle_fixedpoint_run(double *x, double *v, double *E, int64_t P
     free(X);
 }
 
+/* d(y)=(i=Int(mod1(ceil(y*N),N));o=ceil(y*N)-y*N;((i,1-o),(mod1(i-1,N),o)))   AreaFixedPointQuietSimpson13.jl:5 */
+ORACLE_API void oracle_area_stencil(double y, int64_t N, int32_t *idx1, double *wt)
+{
+    double ce = ceil(y * (double)N);
+    double m = fmod(ce, (double)N);
+    if (m < 0.0) m += (double)N;
+    if (m == 0.0) m = (double)N;
+    int64_t i = (int64_t)m;
+    double o = ce - y * (double)N;
+    idx1[0] = (int32_t)i; wt[0] = 1 - o;
+    idx1[1] = (int32_t)jl_imod1(i - 1, N); wt[1] = o;
+}
+
+/* shape 0: Gaussian d(c) of half width hw; shape 1: area d(y).  deposit r[k[1]] += k[2]*w, gather sum(E[k[1]]*k[2]). */
+static void shape_deposit(int shape, const double *x, const double *y, int64_t P, int64_t N, int hw, double w, double *r)
+{
+    if (shape == 0) { oracle_gauss_deposit(x, y, P, N, hw, w, r); return; }
+    for (int64_t i = 0; i < N; ++i) r[i] = 0.0;
+    for (int64_t j = 0; j < P; ++j) {
+        int32_t idx[2]; double wt[2];
+        oracle_area_stencil((x[j] + y[j]) / 2, N, idx, wt);
+        r[idx[0] - 1] += wt[0] * w;
+        r[idx[1] - 1] += wt[1] * w;
+    }
+}
+static double shape_gather(int shape, const double *E, double c, int64_t N, int hw)
+{
+    if (shape == 0) return oracle_gauss_gather(E, c, N, hw);
+    int32_t idx[2]; double wt[2];
+    oracle_area_stencil(c, N, idx, wt);
+    return E[idx[0] - 1] * wt[0] + E[idx[1] - 1] * wt[1];
+}
+
 /* One step of GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 time quadrature of E: three field
  * solves per sweep).  E is 3 x N stored row by row here (E1 | E2 | E3), F likewise; the convergence test is the
  * Frobenius-norm isapprox over the whole 3 x N matrix.  Returns sweeps; D4 as in the plain fixed point but with
- * sum(E[end,:].^2) (line 18). */
+ * sum(E[end,:].^2) (line 18).  shape 1 runs AreaFixedPointQuietSimpson13.jl:7-17 (same schedule, d(y) of its line 5). */
 ORACLE_API int oracle_simpson_step(double *x, double *v, double *E3N, double *X, double *V, double *F3N, double *r,
                                    int64_t P, int64_t N, int hw, double dt, double W, double w, double rtol, double atol,
-                                   int max_sweeps, double *D4)
+                                   int max_sweeps, double *D4, int shape)
 {
     int sweeps = 0;
     double *E1 = E3N, *E2 = E3N + N, *E3 = E3N + 2 * N;
     memcpy(X, x, sizeof(double) * (size_t)P);
     memcpy(V, v, sizeof(double) * (size_t)P);
     for (int64_t i = 0; i < 3 * N; ++i) F3N[i] = NAN;                         /* F.*=NaN */
-    oracle_gauss_deposit(X, X, P, N, hw, w, r);                               /* E[1,:] = solve(rho(X,X))  :9 */
+    shape_deposit(shape, X, X, P, N, hw, w, r);                               /* E[1,:] = solve(rho(X,X))  :9 */
     oracle_solve1d(r, N, E1);
     for (int it = 0; it < max_sweeps; ++it) {                                 /* :10 */
         if (oracle_isapprox(F3N, E3N, 3 * N, rtol, atol)) break;
         memcpy(F3N, E3N, sizeof(double) * (size_t)(3 * N));
         for (int64_t j = 0; j < P; ++j) x[j] = X[j] + (v[j] + V[j]) / 2 * dt; /* :11 */
         for (int64_t j = 0; j < P; ++j)                                       /* :12  ...*dt/6 */
-            v[j] = V[j] + oracle_gauss_gather(E1, (X[j] + X[j]) / 2, N, hw) * dt / 6;
-        oracle_gauss_deposit(X, x, P, N, hw, w, r);                           /* :13 */
+            v[j] = V[j] + shape_gather(shape, E1, (X[j] + X[j]) / 2, N, hw) * dt / 6;
+        shape_deposit(shape, X, x, P, N, hw, w, r);                           /* :13 */
         oracle_solve1d(r, N, E2);
         for (int64_t j = 0; j < P; ++j)                                       /* :14  ...*4dt/6 */
-            v[j] = v[j] + oracle_gauss_gather(E2, (X[j] + x[j]) / 2, N, hw) * (4 * dt) / 6;
-        oracle_gauss_deposit(x, x, P, N, hw, w, r);                           /* :15 */
+            v[j] = v[j] + shape_gather(shape, E2, (X[j] + x[j]) / 2, N, hw) * (4 * dt) / 6;
+        shape_deposit(shape, x, x, P, N, hw, w, r);                           /* :15 */
         oracle_solve1d(r, N, E3);
         for (int64_t j = 0; j < P; ++j)                                       /* :16 */
-            v[j] = v[j] + oracle_gauss_gather(E3, (x[j] + x[j]) / 2, N, hw) * dt / 6;
+            v[j] = v[j] + shape_gather(shape, E3, (x[j] + x[j]) / 2, N, hw) * dt / 6;
         ++sweeps;
     }
     for (int64_t j = 0; j < P; ++j) x[j] = oracle_jl_mod1(x[j]);              /* :17 */
@@ -379,13 +412,14 @@ ORACLE_API int oracle_simpson_step(double *x, double *v, double *E3N, double *X,
 }
 
 ORACLE_API void oracle_simpson_run(double *x, double *v, double *E3N, int64_t P, int64_t N, int hw, double dt, double W,
-                                   double w, double rtol, double atol, int max_sweeps, int64_t T, double *D, int32_t *sweeps)
+                                   double w, double rtol, double atol, int max_sweeps, int64_t T, double *D, int32_t *sweeps,
+                                   int shape)
 {
     double *X = (double *)malloc(sizeof(double) * (size_t)(2 * P + 4 * N));
     double *V = X + P, *F = V + P, *r = F + 3 * N;
     for (int64_t t = 0; t < T; ++t) {
         double d4[4];
-        int s = oracle_simpson_step(x, v, E3N, X, V, F, r, P, N, hw, dt, W, w, rtol, atol, max_sweeps, d4);
+        int s = oracle_simpson_step(x, v, E3N, X, V, F, r, P, N, hw, dt, W, w, rtol, atol, max_sweeps, d4, shape);
         if (D) for (int c = 0; c < 4; ++c) D[c * T + t] = d4[c];
         if (sweeps) sweeps[t] = s;
     }

@@ -28,7 +28,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
 
-NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13 = 1, 2, 3, 4, 5
+NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13 = 1, 2, 3, 4, 5, 6
 DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED = 0, 1, 2
 
 NVCC_FLAGS = [
@@ -379,6 +379,20 @@ def gaussian_fixed_point_quiet_simpson13(N=64, P=None, dt=None, T=2 ** 13, W=32 
     cfg.W = W
     cfg.w = W / cfg.P * N
     cfg.rtol, cfg.atol, cfg.half_width, cfg.max_sweeps = l, 0.0, half_width, max_sweeps
+    return _finish(cfg, rank, nranks, device, T, **over)
+
+
+def area_fixed_point_quiet_simpson13(N=64, P=None, dt=None, T=2 ** 13, W=32 * math.pi ** 2 / 3, l=1e-14, max_sweeps=10,
+                                     rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/AreaFixedPointQuietSimpson13.jl:1-5: the Simpson-1/3 schedule with the 2-cell area shape
+    d(y)=(i=Int(mod1(ceil(y*N),N));o=ceil(y*N)-y*N;((i,1-o),(mod1(i-1,N),o))), l=1e-14."""
+    cfg = default_config(AREA_SIMPSON13)
+    cfg.N = N
+    cfg.P = 32 * N if P is None else P
+    cfg.dt = 1 / (6 * N) if dt is None else dt
+    cfg.W = W
+    cfg.w = W / cfg.P * N
+    cfg.rtol, cfg.atol, cfg.max_sweeps = l, 0.0, max_sweeps
     return _finish(cfg, rank, nranks, device, T, **over)
 
 

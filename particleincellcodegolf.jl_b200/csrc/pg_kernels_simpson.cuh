@@ -20,6 +20,40 @@
 
 namespace pg {
 
+// Particle shape of the Simpson-1/3 scripts: SHAPE 0 = erf-integrated Gaussian (13 cells,
+// GaussianFixedPointQuietSimpson13.jl:5-6), SHAPE 1 = "area"/CIC (2 cells, AreaFixedPointQuietSimpson13.jl:5:
+//     d(y)=(i=Int(mod1(ceil(y*N),N)); o=ceil(y*N)-y*N; ((i,1-o),(mod1(i-1,N),o)))  ).
+// Entry k of a stencil is the Julia (1-based, unwrapped) cell ibase+k; cell0 = (ibase+k-1) & (N-1).
+template <int SHAPE> struct SpShape;
+template <> struct SpShape<0> {
+    static constexpr int NW = GAUSS_NW;
+    __device__ static __forceinline__ void weights(double c, double dN, int &ibase, double (&W)[NW]) { gauss_weights(c, dN, ibase, W); }
+};
+template <> struct SpShape<1> {
+    static constexpr int NW = 2;
+    __device__ static __forceinline__ void weights(double y, double dN, int &ibase, double (&W)[NW])
+    {
+        double yN = y * dN, ce = ceil(yN);
+        double o = ce - yN;
+        ibase = (int)ce - 1; // entries: (i-1, o), (i, 1-o)
+        W[0] = o; W[1] = 1 - o;
+    }
+};
+template <int NW>
+__device__ __forceinline__ double sp_gather(const double *Es, int ibase, const double (&W)[NW], int Nmask)
+{
+    double g = 0.0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) g = fma(Es[(ibase + k - 1) & Nmask], W[k], g);
+    return g;
+}
+template <int NW>
+__device__ __forceinline__ void sp_deposit(fx_t *rs, int ibase, const double (&W)[NW], double fx_scale, int Nmask)
+{
+#pragma unroll
+    for (int k = 0; k < NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale));
+}
+
 struct SPArgs {
     const double *X, *V;
     double *v;
@@ -33,8 +67,10 @@ struct SPArgs {
     int N, k;
 };
 
+template <int SHAPE>
 __global__ void __launch_bounds__(PG_THREADS) sp_pass0(SPArgs a)
 {
+    using S = SpShape<SHAPE>;
     extern __shared__ double smem[];
     fx_t *r1 = reinterpret_cast<fx_t *>(smem);
     const int N = a.N, Nmask = N - 1;
@@ -43,17 +79,19 @@ __global__ void __launch_bounds__(PG_THREADS) sp_pass0(SPArgs a)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
         const double Xj = ld_stream(a.X + j);
-        int ibase; double W[GAUSS_NW];
-        gauss_weights((Xj + Xj) / 2, (double)N, ibase, W); // rho(X,X)
-        gauss_deposit_atomic(r1, ibase, W, a.fx_scale, Nmask);
+        int ibase; double W[S::NW];
+        S::weights((Xj + Xj) / 2, (double)N, ibase, W); // rho(X,X)
+        sp_deposit(r1, ibase, W, a.fx_scale, Nmask);
     }
     __syncthreads();
     flush_grid(r1, a.rho, N);
 }
 
 // Dynamic shared memory: E1[N] doubles, r2[N], r3[N] fixed point.
+template <int SHAPE>
 __global__ void __launch_bounds__(PG_THREADS) sp_pass1(SPArgs a)
 {
+    using S = SpShape<SHAPE>;
     extern __shared__ double smem[];
     const int N = a.N, Nmask = N - 1;
     double *E1 = smem;
@@ -64,14 +102,14 @@ __global__ void __launch_bounds__(PG_THREADS) sp_pass1(SPArgs a)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
         const double Xj = ld_stream(a.X + j), Vj = ld_stream(a.V + j);
-        int ibase; double W[GAUSS_NW];
-        gauss_weights((Xj + Xj) / 2, dN, ibase, W);
-        st_stream(a.xout + j, gauss_gather(E1, ibase, W, Nmask));    // g1, reused by every sweep (:12)
+        int ibase; double W[S::NW];
+        S::weights((Xj + Xj) / 2, dN, ibase, W);
+        st_stream(a.xout + j, sp_gather(E1, ibase, W, Nmask));    // g1, reused by every sweep (:12)
         const double xj = Xj + (Vj + Vj) / 2 * dt;                   // x_1 (v = V)
-        gauss_weights((Xj + xj) / 2, dN, ibase, W);
-        gauss_deposit_atomic(r2, ibase, W, a.fx_scale, Nmask);       // rho(X,x)  :13
-        gauss_weights((xj + xj) / 2, dN, ibase, W);
-        gauss_deposit_atomic(r3, ibase, W, a.fx_scale, Nmask);       // rho(x,x)  :15
+        S::weights((Xj + xj) / 2, dN, ibase, W);
+        sp_deposit(r2, ibase, W, a.fx_scale, Nmask);       // rho(X,x)  :13
+        S::weights((xj + xj) / 2, dN, ibase, W);
+        sp_deposit(r3, ibase, W, a.fx_scale, Nmask);       // rho(x,x)  :15
     }
     __syncthreads();
     flush_grid(r2, a.rho + N, N);
@@ -79,8 +117,10 @@ __global__ void __launch_bounds__(PG_THREADS) sp_pass1(SPArgs a)
 }
 
 // Dynamic shared memory: E2[N], E3[N] doubles, r2[N], r3[N] fixed point, 32 doubles scratch.
+template <int SHAPE>
 __global__ void __launch_bounds__(PG_THREADS) sp_passk(SPArgs a)
 {
+    using S = SpShape<SHAPE>;
     extern __shared__ double smem[];
     const int fk = a.ctrl->final_k;
     if (fk >= 0 && a.k > fk) return;
@@ -98,11 +138,11 @@ __global__ void __launch_bounds__(PG_THREADS) sp_passk(SPArgs a)
         double vj = a.k == 1 ? Vj : ld_stream(a.v + j);
         const double g1 = ld_stream(a.xout + j);
         double xj = Xj + (vj + Vj) / 2 * dt;                          // x_k from v_{k-1}  :11
-        int ibase; double W[GAUSS_NW];
-        gauss_weights((Xj + xj) / 2, dN, ibase, W);
-        const double g2 = gauss_gather(E2, ibase, W, Nmask);
-        gauss_weights((xj + xj) / 2, dN, ibase, W);
-        const double g3 = gauss_gather(E3, ibase, W, Nmask);
+        int ibase; double W[S::NW];
+        S::weights((Xj + xj) / 2, dN, ibase, W);
+        const double g2 = sp_gather(E2, ibase, W, Nmask);
+        S::weights((xj + xj) / 2, dN, ibase, W);
+        const double g3 = sp_gather(E3, ibase, W, Nmask);
         vj = Vj + g1 * dt / 6;                                        // :12
         vj = vj + g2 * (4 * dt) / 6;                                  // :14
         vj = vj + g3 * dt / 6;                                        // :16
@@ -114,10 +154,10 @@ __global__ void __launch_bounds__(PG_THREADS) sp_passk(SPArgs a)
             continue;
         }
         xj = Xj + (vj + Vj) / 2 * dt;                                 // x_{k+1}
-        gauss_weights((Xj + xj) / 2, dN, ibase, W);
-        gauss_deposit_atomic(r2, ibase, W, a.fx_scale, Nmask);
-        gauss_weights((xj + xj) / 2, dN, ibase, W);
-        gauss_deposit_atomic(r3, ibase, W, a.fx_scale, Nmask);
+        S::weights((Xj + xj) / 2, dN, ibase, W);
+        sp_deposit(r2, ibase, W, a.fx_scale, Nmask);
+        S::weights((xj + xj) / 2, dN, ibase, W);
+        sp_deposit(r3, ibase, W, a.fx_scale, Nmask);
     }
     __syncthreads();
     if (final) {

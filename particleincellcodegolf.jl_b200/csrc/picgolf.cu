@@ -264,6 +264,7 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
         c->N = 128; c->P = 64 * c->N; c->dt = 1.0 / (10 * c->N); c->T = 1024; c->W = 1600;
         c->w = c->W / (double)c->P / (1.0 / (double)c->N);
         break;
+    case PICGOLF_AREA_SIMPSON13:  // AreaFixedPointQuietSimpson13.jl:1-4 (l=1e-14 is set after the switch)
     case PICGOLF_GAUSS_SIMPSON13: // GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point)
         quiet = 1;
         /* fall through */
@@ -288,6 +289,7 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
     default:
         return fail(PICGOLF_ERR_ARG, "unknown scheme %d", scheme);
     }
+    if (scheme == PICGOLF_AREA_SIMPSON13) { c->rtol = 1e-14; c->half_width = 1; }
     return 0;
 }
 
@@ -332,7 +334,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     PG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
     h->is2d = c.scheme == PICGOLF_CIC_BORIS_2D3V;
-    h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13;
+    h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13;
     h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT || h->simpson;
     h->ngp = c.scheme == PICGOLF_NGP_LEAPFROG;
     h->nranks = std::max(1, c.nranks);
@@ -373,11 +375,11 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         if (h->simpson) {
             h->smem_sp1 = (size_t)3 * N * 8;
             h->smem_spk = (size_t)(4 * N + 32) * 8;
-            PG_TRY(set_smem(sp_pass0, (size_t)N * 8));
-            PG_TRY(set_smem(sp_pass1, h->smem_sp1));
-            PG_TRY(set_smem(sp_passk, h->smem_spk));
+            PG_TRY(set_smem(sp_pass0<0>, (size_t)N * 8)); PG_TRY(set_smem(sp_pass0<1>, (size_t)N * 8));
+            PG_TRY(set_smem(sp_pass1<0>, h->smem_sp1)); PG_TRY(set_smem(sp_pass1<1>, h->smem_sp1));
+            PG_TRY(set_smem(sp_passk<0>, h->smem_spk)); PG_TRY(set_smem(sp_passk<1>, h->smem_spk));
             PG_TRY(set_smem(solve_simpson23_kernel, h->smem_pass));
-            PG_TRY(occupancy_blocks(sp_passk, PG_THREADS, h->smem_spk, h->sms, h->count, &h->nblocks));
+            PG_TRY(occupancy_blocks(sp_passk<0>, PG_THREADS, h->smem_spk, h->sms, h->count, &h->nblocks));
         } else if (h->fixedpoint) {
             PG_TRY(set_smem(fp_pass_atomic<true>, h->smem_pass));
             PG_TRY(set_smem(fp_pass_atomic<false>, h->smem_pass));
@@ -479,7 +481,7 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
     if (cfg->struct_size != (int32_t)sizeof(picgolf_config))
         return fail(PICGOLF_ERR_ARG, "struct_size %d != %zu (header/library mismatch)", cfg->struct_size, sizeof(picgolf_config));
     const picgolf_config &c = *cfg;
-    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_GAUSS_SIMPSON13) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_AREA_SIMPSON13) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
     if (c.P < 1) return fail(PICGOLF_ERR_ARG, "P must be >= 1");
     if (!(c.dt > 0) || !isfinite(c.dt)) return fail(PICGOLF_ERR_ARG, "dt must be positive and finite");
     if (!isfinite(c.w)) return fail(PICGOLF_ERR_ARG, "w must be finite");
@@ -490,10 +492,10 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
     } else {
         if (c.N < 16 || c.N > 8192) return fail(PICGOLF_ERR_ARG, "N must be in 16..8192");
         if (!is_pow2(c.N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N);
-        if (c.scheme != PICGOLF_NGP_LEAPFROG && c.half_width != 6 && c.half_width != 7)
+        if (c.scheme != PICGOLF_NGP_LEAPFROG && c.scheme != PICGOLF_AREA_SIMPSON13 && c.half_width != 6 && c.half_width != 7)
             return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
-        if (c.scheme == PICGOLF_GAUSS_SIMPSON13 && c.N > 4096) return fail(PICGOLF_ERR_ARG, "Simpson-1/3 scheme: N must be <= 4096");
-        if ((c.scheme == PICGOLF_GAUSS_FIXEDPOINT || c.scheme == PICGOLF_GAUSS_SIMPSON13) && (c.max_sweeps < 1 || c.max_sweeps > 64))
+        if ((c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13) && c.N > 4096) return fail(PICGOLF_ERR_ARG, "Simpson-1/3 scheme: N must be <= 4096");
+        if ((c.scheme == PICGOLF_GAUSS_FIXEDPOINT || c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13) && (c.max_sweeps < 1 || c.max_sweeps > 64))
             return fail(PICGOLF_ERR_ARG, "max_sweeps must be in 1..64");
     }
     picgolf_handle h = new picgolf_handle_s();
@@ -743,13 +745,16 @@ static int enqueue_simpson_step(picgolf_handle h)
     a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = N; a.k = 0;
     int sp = h->timer.begin(ST_PARTICLES, h->stream);
-    sp_pass0<<<h->nblocks, PG_THREADS, (size_t)N * 8, h->stream>>>(a);
+    const bool area = h->cfg.scheme == PICGOLF_AREA_SIMPSON13;
+    if (area) sp_pass0<1><<<h->nblocks, PG_THREADS, (size_t)N * 8, h->stream>>>(a);
+    else sp_pass0<0><<<h->nblocks, PG_THREADS, (size_t)N * 8, h->stream>>>(a);
     h->timer.end(sp, h->stream);
     h->launches++;
     PG_TRY(allreduce_grid(h, 0, 1));
     PG_TRY(launch_solve1d(h, 0, true)); // E[1,:] = solve(rho(X,X))
     sp = h->timer.begin(ST_PARTICLES, h->stream);
-    sp_pass1<<<h->nblocks, PG_THREADS, h->smem_sp1, h->stream>>>(a);
+    if (area) sp_pass1<1><<<h->nblocks, PG_THREADS, h->smem_sp1, h->stream>>>(a);
+    else sp_pass1<0><<<h->nblocks, PG_THREADS, h->smem_sp1, h->stream>>>(a);
     h->timer.end(sp, h->stream);
     h->launches++;
     SolveSPArgs s;
@@ -764,7 +769,8 @@ static int enqueue_simpson_step(picgolf_handle h)
         h->timer.end(sp, h->stream);
         a.k = k;
         sp = h->timer.begin(ST_PARTICLES, h->stream);
-        sp_passk<<<h->nblocks, PG_THREADS, h->smem_spk, h->stream>>>(a);
+        if (area) sp_passk<1><<<h->nblocks, PG_THREADS, h->smem_spk, h->stream>>>(a);
+        else sp_passk<0><<<h->nblocks, PG_THREADS, h->smem_spk, h->stream>>>(a);
         h->timer.end(sp, h->stream);
         h->launches += 2;
     }

@@ -259,3 +259,21 @@ def test_simpson13_known_answers(oracle):
     for k in range(2):
         d, _, it = n.step()
         assert it == g["swn"][k] and np.array_equal(d, g["Dn"][k])
+
+
+def test_area_simpson13_known_answers(oracle):
+    """src/AreaFixedPointQuietSimpson13.jl:5: d(y) weights sum to 1, cell i=ceil(y*N) gets 1-o, cell i-1 gets o."""
+    for y, N in ((0.3, 64), (0.999, 64), (1e-9, 64), (0.5001, 128)):
+        idx, wt = oracle.area_stencil(y, N)
+        ce = math.ceil(y * N)
+        assert idx[0] == ((ce - 1) % N) + 1 and idx[1] == ((ce - 2) % N) + 1
+        assert abs(wt.sum() - 1) < 1e-15 and abs(wt[1] - (ce - y * N)) < 1e-15
+    g = golden("area_simpson13")
+    T, dt, W = int(g["T"]), float(g["dt"]), float(g["W"])
+    t = np.arange(1, T + 1) * dt
+    sel = (t > 1) & (t < 2.6)
+    assert abs(np.polyfit(t[sel], np.log10(g["D"][sel, 0]), 1)[0] / oracle.growth_slope(W) - 1) < 0.01
+    x0, v0 = oracle.quiet_start(int(g["P"]))
+    s = oracle.Simpson13(x0, v0, int(g["N"]), dt, W, rtol=1e-14, shape=1)
+    Dh, swh = s.run(32)
+    assert np.array_equal(Dh, g["D"][:32]) and np.array_equal(swh, g["sweeps"][:32])

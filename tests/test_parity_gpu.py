@@ -667,3 +667,32 @@ def test_simpson13_quiet_growth(pg, oracle):
     assert abs(slope - np.polyfit(t[sel], np.log10(g["D"][sel, 0]), 1)[0]) < 0.02
     assert np.abs(D[:, 3]).max() < 1e-13 and np.abs(1 - D[:, 2]).max() < 1e-12
     assert sw.min() >= 2 and sw.max() <= 10
+
+
+def test_area_simpson13(pg, oracle):
+    """src/AreaFixedPointQuietSimpson13.jl: Simpson-1/3 schedule with the 2-cell area shape d(y) (line 5), l=1e-14."""
+    g = golden("area_simpson13")
+    sim = pg.area_fixed_point_quiet_simpson13(N=128, P=4096, T=16, W=400.0, l=1e-9)
+    sim.set_particles(g["xr"], g["vr"])
+    sim.step(8)
+    D, sw = sim.diagnostics()
+    x, v = sim.particles()
+    rho, E = sim.fields()
+    assert np.array_equal(sw, g["swn"])
+    assert relnorm(D[:, :3], g["Dn"][:, :3]) < 1e-10
+    assert relnorm(x, g["xn"]) < 1e-10 and relnorm(v, g["vn"]) < 1e-10 and relnorm(rho, g["rn"]) < 1e-10
+    assert relnorm(E, g["En"][256:]) < 1e-10
+    T, dt, W = int(g["T"]), float(g["dt"]), float(g["W"])
+    q = pg.area_fixed_point_quiet_simpson13(T=T)
+    assert q.cfg.rtol == 1e-14 and (q.cfg.N, q.cfg.P) == (64, 2048)
+    q.init_quiet()
+    q.step(16)
+    x, v = q.particles()
+    assert relnorm(x, g["x16"]) < TOL and relnorm(v, g["v16"]) < TOL
+    q.step(T - 16)
+    D, sw = q.diagnostics()
+    t = np.arange(1, T + 1) * dt
+    sel = (t > 1) & (t < 2.6)
+    slope = np.polyfit(t[sel], np.log10(D[sel, 0]), 1)[0]
+    assert abs(slope / oracle.growth_slope(W) - 1) < 0.01
+    assert np.abs(D[:, 3]).max() < 1e-13 and np.abs(1 - D[:, 2]).max() < 1e-12

@@ -123,6 +123,29 @@ def simpson13(T=2048):
          xr=xr, vr=vr, xn=n.x, vn=n.v, En=n.E, rn=n.r, Dn=np.array(Dn), swn=np.array(swn, dtype=np.int32))
 
 
+def area_simpson13(T=1024):
+    """src/AreaFixedPointQuietSimpson13.jl (N=64, P=2048, area shape, l=1e-14, quiet start)."""
+    N, P = 64, 2048
+    dt, W = 1 / (6 * N), 32 * math.pi ** 2 / 3
+    x0, v0 = o.quiet_start(P)
+    s = o.Simpson13(x0, v0, N, dt, W, rtol=1e-14, shape=1)
+    D, sw = np.zeros((T, 4)), np.zeros(T, dtype=np.int32)
+    for t in range(16):
+        D[t], _, sw[t] = s.step()
+    x16, v16 = s.x.copy(), s.v.copy()
+    Dr, swr = s.run(T - 16)
+    D[16:], sw[16:] = Dr, swr
+    rng = np.random.default_rng(17)
+    xr, vr = rng.random(4096), rng.choice([-1.0, 1.0], 4096)
+    n = o.Simpson13(xr, vr, 128, 1 / (6 * 128), 400.0, rtol=1e-9, shape=1)
+    Dn, swn = [], []
+    for t in range(8):
+        d, _, k = n.step()
+        Dn.append(d); swn.append(k)
+    save("area_simpson13", N=N, P=P, dt=dt, W=W, T=T, D=D, sweeps=sw, x16=x16, v16=v16,
+         xr=xr, vr=vr, xn=n.x, vn=n.v, En=n.E, rn=n.r, Dn=np.array(Dn), swn=np.array(swn, dtype=np.int32))
+
+
 def c5_2d3v(steps=4):
     """Config 5 shape at test size: src/Electrostatic2D3V.jl with NX=NY=32, P=NX*NY*8."""
     NX = NY = 32
@@ -175,3 +198,4 @@ if __name__ == "__main__":
     if not args.skip_c3:
         c3_quiet()
         simpson13()
+        area_simpson13()
