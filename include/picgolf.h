@@ -47,7 +47,8 @@ typedef enum picgolf_scheme {
     PICGOLF_GAUSS_FIXEDPOINT = 3, /* src/GaussianFixedPoint.jl:7-12, src/GaussianFixedPointQuiet.jl:8-15 */
     PICGOLF_CIC_BORIS_2D3V = 4,   /* src/Electrostatic2D3V.jl:120-176 */
     PICGOLF_GAUSS_SIMPSON13 = 5,  /* src/GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 quadrature of E, 3 solves/sweep) */
-    PICGOLF_AREA_SIMPSON13 = 6    /* src/AreaFixedPointQuietSimpson13.jl:7-17 (same schedule, 2-cell "area" shape d(y) of line 5) */
+    PICGOLF_AREA_SIMPSON13 = 6,   /* src/AreaFixedPointQuietSimpson13.jl:7-17 (same schedule, 2-cell "area" shape d(y) of line 5) */
+    PICGOLF_GAUSS_BORIS_1D2V = 7  /* src/NGP1D2V.jl:39-63 (1D2V magnetised, erf shape +-7, Boris about z; Bernstein modes) */
 } picgolf_scheme;
 
 /* Deposit accumulation mode. */
@@ -106,7 +107,8 @@ int picgolf_device_count(void);
  * scheme GAUSS_FIXEDPOINT, quiet=0 -> GaussianFixedPoint.jl:1-5 (N=128,P=32N,dt=1/6N,T=1024,W=400,hw 6,l=1e-8)
  * scheme GAUSS_FIXEDPOINT, quiet=1 -> GaussianFixedPointQuiet.jl:1-6 (N=64,P=32N,T=2^13,W=32pi^2/3,hw 7,l=4eps)
  * scheme CIC_BORIS_2D3V -> Electrostatic2D3V.jl:23-25 (NX=NY=128,P=NX*NY*2^5,T=2^13,n0=4pi^2,...)
- * scheme GAUSS_SIMPSON13 -> GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point) */
+ * scheme GAUSS_SIMPSON13 -> GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point)
+ * scheme GAUSS_BORIS_1D2V -> NGP1D2V.jl:22-23 (N=512,P=15N,T=TO=2^14/16 rows,n0=4pi^2,vth,dt,B0,w=n0/P, diag_every=16) */
 int picgolf_config_default(picgolf_config *cfg, int scheme, int quiet);
 
 /* ---- lifetime --------------------------------------------------------------------------- */
@@ -125,6 +127,9 @@ int picgolf_set_particles(picgolf_handle h, const double *x, const double *v, in
 /* 2D3V: x,y in (0,1], vx,vy,vz (Electrostatic2D3V.jl:45-55). */
 int picgolf_set_particles_2d3v(picgolf_handle h, const double *x, const double *y, const double *vx,
                                const double *vy, const double *vz, int64_t count);
+/* 1D2V (NGP1D2V.jl:30-32): x, vx, vy of the local shard. */
+int picgolf_set_particles_1d2v(picgolf_handle h, const double *x, const double *vx, const double *vy, int64_t count);
+int picgolf_get_particles_1d2v(picgolf_handle h, double *x, double *vx, double *vy, int64_t count);
 /* Bit-reversal quiet start on device: x=(bitreverse.(0:P-1).+2.0^63)/2.0^64, v=+-1 by halves
  * (GaussianFixedPointQuiet.jl:2-3), generated from the GLOBAL index so shards agree. */
 int picgolf_init_quiet(picgolf_handle h);
@@ -164,9 +169,13 @@ int picgolf_get_fields_2d(picgolf_handle h, double *rho, double *Ex, double *Ey)
  *       D1 = sum(E.^2)/N/2*(2/W), D2 = sum(v.^2)*W/P/2*(2/W), D3 = D1+D2, D4 = sum(v/P).
  *       (NGPFourierWithDiagnostics.jl:6-7 is the same up to its `E.^2N` parse, see DESIGN.md.)
  *   2D3V: 5 columns K[ti,1:5] (Electrostatic2D3V.jl:166-170).
+ *   1D2V: 5 columns D[ti,1:5] (NGP1D2V.jl:59-61,64; one row per window of diag_every = T/TO steps).
  * sweeps (may be NULL) receives the fixed-point sweep count of each recorded step.
  * rows_out receives the number of rows recorded. */
 int picgolf_get_diagnostics(picgolf_handle h, double *D, int64_t ld, int32_t *sweeps, int64_t *rows_out);
+/* 1D2V: time-averaged field history Es[N, rows] (NGP1D2V.jl:57,64: Es[:,ti] .+= E; Es ./= T/TO), column-major with
+ * leading dimension N; cols_out = windows started so far.  Window length = diag_every steps. */
+int picgolf_get_field_history(picgolf_handle h, double *Es, int64_t max_cols, int64_t *cols_out);
 /* Raw per-step sums (column-major, ld rows): 1D: sum(E.^2), sum(v.^2), sum(v), sweeps;
  * 2D: sum(Ex^2+Ey^2), sum(vx^2+vy^2), sum(vx), sum(vy).  Lets the driver form any K it wants. */
 int picgolf_get_raw_diagnostics(picgolf_handle h, double *raw, int64_t ld, int64_t *rows_out);

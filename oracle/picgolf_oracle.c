@@ -443,6 +443,41 @@ ORACLE_API void oracle_gauss_leapfrog_step(double *x, double *v, int64_t P, int6
     }
 }
 
+/* boris(vx,vy,E,B,dt) of the 1D2V magnetised codes: src/NGP1D2V.jl:5-10 (B along z). */
+ORACLE_API void oracle_boris_1d2v(double *vx, double *vy, double E, double B, double dt)
+{
+    double m1 = *vx + E * dt / 2, m2 = *vy, m3 = 0.0;            /* v- */
+    double t1 = 0.0, t2 = 0.0, t3 = B * dt / 2;
+    double c1 = m2 * t3 - m3 * t2, c2 = m3 * t1 - m1 * t3, c3 = m1 * t2 - m2 * t1;
+    double p1 = m1 + c1, p2 = m2 + c2, p3 = m3 + c3;
+    double q1 = p2 * t3 - p3 * t2, q2 = p3 * t1 - p1 * t3;
+    double den = 1 + (t1 * t1 + t2 * t2 + t3 * t3);
+    double r1 = m1 + 2 * q1 / den, r2 = m2 + 2 * q2 / den;       /* v+ = v- + 2*cross(...)/(1+dot(t,t)) */
+    (void)c3;
+    *vx = r1 + E * dt / 2; *vy = r2;
+}
+
+/* One step of src/NGP1D2V.jl:40-45,55: E = solve(rho(x)); gather at x, boris, x += vx*dt; x = mod(x,1).
+ * rho/E out; raw[0..3] = sum(abs2,E), sum(vx^2+vy^2), sum(vx), sum(vy) after the push (for D, :59-61). */
+ORACLE_API void oracle_1d2v_step(double *x, double *vx, double *vy, int64_t P, int64_t N, int hw, double dt, double B0,
+                                 double w, double *rho, double *E, double *raw)
+{
+    oracle_gauss_deposit(x, x, P, N, hw, w, rho);                 /* rho(x): d.((x.+x)./2) */
+    oracle_solve1d(rho, N, E);
+    for (int64_t j = 0; j < P; ++j) {
+        double Ej = oracle_gauss_gather(E, x[j], N, hw);          /* :42 */
+        oracle_boris_1d2v(&vx[j], &vy[j], Ej, B0, dt);            /* :43 */
+        x[j] += vx[j] * dt;                                       /* :44 */
+    }
+    for (int64_t j = 0; j < P; ++j) x[j] = oracle_jl_mod1(x[j]); /* :55 */
+    if (raw) {
+        double se = 0, s0 = 0, s1 = 0, s2 = 0;
+        for (int64_t i = 0; i < N; ++i) se += E[i] * E[i];
+        for (int64_t j = 0; j < P; ++j) { s0 += vy[j] * vy[j] + vx[j] * vx[j]; s1 += vx[j]; s2 += vy[j]; }
+        raw[0] = se; raw[1] = s0; raw[2] = s1; raw[3] = s2;
+    }
+}
+
 /* Quiet start: x=(bitreverse.(0:P-1).+2.0^63)/2.0^64; v = (j>P/2) ? 1 : -1   GaussianFixedPointQuiet.jl:2-3.
  * Generates global indices [first, first+count) of a P-particle population. */
 ORACLE_API void oracle_quiet_start(int64_t P, int64_t first, int64_t count, double *x, double *v)

@@ -28,7 +28,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
 
-NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13 = 1, 2, 3, 4, 5, 6
+NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13, GAUSS_BORIS_1D2V = 1, 2, 3, 4, 5, 6, 7
 DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED = 0, 1, 2
 
 NVCC_FLAGS = [
@@ -84,6 +84,9 @@ _SIGNATURES = {
     "picgolf_local_range": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "picgolf_set_particles": [_vp, _dp, _dp, _i64],
     "picgolf_set_particles_2d3v": [_vp, _dp, _dp, _dp, _dp, _dp, _i64],
+    "picgolf_set_particles_1d2v": [_vp, _dp, _dp, _dp, _i64],
+    "picgolf_get_particles_1d2v": [_vp, _vp, _vp, _vp, _i64],
+    "picgolf_get_field_history": [_vp, _vp, _i64, C.POINTER(_i64)],
     "picgolf_init_quiet": [_vp],
     "picgolf_init_synthetic": [_vp, C.c_uint64, _d],
     "picgolf_get_particles": [_vp, _vp, _vp, _i64],
@@ -182,6 +185,7 @@ class PIC:
         _check(self._lib.picgolf_local_range(self._h, C.byref(f), C.byref(c)))
         self.first, self.count = f.value, c.value
         self.is2d = cfg.scheme == CIC_BORIS_2D3V
+        self.is1d2v = cfg.scheme == GAUSS_BORIS_1D2V
         self.ncell = cfg.N * (cfg.NY if self.is2d else 1)
 
     # -- lifetime
@@ -207,6 +211,9 @@ class PIC:
         if self.is2d:
             arrs = [_f64(a) for a in (x, y, v, vy, vz)]  # x, y, vx, vy, vz
             _check(self._lib.picgolf_set_particles_2d3v(self._h, *arrs, arrs[0].size))
+        elif self.is1d2v:
+            arrs = [_f64(a) for a in (x, v, vy)]  # x, vx, vy
+            _check(self._lib.picgolf_set_particles_1d2v(self._h, *arrs, arrs[0].size))
         else:
             x, v = _f64(x), _f64(v)
             _check(self._lib.picgolf_set_particles(self._h, x, v, x.size))
@@ -223,6 +230,10 @@ class PIC:
         if self.is2d:
             out = [np.empty(n) for _ in range(5)]
             _check(self._lib.picgolf_get_particles_2d3v(self._h, *[_out_ptr(a) for a in out], n))
+            return tuple(out)
+        if self.is1d2v:
+            out = [np.empty(n) for _ in range(3)]
+            _check(self._lib.picgolf_get_particles_1d2v(self._h, *[_out_ptr(a) for a in out], n))
             return tuple(out)
         x, v = np.empty(n), np.empty(n)
         _check(self._lib.picgolf_get_particles(self._h, _out_ptr(x), _out_ptr(v), n))
@@ -260,11 +271,19 @@ class PIC:
         """(D, sweeps): D is rows x 4 (1D, GaussianFixedPoint.jl:10-11) or rows x 5 (2D K)."""
         rows = _i64()
         _check(self._lib.picgolf_get_diagnostics(self._h, None, 0, None, C.byref(rows)))
-        n, ncol = max(rows.value, 1), 5 if self.is2d else 4
+        n, ncol = max(rows.value, 1), 5 if (self.is2d or self.is1d2v) else 4
         D = np.zeros((n, ncol), order="F")
         sw = np.zeros(n, dtype=np.int32)
         _check(self._lib.picgolf_get_diagnostics(self._h, _out_ptr(D), n, _out_ptr(sw), C.byref(rows)))
         return D[: rows.value], sw[: rows.value]
+
+    def field_history(self):
+        """1D2V: time-averaged field history Es (N x windows), NGP1D2V.jl:57,64."""
+        cols = _i64()
+        _check(self._lib.picgolf_get_field_history(self._h, None, 0, C.byref(cols)))
+        Es = np.zeros((self.cfg.N, max(cols.value, 1)), order="F")
+        _check(self._lib.picgolf_get_field_history(self._h, _out_ptr(Es), Es.shape[1], C.byref(cols)))
+        return Es[:, : cols.value]
 
     def raw_diagnostics(self):
         rows = _i64()
@@ -394,6 +413,25 @@ def area_fixed_point_quiet_simpson13(N=64, P=None, dt=None, T=2 ** 13, W=32 * ma
     cfg.w = W / cfg.P * N
     cfg.rtol, cfg.atol, cfg.max_sweeps = l, 0.0, max_sweeps
     return _finish(cfg, rank, nranks, device, T, **over)
+
+
+def ngp_1d2v(N=512, P=None, T=2 ** 14, TO=None, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/NGP1D2V.jl:22-23  N=512;P=15N;T=2^14;TO=T/16;n0=4pi^2;vth=sqrt(n0)/N/4;dt=1/N/6vth;B0=sqrt(n0)/16;w=n0/P.
+    One diagnostics row / field-history column per window of T/TO steps.  set_particles(x, vx, vy=vy)."""
+    cfg = default_config(GAUSS_BORIS_1D2V)
+    TO = T // 16 if TO is None else TO
+    cfg.N = N
+    cfg.P = 15 * N if P is None else P
+    vth = math.sqrt(n0) / N / 4
+    cfg.W = n0
+    cfg.dt = 1 / N / (6 * vth)
+    cfg.B0 = math.sqrt(n0) / 16
+    cfg.w = n0 / cfg.P
+    cfg.diag_every = max(1, T // TO)
+    cfg.half_width = 7
+    pic = _finish(cfg, rank, nranks, device, TO, **over)
+    pic.vth = vth
+    return pic
 
 
 def electrostatic_2d3v(NX=128, NY=None, P=None, T=2 ** 13, NS=2, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1,

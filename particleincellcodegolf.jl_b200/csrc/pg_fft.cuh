@@ -85,6 +85,7 @@ struct Solve1DArgs {
     double w, fx_inv, rtol, atol;   // fx_inv = 2^-frac
     int N, lg, fixedpoint, k, max_sweeps;
     int store_normE1; // Simpson variant: this is the E1 solve of the step
+    double *hist;     // 1D2V: time-averaged field history column Es[:,ti] += E (NGP1D2V.jl:57), or NULL
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         double e = re[n] / dN;
         double f = a.E[n];
         a.E[n] = e;
+        if (a.hist) a.hist[n] += e;
         double d = f - e;
         d2 = fma(d, d, d2); f2 = fma(f, f, f2); e2 = fma(e, e, e2);
     }

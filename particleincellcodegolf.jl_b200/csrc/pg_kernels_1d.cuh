@@ -454,6 +454,66 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// 1D2V magnetised Boris pass, src/NGP1D2V.jl:41-45,55: gather E at x with the erf shape,
+// boris() about z (:5-10), x += vx*dt, x = mod(x,1); fused with the deposit rho(x) of the next step (:40).
+// 48 B per particle-step (x, vx, vy read + written).  Any particle order; fixed-point deposit grid.
+// ------------------------------------------------------------------------------------------
+struct B1D2VArgs {
+    double *x, *vx, *vy;
+    const double *E;
+    fx_t *rho;
+    double *partials; // [3*gridDim.x] per-block (sum vx^2+vy^2, sum vx, sum vy)
+    long long P;
+    double dt, t3, den, fx_scale; // t3 = B*dt/2, den = 1 + dot(t,t)
+    int N, do_push, do_deposit;
+};
+
+__global__ void __launch_bounds__(PG_THREADS) b1d2v_pass(B1D2VArgs a)
+{
+    extern __shared__ double smem[];
+    const int N = a.N, Nmask = N - 1;
+    double *Es = smem, *scratch = smem + 2 * N;
+    fx_t *rs = reinterpret_cast<fx_t *>(smem + N);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        if (a.do_push) Es[n] = a.E[n];
+        rs[n] = 0ULL;
+    }
+    __syncthreads();
+    const double dN = (double)N, dt = a.dt;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
+        double xj = ld_stream(a.x + j), vx = ld_stream(a.vx + j), vy = ld_stream(a.vy + j);
+        int ibase; double W[GAUSS_NW];
+        if (a.do_push) {
+            gauss_weights(xj, dN, ibase, W);
+            const double Ej = gauss_gather(Es, ibase, W, Nmask);      // sum(k->E[k[1]]*k[2], d(x[j]))  :42
+            const double h = Ej * dt / 2;
+            const double m1 = vx + h, m2 = vy;                         // v- = [vx + E*dt/2, vy, 0]
+            const double p1 = m1 + m2 * a.t3, p2 = m2 - m1 * a.t3;     // v- + cross(v-, t), t = [0,0,B*dt/2]
+            const double r1 = m1 + 2 * (p2 * a.t3) / a.den;            // v+ = v- + 2*cross(.., t)/(1+dot(t,t))
+            const double r2 = m2 - 2 * (p1 * a.t3) / a.den;
+            vx = r1 + h; vy = r2;
+            xj = jl_mod1(xj + vx * dt);                                // x[j] += vx[j]*dt ; x.=mod.(x,1)
+            s0 += vy * vy + vx * vx; s1 += vx; s2 += vy;
+        }
+        if (a.do_deposit) {
+            gauss_weights((xj + xj) / 2, dN, ibase, W);                // rho(x)
+            gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
+        }
+        st_stream(a.x + j, xj); st_stream(a.vx + j, vx); st_stream(a.vy + j, vy);
+    }
+    __syncthreads();
+    if (a.do_deposit) flush_grid(rs, a.rho, N);
+    if (a.do_push) {
+        s0 = block_sum(s0, scratch);
+        s1 = block_sum(s1, scratch);
+        s2 = block_sum(s2, scratch);
+        if (threadIdx.x == 0) { a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // End of step: reduce the per-block partial sums in a fixed order, append the raw diagnostics row
 // (column-major, ld = T): [sum E^2, sum v^2 (2D: vx^2+vy^2), sum v (vx), sweeps (2D: sum vy)].
 // ------------------------------------------------------------------------------------------

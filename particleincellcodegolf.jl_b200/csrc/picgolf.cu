@@ -153,7 +153,9 @@ struct picgolf_handle_s {
     int device = 0, sms = 0;
     cudaStream_t stream = nullptr;
     int64_t first = 0, count = 0;
-    bool is2d = false, fixedpoint = false, ngp = false, simpson = false;
+    bool is2d = false, fixedpoint = false, ngp = false, simpson = false, b1d2v = false, have_deposit = false;
+    double *vy1 = nullptr, *hist = nullptr; // 1D2V: vy array, field history [N x T]
+    size_t smem_b1 = 0;
     size_t smem_sp1 = 0, smem_spk = 0;
     // particles (1D: xb/vb ping-pong for the fixed point; leapfrog and 2D use index 0)
     double *xb[2] = {nullptr, nullptr}, *vb[2] = {nullptr, nullptr};
@@ -278,6 +280,12 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
         }
         c->w = c->W / (double)c->P * (double)c->N;
         break;
+    case PICGOLF_GAUSS_BORIS_1D2V: { // NGP1D2V.jl:22-23
+        c->N = 512; c->P = 15 * c->N; c->T = (1 << 14) / 16; c->diag_every = 16; c->half_width = 7;
+        double n0 = 4 * pi * pi, vth = sqrt(n0) / (double)c->N / 4;
+        c->W = n0; c->dt = 1 / (double)c->N / (6 * vth); c->B0 = sqrt(n0) / 16; c->w = n0 / (double)c->P;
+        break;
+    }
     case PICGOLF_CIC_BORIS_2D3V: { // Electrostatic2D3V.jl:23-25
         c->N = 128; c->NY = 128; c->P = c->N * c->NY * 32; c->T = 1 << 13;
         double NG = sqrt((double)(c->N * c->N + c->NY * c->NY));
@@ -305,7 +313,7 @@ static int destroy_impl(picgolf_handle h)
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
-                    h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off,
+                    h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_fx,
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
                     h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count};
@@ -337,6 +345,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13;
     h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT || h->simpson;
     h->ngp = c.scheme == PICGOLF_NGP_LEAPFROG;
+    h->b1d2v = c.scheme == PICGOLF_GAUSS_BORIS_1D2V;
     h->nranks = std::max(1, c.nranks);
     h->rank = c.rank;
     if (h->rank < 0 || h->rank >= h->nranks) return fail(PICGOLF_ERR_ARG, "rank %d outside [0,%d)", h->rank, h->nranks);
@@ -372,7 +381,15 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
         h->npart = 2;
         PG_TRY(set_smem(solve1d_kernel, h->smem_pass));
-        if (h->simpson) {
+        if (h->b1d2v) {
+            PG_TRY(dalloc(&h->vy1, n));
+            PG_TRY(dalloc(&h->hist, (size_t)N * h->T));
+            PG_CUDA(cudaMemset(h->hist, 0, (size_t)N * h->T * sizeof(double)));
+            h->smem_b1 = (size_t)(2 * N + 32) * 8;
+            h->npart = 3;
+            PG_TRY(set_smem(b1d2v_pass, h->smem_b1));
+            PG_TRY(occupancy_blocks(b1d2v_pass, PG_THREADS, h->smem_b1, h->sms, h->count, &h->nblocks));
+        } else if (h->simpson) {
             h->smem_sp1 = (size_t)3 * N * 8;
             h->smem_spk = (size_t)(4 * N + 32) * 8;
             PG_TRY(set_smem(sp_pass0<0>, (size_t)N * 8)); PG_TRY(set_smem(sp_pass0<1>, (size_t)N * 8));
@@ -481,7 +498,7 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
     if (cfg->struct_size != (int32_t)sizeof(picgolf_config))
         return fail(PICGOLF_ERR_ARG, "struct_size %d != %zu (header/library mismatch)", cfg->struct_size, sizeof(picgolf_config));
     const picgolf_config &c = *cfg;
-    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_AREA_SIMPSON13) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_GAUSS_BORIS_1D2V) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
     if (c.P < 1) return fail(PICGOLF_ERR_ARG, "P must be >= 1");
     if (!(c.dt > 0) || !isfinite(c.dt)) return fail(PICGOLF_ERR_ARG, "dt must be positive and finite");
     if (!isfinite(c.w)) return fail(PICGOLF_ERR_ARG, "w must be finite");
@@ -528,7 +545,8 @@ static int reset_run_state(picgolf_handle h)
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
-    h->pid_valid = false; h->pidpar = 0; h->since_sort = 0;
+    h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
+    if (h->hist) PG_CUDA(cudaMemset(h->hist, 0, (size_t)h->ncell * h->T * sizeof(double)));
     return 0;
 }
 
@@ -536,6 +554,7 @@ PG_API int picgolf_set_particles(picgolf_handle h, const double *x, const double
 {
     if (!h || !x || !v) return fail(PICGOLF_ERR_ARG, "NULL argument");
     if (h->is2d) return fail(PICGOLF_ERR_ARG, "use picgolf_set_particles_2d3v for the 2D3V scheme");
+    if (h->b1d2v) return fail(PICGOLF_ERR_ARG, "use picgolf_set_particles_1d2v for the 1D2V scheme");
     if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
     PG_TRY(use_device(h));
     PG_CUDA(cudaMemcpyAsync(h->xb[0], x, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -556,12 +575,40 @@ PG_API int picgolf_set_particles_2d3v(picgolf_handle h, const double *x, const d
     return reset_run_state(h);
 }
 
+PG_API int picgolf_set_particles_1d2v(picgolf_handle h, const double *x, const double *vx, const double *vy, int64_t count)
+{
+    if (!h || !x || !vx || !vy) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (!h->b1d2v) return fail(PICGOLF_ERR_ARG, "handle is not a 1D2V scheme");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    const size_t b = count * sizeof(double);
+    PG_CUDA(cudaMemcpyAsync(h->xb[0], x, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vb[0], vx, b, cudaMemcpyHostToDevice, h->stream));
+    PG_CUDA(cudaMemcpyAsync(h->vy1, vy, b, cudaMemcpyHostToDevice, h->stream));
+    return reset_run_state(h);
+}
+
+PG_API int picgolf_get_particles_1d2v(picgolf_handle h, double *x, double *vx, double *vy, int64_t count)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (!h->b1d2v) return fail(PICGOLF_ERR_ARG, "handle is not a 1D2V scheme");
+    if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "particles were never set");
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    PG_TRY(use_device(h));
+    const size_t b = count * sizeof(double);
+    if (x) PG_CUDA(cudaMemcpyAsync(x, h->xb[0], b, cudaMemcpyDeviceToHost, h->stream));
+    if (vx) PG_CUDA(cudaMemcpyAsync(vx, h->vb[0], b, cudaMemcpyDeviceToHost, h->stream));
+    if (vy) PG_CUDA(cudaMemcpyAsync(vy, h->vy1, b, cudaMemcpyDeviceToHost, h->stream));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 static int init_grid(picgolf_handle h) { return (int)std::max<int64_t>(1, std::min<int64_t>((h->count + 255) / 256, (int64_t)h->sms * 8)); }
 
 PG_API int picgolf_init_quiet(picgolf_handle h)
 {
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
-    if (h->is2d) return fail(PICGOLF_ERR_ARG, "quiet start is a 1D1V initialisation (GaussianFixedPointQuiet.jl:2-3)");
+    if (h->is2d || h->b1d2v) return fail(PICGOLF_ERR_ARG, "quiet start is a 1D1V initialisation (GaussianFixedPointQuiet.jl:2-3)");
     PG_TRY(use_device(h));
     quiet_start_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P);
     h->launches++;
@@ -572,6 +619,7 @@ PG_API int picgolf_init_quiet(picgolf_handle h)
 PG_API int picgolf_init_synthetic(picgolf_handle h, uint64_t seed, double vth)
 {
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (h->b1d2v) return fail(PICGOLF_ERR_UNSUPPORTED, "1D2V: pass x, vx, vy in with picgolf_set_particles_1d2v");
     PG_TRY(use_device(h));
     if (h->is2d)
         synthetic_2d3v_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4], h->count,
@@ -666,6 +714,11 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
     a.w = c.w; a.fx_inv = h->fx_inv; a.rtol = c.rtol; a.atol = c.atol;
     a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = (h->fixedpoint && !simpson_e1) ? 1 : 0;
     a.k = k; a.max_sweeps = c.max_sweeps; a.store_normE1 = simpson_e1 ? 1 : 0;
+    a.hist = nullptr;
+    if (h->b1d2v) { // Es[:,ti] .+= E with ti = cld(t, T/TO)   NGP1D2V.jl:56-57
+        int64_t ti = h->steps / c.diag_every;
+        if (ti < h->T) a.hist = h->hist + (size_t)ti * c.N;
+    }
     int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
     const int sp2_ = h->timer.begin(ST_SOLVE, h->stream);
     solve1d_kernel<<<1, threads, h->smem_pass, h->stream>>>(a);
@@ -679,7 +732,7 @@ static int launch_step_end(picgolf_handle h, bool record)
     StepEndArgs a;
     a.partials = h->partials; a.epartials = h->is2d ? h->epartials : nullptr; a.raw = h->raw; a.ctrl = h->ctrl;
     a.nblocks = h->nblocks; a.npart = h->npart; a.neblocks = h->is2d ? (int)(h->cfg.NY / ROWS_PER_BLOCK) : 0;
-    a.T = (int)h->T; a.record = record ? 1 : 0; a.is2d = h->is2d ? 1 : 0;
+    a.T = (int)h->T; a.record = record ? 1 : 0; a.is2d = h->npart == 3 ? 1 : 0;
     step_end_kernel<<<1, 256, 0, h->stream>>>(a);
     h->launches++;
     return 0;
@@ -834,6 +887,20 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
     return 0;
 }
 
+static int b1d2v_launch(picgolf_handle h, int do_push, int do_deposit)
+{
+    const picgolf_config &c = h->cfg;
+    B1D2VArgs a;
+    a.x = h->xb[0]; a.vx = h->vb[0]; a.vy = h->vy1; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
+    a.P = h->count; a.dt = c.dt; a.t3 = c.B0 * c.dt / 2; a.den = 1 + (0.0 + 0.0 + a.t3 * a.t3); a.fx_scale = h->fx_scale;
+    a.N = (int)c.N; a.do_push = do_push; a.do_deposit = do_deposit;
+    const int sp = h->timer.begin(ST_PARTICLES, h->stream);
+    b1d2v_pass<<<h->nblocks, PG_THREADS, h->smem_b1, h->stream>>>(a);
+    h->timer.end(sp, h->stream);
+    h->launches++;
+    return 0;
+}
+
 static int launch_solve2d(picgolf_handle h)
 {
     const picgolf_config &c = h->cfg;
@@ -918,6 +985,17 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
         for (int64_t s = 0; s < nsteps && rc == 0; ++s) { rc = step_fixedpoint(h); h->steps++; }
     } else if (h->is2d) {
         for (int64_t s = 0; s < nsteps && rc == 0; ++s) { rc = step_2d3v(h); h->steps++; }
+    } else if (h->b1d2v) {
+        if (!h->have_deposit) rc = b1d2v_launch(h, 0, 1); // rho(x) of the first step   NGP1D2V.jl:40
+        for (int64_t s = 0; s < nsteps && rc == 0; ++s) {
+            rc = allreduce_grid(h);
+            if (rc == 0) rc = launch_solve1d(h, 1);
+            if (rc == 0) rc = b1d2v_launch(h, 1, 1);     // gather, boris, move, wrap + rho(x) of the next step
+            bool record = ((h->steps + 1) % h->cfg.diag_every) == 0; // if mod(t, T/TO) == 0   :58
+            if (rc == 0) rc = launch_step_end(h, record);
+            h->steps++;
+        }
+        h->have_deposit = true;
     } else {
         rc = lf_launch(h, 0, 1); // u(); deposit of the first step
         for (int64_t s = 0; s < nsteps && rc == 0; ++s) {
@@ -1044,7 +1122,17 @@ PG_API int picgolf_get_diagnostics(picgolf_handle h, double *D, int64_t ld, int3
     const int64_t T = h->T;
     for (int64_t t = 0; t < rows; ++t) {
         double se = r[t], s1 = r[T + t], s2 = r[2 * T + t], s3 = r[3 * T + t];
-        if (!h->is2d) {
+        if (h->b1d2v) {
+            if (D) {
+                // D[ti,1:2].+=(sum(abs2,E)/N, sum(vy^2+vx^2)*n0/P)./2; D[ti,3:5].+=sum.((D[ti,1:2],vx/P,vy/P));
+                // D[ti,1:3].*=2/n0; ... D ./= T/TO        NGP1D2V.jl:59-61,64
+                double d1 = (se / (double)c.N) / 2, d2 = (s1 * c.W / (double)c.P) / 2, d3 = d1 + d2, sc = 2 / c.W;
+                double win = (double)c.diag_every;
+                D[t] = d1 * sc / win; D[ld + t] = d2 * sc / win; D[2 * ld + t] = d3 * sc / win;
+                D[3 * ld + t] = s2 / (double)c.P / win; D[4 * ld + t] = s3 / (double)c.P / win;
+            }
+            if (sweeps) sweeps[t] = 1;
+        } else if (!h->is2d) {
             if (D) {
                 // D[t,1:2].=(sum(E.^2)/N,sum(v.^2)*W/P)./2; D[t,3:4].=sum.((D[t,1:2],v/P)); D[t,1:3].*=2/W
                 double d1 = (se / (double)c.N) / 2, d2 = (s1 * c.W / (double)c.P) / 2;
@@ -1060,6 +1148,23 @@ PG_API int picgolf_get_diagnostics(picgolf_handle h, double *D, int64_t ld, int3
             }
             if (sweeps) sweeps[t] = 1;
         }
+    }
+    return 0;
+}
+
+PG_API int picgolf_get_field_history(picgolf_handle h, double *Es, int64_t max_cols, int64_t *cols_out)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (!h->b1d2v) return fail(PICGOLF_ERR_ARG, "field history is kept by the 1D2V scheme only");
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    const picgolf_config &c = h->cfg;
+    int64_t cols = std::min<int64_t>(h->T, (h->steps + c.diag_every - 1) / c.diag_every);
+    if (cols_out) *cols_out = cols;
+    if (Es) {
+        if (max_cols < cols) return fail(PICGOLF_ERR_ARG, "max_cols %lld < %lld", (long long)max_cols, (long long)cols);
+        PG_CUDA(cudaMemcpy(Es, h->hist, (size_t)cols * c.N * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < cols * c.N; ++i) Es[i] /= (double)c.diag_every; // Es ./= T/TO
     }
     return 0;
 }
@@ -1272,7 +1377,7 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     Solve1DArgs a;
     a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
     a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.fx_inv = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N);
-    a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1; a.store_normE1 = 0;
+    a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1; a.store_normE1 = 0; a.hist = nullptr;
     size_t smem = (size_t)(2 * N + 32) * 8;
     int rc = set_smem(solve1d_kernel, smem);
     if (rc == 0) {

@@ -277,3 +277,19 @@ def test_area_simpson13_known_answers(oracle):
     s = oracle.Simpson13(x0, v0, int(g["N"]), dt, W, rtol=1e-14, shape=1)
     Dh, swh = s.run(32)
     assert np.array_equal(Dh, g["D"][:32]) and np.array_equal(swh, g["sweeps"][:32])
+
+
+def test_ngp1d2v_oracle(oracle):
+    """src/NGP1D2V.jl: boris() about z is a rotation for E=0; mean rho = n0/N; fixture reproducible."""
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        vx, vy = rng.standard_normal(2)
+        a, b = oracle.boris_1d2v(vx, vy, 0.0, 1.3, 0.07)
+        assert abs((a * a + b * b) / (vx * vx + vy * vy) - 1) < 4e-16
+    a, b = oracle.boris_1d2v(0.1, 0.2, 2.0, 0.0, 0.01)  # B=0: vx + E dt
+    assert abs(a - 0.12) < 1e-16 and b == 0.2
+    g = golden("ngp1d2v")
+    x, vx, vy = g["x0"].copy(), g["vx0"].copy(), g["vy0"].copy()
+    rho, E, raw = oracle.step_1d2v(x, vx, vy, int(g["N"]), 7, float(g["dt"]), float(g["B0"]), float(g["w"]))
+    assert np.array_equal(rho, g["rho"][0]) and np.array_equal(E, g["E"][0]) and np.array_equal(raw, g["raw"][0])
+    assert abs(rho.mean() / (float(g["n0"]) / int(g["N"])) - 1) < 1e-12

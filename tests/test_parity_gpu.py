@@ -696,3 +696,43 @@ def test_area_simpson13(pg, oracle):
     slope = np.polyfit(t[sel], np.log10(D[sel, 0]), 1)[0]
     assert abs(slope / oracle.growth_slope(W) - 1) < 0.01
     assert np.abs(D[:, 3]).max() < 1e-13 and np.abs(1 - D[:, 2]).max() < 1e-12
+
+
+# =============================================================================================
+# 1D2V magnetised Boris code (src/NGP1D2V.jl)
+# =============================================================================================
+def test_ngp1d2v_steps(pg, oracle):
+    g = golden("ngp1d2v")
+    N = int(g["N"])
+    sim = pg.ngp_1d2v(T=64, TO=16)  # window T/TO = 4 steps
+    assert (sim.cfg.N, sim.cfg.P, sim.cfg.diag_every, sim.cfg.half_width) == (512, 7680, 4, 7)
+    assert sim.cfg.dt == float(g["dt"]) and sim.cfg.B0 == float(g["B0"]) and sim.cfg.w == float(g["w"])
+    sim.set_particles(g["x0"], g["vx0"], vy=g["vy0"])
+    for t in range(8):
+        sim.step(1)
+        rho, E = sim.fields()
+        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-10
+    x, vx, vy = sim.particles()
+    assert relnorm(x, g["x"]) < 1e-11 and relnorm(vx, g["vx"]) < 1e-11 and relnorm(vy, g["vy"]) < 1e-11
+    assert 0 <= x.min() and x.max() <= 1
+    # diagnostics: one row per window, formed as NGP1D2V.jl:59-61,64 from the sums at the window's last step
+    D, _ = sim.diagnostics()
+    assert D.shape == (2, 5)
+    n0, P = float(g["n0"]), int(g["P"])
+    for ti, t in enumerate((3, 7)):
+        se, s0, s1, s2 = g["raw"][t]
+        d1, d2 = (se / N) / 2, (s0 * n0 / P) / 2
+        want = np.array([d1 * 2 / n0, d2 * 2 / n0, (d1 + d2) * 2 / n0, s1 / P, s2 / P]) / 4
+        assert relnorm(D[ti], want) < 1e-10
+    Es = sim.field_history()  # Es[:,ti] = mean of E over the window
+    assert Es.shape == (N, 2)
+    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < 1e-10 and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < 1e-10
+    # stepping in one call gives the same state
+    s2_ = pg.ngp_1d2v(T=64, TO=16)
+    s2_.set_particles(g["x0"], g["vx0"], vy=g["vy0"])
+    s2_.step(8)
+    x2, vx2, vy2 = s2_.particles()
+    assert np.array_equal(x2, x) and np.array_equal(vx2, vx) and np.array_equal(vy2, vy)
+    # Boris rotation alone conserves |v| (E = 0 field: uniform plasma of identical particles has rho = const)
+    a, b = oracle.boris_1d2v(0.3, -0.2, 0.0, 0.7, 0.05)
+    assert abs(a * a + b * b - 0.13) < 1e-16

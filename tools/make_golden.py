@@ -146,6 +146,25 @@ def area_simpson13(T=1024):
          xr=xr, vr=vr, xn=n.x, vn=n.v, En=n.E, rn=n.r, Dn=np.array(Dn), swn=np.array(swn, dtype=np.int32))
 
 
+def ngp1d2v(steps=8):
+    """src/NGP1D2V.jl (N=512, P=15N, erf shape +-7, Boris about z), inputs drawn like :27-32."""
+    from scipy.special import erfinv
+    N = 512
+    P = 15 * N
+    n0 = 4 * math.pi ** 2
+    vth = math.sqrt(n0) / N / 4
+    dt, B0, w = 1 / N / (6 * vth), math.sqrt(n0) / 16, n0 / P
+    rng = np.random.default_rng(19)
+    x0, vx0, vy0 = rng.random(P), vth * erfinv(rng.random(P)), vth * erfinv(rng.random(P))
+    x, vx, vy = x0.copy(), vx0.copy(), vy0.copy()
+    rhos, Es, raws = [], [], []
+    for _ in range(steps):
+        rho, E, raw = o.step_1d2v(x, vx, vy, N, 7, dt, B0, w)
+        rhos.append(rho); Es.append(E); raws.append(raw)
+    save("ngp1d2v", N=N, P=P, dt=dt, B0=B0, w=w, n0=n0, vth=vth, x0=x0, vx0=vx0, vy0=vy0, x=x, vx=vx, vy=vy,
+         rho=np.array(rhos), E=np.array(Es), raw=np.array(raws))
+
+
 def c5_2d3v(steps=4):
     """Config 5 shape at test size: src/Electrostatic2D3V.jl with NX=NY=32, P=NX*NY*8."""
     NX = NY = 32
@@ -194,7 +213,7 @@ if __name__ == "__main__":
     if args.only:
         globals()[args.only]()
         sys.exit(0)
-    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils()
+    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils(); ngp1d2v()
     if not args.skip_c3:
         c3_quiet()
         simpson13()
