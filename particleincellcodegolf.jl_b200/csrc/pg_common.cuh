@@ -34,6 +34,14 @@ __device__ __forceinline__ int ngp_cell0(double x, int N)
     return (int)m;
 }
 
+// Same for a power-of-two grid (all grids the library accepts): floored mod is a two's-complement mask,
+// which spares the hot loops a 64-bit integer division.
+__device__ __forceinline__ int ngp_cell0_pow2(double x, int N)
+{
+    long long r = __double2ll_rn(x * (double)N);
+    return (int)((r - 1) & (long long)(N - 1));
+}
+
 // 0-based wrap of a Julia 1-based stencil index i (any sign): mod1(i,N)-1 == floormod(i-1, N).
 __device__ __forceinline__ int wrap_cell0(int i, int N)
 {

@@ -9,6 +9,7 @@
 #include "pg_common.cuh"
 #include "pg_fft.cuh"
 #include "pg_gauss.cuh"
+#include "pg_tma.cuh"
 
 namespace pg {
 
@@ -363,7 +364,7 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
     if (a.do_kick) {
         xj = jl_mod1(xj + vj / 2 * dt);
         double e;
-        if (SHAPE == 0) e = Es[ngp_cell0(xj, N)];
+        if (SHAPE == 0) e = Es[ngp_cell0_pow2(xj, N)];
         else {
             int ibase; double W[GAUSS_NW];
             gauss_weights(xj, dN, ibase, W);
@@ -375,7 +376,7 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
     }
     if (a.do_deposit) {
         xj = jl_mod1(xj + vj / 2 * dt);
-        if (SHAPE == 0) atomicAdd(&cs[ngp_cell0(xj, N)], 1u);
+        if (SHAPE == 0) atomicAdd(&cs[ngp_cell0_pow2(xj, N)], 1u);
         else {
             int ibase; double W[GAUSS_NW];
             gauss_weights(xj, dN, ibase, W);
@@ -446,6 +447,104 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
             }
         } else flush_grid(rs, a.rho, N);
     }
+    if (a.do_kick) {
+        sv2 = block_sum(sv2, scratch);
+        sv = block_sum(sv, scratch);
+        if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NGP leapfrog pass with TMA-staged particle tiles (the HBM-bound path: 32 B per particle-step).
+// One block per SM streams tiles of LF_TILE particles through a LF_STAGES-deep shared-memory ring:
+//   thread 0 issues `cp.async.bulk` loads of the x and v tiles (completion on an mbarrier), all threads
+//   update the tile in place in shared memory (lf_particle, identical arithmetic to lf_pass<0>), then
+//   thread 0 writes the tile back with bulk stores and refills the stage that was stored one iteration ago.
+// The copy engine moves all particle bytes; the SM only touches shared memory.  Full tiles only; the
+// remainder (< LF_TILE particles) is handled by the scalar tail below.
+// ------------------------------------------------------------------------------------------
+constexpr int LF_TILE = 2048;  // particles per tile: 16 KB of x + 16 KB of v
+constexpr int LF_STAGES = 3;
+__host__ __device__ inline size_t lf_tma_smem_bytes(int N)
+{
+    return (size_t)LF_STAGES * LF_TILE * 16 + (size_t)N * 8 + (size_t)N * 4 + 256 + 64; // ring, Es, counts, scratch, barriers
+}
+
+constexpr int LF_TMA_THREADS = 512;
+__global__ void __launch_bounds__(LF_TMA_THREADS, 1) lf_pass_ngp_tma(LFArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                    // [STAGES][2][TILE]
+    double *Es = ring + (size_t)LF_STAGES * 2 * LF_TILE;
+    unsigned int *cs = reinterpret_cast<unsigned int *>(Es + a.N);
+    double *scratch = reinterpret_cast<double *>(cs + a.N);
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 32);            // [STAGES]
+    const int N = a.N;
+    const long long ntiles = a.P / LF_TILE;
+    const long long mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0; // tiles of this block
+    constexpr uint32_t TILE_BYTES = LF_TILE * 8;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LF_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        if (a.do_kick) Es[n] = a.E[n];
+        cs[n] = 0u;
+    }
+    __syncthreads();
+    auto issue_load = [&](long long it) { // tile number `it` of this block into stage it % STAGES
+        const int s = (int)(it % LF_STAGES);
+        const long long j0 = ((long long)blockIdx.x + it * gridDim.x) * LF_TILE;
+        double *xs = ring + (size_t)s * 2 * LF_TILE, *vs = xs + LF_TILE;
+        mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
+        bulk_load(xs, a.x + j0, TILE_BYTES, &full[s]);
+        bulk_load(vs, a.v + j0, TILE_BYTES, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (long long it = 0; it < LF_STAGES - 1 && it < mine; ++it) issue_load(it);
+    double sv2 = 0.0, sv = 0.0;
+    for (long long it = 0; it < mine; ++it) {
+        const int s = (int)(it % LF_STAGES);
+        double *xs = ring + (size_t)s * 2 * LF_TILE, *vs = xs + LF_TILE;
+        mbar_wait(&full[s], (uint32_t)((it / LF_STAGES) & 1));
+#pragma unroll
+        for (int i = 0; i < LF_TILE / LF_TMA_THREADS; i += 2) { // pairs via 128-bit shared accesses
+            const int p = (i / 2) * LF_TMA_THREADS + threadIdx.x;
+            double2 xa = reinterpret_cast<double2 *>(xs)[p], va = reinterpret_cast<double2 *>(vs)[p];
+            lf_particle<0>(a, Es, nullptr, cs, xa.x, va.x, sv2, sv);
+            lf_particle<0>(a, Es, nullptr, cs, xa.y, va.y, sv2, sv);
+            reinterpret_cast<double2 *>(xs)[p] = xa; reinterpret_cast<double2 *>(vs)[p] = va;
+        }
+        fence_proxy_async(); // the updated tile must be visible to the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long j0 = ((long long)blockIdx.x + it * gridDim.x) * LF_TILE;
+            bulk_store(a.x + j0, xs, TILE_BYTES);
+            bulk_store(a.v + j0, vs, TILE_BYTES);
+            bulk_commit();
+            const long long nxt = it + LF_STAGES - 1; // goes into the stage stored one iteration ago
+            if (nxt < mine) {
+                bulk_wait_read<1>(); // ... whose store must have finished reading shared memory
+                issue_load(nxt);
+            }
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_all<0>();
+    // scalar tail: the last P % LF_TILE particles, spread over the blocks
+    {
+        const long long t0 = ntiles * LF_TILE;
+        for (long long j = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += (long long)gridDim.x * blockDim.x) {
+            double xj = a.x[j], vj = a.v[j];
+            lf_particle<0>(a, Es, nullptr, cs, xj, vj, sv2, sv);
+            a.x[j] = xj; a.v[j] = vj;
+        }
+    }
+    __syncthreads();
+    if (a.do_deposit)
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            unsigned int c = cs[n];
+            if (c) atomicAdd(&a.rho[n], (fx_t)c);
+        }
     if (a.do_kick) {
         sv2 = block_sum(sv2, scratch);
         sv = block_sum(sv, scratch);

@@ -175,6 +175,7 @@ struct picgolf_handle_s {
     int64_t T = 1;
     int nblocks = 1, npart = 2;
     size_t smem_pass = 0, smem_lf = 0;
+    bool ngp_tma = false;
     bool have_particles = false;
     int64_t steps = 0, launches = 0;
     nccl::Comm comm = nullptr;
@@ -432,6 +433,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             h->smem_lf = lf_smem_bytes(0, N);
             PG_TRY(set_smem(lf_pass<0>, h->smem_lf));
             PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_lf, h->sms, (h->count + 3) / 4, &h->nblocks));
+            // large shards stream their particle tiles with TMA bulk copies (one persistent block per SM)
+            h->ngp_tma = c.deposit_mode != PICGOLF_DEPOSIT_ATOMIC && h->count >= (1 << 20) && lf_tma_smem_bytes(N) <= 200 * 1024;
+            if (h->ngp_tma) {
+                h->smem_lf = lf_tma_smem_bytes(N);
+                PG_TRY(set_smem(lf_pass_ngp_tma, h->smem_lf));
+                h->nblocks = h->sms;
+            }
         } else {
             h->smem_lf = lf_smem_bytes(1, N);
             PG_TRY(set_smem(lf_pass<1>, h->smem_lf));
@@ -880,7 +888,8 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
     a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
     const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
-    if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+    if (h->ngp_tma) lf_pass_ngp_tma<<<h->nblocks, LF_TMA_THREADS, h->smem_lf, h->stream>>>(a);
+    else if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
     else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
     h->timer.end(sp5_, h->stream);
     h->launches++;
