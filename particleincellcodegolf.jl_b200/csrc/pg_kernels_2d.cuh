@@ -6,6 +6,7 @@
 // point (order-independent, bit-reproducible; see pg_kernels_1d.cuh).
 #pragma once
 #include "pg_common.cuh"
+#include "pg_tma.cuh"
 
 namespace pg {
 
@@ -247,6 +248,228 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
         }
         __syncthreads();
     }
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+        a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
+    }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant of the tiled kernel (opt-in experiment, PICGOLF_2D_TMA=1: measured slower than
+// particles_2d3v_tiled on B200 because the SM-side work, not the particle streams, limits it; see picgolf.cu).  Same tiles, same windows and
+// the same per-particle arithmetic, but the five particle streams are moved by the copy engine: one persistent
+// 512-thread block per SM owns a contiguous range of work items and streams them in sub-tiles of T2_SUB particles
+// through a T2_STAGES-deep shared-memory ring (`cp.async.bulk` loads completing on mbarriers, in-place update,
+// bulk stores).  Bulk copies need 16-byte alignment, so a sub-tile [a,b) is split into its even-aligned interior
+// (staged) and at most two edge particles (plain global accesses).  The E / deposit window is kept across the
+// consecutive items of a tile and flushed only when the tile changes.
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_SUB = 1024, T2_STAGES = 3, T2_TMA_THREADS = 512;
+constexpr size_t T2_TMA_SMEM = (size_t)T2_STAGES * 5 * T2_SUB * 8 + (size_t)T2_WS * T2_WS * (16 + 8) + 256 + 64;
+
+struct P2DWindow {
+    const double2 *Ew;
+    unsigned int *rlo, *rhi;
+    int ox, oy;
+};
+
+// gather (old position) -> boris -> move -> deposit (new position) for one particle; window or global fallback
+__device__ __forceinline__ void p2d_particle(const P2DArgs &a, const P2DWindow &w, double &x, double &y, double &vx, double &vy,
+                                             double &vz, double &s0, double &s1, double &s2, unsigned int &nslow)
+{
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    Cic4 c;
+    cic4(x, y, NX, NY, c);
+    double ex = 0.0, ey = 0.0;
+    {
+        const int rx = (c.ix[0] - 1 - w.ox) & mx, ry = (c.iy[0] - 1 - w.oy) & my;
+        const bool in = rx <= T2_WS - 2 && ry <= T2_WS - 2;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                double wxy = c.wx[ii] * c.wy[jj];
+                double2 f = in ? w.Ew[rx + ii + (ry + jj) * T2_WS] : __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
+                ex = fma(f.x, wxy, ex);
+                ey = fma(f.y, wxy, ey);
+            }
+    }
+    boris(vx, vy, vz, ex, ey, a.dt, a.t1, a.tscale);
+    x = unimod(x + vx * a.dt, 1.0);
+    y = unimod(y + vy * a.dt, 1.0);
+    cic4(x, y, NX, NY, c);
+    {
+        const int rx = (c.ix[0] - 1 - w.ox) & mx, ry = (c.iy[0] - 1 - w.oy) & my;
+        if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
+            const int r0 = rx + ry * T2_WS;
+            unsigned int lo[4], old[4];
+            fx_t v[4];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int k = ii + 2 * jj;
+                    v[k] = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale);
+                    lo[k] = (unsigned int)v[k];
+                    old[k] = atomicAdd(&w.rlo[r0 + ii + jj * T2_WS], lo[k]);
+                }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int k = ii + 2 * jj;
+                    const unsigned int carry = (old[k] + lo[k]) < old[k] ? 1u : 0u;
+                    const unsigned int hi = (unsigned int)(v[k] >> 32) + carry;
+                    if (hi) atomicAdd(&w.rhi[r0 + ii + jj * T2_WS], hi);
+                }
+        } else {
+            ++nslow;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii)
+                    atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
+        }
+    }
+    s0 += vx * vx + vy * vy; s1 += vx; s2 += vy;
+}
+
+// Walks the sub-tiles of a contiguous range of work items (uniform across the block).
+struct SubTileCursor {
+    unsigned int item, item_end;
+    int tile;
+    long long pos, end; // next particle to hand out / end of the current item
+    __device__ __forceinline__ void open_item(const P2DArgs &a)
+    {
+        int lo = 0, hi = a.ntiles;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        tile = lo;
+        pos = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
+        end = min(pos + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
+    }
+    __device__ __forceinline__ void init(const P2DArgs &a, unsigned int i0, unsigned int i1)
+    {
+        item = i0; item_end = i1; tile = -1; pos = end = 0;
+        if (item < item_end) open_item(a);
+    }
+    // next sub-tile [sa, sb) of tile t; false when the range is exhausted
+    __device__ __forceinline__ bool next(const P2DArgs &a, long long &sa, long long &sb, int &t)
+    {
+        while (item < item_end && pos >= end) {
+            ++item;
+            if (item < item_end) open_item(a);
+        }
+        if (item >= item_end) return false;
+        sa = pos; sb = min(pos + (long long)T2_SUB, end); t = tile;
+        pos = sb;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(T2_TMA_THREADS, 1) particles_2d3v_tma(P2DArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                       // [STAGES][5][T2_SUB]
+    double2 *Ew = reinterpret_cast<double2 *>(ring + (size_t)T2_STAGES * 5 * T2_SUB);
+    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + T2_WS * T2_WS), *rhi = rlo + T2_WS * T2_WS;
+    double *scratch = reinterpret_cast<double *>(rhi + T2_WS * T2_WS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 32);
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double *const gp[5] = {a.x, a.y, a.vx, a.vy, a.vz};
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned int nitems = a.item_off[a.ntiles];
+    const unsigned int i0 = (unsigned int)((unsigned long long)nitems * blockIdx.x / gridDim.x);
+    const unsigned int i1 = (unsigned int)((unsigned long long)nitems * (blockIdx.x + 1) / gridDim.x);
+    SubTileCursor prod, cons;
+    prod.init(a, i0, i1);
+    cons.init(a, i0, i1);
+    long long issued = 0;
+    auto issue_load = [&]() { // thread 0: next sub-tile of the producer cursor into stage issued % STAGES
+        long long sa, sb; int t;
+        if (!prod.next(a, sa, sb, t)) return;
+        const int s = (int)(issued % T2_STAGES);
+        const long long a2 = sa + (sa & 1), b2 = sb - (sb & 1);
+        const uint32_t bytes = b2 > a2 ? (uint32_t)((b2 - a2) * 8) : 0u;
+        mbar_arrive_expect_tx(&full[s], 5 * bytes);
+        if (bytes)
+            for (int q = 0; q < 5; ++q) bulk_load(ring + ((size_t)s * 5 + q) * T2_SUB, gp[q] + a2, bytes, &full[s]);
+        ++issued;
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < T2_STAGES - 1; ++k) issue_load();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    unsigned int nslow = 0;
+    P2DWindow w;
+    w.Ew = Ew; w.rlo = rlo; w.rhi = rhi; w.ox = 0; w.oy = 0;
+    int cur_tile = -1;
+    auto flush_window = [&]() {
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
+            if (v) {
+                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift;
+                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
+                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)v);
+            }
+        }
+    };
+    long long sa, sb, q = 0;
+    int t;
+    while (cons.next(a, sa, sb, t)) {
+        if (t != cur_tile) { // (re)build the window: E2 slice in, deposit limbs flushed and cleared
+            if (cur_tile >= 0) flush_window();
+            __syncthreads();
+            w.ox = (t % a.ntx) * T2_TS - T2_R; w.oy = (t / a.ntx) * T2_TS - T2_R;
+            for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
+                Ew[c] = a.E2[gx + (size_t)gy * NX];
+                rlo[c] = 0u; rhi[c] = 0u;
+            }
+            cur_tile = t;
+            __syncthreads();
+        }
+        const int s = (int)(q % T2_STAGES);
+        double *st = ring + (size_t)s * 5 * T2_SUB;
+        const long long a2 = sa + (sa & 1), b2 = sb - (sb & 1);
+        mbar_wait(&full[s], (uint32_t)((q / T2_STAGES) & 1));
+        for (long long i = threadIdx.x; i < b2 - a2; i += blockDim.x) { // staged interior
+            double x = st[i], y = st[T2_SUB + i], vx = st[2 * T2_SUB + i], vy = st[3 * T2_SUB + i], vz = st[4 * T2_SUB + i];
+            p2d_particle(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
+            st[i] = x; st[T2_SUB + i] = y; st[2 * T2_SUB + i] = vx; st[3 * T2_SUB + i] = vy; st[4 * T2_SUB + i] = vz;
+        }
+        // unaligned edge particles straight from/to global memory (threads of two different warps)
+        long long edge = -1; // an odd start and an odd end can never be the same particle
+        if (threadIdx.x == 0 && (sa & 1)) edge = sa;
+        if (threadIdx.x == 32 && (sb & 1)) edge = sb - 1;
+        if (edge >= 0) {
+            double x = a.x[edge], y = a.y[edge], vx = a.vx[edge], vy = a.vy[edge], vz = a.vz[edge];
+            p2d_particle(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
+            a.x[edge] = x; a.y[edge] = y; a.vx[edge] = vx; a.vy[edge] = vy; a.vz[edge] = vz;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (b2 > a2) {
+                const uint32_t bytes = (uint32_t)((b2 - a2) * 8);
+                for (int k = 0; k < 5; ++k) bulk_store(gp[k] + a2, st + (size_t)k * T2_SUB, bytes);
+            }
+            bulk_commit();
+            bulk_wait_read<1>(); // the stage stored one iteration ago is free again
+            issue_load();
+        }
+        ++q;
+    }
+    if (cur_tile >= 0) { __syncthreads(); flush_window(); }
+    if (threadIdx.x == 0) bulk_wait_all<0>();
     s0 = block_sum(s0, scratch);
     s1 = block_sum(s1, scratch);
     s2 = block_sum(s2, scratch);

@@ -736,3 +736,27 @@ def test_ngp1d2v_steps(pg, oracle):
     # Boris rotation alone conserves |v| (E = 0 field: uniform plasma of identical particles has rho = const)
     a, b = oracle.boris_1d2v(0.3, -0.2, 0.0, 0.7, 0.05)
     assert abs(a * a + b * b - 0.13) < 1e-16
+
+
+def test_2d3v_tma_variant_matches(pg, oracle, monkeypatch):
+    """The opt-in TMA-staged 2D kernel (PICGOLF_2D_TMA=1) must give the same physics as the default tiled kernel
+    (odd work-item boundaries exercise its unaligned edge particles)."""
+    NX = NY = 64
+    P = (1 << 18) + 3
+    rng = np.random.default_rng(51)
+    res = []
+    for tma in (False, True):
+        if tma:
+            monkeypatch.setenv("PICGOLF_2D_TMA", "1")
+        else:
+            monkeypatch.delenv("PICGOLF_2D_TMA", raising=False)
+        sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=8, NS=1, deposit_mode=pg.DEPOSIT_SORTED, sort_every=3)
+        if not res:
+            st = [1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * sim.vth / np.sqrt(2) for _ in range(3)]
+        sim.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
+        sim.step(7)
+        res.append((sim.particles(), sim.fields(), sim.diagnostics()[0]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert relnorm(b, a) < 1e-10
+    assert relnorm(res[1][1][0], res[0][1][0]) < TOL and relnorm(res[1][1][1], res[0][1][1]) < 1e-10
+    assert relnorm(res[1][2][:, :3], res[0][2][:, :3]) < 1e-11
