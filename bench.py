@@ -175,7 +175,7 @@ def run_gpu(args):
     elif args.workload == "ngp":
         passes = float(nroof + 1)
         alg_bytes_launch = 32.0 * per_gpu
-        kernel = "lf_pass<0> (drift + kick + drift + NGP deposit)"
+        kernel = "lf_pass_ngp_tma (TMA-staged tiles: drift + kick + drift + NGP deposit)"
     else:
         passes = float(nroof)
         alg_bytes_launch = 80.0 * per_gpu
