@@ -169,7 +169,7 @@ def run_gpu(args):
     sim.stage_timing(False)
     _, sw2 = sim.diagnostics()
     if args.workload == "gauss_fp":
-        passes = float((sw2[Wm + K:Wm + K + nroof] + 1).sum())  # S solves -> S+1 particle passes per step
+        passes = float(sw2[Wm + K:Wm + K + nroof].sum())  # S solves -> S particle passes per step (the k=0 pass is fused into the previous step's final pass)
         alg_bytes_launch = 32.0 * per_gpu
         kernel = "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)"
     elif args.workload == "ngp":
@@ -199,8 +199,9 @@ def run_gpu(args):
     fp64 = None
     if args.workload == "gauss_fp":
         peak_tf = pg.fp64_peak_tflops()
-        # FP64 instructions per particle-pass measured with ncu (profiles/): first 130, middle 255, final 131
-        fp64_inst = float(sum(130 + 255 * (int(s_) - 1) + 131 for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
+        # FP64 warp-instructions per particle-pass measured with ncu (profiles/): 255 for a pass with two stencils
+        # (middle passes and the final pass with the fused first deposit of the next step)
+        fp64_inst = float(sum(255 * int(s_) for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
         ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
         fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
                 "note": "FP64 lane-instructions of the pass kernels x2 / kernel time; this, not HBM, bounds the erf-shape path"}

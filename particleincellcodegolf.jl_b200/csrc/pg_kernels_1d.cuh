@@ -45,7 +45,8 @@ __device__ __forceinline__ void flush_grid(const fx_t *rs, fx_t *rho, int N)
 // Gaussian fixed point.  Pass k of a step (k = 0..max_sweeps):
 //   k = 0 (FIRST): x_0 = X + ((V+V)/2)*dt; deposit at (x_0+X)/2.
 //   k >= 1: gather E_k at (x_{k-1}+X)/2 -> v_k = V + g*dt.  If the solve that produced E_k declared
-//           the step finished (ctrl->final_k == k): x = mod(x_{k-1},1), accumulate sum v^2, sum v.
+//           the step finished (ctrl->final_k == k): x = mod(x_{k-1},1), accumulate sum v^2, sum v -- and, fused in,
+//           the k = 0 pass of the NEXT step (deposit at x + v*dt/2), so every later step starts at its first solve.
 //           Otherwise x_k = X + ((v_k+V)/2)*dt and deposit at (x_k+X)/2 for solve k+1.
 //   Passes with k > final_k are predicated no-ops (the host never reads the flag mid-step).
 // Note x lags v by one sweep on exit, exactly as in the reference (GaussianFixedPoint.jl:8-9).
@@ -96,9 +97,14 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
             vj = Vj + g * dt; // v[j]=V[j]+sum(...)*dt
             st_stream(a.v + j, vj);
             if (final) {
-                st_stream(a.xout + j, jl_mod1(xj)); // x.=mod.(x,1)
+                const double xw = jl_mod1(xj); // x.=mod.(x,1)
+                st_stream(a.xout + j, xw);
                 sv2 = fma(vj, vj, sv2);
                 sv += vj;
+                // fused first pass of the NEXT step (X.=x; V.=v; x = X + (V+V)/2*dt; deposit at (x+X)/2)
+                xj = xw + (vj + vj) / 2 * dt;
+                gauss_weights((xj + xw) / 2, dN, ibase, W);
+                gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
                 continue;
             }
             xj = Xj + (vj + Vj) / 2 * dt;
@@ -111,9 +117,8 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
         sv2 = block_sum(sv2, scratch);
         sv = block_sum(sv, scratch);
         if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
-    } else {
-        flush_grid(rs, a.rho, N);
     }
+    flush_grid(rs, a.rho, N);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -190,9 +195,8 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
             base = c0 - 6 - WIN_LO;
         }
         if (!FIRST) Ew[lane] = a.E[(base + lane - 1) & Nmask];
-        if (!final)
 #pragma unroll 4
-            for (int r = 0; r < WIN_ROWS; ++r) acc[r * WIN_LD + lane] = 0.0;
+        for (int r = 0; r < WIN_ROWS; ++r) acc[r * WIN_LD + lane] = 0.0;
         __syncwarp();
         // software pipeline: the loads of the next group are issued before the current group is evaluated
         double Xn[NP], Vn[NP], vn[NP];
@@ -259,14 +263,18 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
                     if (live[q]) st_stream(a.v + j[q], vj[q]);
                 }
                 if (final) {
+                    // end of step: x.=mod.(x,1), diagnostics sums -- and the first pass of the NEXT step fused in:
+                    // X.=x; V.=v; x = X + (V+V)/2*dt; deposit at (x+X)/2, so the next step starts at its first solve
 #pragma unroll
-                    for (int q = 0; q < NP; ++q)
+                    for (int q = 0; q < NP; ++q) {
+                        const double xw = jl_mod1(xj[q]);
                         if (live[q]) {
-                            st_stream(a.xout + j[q], jl_mod1(xj[q])); // x.=mod.(x,1)
+                            st_stream(a.xout + j[q], xw);
                             sv2 = fma(vj[q], vj[q], sv2);
                             sv += vj[q];
                         }
-                    continue;
+                        Xj[q] = xw; Vj[q] = vj[q];
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) / 2 * dt;
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
                 if (live[q] && !ok[q]) { ++nslow; slow_deposit(a.rho, mid[q], N, a.fx_scale); }
         }
         __syncwarp();
-        if (!final) {
+        {
             double s = 0.0;
             const double *row = acc + lane * WIN_LD;
 #pragma unroll 8
@@ -328,9 +336,8 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
         sv2 = block_sum(sv2, scratch);
         sv = block_sum(sv, scratch);
         if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
-    } else if (nslow && a.slow_count) {
-        atomicAdd(a.slow_count, (unsigned long long)nslow);
     }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
 }
 
 // ------------------------------------------------------------------------------------------

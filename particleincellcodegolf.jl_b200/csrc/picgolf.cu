@@ -193,8 +193,8 @@ struct picgolf_handle_s {
     int64_t since_sort = 0, sorts = 0;
     size_t smem_sorted = 0;
     // CUDA graphs of one fixed-point step, one per ping-pong parity
-    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
-    int64_t graph_launches = 0;
+    cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr}; // [par + 2*have_deposit]
+    int64_t graph_launches[4] = {0, 0, 0, 0};
     bool graph_failed = false;
 };
 
@@ -788,11 +788,13 @@ static int enqueue_fixedpoint_step(picgolf_handle h)
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
     a.slow_count = h->slow_count; a.K = h->K;
     h->pass_blocks = h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
-    const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
-    if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
-    else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-    h->timer.end(sp3_, h->stream);
-    h->launches++;
+    if (!h->have_deposit) { // only the first step after the particles were set: later ones inherit the fused deposit
+        const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
+        if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
+        else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+        h->timer.end(sp3_, h->stream);
+        h->launches++;
+    }
     for (int k = 1; k <= c.max_sweeps; ++k) {
         PG_TRY(allreduce_grid(h));
         PG_TRY(launch_solve1d(h, k));
@@ -864,7 +866,8 @@ static int step_fixedpoint(picgolf_handle h)
     if (!use_graph) {
         PG_TRY(enqueue(h));
     } else {
-        cudaGraphExec_t &exec = h->step_graph[h->par];
+        const int slot = h->par + 2 * (h->have_deposit ? 1 : 0);
+        cudaGraphExec_t &exec = h->step_graph[slot];
         if (!exec) {
             const int64_t l0 = h->launches;
             cudaGraph_t g = nullptr;
@@ -876,7 +879,7 @@ static int step_fixedpoint(picgolf_handle h)
             }
             if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&exec, g, 0);
             if (g) cudaGraphDestroy(g);
-            h->graph_launches = h->launches - l0;
+            h->graph_launches[slot] = h->launches - l0;
             h->launches = l0;
             if (e != cudaSuccess || rc != 0 || !exec) { // fall back to plain launches for good
                 cudaGetLastError();
@@ -884,14 +887,16 @@ static int step_fixedpoint(picgolf_handle h)
                 h->graph_failed = true;
                 PG_TRY(enqueue(h));
                 h->par ^= 1; h->since_sort++;
+                if (!h->simpson) h->have_deposit = true;
                 return 0;
             }
         }
         PG_CUDA(cudaGraphLaunch(exec, h->stream));
-        h->launches += h->graph_launches;
+        h->launches += h->graph_launches[slot];
     }
     h->par ^= 1;
     h->since_sort++;
+    if (!h->simpson) h->have_deposit = true; // the final pass deposited the next step's first rho
     return 0;
 }
 
