@@ -192,6 +192,13 @@ struct picgolf_handle_s {
     int nbins = 0, K = 1, sort_every = 1, nblocks_sorted = 1;
     int64_t since_sort = 0, sorts = 0;
     size_t smem_sorted = 0;
+    // adaptive re-sort interval (cfg.sort_every == 0): the slow-path counter is copied to pinned memory at every
+    // sort and looked at, without synchronising, at the next one
+    bool sort_auto = false;
+    unsigned long long *slow_host = nullptr, slow_seen = 0;
+    cudaEvent_t slow_ev = nullptr;
+    bool slow_pending = false;
+    int64_t steps_at_probe = 0, steps_at_probe_prev_steps = 0;
     // CUDA graphs of one fixed-point step, one per ping-pong parity
     cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr}; // [par + 2*have_deposit]
     int64_t graph_launches[4] = {0, 0, 0, 0};
@@ -313,6 +320,8 @@ static int destroy_impl(picgolf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->timer.destroy();
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
+    if (h->slow_host) cudaFreeHost(h->slow_host);
+    if (h->slow_ev) cudaEventDestroy(h->slow_ev);
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
@@ -416,6 +425,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 // re-sort before the slowest/fastest particles (|v| ~ 3) have drifted ~5 cells from their bin
                 double cells_per_step = 3.0 * c.dt * (double)N;
                 h->sort_every = c.sort_every > 0 ? c.sort_every : (int)std::max(1.0, std::min(1000.0, floor(5.0 / cells_per_step)));
+                h->sort_auto = c.sort_every <= 0;
                 h->smem_sorted = (size_t)(PG_THREADS / 32) * WIN_WARP_DOUBLES * sizeof(double);
                 PG_TRY(set_smem(fp_pass_sorted<true, SORTED_NP>, h->smem_sorted));
                 PG_TRY(set_smem(fp_pass_sorted<false, SORTED_NP>, h->smem_sorted));
@@ -475,7 +485,8 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         if (h->sorted) {
             const int ntx = std::max(1, NX >> T2_SHIFT), nty = std::max(1, NY >> T2_SHIFT);
             h->nbins = ntx * nty;
-            h->sort_every = c.sort_every > 0 ? c.sort_every : 16; // 4-sigma thermal drift ~0.33 cells/step vs the 8-cell window margin
+            h->sort_every = c.sort_every > 0 ? c.sort_every : 16; // starting point; adapted from the slow-path counter
+            h->sort_auto = c.sort_every <= 0;
             for (int q = 0; q < 5; ++q) PG_TRY(dalloc(&h->p2[1][q], n));
             PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
             PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
@@ -563,6 +574,7 @@ static int reset_run_state(picgolf_handle h)
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
+    h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0;
     if (h->hist) PG_CUDA(cudaMemset(h->hist, 0, (size_t)h->ncell * h->T * sizeof(double)));
     return 0;
 }
@@ -755,9 +767,41 @@ static int launch_step_end(picgolf_handle h, bool record)
     return 0;
 }
 
+// Adaptive re-sort interval.  Called at every sort: if the previous probe of the slow-path counter has landed,
+// compare the fraction of deposits that left their window since then with two thresholds and shorten / lengthen the
+// interval; then start a new probe.  Never synchronises.
+static void adapt_sort_interval(picgolf_handle h)
+{
+    if (!h->sort_auto || !h->slow_count) return;
+    if (!h->slow_host) {
+        if (cudaMallocHost((void **)&h->slow_host, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
+        cudaEventCreateWithFlags(&h->slow_ev, cudaEventDisableTiming);
+        *h->slow_host = 0;
+    }
+    if (h->slow_pending && cudaEventQuery(h->slow_ev) == cudaSuccess) {
+        const unsigned long long now = *h->slow_host;
+        const int64_t steps = std::max<int64_t>(1, h->steps_at_probe_prev_steps);
+        const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)steps);
+        h->slow_seen = now;
+        if (frac > 1e-3) h->sort_every = std::max(2, h->sort_every / 2);
+        else if (frac < 2e-5) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 4));
+        h->slow_pending = false;
+    } else {
+        cudaGetLastError();
+    }
+    if (!h->slow_pending) {
+        cudaMemcpyAsync(h->slow_host, h->slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+        cudaEventRecord(h->slow_ev, h->stream);
+        h->slow_pending = true;
+        h->steps_at_probe_prev_steps = h->steps - h->steps_at_probe;
+        h->steps_at_probe = h->steps;
+    }
+}
+
 // Counting sort of the step-start state (xb[par], vb[par]) by cell into the other ping-pong buffers.
 static int sort_particles_1d(picgolf_handle h)
 {
+    adapt_sort_interval(h);
     const int sp = h->timer.begin(ST_SORT, h->stream);
     SortArgs a;
     memset(&a, 0, sizeof(a));
@@ -949,6 +993,7 @@ static int launch_solve2d(picgolf_handle h)
 // Counting sort of the 2D particle arrays by 16x16-cell tile + the per-tile work list.
 static int sort_particles_2d(picgolf_handle h)
 {
+    adapt_sort_interval(h);
     const int sp = h->timer.begin(ST_SORT, h->stream);
     SortArgs a;
     memset(&a, 0, sizeof(a));
