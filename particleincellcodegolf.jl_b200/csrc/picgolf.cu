@@ -784,7 +784,7 @@ static void adapt_sort_interval(picgolf_handle h)
         const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)steps);
         h->slow_seen = now;
         if (frac > 1e-3) h->sort_every = std::max(2, h->sort_every / 2);
-        else if (frac < 2e-5) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 4));
+        else if (frac < 5e-5) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
         h->slow_pending = false;
     } else {
         cudaGetLastError();
