@@ -80,10 +80,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
-def make_sim(pg, workload, per_gpu, rank, world, device, T):
+def make_sim(pg, workload, per_gpu, rank, world, device, T, deposit_mode=0):
     P = per_gpu * world
     if workload == "gauss_fp":
-        sim = pg.gaussian_fixed_point(N=4096, P=P, T=T, W=400.0, l=1e-8, half_width=6, rank=rank, nranks=world, device=device)
+        sim = pg.gaussian_fixed_point(N=4096, P=P, T=T, W=400.0, l=1e-8, half_width=6, rank=rank, nranks=world, device=device,
+                                      deposit_mode=deposit_mode)
         name = f"config4 scaled Gaussian fixed-point two-stream 1D1V N=4096 P={P} (2^{int(math.log2(per_gpu))}/GPU) +-6 l=1e-8 seeded-uniform start"
         bytes_per_unit = None  # 32*(S+1), needs the measured sweep count
     elif workload == "ngp":
@@ -120,7 +121,8 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, Wm = args.steps, max(args.warmup, 3)
     per_gpu = 1 << args.log2_particles_per_gpu
-    sim, name, bpu = make_sim(pg, args.workload, per_gpu, rank, world, local, T=K + Wm + 64)
+    sim, name, bpu = make_sim(pg, args.workload, per_gpu, rank, world, local, T=K + Wm + 64,
+                              deposit_mode={"auto": 0, "atomic": 1, "sorted": 2, "poly": 3}[args.deposit_mode])
     if world > 1:
         pgd.connect(sim)
     init_sim(sim, args.workload)
@@ -385,6 +387,8 @@ def main():
     ap.add_argument("--workload", default="gauss_fp", choices=["gauss_fp", "ngp", "2d3v"])
     ap.add_argument("--log2-particles-per-gpu", type=int, default=28)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--deposit-mode", default="auto", choices=["auto", "atomic", "sorted", "poly"],
+                    help="gauss_fp only: force a deposit path (A/B runs); auto = what a caller gets")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", dest="others", action="store_false", help="skip the brief NGP and 2D3V runs")

@@ -55,7 +55,9 @@ typedef enum picgolf_scheme {
 typedef enum picgolf_deposit_mode {
     PICGOLF_DEPOSIT_AUTO = 0,     /* library picks (sorted windows when P/N is large) */
     PICGOLF_DEPOSIT_ATOMIC = 1,   /* shared-memory privatised grid + fp64 atomics, any particle order */
-    PICGOLF_DEPOSIT_SORTED = 2    /* cell-sorted particles, register/window accumulation per warp */
+    PICGOLF_DEPOSIT_SORTED = 2,   /* cell-sorted particles, register/window accumulation per warp */
+    PICGOLF_DEPOSIT_POLY = 3      /* Gaussian fixed point only: (cell, sign v)-sorted particles, cell-polynomial gather and
+                                     moment deposit (pg_kernels_poly.cuh); AUTO picks it for >= 1024 particles per cell */
 } picgolf_deposit_mode;
 
 /*

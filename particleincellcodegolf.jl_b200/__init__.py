@@ -29,7 +29,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
 
 NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13, GAUSS_BORIS_1D2V = 1, 2, 3, 4, 5, 6, 7
-DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED = 0, 1, 2
+DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED, DEPOSIT_POLY = 0, 1, 2, 3
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -309,7 +309,8 @@ class PIC:
         return n.value
 
     def sort_stats(self):
-        """(number of cell sorts, particle deposits that took the out-of-window slow path)."""
+        """(number of cell sorts, particle deposits that took the out-of-window slow path -- polynomial mode: mid-stream
+        flushes of a lane's moment set)."""
         a, b = _i64(), _i64()
         _check(self._lib.picgolf_sort_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value

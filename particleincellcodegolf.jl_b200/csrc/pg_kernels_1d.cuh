@@ -64,6 +64,8 @@ struct FPArgs {
     double dt, fx_scale; // fx_scale = 2^frac
     int N, k;
     int K;               // sorted mode: batches of 32 particles per warp chunk
+    const double *G;     // polynomial mode: per-cell gather polynomials [N][18] (pg_kernels_poly.cuh)
+    fx_t *Mg;            // polynomial mode: fixed-point moment grid [N][17]
 };
 
 template <bool FIRST>

@@ -31,13 +31,15 @@ struct SortArgs {
     int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1])
     int N, NY;  // grid
     int tshift; // 2D: log2(tile edge in cells)
+    int vsplit; // 1D: 1 -> key = 2*cell + (v >= 0): each beam keeps its own bins, so a bin drifts as a whole (pg_kernels_poly.cuh)
 };
 
 __device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
 {
     if (a.mode == 0) {
         int c = (int)rint(a.in[0][j] * (double)a.N); // the stencil centre Int(round(x*N)): a bin shares its window rows
-        return c & (a.N - 1);
+        c &= a.N - 1;
+        return a.vsplit ? 2 * c + (a.in[1][j] >= 0.0 ? 1 : 0) : c;
     }
     int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
     int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);

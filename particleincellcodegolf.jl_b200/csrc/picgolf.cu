@@ -16,6 +16,7 @@
 #include "pg_gauss.cuh"
 #include "pg_kernels_1d.cuh"
 #include "pg_kernels_2d.cuh"
+#include "pg_kernels_poly.cuh"
 #include "pg_sort.cuh"
 #include "pg_kernels_simpson.cuh"
 
@@ -192,6 +193,12 @@ struct picgolf_handle_s {
     int nbins = 0, K = 1, sort_every = 1, nblocks_sorted = 1;
     int64_t since_sort = 0, sorts = 0;
     size_t smem_sorted = 0;
+    // cell-polynomial mode (pg_kernels_poly.cuh): per-cell gather polynomials and fixed-point moment grid
+    bool poly = false;
+    double *Gpoly = nullptr;
+    unsigned long long *Mg = nullptr;
+    int nblocks_poly = 1;
+    size_t smem_poly = 0;
     // adaptive re-sort interval (cfg.sort_every == 0): the slow-path counter is copied to pinned memory at every
     // sort and looked at, without synchronising, at the next one
     bool sort_auto = false;
@@ -327,7 +334,7 @@ static int destroy_impl(picgolf_handle h)
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_fx,
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
-                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count};
+                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -418,10 +425,14 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             if (c.deterministic) h->sorted = false;
             else if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
             else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 18) && ppc >= 64;
+            // many particles per cell: cell-polynomial passes (HBM-bound instead of FP64-bound)
+            if (!c.deterministic && (c.deposit_mode == PICGOLF_DEPOSIT_POLY || (c.deposit_mode == PICGOLF_DEPOSIT_AUTO && h->count >= (1 << 22) && ppc >= 1024))) {
+                h->sorted = true; h->poly = true;
+            }
             if (h->sorted) {
                 h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
                 h->K = (h->K + SORTED_NP - 1) / SORTED_NP * SORTED_NP; // whole groups of SORTED_NP batches
-                h->nbins = N;
+                h->nbins = h->poly ? 2 * N : N; // polynomial mode: (cell, sign v) bins
                 // re-sort before the slowest/fastest particles (|v| ~ 3) have drifted ~5 cells from their bin
                 double cells_per_step = 3.0 * c.dt * (double)N;
                 h->sort_every = c.sort_every > 0 ? c.sort_every : (int)std::max(1.0, std::min(1000.0, floor(5.0 / cells_per_step)));
@@ -432,6 +443,17 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 int64_t warps = (h->count + 32LL * h->K - 1) / (32LL * h->K);
                 PG_TRY(occupancy_blocks(fp_pass_sorted<false, SORTED_NP>, PG_THREADS, h->smem_sorted, h->sms, warps * 32, &h->nblocks_sorted));
                 h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
+                if (h->poly) {
+                    if (c.sort_every <= 0) h->sort_every = 8; // starting point; adapted from the thrash-flush counter
+                    h->smem_poly = cp_smem_bytes(PG_THREADS);
+                    PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * N)); PG_TRY(dalloc(&h->Mg, (size_t)CP_NC * N));
+                    PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * N * sizeof(double)));
+                    PG_CUDA(cudaMemset(h->Mg, 0, (size_t)CP_NC * N * sizeof(unsigned long long)));
+                    // one contiguous range of >= 16 rows (of 64 particles) per warp
+                    const int64_t rows = (h->count + 63) / 64;
+                    PG_TRY(occupancy_blocks(fp_pass_poly<false>, PG_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
+                    h->nblocks = std::max(h->nblocks, h->nblocks_poly);
+                }
                 PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
                 PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
                 PG_CUDA(cudaMemset(h->bin_count, 0, h->nbins * sizeof(unsigned int)));
@@ -571,6 +593,7 @@ static int reset_run_state(picgolf_handle h)
     PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, (size_t)h->grid_rows * h->ncell * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
+    if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * h->ncell * sizeof(unsigned long long), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
@@ -783,8 +806,12 @@ static void adapt_sort_interval(picgolf_handle h)
         const int64_t steps = std::max<int64_t>(1, h->steps_at_probe_prev_steps);
         const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)steps);
         h->slow_seen = now;
-        if (frac > 1e-3) h->sort_every = std::max(2, h->sort_every / 2);
-        else if (frac < 5e-5) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
+        // polynomial mode counts every mid-stream flush of a lane's moment set: in (cell, sign v) order a lane changes
+        // cell twice per bin, i.e. ~64/bin_size flushes per particle and pass (4 passes per step assumed); more than a
+        // few times that means lanes alternate between cells (bins sheared over three cells)
+        const double expect = h->poly ? 4.0 * 64.0 * (double)h->nbins / (double)h->count : 0.0;
+        if (frac > 1e-3 + 4.0 * expect) h->sort_every = std::max(2, h->sort_every / 2);
+        else if (frac < 5e-5 + 2.0 * expect) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
         h->slow_pending = false;
     } else {
         cudaGetLastError();
@@ -811,6 +838,7 @@ static int sort_particles_1d(picgolf_handle h)
     a.pid_out = h->pid[1 - h->pidpar];
     a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor;
     a.P = h->count; a.narr = 2; a.nbins = h->nbins; a.mode = 0; a.N = (int)h->cfg.N; a.NY = 1; a.tshift = 0;
+    a.vsplit = h->poly ? 1 : 0;
     const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
     int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 8));
@@ -823,6 +851,43 @@ static int sort_particles_1d(picgolf_handle h)
     return 0;
 }
 
+// Cell-polynomial form of the step (pg_kernels_poly.cuh): per sweep  moments -> rho, [all-reduce], solve, E -> per-cell
+// gather polynomials (+ clear the moments), particle pass.
+static int enqueue_poly_step(picgolf_handle h, FPArgs a)
+{
+    const picgolf_config &c = h->cfg;
+    const int N = (int)c.N;
+    h->pass_blocks = h->nblocks_poly;
+    if (!h->have_deposit) {
+        const int sp = h->timer.begin(ST_PARTICLES, h->stream);
+        fp_pass_poly<true><<<h->nblocks_poly, PG_THREADS, h->smem_poly, h->stream>>>(a);
+        h->timer.end(sp, h->stream);
+        h->launches++;
+    }
+    Mom2RhoArgs m;
+    m.Mg = h->Mg; m.rho = h->rho_fx; m.ctrl = h->ctrl; m.fx_scale = h->fx_scale; m.fx_inv = h->fx_inv; m.N = N;
+    GPolyArgs g;
+    g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N;
+    for (int k = 1; k <= c.max_sweeps; ++k) {
+        int sp = h->timer.begin(ST_SOLVE, h->stream);
+        mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 4 * CPM_CELLS, 0, h->stream>>>(m);
+        h->timer.end(sp, h->stream);
+        PG_TRY(allreduce_grid(h));
+        PG_TRY(launch_solve1d(h, k));
+        g.k = k;
+        sp = h->timer.begin(ST_SOLVE, h->stream);
+        gpoly_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(g);
+        h->timer.end(sp, h->stream);
+        a.k = k;
+        sp = h->timer.begin(ST_PARTICLES, h->stream);
+        fp_pass_poly<false><<<h->nblocks_poly, PG_THREADS, h->smem_poly, h->stream>>>(a);
+        h->timer.end(sp, h->stream);
+        h->launches += 4;
+    }
+    PG_TRY(launch_step_end(h, true));
+    return 0;
+}
+
 static int enqueue_fixedpoint_step(picgolf_handle h)
 {
     const picgolf_config &c = h->cfg;
@@ -830,8 +895,9 @@ static int enqueue_fixedpoint_step(picgolf_handle h)
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
     a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
-    a.slow_count = h->slow_count; a.K = h->K;
+    a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg;
     h->pass_blocks = h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
+    if (h->use_sorted_now && h->poly) return enqueue_poly_step(h, a);
     if (!h->have_deposit) { // only the first step after the particles were set: later ones inherit the fused deposit
         const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
         if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
@@ -1160,7 +1226,7 @@ static int fetch_raw(picgolf_handle h, std::vector<double> &raw, int64_t *rows)
     PG_CUDA(cudaMemcpy(raw.data(), h->raw, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
     if (h->comm) {
         // columns 1,2 (and 3 in 2D) hold local-shard sums: all-reduce them out of place.
-        const size_t ncol = h->is2d ? 3 : 2, cnt = ncol * (size_t)h->T;
+        const size_t ncol = h->npart == 3 ? 3 : 2, cnt = ncol * (size_t)h->T; // particle-derived columns (sweeps column stays local)
         DevTmp tmp;
         PG_TRY(tmp.alloc(cnt * sizeof(double)));
         PG_TRY(nccl::check(nccl::AllReduce(h->raw + h->T, tmp.p, cnt, nccl::Float64, nccl::Sum, h->comm, h->stream),

@@ -415,6 +415,99 @@ def test_sorted_mode_matches_atomic_mode(pg, oracle, start):
     assert sorts == 3 and slow < P // 100  # before steps 1,5,9; almost everything stays inside its window
 
 
+# =============================================================================================
+# cell-polynomial mode (pg_kernels_poly.cuh): moment deposit + per-cell gather polynomials
+# =============================================================================================
+def test_poly_mode_c2_golden(pg, oracle):
+    """Golden config-2 fixture through the polynomial passes.  32 particles per cell in random order: every lane
+    flushes its moment sets all the time and the gather window is restaged every row -- correctness only."""
+    g = golden("c2_fixedpoint")
+    sim = pg.gaussian_fixed_point(T=64, deposit_mode=pg.DEPOSIT_POLY, sort_every=3)
+    sim.set_particles(g["x0"], g["v0"])
+    sim.step(1)  # any-order kernel (lazy first sort)
+    sim.step(1)  # first polynomial step
+    sim2 = pg.gaussian_fixed_point(T=64, deposit_mode=pg.DEPOSIT_ATOMIC)
+    sim2.set_particles(g["x0"], g["v0"])
+    sim2.step(2)
+    for a, b in zip(sim.particles() + sim.fields(), sim2.particles() + sim2.fields()):
+        assert relnorm(a, b) < TOL
+    sim.step(14)
+    D, sw = sim.diagnostics()
+    assert np.array_equal(sw, g["sweeps"])
+    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    x, v = sim.particles()
+    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10
+    assert sim.sort_stats()[0] == 5
+
+
+@pytest.mark.parametrize("start", ["uniform", "quiet"])
+@pytest.mark.parametrize("N,P", [(4096, 1 << 20), (256, (1 << 22) + 77)])
+def test_poly_mode_matches_atomic_mode(pg, oracle, start, N, P):
+    """Polynomial passes against the order-agnostic atomic path over 12 steps with re-sorts, and against the oracle
+    after the first polynomial step; 256 and 16384 particles per cell, ragged tail included."""
+    rng = np.random.default_rng(22)
+    sims = []
+    for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_POLY):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, deposit_mode=mode, sort_every=4)
+        if start == "quiet":
+            sim.init_quiet()
+        else:
+            x0 = rng.random(P) if not sims else x0  # noqa: F821
+            v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0)
+            sim.set_particles(x0, v0)
+        sims.append(sim)
+    a, s = sims
+    x0, v0 = a.particles()
+    a.step(2); s.step(2)  # step 1 runs on the any-order kernel in both; step 2 is the first polynomial one
+    do_oracle = P <= (1 << 20)
+    if do_oracle:
+        fp = oracle.FixedPoint(x0, v0, N, a.cfg.dt, 400.0, hw=6, rtol=1e-8)
+        so = [fp.step()[2] for _ in range(2)]
+    xa, va = a.particles()
+    xs, vs = s.particles()
+    ra, Ea = a.fields()
+    rs, Es = s.fields()
+    assert relnorm(xs, xa) < TOL and relnorm(vs, va) < TOL and relnorm(rs, ra) < TOL
+    escale = max(1e-11 * np.abs(Ea).max(), 1e-12 * np.abs(ra).max() / (2 * np.pi))  # quiet start: E is round-off
+    assert np.abs(Es - Ea).max() < escale
+    if do_oracle:
+        assert relnorm(xs, fp.x) < TOL and relnorm(vs, fp.v) < TOL and relnorm(rs, fp.r) < TOL
+        assert np.abs(Es - fp.E).max() < escale
+        # quiet start: E is round-off and the count of the first polynomial step is decided by noise (its first solve
+        # sees the charge the any-order kernel deposited, the second one the moment form of the same charge)
+        assert list(s.diagnostics()[1][:2 if start == "uniform" else 1]) == so[:2 if start == "uniform" else 1]
+    a.step(10); s.step(10)
+    xa, va = a.particles()
+    xs, vs = s.particles()
+    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    Da, swa = a.diagnostics()
+    Ds, sws = s.diagnostics()
+    if start == "uniform":
+        assert np.array_equal(swa, sws)
+    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    sorts, flushes = s.sort_stats()
+    assert sorts == 3  # before steps 1, 5, 9 (0-based)
+    if P // N >= 4096:
+        # (cell, sign v) bins drift as a whole: a lane changes cell about twice per bin (64/bin_size flushes per
+        # particle and pass); lanes alternating between cells would flush on a large share of their particles
+        assert flushes / (P * float(sws[1:].sum())) < 0.02
+
+
+def test_poly_mode_charge_and_reproducibility(pg):
+    """Total charge is conserved to round-off by the moment form; two runs agree to round-off (the counting sort
+    ranks particles inside a bin with atomics, so the order of the moment sums differs from run to run)."""
+    N, P = 1024, 1 << 22
+    out = []
+    for _ in range(2):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=400.0, deposit_mode=pg.DEPOSIT_POLY, sort_every=100)
+        sim.init_synthetic(seed=5)
+        sim.step(4)
+        rho, E = sim.fields()
+        out.append((rho, E) + sim.particles())
+        assert abs(rho.mean() / 400.0 - 1) < 1e-13
+    assert all(relnorm(a, b) < 1e-13 for a, b in zip(*out))
+
+
 def test_2d3v_tile_sorted_mode(pg, oracle):
     """Tile-sorted 2D path (pg_sort mode 1 + particles_2d3v_tiled): golden fixture with frequent re-sorts,
     then a 128x128 run against the any-order path."""

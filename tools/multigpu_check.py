@@ -28,7 +28,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO):
+    for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO, pg.DEPOSIT_POLY):
         N, P, steps = 4096, 1 << 21, 6
         sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, rank=rank, nranks=world, device=local, deposit_mode=mode, sort_every=3)
         pgd.connect(sim)
@@ -82,6 +82,39 @@ def main():
         print(f"[rank {rank}] 2d3v mode={mode} {e} ok={good}", flush=True)
         ok &= good
         sim.close(); ref.close()
+    # "next" rows: Simpson-1/3 fixed point (3-row grid all-reduce) and the 1D2V Boris code
+    for ctor in (pg.gaussian_fixed_point_quiet_simpson13, pg.area_fixed_point_quiet_simpson13):
+        sim = ctor(N=256, P=1 << 16, T=8, W=400.0, l=1e-9, rank=rank, nranks=world, device=local)
+        pgd.connect(sim)
+        sim.init_synthetic(seed=8)
+        sim.step(3)
+        x, v = sim.particles(); rho, E = sim.fields(); D, sw = sim.diagnostics()
+        ref = ctor(N=256, P=1 << 16, T=8, W=400.0, l=1e-9, device=local)
+        ref.init_synthetic(seed=8); ref.step(3)
+        xr, vr = ref.particles(); rr, Er = ref.fields(); Dr, swr = ref.diagnostics()
+        f, c = sim.first, sim.count
+        good = np.array_equal(x, xr[f:f + c]) and np.array_equal(v, vr[f:f + c]) and np.array_equal(rho, rr) and np.array_equal(E, Er) \
+            and np.array_equal(sw, swr) and rel(D[:, :3], Dr[:, :3]) < 1e-12
+        print(f"[rank {rank}] {ctor.__name__} bit-identical={good} sweeps={list(sw)}", flush=True)
+        ok &= good
+        sim.close(); ref.close()
+    rng = np.random.default_rng(3)
+    P = 1 << 16
+    sim = pg.ngp_1d2v(N=512, P=P, T=64, TO=16, rank=rank, nranks=world, device=local)
+    pgd.connect(sim)
+    xg, vxg, vyg = rng.random(P), sim.vth * rng.standard_normal(P), sim.vth * rng.standard_normal(P)
+    f, c = sim.first, sim.count
+    sim.set_particles(xg[f:f + c], vxg[f:f + c], vy=vyg[f:f + c])
+    sim.step(8)
+    got = sim.particles(); fld = sim.fields(); D, _ = sim.diagnostics(); Es = sim.field_history()
+    ref = pg.ngp_1d2v(N=512, P=P, T=64, TO=16, device=local)
+    ref.set_particles(xg, vxg, vy=vyg); ref.step(8)
+    gr = ref.particles(); fr = ref.fields(); Dr, _ = ref.diagnostics(); Esr = ref.field_history()
+    good = all(np.array_equal(a, b[f:f + c]) for a, b in zip(got, gr)) and np.array_equal(fld[0], fr[0]) and np.array_equal(Es, Esr) \
+        and rel(D, Dr) < 1e-12
+    print(f"[rank {rank}] ngp_1d2v bit-identical={good}", flush=True)
+    ok &= good
+    sim.close(); ref.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
