@@ -173,7 +173,9 @@ def run_gpu(args):
     if args.workload == "gauss_fp":
         passes = float(sw2[Wm + K:Wm + K + nroof].sum())  # S solves -> S particle passes per step (the k=0 pass is fused into the previous step's final pass)
         alg_bytes_launch = 32.0 * per_gpu
-        kernel = "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)"
+        poly = sim.deposit_path == pg.DEPOSIT_POLY
+        kernel = ("fp_pass_poly<FIRST> (per-cell gather polynomial + implicit-midpoint update + register moment deposit)" if poly else
+                  "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)")
     elif args.workload == "ngp":
         passes = float(nroof + 1)
         alg_bytes_launch = 32.0 * per_gpu
@@ -187,7 +189,8 @@ def run_gpu(args):
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
     try:  # per-launch DRAM bytes of the same kernel from the committed ncu --set full capture (only valid at 2^28/GPU)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[args.workload]
+        key = "gauss_fp_poly" if args.workload == "gauss_fp" and sim.deposit_path == pg.DEPOSIT_POLY else args.workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[key]
         if per_gpu == 1 << 28:
             traffic = tj["traffic_bytes"]
     except Exception:
@@ -201,12 +204,15 @@ def run_gpu(args):
     fp64 = None
     if args.workload == "gauss_fp":
         peak_tf = pg.fp64_peak_tflops()
-        # FP64 warp-instructions per particle-pass measured with ncu (profiles/): 255 for a pass with two stencils
-        # (middle passes and the final pass with the fused first deposit of the next step)
-        fp64_inst = float(sum(255 * int(s_) for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
+        # FP64 instructions per particle-pass measured with ncu (profiles/): 255 for a fp_pass_sorted pass with two
+        # stencils (middle passes and the final pass with the fused first deposit of the next step); 90 for fp_pass_poly
+        # (180 warp-instructions per row of 64 particles: DADD 94, DMUL 54, DFMA 32)
+        per_pass = 90 if sim.deposit_path == pg.DEPOSIT_POLY else 255
+        fp64_inst = float(sum(per_pass * int(s_) for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
         ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
         fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
-                "note": "FP64 lane-instructions of the pass kernels x2 / kernel time; this, not HBM, bounds the erf-shape path"}
+                "fp64_instructions_per_particle_pass": per_pass,
+                "note": "FP64 lane-instructions of the pass kernels x2 / kernel time (the second bound of the erf-shape passes besides HBM)"}
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None

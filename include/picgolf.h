@@ -191,8 +191,11 @@ int picgolf_stage_times(picgolf_handle h, double ms[5], int reset);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int picgolf_launch_count(picgolf_handle h, int64_t *launches);
 /* Cell-sorted mode bookkeeping: number of sorts so far and number of particle deposits that fell
- * outside their warp's shared-memory window (slow path) -- a stale-sort indicator. */
+ * outside their warp's shared-memory window (slow path) -- a stale-sort indicator.
+ * In polynomial mode (PICGOLF_DEPOSIT_POLY) the second number counts mid-stream flushes of a lane's moment set. */
 int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_particles);
+/* Which deposit path the handle runs (a picgolf_deposit_mode other than AUTO: what AUTO resolved to). */
+int picgolf_deposit_path(picgolf_handle h, int *mode);
 /* The cudaStream_t the handle enqueues on (for CUDA-event timing by the caller). */
 int picgolf_get_stream(picgolf_handle h, void **stream);
 

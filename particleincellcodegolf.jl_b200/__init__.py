@@ -103,6 +103,7 @@ _SIGNATURES = {
     "picgolf_stage_times": [_vp, C.POINTER(_d * 5), _int],
     "picgolf_launch_count": [_vp, C.POINTER(_i64)],
     "picgolf_sort_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "picgolf_deposit_path": [_vp, C.POINTER(C.c_int)],
     "picgolf_get_stream": [_vp, C.POINTER(_vp)],
     "picgolf_comm_unique_id": [_vp],
     "picgolf_comm_init": [_vp, _vp, _int, _int],
@@ -131,7 +132,8 @@ def load() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise PicGolfError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                    "(nvcc, sm_100a). libpicgolf has no CPU or PyTorch fallback.")
-        L = C.CDLL(LIB_PATH)
+        # PICGOLF_LIB: an alternative build of the same sources (kernel tuning A/B runs, tools/build_variants.sh)
+        L = C.CDLL(os.environ.get("PICGOLF_LIB") or LIB_PATH)
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -314,6 +316,13 @@ class PIC:
         a, b = _i64(), _i64()
         _check(self._lib.picgolf_sort_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    @property
+    def deposit_path(self) -> int:
+        """DEPOSIT_ATOMIC / DEPOSIT_SORTED / DEPOSIT_POLY: what the handle actually runs (AUTO resolved)."""
+        m = C.c_int()
+        _check(self._lib.picgolf_deposit_path(self._h, C.byref(m)))
+        return m.value
 
     @property
     def stream(self) -> int:

@@ -66,6 +66,7 @@ struct FPArgs {
     int K;               // sorted mode: batches of 32 particles per warp chunk
     const double *G;     // polynomial mode: per-cell gather polynomials [N][18] (pg_kernels_poly.cuh)
     fx_t *Mg;            // polynomial mode: fixed-point moment grid [N][17]
+    double dN;           // (double)N
 };
 
 template <bool FIRST>

@@ -205,6 +205,8 @@ struct picgolf_handle_s {
     unsigned long long *slow_host = nullptr, slow_seen = 0;
     cudaEvent_t slow_ev = nullptr;
     bool slow_pending = false;
+    bool force_sort = false, poly_quiet = false; // polynomial mode: per-step flush probe (probe_poly_flushes)
+    cudaEvent_t run_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // end-of-step markers
     int64_t steps_at_probe = 0, steps_at_probe_prev_steps = 0;
     // CUDA graphs of one fixed-point step, one per ping-pong parity
     cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr}; // [par + 2*have_deposit]
@@ -329,6 +331,7 @@ static int destroy_impl(picgolf_handle h)
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
     if (h->slow_host) cudaFreeHost(h->slow_host);
     if (h->slow_ev) cudaEventDestroy(h->slow_ev);
+    for (auto &e : h->run_ev) if (e) cudaEventDestroy(e);
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
@@ -444,14 +447,15 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 PG_TRY(occupancy_blocks(fp_pass_sorted<false, SORTED_NP>, PG_THREADS, h->smem_sorted, h->sms, warps * 32, &h->nblocks_sorted));
                 h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
                 if (h->poly) {
-                    if (c.sort_every <= 0) h->sort_every = 8; // starting point; adapted from the thrash-flush counter
-                    h->smem_poly = cp_smem_bytes(PG_THREADS);
+                    if (c.sort_every <= 0) h->sort_every = 16; // starting point; adapted from the flush counter every step
+                    h->smem_poly = cp_smem_bytes(CP_THREADS);
+                    PG_TRY(set_smem(fp_pass_poly<true>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false>, h->smem_poly));
                     PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * N)); PG_TRY(dalloc(&h->Mg, (size_t)CP_NC * N));
                     PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * N * sizeof(double)));
                     PG_CUDA(cudaMemset(h->Mg, 0, (size_t)CP_NC * N * sizeof(unsigned long long)));
                     // one contiguous range of >= 16 rows (of 64 particles) per warp
                     const int64_t rows = (h->count + 63) / 64;
-                    PG_TRY(occupancy_blocks(fp_pass_poly<false>, PG_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
+                    PG_TRY(occupancy_blocks(fp_pass_poly<false>, CP_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
                     h->nblocks = std::max(h->nblocks, h->nblocks_poly);
                 }
                 PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
@@ -597,7 +601,7 @@ static int reset_run_state(picgolf_handle h)
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
-    h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0;
+    h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0; h->force_sort = false; h->poly_quiet = false;
     if (h->hist) PG_CUDA(cudaMemset(h->hist, 0, (size_t)h->ncell * h->T * sizeof(double)));
     return 0;
 }
@@ -806,12 +810,8 @@ static void adapt_sort_interval(picgolf_handle h)
         const int64_t steps = std::max<int64_t>(1, h->steps_at_probe_prev_steps);
         const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)steps);
         h->slow_seen = now;
-        // polynomial mode counts every mid-stream flush of a lane's moment set: in (cell, sign v) order a lane changes
-        // cell twice per bin, i.e. ~64/bin_size flushes per particle and pass (4 passes per step assumed); more than a
-        // few times that means lanes alternate between cells (bins sheared over three cells)
-        const double expect = h->poly ? 4.0 * 64.0 * (double)h->nbins / (double)h->count : 0.0;
-        if (frac > 1e-3 + 4.0 * expect) h->sort_every = std::max(2, h->sort_every / 2);
-        else if (frac < 5e-5 + 2.0 * expect) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
+        if (frac > 1e-3) h->sort_every = std::max(2, h->sort_every / 2);
+        else if (frac < 5e-5) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
         h->slow_pending = false;
     } else {
         cudaGetLastError();
@@ -825,10 +825,54 @@ static void adapt_sort_interval(picgolf_handle h)
     }
 }
 
+// Polynomial mode: the flush counter is probed EVERY step (a 8-byte asynchronous copy).  The host is allowed to run
+// at most POLY_RUNAHEAD steps ahead of the device (it waits for the end-of-step marker of an OLDER step, so the device
+// queue never drains and no step is ever synchronised internally); the probe it reads is therefore that recent.  In (cell, sign v) order a lane changes cell about twice per bin, i.e. ~64/bin_size
+// flushes per particle and pass; many times that means lanes alternate between cells (a bin sheared over three
+// cells) and every such particle pays 17 REDs -- then the next step re-sorts at once, whatever the interval, and the
+// interval is shortened to what was survived.  Quiet intervals grow by half up to 64 steps.
+constexpr int POLY_RUNAHEAD = 4;
+static void probe_poly_flushes(picgolf_handle h)
+{
+    if (!h->sort_auto || !h->slow_count) return;
+    if (h->steps >= POLY_RUNAHEAD) {
+        cudaEvent_t e = h->run_ev[(h->steps - POLY_RUNAHEAD) & 7];
+        if (e) cudaEventSynchronize(e);
+    }
+    if (!h->slow_host) {
+        if (cudaMallocHost((void **)&h->slow_host, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
+        cudaEventCreateWithFlags(&h->slow_ev, cudaEventDisableTiming);
+        *h->slow_host = 0;
+    }
+    if (h->slow_pending) {
+        if (cudaEventQuery(h->slow_ev) != cudaSuccess) { cudaGetLastError(); return; }
+        const unsigned long long now = *h->slow_host;
+        const int64_t dsteps = h->steps_at_probe - h->steps_at_probe_prev_steps;
+        if (dsteps > 0) {
+            const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)dsteps);
+            const double expect = 4.0 * 64.0 * (double)h->nbins / (double)h->count; // ~4 passes per step
+            h->poly_quiet = frac < 5e-5 + 2.0 * expect;
+            if (frac > 1e-3 + 6.0 * expect && h->since_sort >= 2) {
+                h->force_sort = true;
+                h->sort_every = (int)std::max<int64_t>(2, h->since_sort - POLY_RUNAHEAD);
+            }
+        }
+        h->slow_seen = now;
+        h->steps_at_probe_prev_steps = h->steps_at_probe;
+        h->slow_pending = false;
+    }
+    cudaMemcpyAsync(h->slow_host, h->slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+    cudaEventRecord(h->slow_ev, h->stream);
+    h->slow_pending = true;
+    h->steps_at_probe = h->steps;
+}
+
 // Counting sort of the step-start state (xb[par], vb[par]) by cell into the other ping-pong buffers.
 static int sort_particles_1d(picgolf_handle h)
 {
-    adapt_sort_interval(h);
+    if (!h->poly) adapt_sort_interval(h);
+    else if (h->sort_auto && !h->force_sort && h->poly_quiet) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
+    h->force_sort = false;
     const int sp = h->timer.begin(ST_SORT, h->stream);
     SortArgs a;
     memset(&a, 0, sizeof(a));
@@ -860,7 +904,7 @@ static int enqueue_poly_step(picgolf_handle h, FPArgs a)
     h->pass_blocks = h->nblocks_poly;
     if (!h->have_deposit) {
         const int sp = h->timer.begin(ST_PARTICLES, h->stream);
-        fp_pass_poly<true><<<h->nblocks_poly, PG_THREADS, h->smem_poly, h->stream>>>(a);
+        fp_pass_poly<true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
         h->timer.end(sp, h->stream);
         h->launches++;
     }
@@ -880,7 +924,7 @@ static int enqueue_poly_step(picgolf_handle h, FPArgs a)
         h->timer.end(sp, h->stream);
         a.k = k;
         sp = h->timer.begin(ST_PARTICLES, h->stream);
-        fp_pass_poly<false><<<h->nblocks_poly, PG_THREADS, h->smem_poly, h->stream>>>(a);
+        fp_pass_poly<false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
         h->timer.end(sp, h->stream);
         h->launches += 4;
     }
@@ -895,7 +939,7 @@ static int enqueue_fixedpoint_step(picgolf_handle h)
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
     a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
-    a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg;
+    a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg; a.dN = (double)c.N;
     h->pass_blocks = h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
     if (h->use_sorted_now && h->poly) return enqueue_poly_step(h, a);
     if (!h->have_deposit) { // only the first step after the particles were set: later ones inherit the fused deposit
@@ -970,7 +1014,8 @@ static int step_fixedpoint(picgolf_handle h)
     // cell sort happens before the second one.  A caller that exchanges the whole state every step (bench.py's
     // e2e arm) then never pays for a from-scratch sort + unsort that a single step cannot amortise.
     h->use_sorted_now = h->sorted && (h->pid_valid || h->steps > 0);
-    if (h->use_sorted_now && (!h->pid_valid || h->since_sort >= h->sort_every)) PG_TRY(sort_particles_1d(h));
+    if (h->use_sorted_now && h->poly && h->pid_valid) probe_poly_flushes(h);
+    if (h->use_sorted_now && (!h->pid_valid || h->since_sort >= h->sort_every || h->force_sort)) PG_TRY(sort_particles_1d(h));
     int (*enqueue)(picgolf_handle) = h->simpson ? enqueue_simpson_step : enqueue_fixedpoint_step;
     const bool use_graph = !h->sorted && !h->comm && !h->timer.enabled && h->count <= (1 << 22) && !h->graph_failed;
     if (!use_graph) {
@@ -1007,6 +1052,11 @@ static int step_fixedpoint(picgolf_handle h)
     h->par ^= 1;
     h->since_sort++;
     if (!h->simpson) h->have_deposit = true; // the final pass deposited the next step's first rho
+    if (h->poly && h->sort_auto) { // end-of-step marker for probe_poly_flushes (h->steps is incremented by the caller)
+        cudaEvent_t &e = h->run_ev[h->steps & 7];
+        if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (e) cudaEventRecord(e, h->stream);
+    }
     return 0;
 }
 
@@ -1351,6 +1401,13 @@ PG_API int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_pa
         }
         *slow_particles = (int64_t)n;
     }
+    return 0;
+}
+
+PG_API int picgolf_deposit_path(picgolf_handle h, int *mode)
+{
+    if (!h || !mode) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    *mode = h->poly ? PICGOLF_DEPOSIT_POLY : h->sorted ? PICGOLF_DEPOSIT_SORTED : PICGOLF_DEPOSIT_ATOMIC;
     return 0;
 }
 

@@ -493,6 +493,29 @@ def test_poly_mode_matches_atomic_mode(pg, oracle, start, N, P):
         assert flushes / (P * float(sws[1:].sum())) < 0.02
 
 
+def test_poly_mode_warm_beams_force_resort(pg):
+    """Warm beams shear a (cell, sign v) bin over several cells within a few steps: lanes start to alternate between
+    cells, the per-step flush probe must force re-sorts long before the default interval, and the results must still
+    agree with the any-order path."""
+    N, P = 256, 1 << 22
+    rng = np.random.default_rng(9)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0) + 0.6 * rng.standard_normal(P)
+    a = pg.gaussian_fixed_point(N=N, P=P, T=32, W=400.0, deposit_mode=pg.DEPOSIT_ATOMIC)
+    s = pg.gaussian_fixed_point(N=N, P=P, T=32, W=400.0, deposit_mode=pg.DEPOSIT_POLY)  # sort_every=0: adaptive
+    for sim in (a, s):
+        sim.set_particles(x0, v0)
+        sim.step(24)
+    xa, va = a.particles()
+    xs, vs = s.particles()
+    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    Da, swa = a.diagnostics()
+    Ds, sws = s.diagnostics()
+    assert np.array_equal(swa, sws) and relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    sorts, flushes = s.sort_stats()
+    assert sorts >= 3  # the starting interval alone (16 steps) would give 2
+
+
 def test_poly_mode_charge_and_reproducibility(pg):
     """Total charge is conserved to round-off by the moment form; two runs agree to round-off (the counting sort
     ranks particles inside a bin with atomics, so the order of the moment sums differs from run to run)."""
