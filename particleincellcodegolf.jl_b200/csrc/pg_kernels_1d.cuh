@@ -57,6 +57,7 @@ struct FPArgs {
     double *xout;        // wrapped end-of-step position
     const double *E;     // field of solve k
     fx_t *rho;           // global fixed-point deposit grid (zeroed by the solve that consumed it)
+    fx_t *rho_next;      // grid of the NEXT step's first solve: target of the deposit fused into the final pass
     double *partials;    // [2*gridDim.x] per-block (sum v^2, sum v)
     Ctrl *ctrl;
     unsigned long long *slow_count; // sorted mode: particles that fell outside their warp's window
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
         sv = block_sum(sv, scratch);
         if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
     }
-    flush_grid(rs, a.rho, N);
+    flush_grid(rs, final ? a.rho_next : a.rho, N);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
     const long long nchunks = (a.P + CH - 1) / CH;
     double sv2 = 0.0, sv = 0.0;
     unsigned int nslow = 0;
+    fx_t *const rho_out = final ? a.rho_next : a.rho; // the fused first deposit of the next step has its own grid
     for (long long ch = (long long)blockIdx.x * wpb + warp; ch < nchunks; ch += (long long)gridDim.x * wpb) {
         const long long j0 = ch * CH;
         // window base: smallest cell centre among the first batch of the chunk (same in all lanes)
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
                 });
 #pragma unroll
             for (int q = 0; q < NP; ++q)
-                if (live[q] && !ok[q]) { ++nslow; slow_deposit(a.rho, mid[q], N, a.fx_scale); }
+                if (live[q] && !ok[q]) { ++nslow; slow_deposit(rho_out, mid[q], N, a.fx_scale); }
         }
         __syncwarp();
         {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
             const double *row = acc + lane * WIN_LD;
 #pragma unroll 8
             for (int c = 0; c < 32; ++c) s += row[(c + lane) & 31]; // skewed: lane r starts at column r (distinct banks)
-            if (s != 0.0) atomicAdd(&a.rho[(base + lane - 1) & Nmask], to_fx(s, a.fx_scale)); // one integer RED per window cell
+            if (s != 0.0) atomicAdd(&rho_out[(base + lane - 1) & Nmask], to_fx(s, a.fx_scale)); // one integer RED per window cell
         }
         __syncwarp();
     }

@@ -165,6 +165,10 @@ struct picgolf_handle_s {
     // grids
     double *rho_last = nullptr, *E = nullptr;
     unsigned long long *rho_fx = nullptr;                     // integer deposit grid (NGP counts / fixed point), 1D and 2D
+    // Gaussian fixed point: the final pass of a step deposits the NEXT step's first charge into rho_next, not into
+    // rho_fx, so that the all-reduces the host enqueues for the remaining (predicated-off) sweeps of this step only
+    // ever sum zeros; the two grids swap roles at the end of every step.
+    unsigned long long *rho_next = nullptr, *rho_base[2] = {nullptr, nullptr};
     double fx_scale = 1.0, fx_inv = 1.0;                      // 2^frac, 2^-frac
     double2 *tw = nullptr, *twy = nullptr, *Z = nullptr, *E2 = nullptr;
     double *epartials = nullptr;
@@ -335,7 +339,7 @@ static int destroy_impl(picgolf_handle h)
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
-                    h->rho_last, h->E, h->rho_fx,
+                    h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
                     h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -389,6 +393,12 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->grid_rows = rows;
         PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, (size_t)rows * N));
         PG_TRY(dalloc(&h->rho_fx, (size_t)rows * N));
+        if (h->fixedpoint && !h->simpson) {
+            h->rho_base[0] = h->rho_fx;
+            PG_TRY(dalloc(&h->rho_base[1], (size_t)N));
+            PG_CUDA(cudaMemset(h->rho_base[1], 0, (size_t)N * sizeof(unsigned long long)));
+            h->rho_next = h->rho_base[1];
+        }
         PG_CUDA(cudaMemset(h->rho_last, 0, N * sizeof(double)));
         PG_CUDA(cudaMemset(h->E, 0, (size_t)rows * N * sizeof(double)));
         PG_CUDA(cudaMemset(h->rho_fx, 0, (size_t)rows * N * sizeof(unsigned long long)));
@@ -594,7 +604,9 @@ static int reset_run_state(picgolf_handle h)
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
+    if (h->rho_base[0]) { h->rho_fx = h->rho_base[0]; h->rho_next = h->rho_base[1]; }
     PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, (size_t)h->grid_rows * h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, (size_t)h->ncell * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
     if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * h->ncell * sizeof(unsigned long long), h->stream));
@@ -937,7 +949,7 @@ static int enqueue_fixedpoint_step(picgolf_handle h)
     const picgolf_config &c = h->cfg;
     FPArgs a;
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
-    a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials; a.ctrl = h->ctrl;
+    a.E = h->E; a.rho = h->rho_fx; a.rho_next = h->rho_next; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
     a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg; a.dN = (double)c.N;
     h->pass_blocks = h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
@@ -1042,7 +1054,7 @@ static int step_fixedpoint(picgolf_handle h)
                 h->graph_failed = true;
                 PG_TRY(enqueue(h));
                 h->par ^= 1; h->since_sort++;
-                if (!h->simpson) h->have_deposit = true;
+                if (!h->simpson) { h->have_deposit = true; std::swap(h->rho_fx, h->rho_next); }
                 return 0;
             }
         }
@@ -1051,7 +1063,10 @@ static int step_fixedpoint(picgolf_handle h)
     }
     h->par ^= 1;
     h->since_sort++;
-    if (!h->simpson) h->have_deposit = true; // the final pass deposited the next step's first rho
+    if (!h->simpson) { // the final pass deposited the next step's first rho (atomic / sorted kernels: into rho_next)
+        h->have_deposit = true;
+        std::swap(h->rho_fx, h->rho_next);
+    }
     if (h->poly && h->sort_auto) { // end-of-step marker for probe_poly_flushes (h->steps is incremented by the caller)
         cudaEvent_t &e = h->run_ev[h->steps & 7];
         if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
