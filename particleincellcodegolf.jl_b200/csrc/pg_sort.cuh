@@ -32,14 +32,19 @@ struct SortArgs {
     int N, NY;  // grid
     int tshift; // 2D: log2(tile edge in cells)
     int vsplit; // 1D: 1 -> key = 2*cell + (v >= 0): each beam keeps its own bins, so a bin drifts as a whole (pg_kernels_poly.cuh)
+    int sublg;  // 1D with vsplit: log2 of the position sub-bins per cell (key = ((2*cell + sign) << sublg) + sub): particles of a
+                // bin stay ordered by position, so the rows of 64 particles a warp of fp_pass_poly evaluates lie in ONE cell
+                // except where a cell boundary cuts through the bin
 };
 
 __device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
 {
     if (a.mode == 0) {
         int c = (int)rint(a.in[0][j] * (double)a.N); // the stencil centre Int(round(x*N)): a bin shares its window rows
-        c &= a.N - 1;
-        return a.vsplit ? 2 * c + (a.in[1][j] >= 0.0 ? 1 : 0) : c;
+        if (!a.vsplit) return c & (a.N - 1);
+        const double d = a.in[0][j] * (double)a.N - (double)c; // offset from the cell centre, [-1/2, 1/2]
+        const int sub = min((1 << a.sublg) - 1, max(0, (int)((d + 0.5) * (double)(1 << a.sublg))));
+        return (((c & (a.N - 1)) * 2 + (a.in[1][j] >= 0.0 ? 1 : 0)) << a.sublg) + sub;
     }
     int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
     int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);
@@ -140,6 +145,53 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
             }
         }
         __syncthreads();
+    }
+}
+
+// Counting sort for many bins (polynomial mode: up to 65536 (cell, sign v, sub-cell) bins, too many for per-block
+// shared-memory tables): lanes of a warp holding the same key are grouped with match.any, one global atomic per group.
+// On the nearly sorted arrays of a re-sort a warp row holds one or two keys.
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_match_kernel(SortArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nrow = (a.P + 31) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrow; r += stride >> 5) {
+        const long long j = (r << 5) + lane;
+        const int key = j < a.P ? sort_key(a, j) : -1 - lane; // dead lanes: unique negative keys
+        const unsigned int grp = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(grp) - 1) atomicAdd(&a.bin_count[key], (unsigned int)__popc(grp));
+    }
+}
+
+template <int NARR>
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_match_kernel(SortArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nrow = (a.P + 31) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrow; r += stride >> 5) {
+        const long long j = (r << 5) + lane;
+        const bool live = j < a.P;
+        const int key = live ? sort_key(a, j) : -1 - lane;
+        double val[NARR];
+        unsigned int id = 0;
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < NARR; ++q) val[q] = __ldcs(a.in[q] + j);
+            id = a.pid_in ? __ldcs(a.pid_in + j) : (unsigned int)j;
+        }
+        const unsigned int grp = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(grp) - 1;
+        unsigned int base = 0;
+        if (live && lane == leader) base = atomicAdd(&a.bin_cursor[key], (unsigned int)__popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) {
+            const long long d = (long long)base + __popc(grp & ((1u << lane) - 1u));
+#pragma unroll
+            for (int q = 0; q < NARR; ++q) a.out[q][d] = val[q];
+            a.pid_out[d] = id;
+        }
     }
 }
 

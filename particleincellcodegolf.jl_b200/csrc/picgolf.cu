@@ -22,6 +22,11 @@
 
 using namespace pg;
 
+#ifndef PG_POLY_SUBLG
+#define PG_POLY_SUBLG 3
+#endif
+constexpr int POLY_SUBLG = PG_POLY_SUBLG; // polynomial mode: up to 2^3 position sub-bins per (cell, sign v) bin
+
 #define PG_API extern "C" __attribute__((visibility("default")))
 
 // ------------------------------------------------------------------------------------------
@@ -201,7 +206,7 @@ struct picgolf_handle_s {
     bool poly = false;
     double *Gpoly = nullptr;
     unsigned long long *Mg = nullptr;
-    int nblocks_poly = 1;
+    int nblocks_poly = 1, sublg = 0;
     size_t smem_poly = 0;
     // adaptive re-sort interval (cfg.sort_every == 0): the slow-path counter is copied to pinned memory at every
     // sort and looked at, without synchronising, at the next one
@@ -445,7 +450,10 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             if (h->sorted) {
                 h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
                 h->K = (h->K + SORTED_NP - 1) / SORTED_NP * SORTED_NP; // whole groups of SORTED_NP batches
-                h->nbins = h->poly ? 2 * N : N; // polynomial mode: (cell, sign v) bins
+                // polynomial mode: (cell, sign v, sub-cell position) bins, at most 65536 (sort_scan_kernel)
+                h->sublg = 0;
+                if (h->poly) { while (h->sublg < POLY_SUBLG && ((int64_t)2 * N << (h->sublg + 1)) <= 65536) ++h->sublg; }
+                h->nbins = h->poly ? (2 * N) << h->sublg : N;
                 // re-sort before the slowest/fastest particles (|v| ~ 3) have drifted ~5 cells from their bin
                 double cells_per_step = 3.0 * c.dt * (double)N;
                 h->sort_every = c.sort_every > 0 ? c.sort_every : (int)std::max(1.0, std::min(1000.0, floor(5.0 / cells_per_step)));
@@ -473,8 +481,10 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 PG_CUDA(cudaMemset(h->bin_count, 0, h->nbins * sizeof(unsigned int)));
                 PG_TRY(dalloc(&h->slow_count, 1));
                 PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
-                PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
-                PG_TRY(set_smem(sort_scatter_kernel<2>, (size_t)h->nbins * 8));
+                if (!h->poly) {
+                    PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
+                    PG_TRY(set_smem(sort_scatter_kernel<2>, (size_t)h->nbins * 8));
+                }
             }
         } else if (h->ngp) {
             h->smem_lf = lf_smem_bytes(0, N);
@@ -862,7 +872,7 @@ static void probe_poly_flushes(picgolf_handle h)
         const int64_t dsteps = h->steps_at_probe - h->steps_at_probe_prev_steps;
         if (dsteps > 0) {
             const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)dsteps);
-            const double expect = 4.0 * 64.0 * (double)h->nbins / (double)h->count; // ~4 passes per step
+            const double expect = 4.0 * 64.0 * (double)(h->nbins >> h->sublg) / (double)h->count; // ~4 passes per step
             h->poly_quiet = frac < 5e-5 + 2.0 * expect;
             if (frac > 1e-3 + 6.0 * expect && h->since_sort >= 2) {
                 h->force_sort = true;
@@ -894,13 +904,19 @@ static int sort_particles_1d(picgolf_handle h)
     a.pid_out = h->pid[1 - h->pidpar];
     a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor;
     a.P = h->count; a.narr = 2; a.nbins = h->nbins; a.mode = 0; a.N = (int)h->cfg.N; a.NY = 1; a.tshift = 0;
-    a.vsplit = h->poly ? 1 : 0;
+    a.vsplit = h->poly ? 1 : 0; a.sublg = h->sublg;
     const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
     int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 8));
-    sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
-    sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
-    sort_scatter_kernel<2><<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    if (h->poly) { // too many bins for shared-memory tables: warp-aggregated global atomics
+        sort_hist_match_kernel<<<h->sms * 8, SORT_THREADS, 0, h->stream>>>(a);
+        sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
+        sort_scatter_match_kernel<2><<<h->sms * 8, SORT_THREADS, 0, h->stream>>>(a);
+    } else {
+        sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
+        sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
+        sort_scatter_kernel<2><<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
+    }
     h->launches += 3;
     h->timer.end(sp, h->stream);
     h->par ^= 1; h->pidpar ^= 1; h->pid_valid = true; h->since_sort = 0; h->sorts++;
