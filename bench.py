@@ -164,7 +164,7 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel (the particle pass), timed live with CUDA events ------
     sim.stage_timing(True)
     sim.stage_times(reset=True)
-    nroof = 12  # long enough to contain a re-sort of the (nearly sorted) particle arrays
+    nroof = 40 if (args.workload == "gauss_fp" and sim.deposit_path == pg.DEPOSIT_POLY) else 12  # long enough to contain a re-sort
     s0 = sim.sort_stats()[0]
     sim.step(nroof)
     st = sim.stage_times(reset=True)

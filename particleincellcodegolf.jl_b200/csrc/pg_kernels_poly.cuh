@@ -30,11 +30,13 @@ constexpr int CP_WG = 8;         // cells in a warp's gather window
 constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned,
                                  // and two neighbouring rows (144 B apart) never share a bank within one 128-bit access
 
+// 3 blocks of 128 threads per SM (166 registers per thread) measured 2.5 % faster than 2 x 256 (128 registers):
+// the compiler uses the extra registers to overlap the coefficient loads of the two particles of a lane.
 #ifndef PG_CP_THREADS
-#define PG_CP_THREADS 256
+#define PG_CP_THREADS 128
 #endif
 #ifndef PG_CP_MINBLOCKS
-#define PG_CP_MINBLOCKS 2
+#define PG_CP_MINBLOCKS 3
 #endif
 constexpr int CP_THREADS = PG_CP_THREADS; // threads per block of fp_pass_poly
 constexpr int CP_STAGES = 4;     // rows of particle data in flight per warp (cp.async ring, 1.5 KB per stage)
@@ -345,12 +347,13 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
             for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) / 2 * dt;
         }
+        {
+            int cell[2];
+            double t[2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            int cell;
-            double t;
-            cp_centre((xj[q] + Xj[q]) / 2, dN, cell, t);
-            cp_deposit(cell, t, A, B, a.Mg, a.fx_scale, Nmask, nflush);
+            for (int q = 0; q < 2; ++q) cp_centre((xj[q] + Xj[q]) / 2, dN, cell[q], t[q]);
+            cp_deposit(cell[0], t[0], A, B, a.Mg, a.fx_scale, Nmask, nflush);
+            cp_deposit(cell[1], t[1], A, B, a.Mg, a.fx_scale, Nmask, nflush);
         }
     }
     cp_async_wait<0>();

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortArgs a)
     }
 }
 
-// One block of 1024 threads; bins <= 65536.
+// One block of 1024 threads; any number of bins (each thread scans a contiguous run).
 __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count, unsigned int *bin_cursor,
                                                         unsigned int *bin_start, int nbins)
 {

@@ -23,9 +23,10 @@
 using namespace pg;
 
 #ifndef PG_POLY_SUBLG
-#define PG_POLY_SUBLG 3
+#define PG_POLY_SUBLG 5
 #endif
-constexpr int POLY_SUBLG = PG_POLY_SUBLG; // polynomial mode: up to 2^3 position sub-bins per (cell, sign v) bin
+constexpr int POLY_MAXBINS = 1 << 18;
+constexpr int POLY_SUBLG = PG_POLY_SUBLG; // polynomial mode: up to 2^5 position sub-bins per (cell, sign v) bin
 
 #define PG_API extern "C" __attribute__((visibility("default")))
 
@@ -450,9 +451,12 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             if (h->sorted) {
                 h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
                 h->K = (h->K + SORTED_NP - 1) / SORTED_NP * SORTED_NP; // whole groups of SORTED_NP batches
-                // polynomial mode: (cell, sign v, sub-cell position) bins, at most 65536 (sort_scan_kernel)
+                // polynomial mode: (cell, sign v, sub-cell position) bins, at most POLY_MAXBINS and >= 512 particles each
                 h->sublg = 0;
-                if (h->poly) { while (h->sublg < POLY_SUBLG && ((int64_t)2 * N << (h->sublg + 1)) <= 65536) ++h->sublg; }
+                if (h->poly) {
+                    while (h->sublg < POLY_SUBLG && ((int64_t)2 * N << (h->sublg + 1)) <= POLY_MAXBINS &&
+                           h->count / ((int64_t)2 * N << (h->sublg + 1)) >= 512) ++h->sublg;
+                }
                 h->nbins = h->poly ? (2 * N) << h->sublg : N;
                 // re-sort before the slowest/fastest particles (|v| ~ 3) have drifted ~5 cells from their bin
                 double cells_per_step = 3.0 * c.dt * (double)N;
