@@ -21,6 +21,8 @@ module PicGolf
 const LIB = get(ENV, "PICGOLF_LIB", joinpath(@__DIR__, "..", "particleincellcodegolf.jl_b200", "lib", "libpicgolf.so"))
 
 const NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13 = Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
+const AREA_SIMPSON13, GAUSS_BORIS_1D2V, GAUSS_BORIS_1D2V2S = Int32(6), Int32(7), Int32(8)
+const DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED, DEPOSIT_POLY = Int32(0), Int32(1), Int32(2), Int32(3)
 
 # Mirror of `picgolf_config` (include/picgolf.h) -- field order and types must match.
 Base.@kwdef mutable struct Config
@@ -48,6 +50,7 @@ Base.@kwdef mutable struct Config
     reserved_::Int32 = 0
     local_first::Int64 = -1
     local_count::Int64 = -1
+    mass_ratio::Float64 = 0.0
 end
 
 struct PicGolfError <: Exception
@@ -84,6 +87,11 @@ function set_particles!(s::Sim, x, y, vx, vy, vz)   # src/Electrostatic2D3V.jl:4
     GC.@preserve x y vx vy vz check(ccall((:picgolf_set_particles_2d3v, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
         s.h, x, y, vx, vy, vz, length(x)))
+end
+
+function set_particles!(s::Sim, x::Vector{Float64}, vx::Vector{Float64}, vy::Vector{Float64})   # src/NGP1D2V.jl:27-32, NGP1D2V2S.jl:17-20
+    GC.@preserve x vx vy check(ccall((:picgolf_set_particles_1d2v, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64), s.h, x, vx, vy, length(x)))
 end
 
 init_quiet!(s::Sim) = check(ccall((:picgolf_init_quiet, LIB), Cint, (Ptr{Cvoid},), s.h))

@@ -48,7 +48,10 @@ typedef enum picgolf_scheme {
     PICGOLF_CIC_BORIS_2D3V = 4,   /* src/Electrostatic2D3V.jl:120-176 */
     PICGOLF_GAUSS_SIMPSON13 = 5,  /* src/GaussianFixedPointQuietSimpson13.jl:8-18 (Simpson-1/3 quadrature of E, 3 solves/sweep) */
     PICGOLF_AREA_SIMPSON13 = 6,   /* src/AreaFixedPointQuietSimpson13.jl:7-17 (same schedule, 2-cell "area" shape d(y) of line 5) */
-    PICGOLF_GAUSS_BORIS_1D2V = 7  /* src/NGP1D2V.jl:39-63 (1D2V magnetised, erf shape +-7, Boris about z; Bernstein modes) */
+    PICGOLF_GAUSS_BORIS_1D2V = 7, /* src/NGP1D2V.jl:39-63 (1D2V magnetised, erf shape +-7, Boris about z; Bernstein modes) */
+    PICGOLF_GAUSS_BORIS_1D2V2S = 8 /* src/NGP1D2V2S.jl:31-53: two species of P particles each, stored one after the other
+                                    * (global indices [0,P): q = -1, q/m = -1; [P,2P): q = +1, q/m = 1/mass_ratio);
+                                    * same entry points as the 1D2V scheme, arrays of 2P */
 } picgolf_scheme;
 
 /* Deposit accumulation mode. */
@@ -70,7 +73,7 @@ typedef struct picgolf_config {
     int32_t scheme;          /* picgolf_scheme */
     int64_t N;               /* 1D: grid cells N (power of two, 8..4096*4).  2D: NX */
     int64_t NY;              /* 2D only */
-    int64_t P;               /* GLOBAL particle count (all ranks) */
+    int64_t P;               /* GLOBAL particle count (all ranks); 1D2V2S: per species (the handle holds 2P particles) */
     int64_t T;               /* capacity of the diagnostics trace in rows (steps recorded) */
     double dt;               /* time step */
     double W;                /* mean charge density (rho averages to W); 2D: n0 */
@@ -92,6 +95,7 @@ typedef struct picgolf_config {
     int32_t reserved_;
     int64_t local_first;     /* first global particle index owned (0-based); -1 = even split by rank */
     int64_t local_count;     /* particles owned; -1 = even split by rank */
+    double mass_ratio;       /* 1D2V2S: M, mass of a species-2 particle in units of species 1 (NGP1D2V2S.jl:13 M=8) */
 } picgolf_config;
 
 typedef struct picgolf_handle_s *picgolf_handle;
@@ -110,7 +114,9 @@ int picgolf_device_count(void);
  * scheme GAUSS_FIXEDPOINT, quiet=1 -> GaussianFixedPointQuiet.jl:1-6 (N=64,P=32N,T=2^13,W=32pi^2/3,hw 7,l=4eps)
  * scheme CIC_BORIS_2D3V -> Electrostatic2D3V.jl:23-25 (NX=NY=128,P=NX*NY*2^5,T=2^13,n0=4pi^2,...)
  * scheme GAUSS_SIMPSON13 -> GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point)
- * scheme GAUSS_BORIS_1D2V -> NGP1D2V.jl:22-23 (N=512,P=15N,T=TO=2^14/16 rows,n0=4pi^2,vth,dt,B0,w=n0/P, diag_every=16) */
+ * scheme GAUSS_BORIS_1D2V -> NGP1D2V.jl:22-23 (N=512,P=15N,T=TO=2^14/16 rows,n0=4pi^2,vth,dt,B0,w=n0/P, diag_every=16)
+ * scheme GAUSS_BORIS_1D2V2S -> NGP1D2V2S.jl:13-14 (N=256,P=8N per species,M=8,T=TO=32 rows,diag_every=2^16/32,
+ *        vth=sqrt(n0)/N/8,dt=1/N/16vth,B0=sqrt(n0)/8,w=n0/2P) */
 int picgolf_config_default(picgolf_config *cfg, int scheme, int quiet);
 
 /* ---- lifetime --------------------------------------------------------------------------- */

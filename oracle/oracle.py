@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.oracle_simpson_run.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _d, C.c_int, _i64, _vp, _vp, C.c_int]
         L.oracle_boris_1d2v.argtypes = [_dp, _dp, _d, _d, _d]
         L.oracle_1d2v_step.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _dp, _dp, _vp]
+        L.oracle_boris_1d2v_qm.argtypes = [_dp, _dp, _d, _d, _d, _d]
+        L.oracle_1d2v2s_step.argtypes = [_dp, _dp, _dp, _i64, _i64, C.c_int, _d, _d, _d, _d, _dp, _dp, _vp]
         L.oracle_gauss_leapfrog_step.argtypes = [_dp, _dp, _i64, _i64, C.c_int, _d, _d, _dp, _dp, _vp]
         L.oracle_quiet_start.argtypes = [_i64, _i64, _i64, _dp, _dp]
         L.oracle_growth_slope.restype = _d
@@ -241,6 +243,21 @@ def step_1d2v(x, vx, vy, N, hw, dt, B0, w):
     """src/NGP1D2V.jl:40-45,55 in place on x, vx, vy.  Returns (rho, E, raw[sumE2, sum v^2, sum vx, sum vy])."""
     rho, E, raw = np.empty(N), np.empty(N), np.empty(4)
     lib().oracle_1d2v_step(x, vx, vy, x.size, N, hw, dt, B0, w, rho, E, _ptr(raw))
+    return rho, E, raw
+
+
+def boris_1d2v_qm(vx, vy, E, B, dt, q_m):
+    """src/NGP1D2V2S.jl:5-11"""
+    a, b = np.array([vx], dtype=np.float64), np.array([vy], dtype=np.float64)
+    lib().oracle_boris_1d2v_qm(a, b, E, B, dt, q_m)
+    return a[0], b[0]
+
+
+def step_1d2v2s(x, vx, vy, N, hw, dt, B0, w, M):
+    """src/NGP1D2V2S.jl:31-49 in place on the concatenated [species 1 | species 2] arrays (length 2P).
+    Returns (rho, E, raw[sumE2, mass-weighted sum v^2, sum vx, sum vy])."""
+    rho, E, raw = np.empty(N), np.empty(N), np.empty(4)
+    lib().oracle_1d2v2s_step(x, vx, vy, x.size // 2, N, hw, dt, B0, w, M, rho, E, _ptr(raw))
     return rho, E, raw
 
 

@@ -478,6 +478,58 @@ ORACLE_API void oracle_1d2v_step(double *x, double *vx, double *vy, int64_t P, i
     }
 }
 
+/* boris(vx,vy,E,B,dt,q_m) of the two-species code: src/NGP1D2V2S.jl:5-11 (dt2q_m = dt/2*q_m scales both E and B). */
+ORACLE_API void oracle_boris_1d2v_qm(double *vx, double *vy, double E, double B, double dt, double q_m)
+{
+    double h = dt / 2 * q_m;
+    double m1 = *vx + E * h, m2 = *vy, m3 = 0.0;                 /* v- */
+    double t1 = 0.0, t2 = 0.0, t3 = B * h;
+    double c1 = m2 * t3 - m3 * t2, c2 = m3 * t1 - m1 * t3;
+    double p1 = m1 + c1, p2 = m2 + c2, p3 = m3 + (m1 * t2 - m2 * t1);
+    double q1 = p2 * t3 - p3 * t2, q2 = p3 * t1 - p1 * t3;
+    double den = 1 + (t1 * t1 + t2 * t2 + t3 * t3);
+    double r1 = m1 + 2 * q1 / den, r2 = m2 + 2 * q2 / den;
+    *vx = r1 + E * h; *vy = r2;
+}
+
+/* One step of src/NGP1D2V2S.jl:31-49 on the concatenated arrays [species 1 (q=-1, q/m=-1) | species 2 (q=+1, q/m=1/M)],
+ * P particles per species: rho() = rho(x1,-1) then rho(x2,+1) with r[k[1]] += q*k[2]*w (:24-25); solve; per species
+ * gather at x, boris(..., q_m), x += vx*dt; x = mod(x,1).  raw[0..3] = sum(abs2,E),
+ * sum(vy1^2+vx1^2 + M*(vy2^2+vx2^2)), sum(vx1 + M*vx2), sum(vy1 + M*vy2)  (the sums behind D, :51-52). */
+ORACLE_API void oracle_1d2v2s_step(double *x, double *vx, double *vy, int64_t P, int64_t N, int hw, double dt, double B0,
+                                   double w, double M, double *rho, double *E, double *raw)
+{
+    int32_t idx[32]; double wt[32];
+    for (int64_t i = 0; i < N; ++i) rho[i] = 0.0;
+    for (int sp = 0; sp < 2; ++sp) {
+        double q = sp == 0 ? -1.0 : 1.0;
+        for (int64_t j = sp * P; j < (sp + 1) * P; ++j) {
+            oracle_gauss_stencil(x[j], N, hw, idx, wt);
+            for (int k = 0; k <= 2 * hw; ++k) rho[idx[k] - 1] += q * wt[k] * w;
+        }
+    }
+    oracle_solve1d(rho, N, E);
+    for (int sp = 0; sp < 2; ++sp) {
+        double q_m = sp == 0 ? -1.0 : 1 / M;
+        for (int64_t j = sp * P; j < (sp + 1) * P; ++j) {
+            double Ej = oracle_gauss_gather(E, x[j], N, hw);
+            oracle_boris_1d2v_qm(&vx[j], &vy[j], Ej, B0, dt, q_m);
+            x[j] += vx[j] * dt;
+        }
+    }
+    for (int64_t j = 0; j < 2 * P; ++j) x[j] = oracle_jl_mod1(x[j]);
+    if (raw) {
+        double se = 0, s0 = 0, s1 = 0, s2 = 0;
+        for (int64_t i = 0; i < N; ++i) se += E[i] * E[i];
+        for (int64_t i = 0; i < P; ++i) {
+            s0 += vy[i] * vy[i] + vx[i] * vx[i] + M * (vy[P + i] * vy[P + i] + vx[P + i] * vx[P + i]);
+            s1 += vx[i] + M * vx[P + i];
+            s2 += vy[i] + M * vy[P + i];
+        }
+        raw[0] = se; raw[1] = s0; raw[2] = s1; raw[3] = s2;
+    }
+}
+
 /* Quiet start: x=(bitreverse.(0:P-1).+2.0^63)/2.0^64; v = (j>P/2) ? 1 : -1   GaussianFixedPointQuiet.jl:2-3.
  * Generates global indices [first, first+count) of a P-particle population. */
 ORACLE_API void oracle_quiet_start(int64_t P, int64_t first, int64_t count, double *x, double *v)

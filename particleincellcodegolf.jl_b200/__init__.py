@@ -29,6 +29,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
 
 NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13, GAUSS_BORIS_1D2V = 1, 2, 3, 4, 5, 6, 7
+GAUSS_BORIS_1D2V2S = 8
 DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_SORTED, DEPOSIT_POLY = 0, 1, 2, 3
 
 NVCC_FLAGS = [
@@ -65,7 +66,7 @@ class Config(C.Structure):
         ("half_width", C.c_int32), ("max_sweeps", C.c_int32), ("diag_every", C.c_int32), ("deposit_mode", C.c_int32),
         ("deterministic", C.c_int32), ("sort_every", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
-        ("local_first", C.c_int64), ("local_count", C.c_int64),
+        ("local_first", C.c_int64), ("local_count", C.c_int64), ("mass_ratio", C.c_double),
     ]
 
 
@@ -187,7 +188,7 @@ class PIC:
         _check(self._lib.picgolf_local_range(self._h, C.byref(f), C.byref(c)))
         self.first, self.count = f.value, c.value
         self.is2d = cfg.scheme == CIC_BORIS_2D3V
-        self.is1d2v = cfg.scheme == GAUSS_BORIS_1D2V
+        self.is1d2v = cfg.scheme in (GAUSS_BORIS_1D2V, GAUSS_BORIS_1D2V2S)
         self.ncell = cfg.N * (cfg.NY if self.is2d else 1)
 
     # -- lifetime
@@ -437,6 +438,26 @@ def ngp_1d2v(N=512, P=None, T=2 ** 14, TO=None, n0=4 * math.pi ** 2, rank=0, nra
     cfg.dt = 1 / N / (6 * vth)
     cfg.B0 = math.sqrt(n0) / 16
     cfg.w = n0 / cfg.P
+    cfg.diag_every = max(1, T // TO)
+    cfg.half_width = 7
+    pic = _finish(cfg, rank, nranks, device, TO, **over)
+    pic.vth = vth
+    return pic
+
+
+def ngp_1d2v_2s(N=256, P=None, T=2 ** 16, TO=None, M=8.0, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1, **over) -> PIC:
+    """src/NGP1D2V2S.jl:13-14  N=256;P=8N;T=2^16;TO=T/32;M=8;n0=4pi^2;vth=sqrt(n0)/N/8;dt=1/N/16vth;B0=sqrt(n0)/8;w=n0/2P.
+    P particles per species; set_particles(x, vx, vy=vy) takes the two species one after the other ([x1; x2], ...)."""
+    cfg = default_config(GAUSS_BORIS_1D2V2S)
+    TO = T // 32 if TO is None else TO
+    cfg.N = N
+    cfg.P = 8 * N if P is None else P
+    vth = math.sqrt(n0) / N / 8
+    cfg.W = n0
+    cfg.dt = 1 / N / (16 * vth)
+    cfg.B0 = math.sqrt(n0) / 8
+    cfg.w = n0 / (2 * cfg.P)
+    cfg.mass_ratio = M
     cfg.diag_every = max(1, T // TO)
     cfg.half_width = 7
     pic = _finish(cfg, rank, nranks, device, TO, **over)

@@ -569,13 +569,19 @@ __global__ void __launch_bounds__(LF_TMA_THREADS, 1) lf_pass_ngp_tma(LFArgs a)
 // boris() about z (:5-10), x += vx*dt, x = mod(x,1); fused with the deposit rho(x) of the next step (:40).
 // 48 B per particle-step (x, vx, vy read + written).  Any particle order; fixed-point deposit grid.
 // ------------------------------------------------------------------------------------------
+// Two-species variant, src/NGP1D2V2S.jl:5-11,24-25,31-52: the particle arrays hold species 1 (global indices < Psp:
+// q = -1, q/m = -1) followed by species 2 (q = +1, q/m = 1/M); boris(vx,vy,E,B,dt,q_m) scales E and B by
+// dt2q_m = dt/2*q_m; the deposit is r[k[1]] += q*k[2]*w; the kinetic sums weigh species 2 with its mass M.
 struct B1D2VArgs {
     double *x, *vx, *vy;
     const double *E;
     fx_t *rho;
-    double *partials; // [3*gridDim.x] per-block (sum vx^2+vy^2, sum vx, sum vy)
+    double *partials; // [3*gridDim.x] per-block (sum m(vx^2+vy^2), sum m vx, sum m vy), m = 1 or M
     long long P;
-    double dt, t3, den, fx_scale; // t3 = B*dt/2, den = 1 + dot(t,t)
+    double dt, B0, fx_scale;
+    double M;         // mass ratio of species 2 (two-species scheme)
+    long long first;  // global index of local particle 0
+    long long Psp;    // particles per species; < 0: single species (NGP1D2V.jl: q = 1, q/m = 1)
     int N, do_push, do_deposit;
 };
 
@@ -595,21 +601,31 @@ __global__ void __launch_bounds__(PG_THREADS) b1d2v_pass(B1D2VArgs a)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += stride) {
         double xj = ld_stream(a.x + j), vx = ld_stream(a.vx + j), vy = ld_stream(a.vy + j);
+        const bool sp2 = a.Psp >= 0 && a.first + j >= a.Psp;           // second species of NGP1D2V2S.jl
+        const double q = (a.Psp >= 0 && !sp2) ? -1.0 : 1.0;
+        const double q_m = a.Psp < 0 ? 1.0 : (sp2 ? 1 / a.M : -1.0);
+        const double mass = sp2 ? a.M : 1.0;
         int ibase; double W[GAUSS_NW];
         if (a.do_push) {
             gauss_weights(xj, dN, ibase, W);
             const double Ej = gauss_gather(Es, ibase, W, Nmask);      // sum(k->E[k[1]]*k[2], d(x[j]))  :42
-            const double h = Ej * dt / 2;
-            const double m1 = vx + h, m2 = vy;                         // v- = [vx + E*dt/2, vy, 0]
-            const double p1 = m1 + m2 * a.t3, p2 = m2 - m1 * a.t3;     // v- + cross(v-, t), t = [0,0,B*dt/2]
-            const double r1 = m1 + 2 * (p2 * a.t3) / a.den;            // v+ = v- + 2*cross(.., t)/(1+dot(t,t))
-            const double r2 = m2 - 2 * (p1 * a.t3) / a.den;
+            // dt2q_m = dt/2*q_m (NGP1D2V2S.jl:6); with q_m = 1 the products below are bit-identical to the
+            // E*dt/2 and B*dt/2 of NGP1D2V.jl:6-7 (halving is exact)
+            const double hq = dt / 2 * q_m;
+            const double h = Ej * hq, t3 = a.B0 * hq;
+            const double den = 1 + (0.0 + 0.0 + t3 * t3);
+            const double m1 = vx + h, m2 = vy;                         // v- = [vx + E*dt2q_m, vy, 0]
+            const double p1 = m1 + m2 * t3, p2 = m2 - m1 * t3;         // v- + cross(v-, t), t = [0,0,B*dt2q_m]
+            const double r1 = m1 + 2 * (p2 * t3) / den;                // v+ = v- + 2*cross(.., t)/(1+dot(t,t))
+            const double r2 = m2 - 2 * (p1 * t3) / den;
             vx = r1 + h; vy = r2;
             xj = jl_mod1(xj + vx * dt);                                // x[j] += vx[j]*dt ; x.=mod.(x,1)
-            s0 += vy * vy + vx * vx; s1 += vx; s2 += vy;
+            s0 += mass * (vy * vy + vx * vx); s1 += mass * vx; s2 += mass * vy;
         }
         if (a.do_deposit) {
             gauss_weights((xj + xj) / 2, dN, ibase, W);                // rho(x)
+#pragma unroll
+            for (int k = 0; k < GAUSS_NW; ++k) W[k] *= q;              // r[k[1]] += q*k[2]*w   NGP1D2V2S.jl:24
             gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
         }
         st_stream(a.x + j, xj); st_stream(a.vx + j, vx); st_stream(a.vy + j, vy);

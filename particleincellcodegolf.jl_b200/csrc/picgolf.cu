@@ -314,6 +314,12 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
         c->W = n0; c->dt = 1 / (double)c->N / (6 * vth); c->B0 = sqrt(n0) / 16; c->w = n0 / (double)c->P;
         break;
     }
+    case PICGOLF_GAUSS_BORIS_1D2V2S: { // NGP1D2V2S.jl:13-14
+        c->N = 256; c->P = 8 * c->N; c->T = 32; c->diag_every = (1 << 16) / 32; c->half_width = 7; c->mass_ratio = 8;
+        double n0 = 4 * pi * pi, vth = sqrt(n0) / (double)c->N / 8;
+        c->W = n0; c->dt = 1 / (double)c->N / (16 * vth); c->B0 = sqrt(n0) / 8; c->w = n0 / (double)(2 * c->P);
+        break;
+    }
     case PICGOLF_CIC_BORIS_2D3V: { // Electrostatic2D3V.jl:23-25
         c->N = 128; c->NY = 128; c->P = c->N * c->NY * 32; c->T = 1 << 13;
         double NG = sqrt((double)(c->N * c->N + c->NY * c->NY));
@@ -376,17 +382,18 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13;
     h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT || h->simpson;
     h->ngp = c.scheme == PICGOLF_NGP_LEAPFROG;
-    h->b1d2v = c.scheme == PICGOLF_GAUSS_BORIS_1D2V;
+    h->b1d2v = c.scheme == PICGOLF_GAUSS_BORIS_1D2V || c.scheme == PICGOLF_GAUSS_BORIS_1D2V2S;
+    const int64_t total = c.scheme == PICGOLF_GAUSS_BORIS_1D2V2S ? 2 * c.P : c.P; // particles held by all ranks together
     h->nranks = std::max(1, c.nranks);
     h->rank = c.rank;
     if (h->rank < 0 || h->rank >= h->nranks) return fail(PICGOLF_ERR_ARG, "rank %d outside [0,%d)", h->rank, h->nranks);
     if (c.local_first >= 0 && c.local_count >= 0) { h->first = c.local_first; h->count = c.local_count; }
     else { // even split, remainder to the low ranks
-        int64_t q = c.P / h->nranks, r = c.P % h->nranks;
+        int64_t q = total / h->nranks, r = total % h->nranks;
         h->first = q * h->rank + std::min<int64_t>(h->rank, r);
         h->count = q + (h->rank < r ? 1 : 0);
     }
-    if (h->first < 0 || h->first + h->count > c.P) return fail(PICGOLF_ERR_ARG, "local shard outside [0,P)");
+    if (h->first < 0 || h->first + h->count > total) return fail(PICGOLF_ERR_ARG, "local shard outside [0,P)");
     h->T = std::max<int64_t>(1, c.T);
 
     const size_t n = (size_t)h->count;
@@ -411,7 +418,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         if (!h->ngp) {
             // fixed-point format of the Gaussian deposit grid: weights are <= 1 and sum to 1 per particle, so
             // no cell can exceed P (all ranks) -> 62 - ceil(log2(P+1)) fractional bits can never overflow.
-            int frac = std::max(8, std::min(60, 62 - ilog2(c.P + 1)));
+            int frac = std::max(8, std::min(60, 62 - ilog2(total + 1)));
             h->fx_scale = ldexp(1.0, frac); h->fx_inv = ldexp(1.0, -frac);
         }
         PG_TRY(make_twiddles(&h->tw, N));
@@ -576,7 +583,8 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
     if (cfg->struct_size != (int32_t)sizeof(picgolf_config))
         return fail(PICGOLF_ERR_ARG, "struct_size %d != %zu (header/library mismatch)", cfg->struct_size, sizeof(picgolf_config));
     const picgolf_config &c = *cfg;
-    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_GAUSS_BORIS_1D2V) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.scheme < PICGOLF_NGP_LEAPFROG || c.scheme > PICGOLF_GAUSS_BORIS_1D2V2S) return fail(PICGOLF_ERR_ARG, "unknown scheme %d", c.scheme);
+    if (c.scheme == PICGOLF_GAUSS_BORIS_1D2V2S && !(c.mass_ratio > 0)) return fail(PICGOLF_ERR_ARG, "mass_ratio must be positive");
     if (c.P < 1) return fail(PICGOLF_ERR_ARG, "P must be >= 1");
     if (!(c.dt > 0) || !isfinite(c.dt)) return fail(PICGOLF_ERR_ARG, "dt must be positive and finite");
     if (!isfinite(c.w)) return fail(PICGOLF_ERR_ARG, "w must be finite");
@@ -1115,7 +1123,8 @@ static int b1d2v_launch(picgolf_handle h, int do_push, int do_deposit)
     const picgolf_config &c = h->cfg;
     B1D2VArgs a;
     a.x = h->xb[0]; a.vx = h->vb[0]; a.vy = h->vy1; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
-    a.P = h->count; a.dt = c.dt; a.t3 = c.B0 * c.dt / 2; a.den = 1 + (0.0 + 0.0 + a.t3 * a.t3); a.fx_scale = h->fx_scale;
+    a.P = h->count; a.dt = c.dt; a.B0 = c.B0; a.fx_scale = h->fx_scale;
+    a.M = c.mass_ratio; a.first = h->first; a.Psp = c.scheme == PICGOLF_GAUSS_BORIS_1D2V2S ? c.P : -1;
     a.N = (int)c.N; a.do_push = do_push; a.do_deposit = do_deposit;
     const int sp = h->timer.begin(ST_PARTICLES, h->stream);
     b1d2v_pass<<<h->nblocks, PG_THREADS, h->smem_b1, h->stream>>>(a);

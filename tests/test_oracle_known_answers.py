@@ -293,3 +293,26 @@ def test_ngp1d2v_oracle(oracle):
     rho, E, raw = oracle.step_1d2v(x, vx, vy, int(g["N"]), 7, float(g["dt"]), float(g["B0"]), float(g["w"]))
     assert np.array_equal(rho, g["rho"][0]) and np.array_equal(E, g["E"][0]) and np.array_equal(raw, g["raw"][0])
     assert abs(rho.mean() / (float(g["n0"]) / int(g["N"])) - 1) < 1e-12
+
+
+def test_two_species_1d2v_known_answers(oracle):
+    """src/NGP1D2V2S.jl: boris with q_m = 1 is the single-species boris bit for bit; with coincident species of equal
+    mass the plasma is exactly neutral (rho = 0, E = 0) and every particle just gyrates (|v| conserved, electrons and
+    ions turning in opposite senses)."""
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        vx, vy, E, B, dt = rng.standard_normal(5)
+        assert oracle.boris_1d2v(vx, vy, E, B, abs(dt)) == oracle.boris_1d2v_qm(vx, vy, E, B, abs(dt), 1.0)
+    N, P = 64, 512
+    x1 = rng.random(P)
+    x = np.concatenate([x1, x1])
+    vx = np.concatenate([rng.standard_normal(P)] * 2) * 1e-3
+    vy = np.concatenate([rng.standard_normal(P)] * 2) * 1e-3
+    v2 = vx ** 2 + vy ** 2
+    vx0 = vx.copy()
+    rho, E, raw = oracle.step_1d2v2s(x, vx, vy, N, 7, 0.01, 2.0, 1.0, 1.0)
+    assert np.abs(rho).max() < 1e-13 and np.abs(E).max() < 1e-13
+    assert np.abs(vx ** 2 + vy ** 2 - v2).max() < 1e-18
+    # opposite charge-to-mass ratios rotate in opposite senses by the same angle
+    d1, d2 = vx[:P] - vx0[:P], vx[P:] - vx0[P:]
+    assert np.allclose(vy[:P] * 0 + d1, -d2 + 2 * (np.cos(2 * np.arctan(0.01)) - 1) * vx0[:P], atol=1e-12)

@@ -854,6 +854,50 @@ def test_ngp1d2v_steps(pg, oracle):
     assert abs(a * a + b * b - 0.13) < 1e-16
 
 
+def test_ngp1d2v2s_steps(pg, oracle):
+    """Two-species magnetised code (src/NGP1D2V2S.jl): golden fixture, diagnostics with the mass-weighted sums, and a
+    live-oracle run with another mass ratio."""
+    g = golden("ngp1d2v2s")
+    N, P, M = int(g["N"]), int(g["P"]), float(g["M"])
+    sim = pg.ngp_1d2v_2s(T=64, TO=16)  # window T/TO = 4 steps
+    assert (sim.cfg.N, sim.cfg.P, sim.cfg.diag_every, sim.cfg.half_width, sim.count) == (256, 2048, 4, 7, 4096)
+    assert sim.cfg.dt == float(g["dt"]) and sim.cfg.B0 == float(g["B0"]) and sim.cfg.w == float(g["w"]) and sim.cfg.mass_ratio == M
+    sim.set_particles(g["x0"], g["vx0"], vy=g["vy0"])
+    for t in range(8):
+        sim.step(1)
+        rho, E = sim.fields()
+        # the two species neutralise each other (exactly so at the first step: both are loaded on a uniform lattice and the
+        # integer charge grid sums to exactly 0, the oracle to 1e-17): compare on the scale of one species' density
+        assert np.abs(rho - g["rho"][t]).max() < TOL * float(g["n0"])
+        assert np.abs(E - g["E"][t]).max() < max(1e-10 * np.abs(g["E"][t]).max(), 1e-13 * float(g["n0"]))
+    x, vx, vy = sim.particles()
+    assert relnorm(x, g["x"]) < 1e-11 and relnorm(vx, g["vx"]) < 1e-11 and relnorm(vy, g["vy"]) < 1e-11
+    D, _ = sim.diagnostics()
+    assert D.shape == (2, 5)
+    n0 = float(g["n0"])
+    for ti, t in enumerate((3, 7)):  # NGP1D2V2S.jl:50-53,56
+        se, s0, s1, s2 = g["raw"][t]
+        d1, d2 = (se / N) / 2, (s0 * n0 / P) / 2
+        want = np.array([d1 * 2 / n0, d2 * 2 / n0, (d1 + d2) * 2 / n0, s1 / P, s2 / P]) / 4
+        assert np.abs(D[ti] - want).max() < 1e-10 * np.abs(want).max()
+    Es = sim.field_history()
+    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < 1e-10 and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < 1e-10
+    # another mass ratio and size against the live oracle
+    rng = np.random.default_rng(4)
+    N2, P2, M2 = 128, 3000, 100.0
+    s2_ = pg.ngp_1d2v_2s(N=N2, P=P2, T=16, TO=16, M=M2)
+    x0, vx0, vy0 = rng.random(2 * P2), s2_.vth * rng.standard_normal(2 * P2), s2_.vth * rng.standard_normal(2 * P2)
+    s2_.set_particles(x0, vx0, vy=vy0)
+    s2_.step(3)
+    xo, vxo, vyo = x0.copy(), vx0.copy(), vy0.copy()
+    for _ in range(3):
+        ro, Eo, _ = oracle.step_1d2v2s(xo, vxo, vyo, N2, 7, s2_.cfg.dt, s2_.cfg.B0, s2_.cfg.w, M2)
+    xs, vxs, vys = s2_.particles()
+    rs, Es2 = s2_.fields()
+    assert relnorm(xs, xo) < 1e-11 and relnorm(vxs, vxo) < 1e-11 and relnorm(vys, vyo) < 1e-11 and relnorm(Es2, Eo) < 1e-10
+    assert np.abs(rs - ro).max() < TOL * n0
+
+
 def test_2d3v_tma_variant_matches(pg, oracle, monkeypatch):
     """The opt-in TMA-staged 2D kernel (PICGOLF_2D_TMA=1) must give the same physics as the default tiled kernel
     (odd work-item boundaries exercise its unaligned edge particles)."""

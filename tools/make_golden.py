@@ -165,6 +165,30 @@ def ngp1d2v(steps=8):
          rho=np.array(rhos), E=np.array(Es), raw=np.array(raws))
 
 
+def ngp1d2v2s(steps=8):
+    """SURVEY 8f rank 2, two species: src/NGP1D2V2S.jl (N=256, P=8N per species, M=8); x as :17-18 (bit-reversed, second
+    species shifted by pi), velocities drawn like NGP1D2V.jl:30-31 (the R(igr) sequences of :19-20 need Roots.jl)."""
+    from scipy.special import erfinv
+    N = 256
+    P = 8 * N
+    M = 8.0
+    n0 = 4 * math.pi ** 2
+    vth = math.sqrt(n0) / N / 8
+    dt, B0, w = 1 / N / (16 * vth), math.sqrt(n0) / 8, n0 / (2 * P)
+    rng = np.random.default_rng(23)
+    xq, _ = o.quiet_start(P)
+    x0 = np.concatenate([np.mod(xq, 1), np.mod(xq + math.pi, 1)])
+    vx1, vy1 = vth * erfinv(rng.random(P)), vth * erfinv(rng.random(P))
+    vx0, vy0 = np.concatenate([vx1, vx1 / math.sqrt(M)]), np.concatenate([vy1, vy1 / math.sqrt(M)])
+    x, vx, vy = x0.copy(), vx0.copy(), vy0.copy()
+    rhos, Es, raws = [], [], []
+    for _ in range(steps):
+        rho, E, raw = o.step_1d2v2s(x, vx, vy, N, 7, dt, B0, w, M)
+        rhos.append(rho); Es.append(E); raws.append(raw)
+    save("ngp1d2v2s", N=N, P=P, M=M, dt=dt, B0=B0, w=w, n0=n0, vth=vth, x0=x0, vx0=vx0, vy0=vy0, x=x, vx=vx, vy=vy,
+         rho=np.array(rhos), E=np.array(Es), raw=np.array(raws))
+
+
 def c5_2d3v(steps=4):
     """Config 5 shape at test size: src/Electrostatic2D3V.jl with NX=NY=32, P=NX*NY*8."""
     NX = NY = 32
@@ -213,7 +237,7 @@ if __name__ == "__main__":
     if args.only:
         globals()[args.only]()
         sys.exit(0)
-    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils(); ngp1d2v()
+    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils(); ngp1d2v(); ngp1d2v2s()
     if not args.skip_c3:
         c3_quiet()
         simpson13()

@@ -115,6 +115,22 @@ def main():
     print(f"[rank {rank}] ngp_1d2v bit-identical={good}", flush=True)
     ok &= good
     sim.close(); ref.close()
+    # two-species 1D2V: the species boundary falls inside rank 0's shard for world = 3.. and between shards for world = 2
+    P2 = 1 << 15
+    sim = pg.ngp_1d2v_2s(N=256, P=P2, T=64, TO=16, M=8.0, rank=rank, nranks=world, device=local)
+    pgd.connect(sim)
+    xg, vxg, vyg = rng.random(2 * P2), sim.vth * rng.standard_normal(2 * P2), sim.vth * rng.standard_normal(2 * P2)
+    f, c = sim.first, sim.count
+    sim.set_particles(xg[f:f + c], vxg[f:f + c], vy=vyg[f:f + c])
+    sim.step(8)
+    got = sim.particles(); fld = sim.fields(); D, _ = sim.diagnostics()
+    ref = pg.ngp_1d2v_2s(N=256, P=P2, T=64, TO=16, M=8.0, device=local)
+    ref.set_particles(xg, vxg, vy=vyg); ref.step(8)
+    gr = ref.particles(); fr = ref.fields(); Dr, _ = ref.diagnostics()
+    good = all(np.array_equal(a, b[f:f + c]) for a, b in zip(got, gr)) and np.array_equal(fld[0], fr[0]) and rel(D, Dr) < 1e-12
+    print(f"[rank {rank}] ngp_1d2v_2s bit-identical={good}", flush=True)
+    ok &= good
+    sim.close(); ref.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
