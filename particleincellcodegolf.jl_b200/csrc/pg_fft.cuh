@@ -72,6 +72,107 @@ __device__ __forceinline__ void fft_smem(double *re, double *im, int n, int batc
     }
 }
 
+// Radix-2^2 form of fft_smem: two consecutive radix-2 stages are carried out in registers on four elements, with the SAME
+// butterflies, twiddle-table entries and operation order as fft_smem -- the results are bit-identical -- but half the
+// shared-memory round trips and block barriers (N = 4096: 6 + 6 passes instead of 12 + 12).  A leftover single stage
+// (odd log2 n) runs first (forward) or last (inverse) as a plain radix-2 pass.
+template <bool INVERSE>
+__device__ __forceinline__ void fft_smem4(double *re, double *im, int n, int batch, int estride, int bstride,
+                                          const double2 *__restrict__ tw, int twN)
+{
+#ifdef PG_FFT_RADIX2 // A/B builds (tools/fft_radix_check.py): plain radix-2 passes
+    fft_smem<INVERSE>(re, im, n, batch, estride, bstride, tw, twN);
+    return;
+#endif
+    const int nh = n >> 1, nq = n >> 2;
+    int lg = 0;
+    while ((1 << lg) < n) ++lg;
+    auto radix2 = [&](int half) { // one stage of fft_smem
+        const int tws = twN / (2 * half), total = batch * nh;
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            int b = t / nh, u = t - b * nh;
+            int pos = u & (half - 1), grp = u / half;
+            int i = b * bstride + (grp * 2 * half + pos) * estride, j = i + half * estride;
+            double2 w = __ldg(&tw[pos * tws]);
+            if (!INVERSE) {
+                double ar = re[i], ai = im[i], br = re[j], bi = im[j];
+                re[i] = ar + br; im[i] = ai + bi;
+                double dr = ar - br, di = ai - bi;
+                re[j] = dr * w.x - di * w.y;
+                im[j] = dr * w.y + di * w.x;
+            } else {
+                double br = re[j], bi = im[j];
+                double tr = br * w.x + bi * w.y;
+                double ti = bi * w.x - br * w.y;
+                double ar = re[i], ai = im[i];
+                re[j] = ar - tr; im[j] = ai - ti;
+                re[i] = ar + tr; im[i] = ai + ti;
+            }
+        }
+        __syncthreads();
+    };
+    if (n < 4) { // n = 2: a single stage
+        if (n == 2) radix2(1);
+        return;
+    }
+    const int total = batch * nq;
+    if (!INVERSE) {
+        int half = nh;
+        if (lg & 1) { radix2(half); half >>= 1; }
+        for (; half >= 2; half >>= 2) { // stages `half` and `half/2`
+            const int q = half >> 1;
+            const int tws1 = twN / (2 * half), tws2 = twN / half;
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                int b = t / nq, u = t - b * nq;
+                int pos = u & (q - 1), grp = u / q;
+                int ia = b * bstride + (grp * 2 * half + pos) * estride;
+                int ib = ia + q * estride, ic = ia + half * estride, id = ic + q * estride;
+                double2 w1 = __ldg(&tw[pos * tws1]), w1q = __ldg(&tw[(pos + q) * tws1]), w2 = __ldg(&tw[pos * tws2]);
+                double ar = re[ia], ai = im[ia], br = re[ib], bi = im[ib], cr = re[ic], ci = im[ic], dr = re[id], di = im[id];
+                // stage `half`: (a,c) with w1, (b,d) with w1q
+                double a1r = ar + cr, a1i = ai + ci, er = ar - cr, ei = ai - ci;
+                double c1r = er * w1.x - ei * w1.y, c1i = er * w1.y + ei * w1.x;
+                double b1r = br + dr, b1i = bi + di, fr = br - dr, fi = bi - di;
+                double d1r = fr * w1q.x - fi * w1q.y, d1i = fr * w1q.y + fi * w1q.x;
+                // stage `half/2`: (a',b') and (c',d') with w2
+                re[ia] = a1r + b1r; im[ia] = a1i + b1i;
+                double gr = a1r - b1r, gi = a1i - b1i;
+                re[ib] = gr * w2.x - gi * w2.y; im[ib] = gr * w2.y + gi * w2.x;
+                re[ic] = c1r + d1r; im[ic] = c1i + d1i;
+                double hr = c1r - d1r, hi = c1i - d1i;
+                re[id] = hr * w2.x - hi * w2.y; im[id] = hr * w2.y + hi * w2.x;
+            }
+            __syncthreads();
+        }
+    } else {
+        int q = 1;
+        for (int done = 0; done + 2 <= lg; done += 2, q <<= 2) { // stages `q` and `2q`
+            const int half = 2 * q;
+            const int tws1 = twN / (2 * q), tws2 = twN / (2 * half);
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                int b = t / nq, u = t - b * nq;
+                int pos = u & (q - 1), grp = u / q;
+                int ia = b * bstride + (grp * 4 * q + pos) * estride;
+                int ib = ia + q * estride, ic = ia + half * estride, id = ic + q * estride;
+                double2 w1 = __ldg(&tw[pos * tws1]), w2 = __ldg(&tw[pos * tws2]), w2q = __ldg(&tw[(pos + q) * tws2]);
+                double ar = re[ia], ai = im[ia], br = re[ib], bi = im[ib], cr = re[ic], ci = im[ic], dr = re[id], di = im[id];
+                // stage `q`: (a,b) and (c,d) with conj(w1)
+                double tr = br * w1.x + bi * w1.y, ti = bi * w1.x - br * w1.y;
+                double b1r = ar - tr, b1i = ai - ti, a1r = ar + tr, a1i = ai + ti;
+                double ur = dr * w1.x + di * w1.y, ui = di * w1.x - dr * w1.y;
+                double d1r = cr - ur, d1i = ci - ui, c1r = cr + ur, c1i = ci + ui;
+                // stage `2q`: (a',c') with conj(w2), (b',d') with conj(w2q)
+                double vr = c1r * w2.x + c1i * w2.y, vi = c1i * w2.x - c1r * w2.y;
+                re[ic] = a1r - vr; im[ic] = a1i - vi; re[ia] = a1r + vr; im[ia] = a1i + vi;
+                double xr = d1r * w2q.x + d1i * w2q.y, xi = d1i * w2q.x - d1r * w2q.y;
+                re[id] = b1r - xr; im[id] = b1i - xi; re[ib] = b1r + xr; im[ib] = b1i + xi;
+            }
+            __syncthreads();
+        }
+        if (lg & 1) radix2(nh);
+    }
+}
+
 __device__ __forceinline__ int bitrev(int v, int lg) { return (int)(__brev((unsigned)v) >> (32 - lg)); }
 
 struct Solve1DArgs {
@@ -103,7 +204,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         re[n] = r; im[n] = 0.0;
     }
     __syncthreads();
-    fft_smem<false>(re, im, N, 1, 1, 0, a.tw, N);
+    fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
         int s = bitrev(p, a.lg); // frequency slot held at position p
@@ -117,7 +218,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         }
     }
     __syncthreads();
-    fft_smem<true>(re, im, N, 1, 1, 0, a.tw, N);
+    fft_smem4<true>(re, im, N, 1, 1, 0, a.tw, N);
     double d2 = 0.0, f2 = 0.0, e2 = 0.0;
     const double dN = (double)N;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -184,7 +285,7 @@ __global__ void __launch_bounds__(512) solve2d_rows_fwd(Solve2DArgs a)
         re[t] = v; im[t] = 0.0;
     }
     __syncthreads();
-    fft_smem<false>(re, im, NX, R, 1, NX, a.twx, NX);
+    fft_smem4<false>(re, im, NX, R, 1, NX, a.twx, NX);
     for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {
         int r = t / NX, i = t - r * NX;
         a.Z[(size_t)i + (size_t)(j0 + r) * NX] = make_double2(re[t], im[t]);
@@ -205,7 +306,7 @@ __global__ void __launch_bounds__(512) solve2d_cols(Solve2DArgs a)
         re[c * LD + j] = z.x; im[c * LD + j] = z.y;
     }
     __syncthreads();
-    fft_smem<false>(re, im, NY, C, 1, LD, a.twy, NY);
+    fft_smem4<false>(re, im, NY, C, 1, LD, a.twy, NY);
     for (int t = threadIdx.x; t < C * NY; t += blockDim.x) {
         int c = t / NY, q = t - c * NY;
         int ix = bitrev(p0 + c, a.lgx), iy = bitrev(q, a.lgy); // frequency slots (0-based)
@@ -224,7 +325,7 @@ __global__ void __launch_bounds__(512) solve2d_cols(Solve2DArgs a)
         re[c * LD + q] = zr; im[c * LD + q] = zi;
     }
     __syncthreads();
-    fft_smem<true>(re, im, NY, C, 1, LD, a.twy, NY);
+    fft_smem4<true>(re, im, NY, C, 1, LD, a.twy, NY);
     for (int t = threadIdx.x; t < C * NY; t += blockDim.x) {
         int j = t / C, c = t - j * C;
         a.Z[(size_t)(p0 + c) + (size_t)j * NX] = make_double2(re[c * LD + j], im[c * LD + j]);
@@ -244,7 +345,7 @@ __global__ void __launch_bounds__(512) solve2d_rows_inv(Solve2DArgs a)
         re[t] = z.x; im[t] = z.y;
     }
     __syncthreads();
-    fft_smem<true>(re, im, NX, R, 1, NX, a.twx, NX);
+    fft_smem4<true>(re, im, NX, R, 1, NX, a.twx, NX);
     const double inv = (double)NX * (double)a.NY;
     double e2 = 0.0;
     for (int t = threadIdx.x; t < R * NX; t += blockDim.x) {

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(1024) solve_simpson23_kernel(SolveSPArgs a)
         re[n] = r; im[n] = 0.0;
     }
     __syncthreads();
-    fft_smem<false>(re, im, N, 1, 1, 0, a.tw, N);
+    fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
         int s = bitrev(p, a.lg);
         if (s == 0) { re[p] = 0.0; im[p] = 0.0; }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(1024) solve_simpson23_kernel(SolveSPArgs a)
         }
     }
     __syncthreads();
-    fft_smem<true>(re, im, N, 1, 1, 0, a.tw, N);
+    fft_smem4<true>(re, im, N, 1, 1, 0, a.tw, N);
     double d2 = 0.0, f2 = 0.0, e2 = 0.0;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double e = re[n] / (double)N, f = E[n];
