@@ -361,7 +361,7 @@ def cpu_baseline(workload, log2p, steps):
         dt = time.perf_counter() - t0
         extra = {}
         sample = f"256x256 P=2^{log2p}, {steps} steps, {cores} threads with per-thread grids (Electrostatic2D3V.jl:114,126-141)"
-    out = {"value": P * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+    out = {"value": P * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sample_ms_per_step": dt / steps * 1e3,
            "note": "C restatement of the Julia loop (oracle/picgolf_oracle.c, gcc -O2), not Julia: julia is not installed"}
     out.update(extra)
     return out
@@ -376,7 +376,7 @@ def run_reference(args):
     per_gpu = 1 << args.log2_particles_per_gpu
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": cpu["sample_ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: same configuration as the GPU arm ({per_gpu * max(world, args.gpus)} particles), timed on a bounded sample",
                        "sample": cpu["sample"]},
             "cpu_baseline": cpu,
