@@ -10,10 +10,11 @@
 // stencil evaluations (~255 FP64 instructions in fp_pass_sorted), which moves the pass from the FP64 pipe to HBM.
 //
 // fp_pass_poly: every warp streams ONE contiguous range of the (cell, sign v)-sorted particle arrays with 128-bit
-// loads (2 particles per lane and row).  Deposit: each lane keeps two private moment sets in registers, one for the
-// even and one for the odd cell it is currently in (a drifting bin straddles two neighbouring cells); a set is
-// flushed with 17 integer REDs into the fixed-point moment grid Mg only when the lane moves on to another cell of
-// that parity -- a few times per pass in sorted order, so there are no shared-memory or per-particle atomics at all.
+// loads (2 particles per lane and row).  Deposit: each lane keeps the moment set of the cell it is currently in in
+// registers and a spare set -- the other cell of the drifting bin, which straddles two neighbouring cells -- in a
+// private shared-memory column; a set is flushed with 17 integer REDs into the fixed-point moment grid Mg only when
+// the lane meets a third cell -- a few times per pass in sorted order, so there are no shared-memory or per-particle
+// atomics at all.
 // Gather: the G rows of the CP_WG cells around the warp's position are staged in shared memory; a particle reads the
 // 17 coefficients of its own cell (lanes in the same cell broadcast).  Any particle order is handled correctly
 // (window reloads, global-memory gather, early flushes); order only decides the speed, and the mid-stream flushes
@@ -30,8 +31,8 @@ constexpr int CP_WG = 8;         // cells in a warp's gather window
 constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned,
                                  // and two neighbouring rows (144 B apart) never share a bank within one 128-bit access
 
-// 3 blocks of 128 threads per SM (166 registers per thread) measured 2.5 % faster than 2 x 256 (128 registers):
-// the compiler uses the extra registers to overlap the coefficient loads of the two particles of a lane.
+// 3 blocks of 128 threads per SM (160 registers per thread): 4 x 128 at 128 registers measured the same, 5 x 128 at 96
+// registers 19 % slower -- the compiler needs the registers to overlap the coefficient loads of a lane's two particles.
 #ifndef PG_CP_THREADS
 #define PG_CP_THREADS 128
 #endif
@@ -44,7 +45,8 @@ constexpr int CP_STAGE_D2 = 96;  // double2 slots per stage: X, V, v pairs of th
 
 __host__ __device__ inline size_t cp_smem_bytes(int threads)
 {
-    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2));
+    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2)) +
+           (size_t)threads * CP_NM * sizeof(double); // + the spare moment set of every lane
 }
 
 // 16-byte asynchronous global -> shared copy (L2 only); each lane later reads back exactly the bytes it copied itself,
@@ -162,27 +164,49 @@ __device__ __forceinline__ void cp_flush(CPSet &s, fx_t *Mg, double fx_scale, in
     }
 }
 
-// Deposit of one particle with centre `cell` and offset t: M[cell][n] += t^n.  A holds the even cell the lane is in,
-// B the odd one.  (A branch-free variant -- sum over all particles plus an FMA-masked sum over the odd ones -- was
-// measured 4 % slower: 46 instead of 30..53 FP64 instructions per particle.)
-__device__ __forceinline__ void cp_deposit(int cell, double t, CPSet &A, CPSet &B, fx_t *Mg, double fx_scale, int Nmask,
-                                           unsigned int &nflush)
+// The moment set of the lane's CURRENT cell lives in registers (CPSet); the set of the other cell of the drifting bin
+// (the "spare") in a lane-private shared-memory column col[n*blockDim.x] (conflict-free), exchanged with the register
+// set when the lane changes over.  (Both sets in registers, selected by cell parity: 4 % slower, 32 registers more;
+// a branch-free sum / odd-sum form: another 4 % slower.  Both measured on B200.)
+struct CPSpare { int cnt, cell; };
+
+__device__ __forceinline__ void cp_flush_spare(CPSpare &sp, double *col, int stride, fx_t *Mg, double fx_scale, int Nmask)
 {
+    if (sp.cnt) {
+        fx_t *p = Mg + (size_t)((sp.cell - 1) & Nmask) * CP_NC;
+        atomicAdd(p, to_fx((double)sp.cnt, fx_scale));
+#pragma unroll
+        for (int n = 0; n < CP_NM; ++n) { atomicAdd(p + 1 + n, to_fx(col[n * stride], fx_scale)); col[n * stride] = 0.0; }
+        sp.cnt = 0;
+    }
+}
+
+__device__ __forceinline__ void cp_deposit1(int cell, double t, CPSet &P, CPSpare &sp, double *col, int stride, fx_t *Mg,
+                                            double fx_scale, int Nmask, unsigned int &nflush)
+{
+    if (cell != P.cell) { // rare in sorted order
+        if (cell == sp.cell) { // change over to the other cell of the bin: exchange the two sets
+#pragma unroll
+            for (int n = 0; n < CP_NM; ++n) { const double m = col[n * stride]; col[n * stride] = P.m[n]; P.m[n] = m; }
+            const int c = sp.cnt; sp.cnt = P.cnt; P.cnt = c;
+            sp.cell = P.cell; P.cell = cell;
+            ++nflush; // exchanges count as well: lanes alternating between the two cells pay 32 shared accesses each time
+        } else {               // a third cell: retire the spare, park the current set
+            nflush += sp.cnt > 0;
+            cp_flush_spare(sp, col, stride, Mg, fx_scale, Nmask);
+#pragma unroll
+            for (int n = 0; n < CP_NM; ++n) { col[n * stride] = P.m[n]; P.m[n] = 0.0; }
+            sp.cnt = P.cnt; sp.cell = P.cell;
+            P.cnt = 0; P.cell = cell;
+        }
+    }
+    P.cnt++;
     const double t2 = t * t;
-    double p[CP_NM];
-    p[0] = t; p[1] = t2;
+    double pa = t, pb = t2;
 #pragma unroll
-    for (int n = 2; n < CP_NM; ++n) p[n] = p[n - 2] * t2;
-    if (cell & 1) {
-        if (cell != B.cell) { nflush += B.cnt > 0; cp_flush(B, Mg, fx_scale, Nmask); B.cell = cell; }
-        B.cnt++;
-#pragma unroll
-        for (int n = 0; n < CP_NM; ++n) B.m[n] += p[n];
-    } else {
-        if (cell != A.cell) { nflush += A.cnt > 0; cp_flush(A, Mg, fx_scale, Nmask); A.cell = cell; }
-        A.cnt++;
-#pragma unroll
-        for (int n = 0; n < CP_NM; ++n) A.m[n] += p[n];
+    for (int n = 0; n < CP_NM; n += 2) {
+        P.m[n] += pa; P.m[n + 1] += pb;
+        if (n + 2 < CP_NM) { pa *= t2; pb *= t2; }
     }
 }
 
@@ -266,10 +290,13 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     const int r0 = min(rows, gw * rpw), r1 = min(rows, r0 + rpw);
     const double2 *X2 = reinterpret_cast<const double2 *>(a.X), *V2 = reinterpret_cast<const double2 *>(a.V);
     double2 *v2 = reinterpret_cast<double2 *>(a.v), *xo2 = reinterpret_cast<double2 *>(a.xout);
-    CPSet A, B;
+    CPSet A;
+    CPSpare spare;
+    double *col = smem + wpb * (CP_GS * CP_WG + 2 * CP_STAGES * CP_STAGE_D2) + threadIdx.x;
+    const int cstride = blockDim.x;
 #pragma unroll
-    for (int n = 0; n < CP_NM; ++n) { A.m[n] = 0.0; B.m[n] = 0.0; }
-    A.cnt = 0; B.cnt = 0; A.cell = 0x40000000; B.cell = 0x40000001;
+    for (int n = 0; n < CP_NM; ++n) { A.m[n] = 0.0; col[n * cstride] = 0.0; }
+    A.cnt = 0; A.cell = 0x40000000; spare.cnt = 0; spare.cell = 0x40000001;
     int gb = 0x40000000; // Julia index of window slot 0; the first row always restages (see `staged`)
     bool staged = false;
     double sv2 = 0.0, sv = 0.0;
@@ -354,13 +381,13 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             double t[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) cp_centre(xj[q] + Xj[q], dN, cell[q], t[q]);
-            cp_deposit(cell[0], t[0], A, B, a.Mg, a.fx_scale, Nmask, nflush);
-            cp_deposit(cell[1], t[1], A, B, a.Mg, a.fx_scale, Nmask, nflush);
+            cp_deposit1(cell[0], t[0], A, spare, col, cstride, a.Mg, a.fx_scale, Nmask, nflush);
+            cp_deposit1(cell[1], t[1], A, spare, col, cstride, a.Mg, a.fx_scale, Nmask, nflush);
         }
     }
     cp_async_wait<0>();
     cp_flush(A, a.Mg, a.fx_scale, Nmask);
-    cp_flush(B, a.Mg, a.fx_scale, Nmask);
+    cp_flush_spare(spare, col, cstride, a.Mg, a.fx_scale, Nmask);
     // ragged tail of the shard: fewer than 64 particles, first warp of the last block
     if (blockIdx.x == gridDim.x - 1 && warp == 0) {
         const long long j = ((long long)rows << 6) + lane;
