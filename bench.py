@@ -205,9 +205,10 @@ def run_gpu(args):
     if args.workload == "gauss_fp":
         peak_tf = pg.fp64_peak_tflops()
         # FP64 instructions per particle-pass measured with ncu (profiles/): 255 for a fp_pass_sorted pass with two
-        # stencils (middle passes and the final pass with the fused first deposit of the next step); 90 for fp_pass_poly
-        # (180 warp-instructions per row of 64 particles: DADD 94, DMUL 54, DFMA 32)
-        per_pass = 90 if sim.deposit_path == pg.DEPOSIT_POLY else 255
+        # stencils (middle passes and the final pass with the fused first deposit of the next step); 68 for fp_pass_poly
+        # (FP64 pipe active 57.6 % of 3.25 M cycles = 132 warp-instructions per row of 64 particles in the first and
+        # middle passes, 144 in the final pass: mean over a 3-sweep step 68 per particle)
+        per_pass = 68 if sim.deposit_path == pg.DEPOSIT_POLY else 255
         fp64_inst = float(sum(per_pass * int(s_) for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
         ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
         fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
