@@ -333,6 +333,40 @@ def test_scaled_config4_properties(pg, oracle):
     assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL
 
 
+def test_config4_full_size_properties(pg):
+    """BASELINE.json config 4 at its full single-GPU size (N=4096, 2^28 particles, quiet two-stream start) through the
+    path a caller gets (AUTO -> cell-polynomial passes): size-independent properties, and agreement of two different
+    algorithms (polynomial passes vs the 13-weight window kernel) on the same 2^26-particle run."""
+    N, P = 4096, 1 << 28
+    sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=400.0, l=1e-8)
+    assert sim.deposit_path == pg.DEPOSIT_POLY
+    sim.init_quiet()
+    sim.step(4)
+    rho, E = sim.fields()
+    D, sw = sim.diagnostics()
+    assert abs(rho.mean() / 400.0 - 1) < 1e-12           # charge conservation: mean rho == W
+    assert abs(E.sum()) < 1e-9 * np.abs(E).max() * N + 1e-20  # xi[1]=0: zero-mean field
+    assert np.abs(D[:, 3]).max() < 1e-14                 # mean momentum of the symmetric beams
+    assert np.abs(D[:, 2] - 1).max() < 1e-12             # energy: D3 = 1 while the field is round-off
+    assert sw.max() <= 3
+    x, v = sim.particles()
+    assert 0 <= x.min() and x.max() <= 1 and np.abs(np.abs(v) - 1).max() < 1e-12  # round-off field: the beams stay cold
+    xq, vq = pg.quiet_start(P, 12345, 1000)              # caller's order is restored: particle j drifted by v*t
+    assert np.abs(np.mod(x[12345:13345] - xq - 4 * sim.cfg.dt * vq + 0.5, 1) - 0.5).max() < 1e-12
+    sim.close(); del x, v
+    P2 = 1 << 26
+    out = []
+    for mode in (pg.DEPOSIT_POLY, pg.DEPOSIT_SORTED):
+        s2 = pg.gaussian_fixed_point(N=N, P=P2, T=8, W=400.0, l=1e-8, deposit_mode=mode)
+        s2.init_synthetic(seed=3)
+        s2.step(5)
+        out.append(s2.fields() + s2.particles() + (s2.diagnostics()[1],))
+        s2.close()
+    (ra, Ea, xa, va, swa), (rb, Eb, xb, vb, swb) = out
+    assert np.array_equal(swa, swb)
+    assert relnorm(ra, rb) < TOL and relnorm(Ea, Eb) < 1e-10 and relnorm(xa, xb) < TOL and relnorm(va, vb) < TOL
+
+
 def test_scaled_ngp_properties(pg, oracle):
     """Config-1-scaled NGP (N=4096): rho is an exact histogram whatever the size."""
     N, P = 4096, 1 << 22
