@@ -125,6 +125,7 @@ def run_gpu(args):
                               deposit_mode={"auto": 0, "atomic": 1, "sorted": 2, "poly": 3}[args.deposit_mode])
     if world > 1:
         pgd.connect(sim)
+    sim_peer = world > 1 and sim.peer_status[0]
     init_sim(sim, args.workload)
     stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local))
 
@@ -257,6 +258,33 @@ def run_gpu(args):
         e2e = {"value": P * Ke / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncomp * n, "d2h_bytes_per_step": 8 * ncomp * n,
                "steps": Ke, "ms_per_step": ems / Ke, "wall_ms_per_step": wall / Ke,
                "what": "per step: picgolf_set_particles (pinned host -> HBM), picgolf_step(1), picgolf_get_particles (HBM -> host)"}
+        # second reading of "inputs in, result out": the particle state goes in every step, only the step's fields
+        # (rho, E) and its diagnostics row come back
+        def one_fields():
+            if ncomp == 2:
+                pg._check(lib.picgolf_set_particles(hnd, host[0], host[1], n))
+            else:
+                pg._check(lib.picgolf_set_particles_2d3v(hnd, *host, n))
+            pg._check(lib.picgolf_step(hnd, 1))
+            fl = sim.fields()
+            sim.diagnostics()
+            return sum(a.nbytes for a in fl) + 40
+        one_fields()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(Ke):
+            d2h = one_fields()
+        f1.record(stream)
+        barrier()
+        fms = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([fms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+        e2e["state_in_fields_out"] = {"value": P * Ke / (fms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncomp * n,
+                                      "d2h_bytes_per_step": int(d2h), "ms_per_step": fms / Ke,
+                                      "what": "per step: picgolf_set_particles, picgolf_step(1), picgolf_get_fields + picgolf_get_diagnostics"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------
     cpu = None
@@ -302,7 +330,9 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "particles_per_gpu": per_gpu, "l2": "inputs_exceed_l2 (8*particles*arrays bytes >> 126 MB)",
-                       "parallelism": f"particle-sharded x{world}, rho all-reduce per sweep"},
+                       "parallelism": f"particle-sharded x{world}, rho summed once per sweep: " + (
+                           "NVLink peer-memory loads fused into the solve kernel (pg_peer.cuh)" if (world > 1 and sim_peer) else
+                           "ncclAllReduce" if world > 1 else "single GPU")},
             "mean_sweeps_per_step": mean_sweeps, "particle_sweeps_per_s": value * mean_sweeps,
             "algorithmic_bytes_per_particle_step": bpu,
             "hbm_roofline_frac_step": (value / world) * bpu / (peak * 1e9),

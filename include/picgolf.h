@@ -211,6 +211,14 @@ int picgolf_get_stream(picgolf_handle h, void **stream);
  * MPI, a file); then every rank calls picgolf_comm_init. */
 int picgolf_comm_unique_id(void *id128);
 int picgolf_comm_init(picgolf_handle h, const void *id128, int nranks, int rank);
+/* Optional, after picgolf_comm_init: sum the 1D charge grids over NVLink peer memory inside the solve kernel instead of
+ * one ncclAllReduce per sweep (pg_peer.cuh; one process per GPU on ONE node).  Every rank calls picgolf_peer_export
+ * (64-byte cudaIpc handle out), the nranks handles are gathered in rank order (torch.distributed / MPI), then every
+ * rank calls picgolf_peer_connect.  picgolf_peer_status: whether it is in use, and whether a wait ever timed out
+ * (a rank died: the results after that are undefined). */
+int picgolf_peer_export(picgolf_handle h, void *handle64);
+int picgolf_peer_connect(picgolf_handle h, const void *handles, int nranks, int rank);
+int picgolf_peer_status(picgolf_handle h, int *enabled, int *timed_out);
 
 /* ---- stage-level entry points (parity tests call these through the same ABI) -------------- */
 /* f(x)=Int(mod1(round(x*N),N)) (NGPFourier.jl:3); idx1 is 1-based like Julia. */

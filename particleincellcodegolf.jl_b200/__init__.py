@@ -108,6 +108,9 @@ _SIGNATURES = {
     "picgolf_get_stream": [_vp, C.POINTER(_vp)],
     "picgolf_comm_unique_id": [_vp],
     "picgolf_comm_init": [_vp, _vp, _int, _int],
+    "picgolf_peer_export": [_vp, _vp],
+    "picgolf_peer_connect": [_vp, _vp, _int, _int],
+    "picgolf_peer_status": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "picgolf_stage_ngp_index": [_dp, _i64, _i64, _ip],
     "picgolf_stage_mod1": [_dp, _i64, _dp],
     "picgolf_stage_gauss_stencil": [_dp, _i64, _i64, _int, _ip, _dp],
@@ -335,6 +338,25 @@ class PIC:
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _check(self._lib.picgolf_comm_init(self._h, buf, self.cfg.nranks, self.cfg.rank))
+
+    def peer_export(self) -> bytes:
+        """64-byte cudaIpc handle of this rank's published charge grid (pg_peer.cuh)."""
+        buf = C.create_string_buffer(64)
+        _check(self._lib.picgolf_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles: bytes) -> None:
+        """handles: the nranks 64-byte handles in rank order."""
+        assert len(handles) == 64 * self.cfg.nranks
+        buf = C.create_string_buffer(handles, len(handles))
+        _check(self._lib.picgolf_peer_connect(self._h, buf, self.cfg.nranks, self.cfg.rank))
+
+    @property
+    def peer_status(self):
+        """(peer-memory reduction in use, a wait timed out)."""
+        a, b = C.c_int(), C.c_int()
+        _check(self._lib.picgolf_peer_status(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
 
 
 def comm_unique_id() -> bytes:

@@ -9,6 +9,7 @@
 // natural out), so no permutation pass is needed.  cuFFT is not used anywhere.
 #pragma once
 #include "pg_common.cuh"
+#include "pg_peer.cuh"
 
 namespace pg {
 
@@ -187,6 +188,7 @@ struct Solve1DArgs {
     int N, lg, fixedpoint, k, max_sweeps;
     int store_normE1; // Simpson variant: this is the E1 solve of the step
     double *hist;     // 1D2V: time-averaged field history column Es[:,ti] += E (NGP1D2V.jl:57), or NULL
+    PeerArgs peer;    // multi-GPU: sum the ranks' grids over peer memory here (pg_peer.cuh); nranks <= 1: rho_fx is the sum
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -196,14 +198,18 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     double *re = smem, *im = smem + a.N, *scratch = smem + 2 * a.N;
     if (a.fixedpoint && a.ctrl->final_k >= 0) return; // step already converged: predicated no-op
     const int N = a.N;
+    const bool peers = a.peer.nranks > 1 && !a.rho_in;
+    if (peers) peer_gather_begin(a.peer);
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double r;
         if (a.rho_in) r = a.rho_in[n];
+        else if (peers) r = (double)peer_sum(a.peer, n) * a.fx_inv * a.w; // the publish kernel cleared rho_fx
         else { r = (double)(long long)a.rho_fx[n] * a.fx_inv * a.w; a.rho_fx[n] = 0ULL; }
         a.rho_last[n] = r;
         re[n] = r; im[n] = 0.0;
     }
     __syncthreads();
+    if (peers) peer_gather_end(a.peer);
     fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
     for (int p = threadIdx.x; p < N; p += blockDim.x) {

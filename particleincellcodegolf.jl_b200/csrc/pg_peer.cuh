@@ -1,0 +1,101 @@
+// pg_peer.cuh -- sum of the per-GPU charge grids over NVLink peer memory, fused into the field solve.
+//
+// The reference sums its per-thread grids with `phi .= sum(ns, dims=3)` (src/Electrostatic2D3V.jl:139-141); across GPUs
+// that sum was one ncclAllReduce per sweep, enqueued by the host for ALL max_sweeps sweeps of a step because the host
+// never learns the sweep count -- at 8 GPUs ten 32-us collectives per step, seven of them summing zeros.  Here every
+// rank copies its integer grid into a buffer the other ranks can read (cudaIpc), raises a flag, and the solve kernel of
+// every rank waits for the flags and adds up the nranks grids itself with plain loads over NVLink (64-bit integer adds
+// in rank order: bit-identical on all ranks and to the NCCL sum).  A predicated-off sweep costs nothing.
+//
+// Protocol (seq = host-side count of enqueued sweeps, slot = seq & 1):
+//   publish(seq):  wait until every peer's `done` >= the sequence number this slot last carried (nobody still reads
+//                  it); copy rho -> data[slot], clear rho; fence; ready = seq.
+//   solve(seq):    wait until every peer's `ready` >= seq; rho[n] = sum_q peer[q].data[slot][n]; then done = seq.
+// A rank publishes sweep s+1 only after its own solve(s), and solve(s) needs every peer's publish(s): no rank is ever
+// more than one real sweep ahead, and with the `done` handshake two slots suffice.  Waits give up after ~2 s and raise
+// an error flag instead of hanging the GPU.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+constexpr int PEER_MAX = 16;
+constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;
+
+struct PeerPub {
+    unsigned long long ready;       // highest sweep sequence number whose grid this rank has published
+    unsigned long long done;        // highest sequence number this rank has finished reading from all peers
+    unsigned long long last_pub[2]; // per slot: the sequence number of its content
+    unsigned long long pad_[12];    // header = 128 bytes; fx_t data[2][ncell] follows
+};
+
+struct PeerArgs {
+    PeerPub *peer[PEER_MAX]; // peer[rank] is this rank's own buffer
+    int nranks, rank;        // nranks <= 1: not in use
+    unsigned long long seq;
+    long long ncell;
+    int *error;
+};
+
+__device__ __forceinline__ fx_t *peer_data(PeerPub *p, int slot, long long ncell) { return reinterpret_cast<fx_t *>(p + 1) + (size_t)slot * ncell; }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void peer_wait(const unsigned long long *flag, unsigned long long need, int *error)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < need) {
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { *error = 1; return; }
+        __nanosleep(64);
+    }
+}
+
+// One block.  rho: this rank's integer charge grid (cleared here, like the solve does on a single GPU).
+__global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rho, const int *final_k, int fixedpoint)
+{
+    if (fixedpoint && *final_k >= 0) return; // step already converged: predicated no-op, like the solve
+    PeerPub *me = p.peer[p.rank];
+    const int slot = (int)(p.seq & 1ULL);
+    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->done, me->last_pub[slot], p.error);
+    __syncthreads();
+    fx_t *dst = peer_data(me, slot, p.ncell);
+    for (long long n = threadIdx.x; n < p.ncell; n += blockDim.x) { dst[n] = rho[n]; rho[n] = 0ULL; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { me->last_pub[slot] = p.seq; st_release_sys(&me->ready, p.seq); }
+}
+
+// In the solve kernel (one block): wait for all grids of this sweep, then peer_sum(n) for every cell, then peer_done().
+__device__ __forceinline__ void peer_gather_begin(const PeerArgs &p)
+{
+    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->ready, p.seq, p.error);
+    __syncthreads();
+}
+__device__ __forceinline__ long long peer_sum(const PeerArgs &p, long long n)
+{
+    const int slot = (int)(p.seq & 1ULL);
+    unsigned long long s = 0ULL;
+    for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(peer_data(p.peer[q], slot, p.ncell) + n);
+    return (long long)s;
+}
+__device__ __forceinline__ void peer_gather_end(const PeerArgs &p) // after a __syncthreads() that follows the last peer_sum
+{
+    if (threadIdx.x == 0) st_release_sys(&p.peer[p.rank]->done, p.seq);
+}
+
+} // namespace pg

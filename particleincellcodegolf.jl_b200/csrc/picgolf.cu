@@ -192,6 +192,12 @@ struct picgolf_handle_s {
     int64_t steps = 0, launches = 0;
     nccl::Comm comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory reduction of the charge grid (pg_peer.cuh): this rank's exported buffer, the opened peer buffers,
+    // the sweep sequence counter, and the device-side time-out flag
+    PeerPub *peer_mine = nullptr, *peer_ptr[PEER_MAX] = {};
+    bool peer_ok = false, peer_this_solve = false;
+    unsigned long long peer_seq = 0;
+    int *peer_err = nullptr;
     StageTimer timer;
     // cell-sorted mode
     bool sorted = false, pid_valid = false, use_sorted_now = false;
@@ -349,6 +355,9 @@ static int destroy_impl(picgolf_handle h)
     if (h->slow_ev) cudaEventDestroy(h->slow_ev);
     for (auto &e : h->run_ev) if (e) cudaEventDestroy(e);
     if (h->comm && nccl::CommDestroy) nccl::CommDestroy(h->comm);
+    for (int q = 0; q < PEER_MAX; ++q) if (h->peer_ptr[q] && q != h->rank) cudaIpcCloseMemHandle(h->peer_ptr[q]);
+    if (h->peer_mine) cudaFree(h->peer_mine);
+    if (h->peer_err) cudaFree(h->peer_err);
     void *ptrs[] = {h->xb[0], h->xb[1], h->vb[0], h->vb[1], h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4],
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
@@ -784,9 +793,29 @@ PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, do
 // ------------------------------------------------------------------------------------------
 // the loop body
 // ------------------------------------------------------------------------------------------
+static PeerArgs peer_args(picgolf_handle h)
+{
+    PeerArgs p;
+    memset(&p, 0, sizeof(p));
+    for (int q = 0; q < h->nranks; ++q) p.peer[q] = h->peer_ptr[q];
+    p.nranks = h->nranks; p.rank = h->rank; p.seq = h->peer_seq; p.ncell = h->ncell; p.error = h->peer_err;
+    return p;
+}
+
 static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
 {
+    h->peer_this_solve = false;
     if (!h->comm) return 0;
+    if (h->peer_ok && !h->is2d && !h->simpson && row0 == 0 && nrows == 1) {
+        // 1D schemes: publish this rank's grid; the solve kernel that follows adds the ranks' grids up itself
+        const int sp = h->timer.begin(ST_REDUCE, h->stream);
+        h->peer_seq++;
+        peer_publish_kernel<<<1, 1024, 0, h->stream>>>(peer_args(h), h->rho_fx, &h->ctrl->final_k, h->fixedpoint ? 1 : 0);
+        h->timer.end(sp, h->stream);
+        h->launches++;
+        h->peer_this_solve = true;
+        return 0;
+    }
     const int sp1_ = h->timer.begin(ST_REDUCE, h->stream);
     int rc;
     // integer grid: two's-complement sums are exact and order independent
@@ -800,11 +829,13 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
 {
     const picgolf_config &c = h->cfg;
     Solve1DArgs a;
+    memset(&a, 0, sizeof(a));
     a.rho_in = nullptr; a.rho_fx = h->rho_fx; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
     a.w = c.w; a.fx_inv = h->fx_inv; a.rtol = c.rtol; a.atol = c.atol;
     a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = (h->fixedpoint && !simpson_e1) ? 1 : 0;
     a.k = k; a.max_sweeps = c.max_sweeps; a.store_normE1 = simpson_e1 ? 1 : 0;
     a.hist = nullptr;
+    if (h->peer_this_solve) a.peer = peer_args(h);
     if (h->b1d2v) { // Es[:,ti] .+= E with ti = cld(t, T/TO)   NGP1D2V.jl:56-57
         int64_t ti = h->steps / c.diag_every;
         if (ti < h->T) a.hist = h->hist + (size_t)ti * c.N;
@@ -1465,6 +1496,62 @@ PG_API int picgolf_get_stream(picgolf_handle h, void **stream)
 // ------------------------------------------------------------------------------------------
 // multi-GPU
 // ------------------------------------------------------------------------------------------
+// Peer-memory reduction (pg_peer.cuh).  export: allocate this rank's published-grid buffer and return its 64-byte
+// cudaIpc handle; connect: open the nranks handles (own slot: the local pointer).  Both after picgolf_comm_init
+// (NCCL stays for the diagnostics sums, the 2D and Simpson grids, and as the fallback when this is not set up).
+PG_API int picgolf_peer_export(picgolf_handle h, void *handle64)
+{
+    if (!h || !handle64) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (h->nranks > PEER_MAX) return fail(PICGOLF_ERR_UNSUPPORTED, "peer reduction supports up to %d ranks", PEER_MAX);
+    PG_TRY(use_device(h));
+    if (!h->peer_mine) {
+        const size_t bytes = sizeof(PeerPub) + (size_t)2 * h->ncell * sizeof(unsigned long long);
+        PG_CUDA(cudaMalloc((void **)&h->peer_mine, bytes));
+        PG_CUDA(cudaMemset(h->peer_mine, 0, bytes));
+        PG_TRY(dalloc(&h->peer_err, 1));
+        PG_CUDA(cudaMemset(h->peer_err, 0, sizeof(int)));
+    }
+    cudaIpcMemHandle_t ipc;
+    PG_CUDA(cudaIpcGetMemHandle(&ipc, h->peer_mine));
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &ipc, 64);
+    return 0;
+}
+
+PG_API int picgolf_peer_connect(picgolf_handle h, const void *handles, int nranks, int rank)
+{
+    if (!h || !handles) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (nranks != h->nranks || rank != h->rank) return fail(PICGOLF_ERR_ARG, "peer_connect (rank %d of %d) does not match the handle (rank %d of %d)", rank, nranks, h->rank, h->nranks);
+    if (!h->peer_mine) return fail(PICGOLF_ERR_STATE, "call picgolf_peer_export first");
+    if (!h->comm) return fail(PICGOLF_ERR_STATE, "call picgolf_comm_init first");
+    PG_TRY(use_device(h));
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) { h->peer_ptr[q] = h->peer_mine; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)handles + (size_t)64 * q, 64);
+        void *p = nullptr;
+        PG_CUDA(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_ptr[q] = (PeerPub *)p;
+    }
+    h->peer_ok = true;
+    return 0;
+}
+
+PG_API int picgolf_peer_status(picgolf_handle h, int *enabled, int *timed_out)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (enabled) *enabled = h->peer_ok ? 1 : 0;
+    if (timed_out) {
+        *timed_out = 0;
+        if (h->peer_err) {
+            PG_TRY(use_device(h));
+            PG_CUDA(cudaStreamSynchronize(h->stream));
+            PG_CUDA(cudaMemcpy(timed_out, h->peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
 PG_API int picgolf_comm_unique_id(void *id128)
 {
     if (!id128) return fail(PICGOLF_ERR_ARG, "NULL argument");
@@ -1618,6 +1705,7 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     PG_TRY(dr.upload(rho, N * 8)); PG_TRY(dl.alloc(N * 8)); PG_TRY(dE.zero(N * 8)); PG_TRY(dctrl.zero(sizeof(Ctrl)));
     PG_TRY(make_twiddles(&tw, (int)N));
     Solve1DArgs a;
+    memset(&a, 0, sizeof(a));
     a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
     a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.fx_inv = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N);
     a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1; a.store_normE1 = 0; a.hist = nullptr;

@@ -2,7 +2,8 @@
 range, every rank holds a full grid, rho is summed with one NCCL all-reduce per sweep inside
 libpicgolf (the CPU analogue is the per-thread grids + `phi .= sum(ns, dims=3)` of
 src/Electrostatic2D3V.jl:114,126-141).  torch.distributed is used only to ship the 128-byte NCCL
-unique id from rank 0 to the other ranks."""
+unique id from rank 0 to the other ranks and to all-gather the 64-byte cudaIpc handles of the peer-memory reduction
+(pg_peer.cuh), which replaces the per-sweep all-reduce of the 1D schemes."""
 from __future__ import annotations
 
 import os
@@ -27,8 +28,9 @@ def broadcast_bytes(payload, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def connect(pic: PIC) -> None:
-    """Create the handle's NCCL communicator (collective over all ranks of the default group)."""
+def connect(pic: PIC, peer: bool = True) -> None:
+    """Create the handle's NCCL communicator (collective over all ranks of the default group) and, unless peer=False or
+    PICGOLF_NO_PEER is set, the peer-memory reduction of the 1D charge grids."""
     import torch.distributed as dist
 
     if pic.cfg.nranks == 1:
@@ -36,3 +38,43 @@ def connect(pic: PIC) -> None:
     uid = comm_unique_id() if dist.get_rank() == 0 else None
     uid = broadcast_bytes(uid, 128, src=0)
     pic.comm_init(uid)
+    if peer and os.environ.get("PICGOLF_NO_PEER") is None:
+        connect_peers(pic)
+
+
+def gather_bytes(payload: bytes) -> bytes:
+    """All-gather equal-length byte strings over the default group, concatenated in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
+
+def connect_peers(pic: PIC) -> bool:
+    """Set up the peer-memory reduction of the 1D charge grids (pg_peer.cuh): exchange the cudaIpc handles and open
+    them.  All ranks of one node; if any rank cannot (no peer access, more than 16 ranks), every rank stays on NCCL."""
+    import torch
+    import torch.distributed as dist
+
+    handle, ok = b"\0" * 64, 1
+    try:
+        handle = pic.peer_export()
+    except Exception:
+        ok = 0
+    handles = gather_bytes(handle + bytes([ok]))
+    n = dist.get_world_size()
+    if not all(handles[65 * q + 64] for q in range(n)):
+        return False
+    try:
+        pic.peer_connect(b"".join(handles[65 * q:65 * q + 64] for q in range(n)))
+    except Exception:
+        ok = 0
+    # the switch must be collective: a rank that failed to open a handle keeps everyone on NCCL
+    flags = gather_bytes(bytes([ok]))
+    if not all(flags):
+        raise RuntimeError("peer-memory reduction: some ranks could not open the cudaIpc handles (set PICGOLF_NO_PEER=1)")
+    return True

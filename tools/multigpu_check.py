@@ -28,6 +28,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    peer_seen = None
     for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO, pg.DEPOSIT_POLY):
         N, P, steps = 4096, 1 << 21, 6
         sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, rank=rank, nranks=world, device=local, deposit_mode=mode, sort_every=3)
@@ -48,7 +49,9 @@ def main():
         good = max(e.values()) < 1e-10 and np.array_equal(sw, swr) and abs(D[:, 3] - Dr[:, 3]).max() < 1e-13
         if mode == pg.DEPOSIT_ATOMIC:
             good = good and np.array_equal(rho, rr)  # integer accumulation: independent of the GPU count
-        print(f"[rank {rank}] fixed-point mode={mode} {e} sweeps={list(sw)} bit_equal_rho={np.array_equal(rho, rr)} ok={good}", flush=True)
+        peer_seen = sim.peer_status
+        good = good and not peer_seen[1]
+        print(f"[rank {rank}] fixed-point mode={mode} {e} sweeps={list(sw)} bit_equal_rho={np.array_equal(rho, rr)} peer(enabled,timed_out)={peer_seen} ok={good}", flush=True)
         ok &= good
         sim.close(); ref.close()
     # NGP
