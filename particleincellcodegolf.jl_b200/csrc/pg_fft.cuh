@@ -27,6 +27,7 @@ struct Ctrl {
     double normE1sq;
     double sp_acc[6];
     unsigned int sp_arrive, pad2_;
+    unsigned long long flush_global; // multi-GPU polynomial mode: sum over the ranks of the flush counters (pg_peer.cuh)
 };
 
 // Batched in-place FFT on shared memory.  Element e of batch b lives at [b*bstride + e*estride].
@@ -199,7 +200,10 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     if (a.fixedpoint && a.ctrl->final_k >= 0) return; // step already converged: predicated no-op
     const int N = a.N;
     const bool peers = a.peer.nranks > 1 && !a.rho_in;
-    if (peers) peer_gather_begin(a.peer);
+    if (peers) {
+        peer_gather_begin(a.peer);
+        if (threadIdx.x == 0) a.ctrl->flush_global = peer_flush_sum(a.peer);
+    }
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double r;
         if (a.rho_in) r = a.rho_in[n];

@@ -26,7 +26,8 @@ struct PeerPub {
     unsigned long long ready;       // highest sweep sequence number whose grid this rank has published
     unsigned long long done;        // highest sequence number this rank has finished reading from all peers
     unsigned long long last_pub[2]; // per slot: the sequence number of its content
-    unsigned long long pad_[12];    // header = 128 bytes; fx_t data[2][ncell] follows
+    unsigned long long flushes;     // this rank's cumulative flush counter (polynomial mode), summed next to the grid
+    unsigned long long pad_[11];    // header = 128 bytes; fx_t data[2][ncell] follows
 };
 
 struct PeerArgs {
@@ -35,6 +36,7 @@ struct PeerArgs {
     unsigned long long seq;
     long long ncell;
     int *error;
+    const unsigned long long *flush_src; // this rank's flush counter, or NULL
 };
 
 __device__ __forceinline__ fx_t *peer_data(PeerPub *p, int slot, long long ncell) { return reinterpret_cast<fx_t *>(p + 1) + (size_t)slot * ncell; }
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rh
     __syncthreads();
     fx_t *dst = peer_data(me, slot, p.ncell);
     for (long long n = threadIdx.x; n < p.ncell; n += blockDim.x) { dst[n] = rho[n]; rho[n] = 0ULL; }
+    if (threadIdx.x == 0) me->flushes = p.flush_src ? *p.flush_src : 0ULL;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) { me->last_pub[slot] = p.seq; st_release_sys(&me->ready, p.seq); }
@@ -92,6 +95,12 @@ __device__ __forceinline__ long long peer_sum(const PeerArgs &p, long long n)
     unsigned long long s = 0ULL;
     for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(peer_data(p.peer[q], slot, p.ncell) + n);
     return (long long)s;
+}
+__device__ __forceinline__ unsigned long long peer_flush_sum(const PeerArgs &p) // after peer_gather_begin
+{
+    unsigned long long s = 0ULL;
+    for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(&p.peer[q]->flushes);
+    return s;
 }
 __device__ __forceinline__ void peer_gather_end(const PeerArgs &p) // after a __syncthreads() that follows the last peer_sum
 {

@@ -221,7 +221,8 @@ struct picgolf_handle_s {
     unsigned long long *slow_host = nullptr, slow_seen = 0;
     cudaEvent_t slow_ev = nullptr;
     bool slow_pending = false;
-    bool force_sort = false, poly_quiet = false; // polynomial mode: per-step flush probe (probe_poly_flushes)
+    bool force_sort = false, poly_quiet = false, probe_have_prev = false; // polynomial mode: per-step flush probe (probe_poly_flushes)
+    int64_t probe_step[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     cudaEvent_t run_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // end-of-step markers
     int64_t steps_at_probe = 0, steps_at_probe_prev_steps = 0;
     // CUDA graphs of one fixed-point step, one per ping-pong parity
@@ -644,7 +645,8 @@ static int reset_run_state(picgolf_handle h)
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
-    h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0; h->force_sort = false; h->poly_quiet = false;
+    h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0; h->force_sort = false; h->poly_quiet = false; h->probe_have_prev = false;
+    for (auto &ps : h->probe_step) ps = -1;
     if (h->hist) PG_CUDA(cudaMemset(h->hist, 0, (size_t)h->ncell * h->T * sizeof(double)));
     return 0;
 }
@@ -799,6 +801,7 @@ static PeerArgs peer_args(picgolf_handle h)
     memset(&p, 0, sizeof(p));
     for (int q = 0; q < h->nranks; ++q) p.peer[q] = h->peer_ptr[q];
     p.nranks = h->nranks; p.rank = h->rank; p.seq = h->peer_seq; p.ncell = h->ncell; p.error = h->peer_err;
+    p.flush_src = h->slow_count;
     return p;
 }
 
@@ -865,6 +868,8 @@ static int launch_step_end(picgolf_handle h, bool record)
 static void adapt_sort_interval(picgolf_handle h)
 {
     if (!h->sort_auto || !h->slow_count) return;
+    if (h->comm) return; // several GPUs: the probe below is timing dependent -- every rank keeps the same fixed interval,
+                         // otherwise the ranks would sort at different steps and wait for each other's sorts
     if (!h->slow_host) {
         if (cudaMallocHost((void **)&h->slow_host, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
         cudaEventCreateWithFlags(&h->slow_ev, cudaEventDisableTiming);
@@ -890,46 +895,52 @@ static void adapt_sort_interval(picgolf_handle h)
     }
 }
 
-// Polynomial mode: the flush counter is probed EVERY step (a 8-byte asynchronous copy).  The host is allowed to run
-// at most POLY_RUNAHEAD steps ahead of the device (it waits for the end-of-step marker of an OLDER step, so the device
-// queue never drains and no step is ever synchronised internally); the probe it reads is therefore that recent.  In (cell, sign v) order a lane changes cell about twice per bin, i.e. ~64/bin_size
-// flushes per particle and pass; many times that means lanes alternate between cells (a bin sheared over three
-// cells) and every such particle pays 17 REDs -- then the next step re-sorts at once, whatever the interval, and the
-// interval is shortened to what was survived.  Quiet intervals grow by half up to 64 steps.
+// Polynomial mode: the flush counter is probed EVERY step: an 8-byte asynchronous copy into a ring of pinned slots at
+// the start of the step.  The host runs at most POLY_RUNAHEAD steps ahead of the device (it waits for the end-of-step
+// marker of an OLDER step, so the device queue never drains and no step is ever synchronised internally), and at step
+// s it reads the slot filled at the start of step s - POLY_RUNAHEAD, which has certainly landed.  The decision is
+// therefore a deterministic function of the step number and of the counter -- on several GPUs the counter is the SUM
+// over the ranks (formed by the solve kernel next to the grid sum, pg_peer.cuh), so all ranks re-sort at the same steps
+// and nobody waits for somebody else's sort.  Several times the count expected in sorted order means lanes alternate
+// between cells all the time (warm beams shear a bin over several cells) -- then the next step re-sorts at once,
+// whatever the interval, and the interval is shortened to what was survived.  Quiet intervals grow by half up to 64.
 constexpr int POLY_RUNAHEAD = 4;
 static void probe_poly_flushes(picgolf_handle h)
 {
     if (!h->sort_auto || !h->slow_count) return;
-    if (h->steps >= POLY_RUNAHEAD) {
-        cudaEvent_t e = h->run_ev[(h->steps - POLY_RUNAHEAD) & 7];
-        if (e) cudaEventSynchronize(e);
-    }
+    if (h->comm && !h->peer_ok) return; // NCCL-only fallback: no global counter -> fixed interval on every rank
     if (!h->slow_host) {
-        if (cudaMallocHost((void **)&h->slow_host, sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
-        cudaEventCreateWithFlags(&h->slow_ev, cudaEventDisableTiming);
-        *h->slow_host = 0;
+        if (cudaMallocHost((void **)&h->slow_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
+        for (int i = 0; i < 8; ++i) { h->slow_host[i] = 0; h->probe_step[i] = -1; }
     }
-    if (h->slow_pending) {
-        if (cudaEventQuery(h->slow_ev) != cudaSuccess) { cudaGetLastError(); return; }
-        const unsigned long long now = *h->slow_host;
-        const int64_t dsteps = h->steps_at_probe - h->steps_at_probe_prev_steps;
-        if (dsteps > 0) {
-            const double frac = (double)(now - h->slow_seen) / ((double)h->count * (double)dsteps);
-            const double expect = 4.0 * 64.0 * (double)(h->nbins >> h->sublg) / (double)h->count; // ~4 passes per step
-            h->poly_quiet = frac < 5e-5 + 2.0 * expect;
-            if (frac > 1e-3 + 6.0 * expect && h->since_sort >= 2) {
-                h->force_sort = true;
-                h->sort_every = (int)std::max<int64_t>(2, h->since_sort - POLY_RUNAHEAD);
+    const int64_t s = h->steps;
+    if (s >= POLY_RUNAHEAD) {
+        cudaEvent_t e = h->run_ev[(s - POLY_RUNAHEAD) & 7];
+        if (e) cudaEventSynchronize(e);
+        const int idx = (int)((s - POLY_RUNAHEAD) & 7);
+        if (h->probe_step[idx] == s - POLY_RUNAHEAD) {
+            const unsigned long long now = h->slow_host[idx];
+            if (h->probe_have_prev) {
+                const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during one step
+                // expected in sorted order, per particle and pass: a lane meets ~2 new cells per (cell, sign v) group
+                // (64*groups/P), and inside the one sub-bin of a group that a cell boundary cuts through it alternates
+                // between the two cells on every other particle (1/(2*subbins)); ~4 passes per step
+                const double expect = 4.0 * (64.0 * (double)(h->nbins >> h->sublg) / (double)h->cfg.P + 0.5 / (double)(1 << h->sublg));
+                h->poly_quiet = frac < 5e-5 + 1.5 * expect;
+                if (frac > 1e-3 + 3.0 * expect && h->since_sort >= 2 + POLY_RUNAHEAD) {
+                    h->force_sort = true;
+                    h->sort_every = (int)std::max<int64_t>(2, h->since_sort - POLY_RUNAHEAD);
+                }
             }
+            h->slow_seen = now;
+            h->probe_have_prev = true;
+        } else {
+            h->probe_have_prev = false;
         }
-        h->slow_seen = now;
-        h->steps_at_probe_prev_steps = h->steps_at_probe;
-        h->slow_pending = false;
     }
-    cudaMemcpyAsync(h->slow_host, h->slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
-    cudaEventRecord(h->slow_ev, h->stream);
-    h->slow_pending = true;
-    h->steps_at_probe = h->steps;
+    const void *src = h->comm ? (const void *)&h->ctrl->flush_global : (const void *)h->slow_count;
+    cudaMemcpyAsync(&h->slow_host[s & 7], src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+    h->probe_step[s & 7] = s;
 }
 
 // Counting sort of the step-start state (xb[par], vb[par]) by cell into the other ping-pong buffers.
