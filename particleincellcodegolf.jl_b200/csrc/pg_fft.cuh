@@ -190,6 +190,7 @@ struct Solve1DArgs {
     int store_normE1; // Simpson variant: this is the E1 solve of the step
     double *hist;     // 1D2V: time-averaged field history column Es[:,ti] += E (NGP1D2V.jl:57), or NULL
     PeerArgs peer;    // multi-GPU: sum the ranks' grids over peer memory here (pg_peer.cuh); nranks <= 1: rho_fx is the sum
+    int flush_slot;   // NCCL path, polynomial mode: rho_fx[N] holds the all-reduced flush counter
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     }
     __syncthreads();
     if (peers) peer_gather_end(a.peer);
+    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
     fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
     for (int p = threadIdx.x; p < N; p += blockDim.x) {

@@ -101,6 +101,7 @@ struct Mom2RhoArgs {
     const Ctrl *ctrl;
     double fx_scale, fx_inv;
     int N;
+    const unsigned long long *flush_src; // NCCL path on several GPUs: this rank's flush counter goes to rho[N] and is summed with the grid
 };
 constexpr int CPM_CELLS = 64;
 
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(4 * CPM_CELLS) mom2rho_kernel(Mom2RhoArgs a)
     if (a.ctrl->final_k >= 0) return; // converged: the moments belong to the next step's first solve
     const int N = a.N, Nmask = N - 1;
     const int i0 = blockIdx.x * CPM_CELLS;
+    if (a.flush_src && blockIdx.x == 0 && threadIdx.x == 0) a.rho[N] = *a.flush_src;
     for (int t = threadIdx.x; t < (CPM_CELLS + 12) * CP_NC; t += blockDim.x) {
         const int c = t / CP_NC, n = t - c * CP_NC;
         Ms[t] = (double)(long long)a.Mg[(size_t)((i0 + c - 6) & Nmask) * CP_NC + n] * a.fx_inv;

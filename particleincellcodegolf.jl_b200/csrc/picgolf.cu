@@ -415,16 +415,16 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         const int rows = h->simpson ? 3 : 1; // Simpson-1/3: E1|E2|E3 and rho1|rho2|rho3
         h->grid_rows = rows;
         PG_TRY(dalloc(&h->rho_last, N)); PG_TRY(dalloc(&h->E, (size_t)rows * N));
-        PG_TRY(dalloc(&h->rho_fx, (size_t)rows * N));
+        PG_TRY(dalloc(&h->rho_fx, (size_t)rows * N + 1)); // + 1: the flush counter rides along with the NCCL all-reduce
         if (h->fixedpoint && !h->simpson) {
             h->rho_base[0] = h->rho_fx;
-            PG_TRY(dalloc(&h->rho_base[1], (size_t)N));
-            PG_CUDA(cudaMemset(h->rho_base[1], 0, (size_t)N * sizeof(unsigned long long)));
+            PG_TRY(dalloc(&h->rho_base[1], (size_t)N + 1));
+            PG_CUDA(cudaMemset(h->rho_base[1], 0, ((size_t)N + 1) * sizeof(unsigned long long)));
             h->rho_next = h->rho_base[1];
         }
         PG_CUDA(cudaMemset(h->rho_last, 0, N * sizeof(double)));
         PG_CUDA(cudaMemset(h->E, 0, (size_t)rows * N * sizeof(double)));
-        PG_CUDA(cudaMemset(h->rho_fx, 0, (size_t)rows * N * sizeof(unsigned long long)));
+        PG_CUDA(cudaMemset(h->rho_fx, 0, ((size_t)rows * N + 1) * sizeof(unsigned long long)));
         if (!h->ngp) {
             // fixed-point format of the Gaussian deposit grid: weights are <= 1 and sum to 1 per particle, so
             // no cell can exceed P (all ranks) -> 62 - ceil(log2(P+1)) fractional bits can never overflow.
@@ -638,7 +638,7 @@ static int reset_run_state(picgolf_handle h)
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
     if (h->rho_base[0]) { h->rho_fx = h->rho_base[0]; h->rho_next = h->rho_base[1]; }
     PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, (size_t)h->grid_rows * h->ncell * sizeof(unsigned long long), h->stream));
-    if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, (size_t)h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, ((size_t)h->ncell + 1) * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
     if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * h->ncell * sizeof(unsigned long long), h->stream));
@@ -823,7 +823,9 @@ static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
     int rc;
     // integer grid: two's-complement sums are exact and order independent
     unsigned long long *g = h->rho_fx + (size_t)row0 * h->ncell;
-    rc = nccl::AllReduce(g, g, (size_t)nrows * h->ncell, nccl::Int64, nccl::Sum, h->comm, h->stream);
+    // polynomial mode: slot ncell carries this rank's flush counter (written by mom2rho_kernel) -> global sum for the probe
+    const size_t extra = (h->poly && h->use_sorted_now && row0 == 0 && nrows == 1) ? 1 : 0;
+    rc = nccl::AllReduce(g, g, (size_t)nrows * h->ncell + extra, nccl::Int64, nccl::Sum, h->comm, h->stream);
     h->timer.end(sp1_, h->stream);
     return nccl::check(rc, "ncclAllReduce(rho)");
 }
@@ -839,6 +841,7 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
     a.k = k; a.max_sweeps = c.max_sweeps; a.store_normE1 = simpson_e1 ? 1 : 0;
     a.hist = nullptr;
     if (h->peer_this_solve) a.peer = peer_args(h);
+    a.flush_slot = (h->comm && !h->peer_ok && h->poly && h->use_sorted_now) ? 1 : 0;
     if (h->b1d2v) { // Es[:,ti] .+= E with ti = cld(t, T/TO)   NGP1D2V.jl:56-57
         int64_t ti = h->steps / c.diag_every;
         if (ti < h->T) a.hist = h->hist + (size_t)ti * c.N;
@@ -908,7 +911,6 @@ constexpr int POLY_RUNAHEAD = 4;
 static void probe_poly_flushes(picgolf_handle h)
 {
     if (!h->sort_auto || !h->slow_count) return;
-    if (h->comm && !h->peer_ok) return; // NCCL-only fallback: no global counter -> fixed interval on every rank
     if (!h->slow_host) {
         if (cudaMallocHost((void **)&h->slow_host, 8 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); h->sort_auto = false; return; }
         for (int i = 0; i < 8; ++i) { h->slow_host[i] = 0; h->probe_step[i] = -1; }
@@ -992,6 +994,7 @@ static int enqueue_poly_step(picgolf_handle h, FPArgs a)
     }
     Mom2RhoArgs m;
     m.Mg = h->Mg; m.rho = h->rho_fx; m.ctrl = h->ctrl; m.fx_scale = h->fx_scale; m.fx_inv = h->fx_inv; m.N = N;
+    m.flush_src = (h->comm && !h->peer_ok) ? h->slow_count : nullptr;
     GPolyArgs g;
     g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N;
     for (int k = 1; k <= c.max_sweeps; ++k) {

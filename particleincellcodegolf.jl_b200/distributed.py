@@ -28,9 +28,9 @@ def broadcast_bytes(payload, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def connect(pic: PIC, peer: bool = True) -> None:
-    """Create the handle's NCCL communicator (collective over all ranks of the default group) and, unless peer=False or
-    PICGOLF_NO_PEER is set, the peer-memory reduction of the 1D charge grids."""
+def connect(pic: PIC, peer=None) -> None:
+    """Create the handle's NCCL communicator (collective over all ranks of the default group) and, with peer=True or
+    PICGOLF_PEER=1, the peer-memory reduction of the 1D charge grids (pg_peer.cuh; opt-in for now)."""
     import torch.distributed as dist
 
     if pic.cfg.nranks == 1:
@@ -38,7 +38,9 @@ def connect(pic: PIC, peer: bool = True) -> None:
     uid = comm_unique_id() if dist.get_rank() == 0 else None
     uid = broadcast_bytes(uid, 128, src=0)
     pic.comm_init(uid)
-    if peer and os.environ.get("PICGOLF_NO_PEER") is None:
+    if peer is None:
+        peer = os.environ.get("PICGOLF_PEER") is not None
+    if peer:
         connect_peers(pic)
 
 
@@ -76,5 +78,5 @@ def connect_peers(pic: PIC) -> bool:
     # the switch must be collective: a rank that failed to open a handle keeps everyone on NCCL
     flags = gather_bytes(bytes([ok]))
     if not all(flags):
-        raise RuntimeError("peer-memory reduction: some ranks could not open the cudaIpc handles (set PICGOLF_NO_PEER=1)")
+        raise RuntimeError("peer-memory reduction: some ranks could not open the cudaIpc handles (unset PICGOLF_PEER)")
     return True
