@@ -79,6 +79,17 @@ def lib() -> C.CDLL:
         L.oracle_2d3v_step.argtypes = [_dp] * 5 + [_i64, _i64, _i64, _d, _d, _d, _dp, _dp, _dp, C.c_int]
         L.oracle_2d3v_diagnostics.argtypes = [_dp, _dp, _i64, _i64, _dp, _dp, _i64, _d, _dp]
         L.oracle_max_threads.restype = C.c_int
+        _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+        L.oracle_es_halton.restype = _d
+        L.oracle_es_halton.argtypes = [_i64, _i64, _d]
+        L.oracle_es_shape.restype = C.c_int
+        L.oracle_es_shape.argtypes = [C.c_int, _d, _d, _lp, _dp]
+        L.oracle_es_boris.argtypes = [_dp, _d, _d, _dp, _d, _d]
+        L.oracle_es_loop.argtypes = [C.c_int, _lp, _ip, _dp, _dp, _dp] + [_dp] * 5 + [_i64, _i64, _d, _d, _d, _dp, _dp, C.c_int,
+                                     _dp, _dp, _dp, _dp, C.c_int]
+        L.oracle_es_diagnose.argtypes = [C.c_int, _lp, _dp, _dp, _dp, _dp, _dp, _i64, _i64, _dp, _dp]
+        L.oracle_es_species.restype = _d
+        L.oracle_es_species.argtypes = [_i64, _d, _d, _d, _d, _dp] + [_dp] * 5
         _lib = L
     return _lib
 
@@ -318,3 +329,85 @@ def diagnostics_2d3v(Ex, Ey, NX, NY, vx, vy, w):
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+# ---------------------------------------------------------------- PIC2D3V.jl ElectrostaticField path
+SHAPE_NGP, SHAPE_AREA, SHAPE_BSPLINE0 = 0, 1, 10  # BSplineWeighting{N} = 10 + N
+
+
+def es_halton(i, base, seed=0.0):
+    return lib().oracle_es_halton(int(i), int(base), float(seed))
+
+
+def es_shape(shape, z, NZ_Lz):
+    """depositindicesfractions: (first index (1-based, unwrapped), fractions)."""
+    j0, wt = np.zeros(1, dtype=np.int64), np.zeros(6)
+    n = lib().oracle_es_shape(int(shape), float(z), float(NZ_Lz), j0, wt)
+    return int(j0[0]), wt[:n].copy()
+
+
+def es_boris(v, Ex, Ey, B, dt, q_m):
+    v = np.array(v, dtype=np.float64)
+    lib().oracle_es_boris(v, float(Ex), float(Ey), _f64(B), float(dt), float(q_m))
+    return v
+
+
+def es_species(P, vth, density, Lx=1.0, Ly=1.0):
+    """Species(P, vth, density, shape; Lx, Ly): returns x, y, vx, vy, vz, weight (erfinv from scipy)."""
+    from scipy.special import erfinv
+    seed = 1 / np.sqrt(2.0)
+    einv = np.concatenate([erfinv(2 * np.array([es_halton(i, b, seed) for i in range(P)]) - 1) for b in (5, 7, 9)])
+    out = [np.empty(P) for _ in range(5)]
+    w = lib().oracle_es_species(P, float(vth), float(density), float(Lx), float(Ly), _f64(einv), *out)
+    return (*out, w)
+
+
+class ESField:
+    """State of PIC2D3V.ElectrostaticField + plasma + ElectrostaticDiagnostics, stepped by loop!/diagnose!
+    (PIC2D3V.jl:530-581,1301-1330).  species: list of dicts(x,y,vx,vy,vz,charge,mass,weight,shape)."""
+
+    def __init__(self, species, NX, NY, Lx, Ly, dt, B, NT, ntskip=1, ngskip=1, accumulate=True, nthreads=1):
+        self.NX, self.NY, self.Lx, self.Ly, self.dt = NX, NY, float(Lx), float(Ly), float(dt)
+        self.B = _f64(B)
+        self.sP = np.array([len(s["x"]) for s in species], dtype=np.int64)
+        self.sshape = np.array([s["shape"] for s in species], dtype=np.int32)
+        self.scharge = _f64([s["charge"] for s in species])
+        self.smass = _f64([s["mass"] for s in species])
+        self.sweight = _f64([s["weight"] for s in species])
+        cat = lambda k: _f64(np.concatenate([np.asarray(s[k], dtype=np.float64) for s in species])).copy()
+        self.x, self.y, self.vx, self.vy, self.vz = cat("x"), cat("y"), cat("vx"), cat("vy"), cat("vz")
+        self.hn = (NX + 6) * (NY + 6)
+        self.Exy = np.zeros(2 * self.hn)
+        self.rho, self.Ex, self.Ey, self.phir = (np.zeros(NX * NY) for _ in range(4))
+        self.accumulate, self.nthreads = int(bool(accumulate)), nthreads
+        self.ntskip, self.ngskip, self.t, self.ti = ntskip, ngskip, 0, 0
+        ND = NT // ntskip
+        self.scalars = np.zeros((ND, 8))  # kinetic, field, pmom[3], cmom[3]
+        nxd, nyd = NX // ngskip, NY // ngskip
+        self.Exs, self.Eys, self.phis = (np.zeros((nxd, nyd, ND), order="F") for _ in range(3))
+
+    def exy_interior(self):
+        """Exy[c, 1:NX, 1:NY] as two flat column-major NX*NY arrays."""
+        NX, NY = self.NX, self.NY
+        g = self.Exy.reshape(2, NY + 6, NX + 6)
+        return g[0, 2:NY + 2, 2:NX + 2].ravel().copy(), g[1, 2:NY + 2, 2:NX + 2].ravel().copy()
+
+    def step(self):
+        """loop!(plasma, field, to, t, _); diagnose!(diagnostics, field, plasma, t, to)   2D3V.jl:123-126"""
+        L = lib()
+        L.oracle_es_loop(len(self.sP), self.sP, self.sshape, self.scharge, self.smass, self.sweight, self.x, self.y, self.vx,
+                         self.vy, self.vz, self.NX, self.NY, self.Lx, self.Ly, self.dt, self.B, self.Exy, self.accumulate,
+                         self.rho, self.Ex, self.Ey, self.phir, self.nthreads)
+        t = self.t
+        if t % self.ntskip == 0:
+            self.ti += 1
+            if self.ti <= self.scalars.shape[0]:
+                L.oracle_es_diagnose(len(self.sP), self.sP, self.smass, self.sweight, self.vx, self.vy, self.vz, self.NX, self.NY,
+                                     self.Exy, self.scalars[self.ti - 1])
+        if 1 <= self.ti <= self.Exs.shape[2]:
+            g = self.ngskip
+            sub = lambda a: a.reshape(self.NY, self.NX).T[::g, ::g]
+            self.Exs[:, :, self.ti - 1] += sub(self.Ex) / self.ntskip
+            self.Eys[:, :, self.ti - 1] += sub(self.Ey) / self.ntskip
+            self.phis[:, :, self.ti - 1] += sub(self.phir) / self.ntskip
+        self.t += 1

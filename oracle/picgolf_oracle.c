@@ -738,6 +738,262 @@ ORACLE_API void oracle_2d3v_diagnostics(const double *Ex, const double *Ey, int6
     K5[0] = se / (double)(NX * NY); K5[1] = sk; K5[2] = K5[0] + K5[1]; K5[3] = sx / (double)P; K5[4] = sy / (double)P;
 }
 
+
+/* ------------------------------------------------------------------ */
+/* PIC2D3V.jl: the ElectrostaticField path          */
+/* Species / shapes / halo grids / loop! / diagnose!, restated literally. */
+/* ------------------------------------------------------------------ */
+
+/* unimod(x, n) = x > n ? x - n : x > 0 ? x : x + n        PIC2D3V.jl:10 */
+static inline double es_unimod_d(double x, double n) { return x > n ? x - n : (x > 0 ? x : x + n); }
+static inline int64_t es_unimod_i(int64_t x, int64_t n) { return x > n ? x - n : (x > 0 ? x : x + n); }
+
+/* halton(i, base, seed)                                   PIC2D3V.jl:29-37 */
+ORACLE_API double oracle_es_halton(int64_t i, int64_t base, double seed)
+{
+    double result = 0.0, f = 1.0;
+    while (i > 0) {
+        f = f / (double)base;
+        result += f * (double)(i % base);
+        i /= base;
+    }
+    return oracle_jl_mod1(result + seed);
+}
+
+/* bspline(::BSplineWeighting{N}, x)                       PIC2D3V.jl:1124-1163 (written @fastmath there: the compiler
+ * may reassociate, so the last bits are not defined by the source; this is the plain left-to-right reading). */
+static int es_bspline(int N, double x, double *f)
+{
+#define P2(a) ((a) * (a))
+#define P3(a) ((a) * (a) * (a))
+#define P4(a) (((a) * (a)) * ((a) * (a)))
+#define P5(a) ((((a) * (a)) * ((a) * (a))) * (a))
+    switch (N) {
+    case 0: f[0] = 1.0; return 1;
+    case 1: f[0] = x; f[1] = 1 - x; return 2;
+    case 2:
+        f[0] = 9.0 / 8 + 3.0 / 2 * (x - 1.5) + 1.0 / 2 * P2(x - 1.5);
+        f[1] = 3.0 / 4 - P2(x - 0.5);
+        f[2] = 9.0 / 8 - 3.0 / 2 * (x + 0.5) + 1.0 / 2 * P2(x + 0.5);
+        return 3;
+    case 3:
+        f[0] = 4.0 / 3 + 2 * (x - 2) + P2(x - 2) + 1.0 / 6 * P3(x - 2);
+        f[1] = 2.0 / 3 - P2(x - 1) - 1.0 / 2 * P3(x - 1);
+        f[2] = 2.0 / 3 - P2(x) + 1.0 / 2 * P3(x);
+        f[3] = 4.0 / 3 - 2 * (x + 1) + P2(x + 1) - 1.0 / 6 * P3(x + 1);
+        return 4;
+    case 4:
+        f[0] = 625.0 / 384 + 125.0 / 48 * (x - 2.5) + 25.0 / 16 * P2(x - 2.5) + 5.0 / 12 * P3(x - 2.5) + 1.0 / 24 * P4(x - 2.5);
+        f[1] = 55.0 / 96 - 5.0 / 24 * (x - 1.5) - 5.0 / 4 * P2(x - 1.5) - 5.0 / 6 * P3(x - 1.5) - 1.0 / 6 * P4(x - 1.5);
+        f[2] = 115.0 / 192 - 5.0 / 8 * P2(x - 0.5) + 1.0 / 4 * P4(x - 0.5);
+        f[3] = 55.0 / 96 + 5.0 / 24 * (x + 0.5) - 5.0 / 4 * P2(x + 0.5) + 5.0 / 6 * P3(x + 0.5) - 1.0 / 6 * P4(x + 0.5);
+        f[4] = 625.0 / 384 - 125.0 / 48 * (x + 1.5) + 25.0 / 16 * P2(x + 1.5) - 5.0 / 12 * P3(x + 1.5) + 1.0 / 24 * P4(x + 1.5);
+        return 5;
+    case 5:
+        f[0] = 243.0 / 120 + 81.0 / 24 * (x - 3) + 9.0 / 4 * P2(x - 3) + 3.0 / 4 * P3(x - 3) + 1.0 / 8 * P4(x - 3) + 1.0 / 120 * P5(x - 3);
+        f[1] = 17.0 / 40 - 5.0 / 8 * (x - 2) - 7.0 / 4 * P2(x - 2) - 5.0 / 4 * P3(x - 2) - 3.0 / 8 * P4(x - 2) - 1.0 / 24 * P5(x - 2);
+        f[2] = 22.0 / 40 - 1.0 / 2 * P2(x - 1) + 1.0 / 4 * P4(x - 1) + 1.0 / 12 * P5(x - 1);
+        f[3] = 22.0 / 40 - 1.0 / 2 * P2(x + 0) + 1.0 / 4 * P4(x - 0) - 1.0 / 12 * P5(x - 0);
+        f[4] = 17.0 / 40 + 5.0 / 8 * (x + 1) - 7.0 / 4 * P2(x + 1) + 5.0 / 4 * P3(x + 1) - 3.0 / 8 * P4(x + 1) + 1.0 / 24 * P5(x + 1);
+        f[5] = 243.0 / 120 - 81.0 / 24 * (x + 2) + 9.0 / 4 * P2(x + 2) - 3.0 / 4 * P3(x + 2) + 1.0 / 8 * P4(x + 2) - 1.0 / 120 * P5(x + 2);
+        return 6;
+    }
+#undef P2
+#undef P3
+#undef P4
+#undef P5
+    return 0;
+}
+
+/* depositindicesfractions(s, z, NZ, NZ_Lz) + gridinteractiontuple   PIC2D3V.jl:1105-1121,1165-1188.
+ * shape: 0 NGPWeighting, 1 AreaWeighting, 10+N BSplineWeighting{N}.  Returns the number of (index, fraction) pairs;
+ * *j0 is the first index, 1-based and NOT wrapped ("no need for unimod with offset arrays" :1108,1117).
+ * The reference asserts 0 < r <= 1 (:1111); r == 0 (z exactly on a cell edge) throws there and is carried through here. */
+static int es_shape(int shape, double z, double NZ_Lz, int64_t *j0, double *wt)
+{
+    double zNZ = z * NZ_Lz;
+    int64_t i = (int64_t)ceil(zNZ);
+    double r = (double)i - zNZ;
+    if (shape == 0) { *j0 = i; wt[0] = 1; return 1; }                       /* ((i, 1), ) */
+    if (shape == 1) { *j0 = i; wt[0] = 1 - r; wt[1] = r; return 2; }        /* ((i, 1-r), (i+1, r)) */
+    int N = shape - 10;
+    int64_t j; double zz;
+    if (N & 1) { j = i; zz = 1 - r; }                                       /* _bsplineinputs, odd N  :1168 */
+    else { int q = r > 0.5; j = i + q; zz = (double)q + 0.5 - r; }          /* even N                 :1169-1172 */
+    *j0 = j - N / 2;                                                        /* indices: (j-fld(N,2)):(j+cld(N,2)) */
+    return es_bspline(N, zz, wt);
+}
+
+ORACLE_API int oracle_es_shape(int shape, double z, double NZ_Lz, int64_t *j0, double *wt6)
+{
+    return es_shape(shape, z, NZ_Lz, j0, wt6);
+}
+
+/* (boris::ElectrostaticBoris)(vx, vy, vz, Ex, Ey, q_m)     PIC2D3V.jl:44-54; t = B*dt/2, t2 = dot(t,t). */
+static inline void es_cross(const double *a, const double *b, double *c)
+{
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+ORACLE_API void oracle_es_boris(double *v, double Ex, double Ey, const double *B, double dt, double q_m)
+{
+    double t[3] = { B[0] * dt / 2, B[1] * dt / 2, B[2] * dt / 2 };
+    double t2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    double dt_2 = dt / 2;
+    double e2[3] = { Ex * dt_2 * q_m, Ey * dt_2 * q_m, 0.0 * dt_2 * q_m };
+    double vm[3] = { v[0] + e2[0], v[1] + e2[1], v[2] + e2[2] };
+    double c1[3], s[3], c2[3];
+    es_cross(vm, t, c1);
+    for (int k = 0; k < 3; ++k) s[k] = vm[k] + c1[k];
+    es_cross(s, t, c2);
+    double den = 1 + q_m * q_m * t2;
+    for (int k = 0; k < 3; ++k) v[k] = (vm[k] + c2[k] * (q_m * q_m) * 2 / den) + e2[k];
+}
+
+/* Halo ("offset") arrays of ElectrostaticField, buffer = 3: indices -(buffer-1):NZ+buffer   PIC2D3V.jl:284-287 */
+#define ES_BUF 3
+static inline size_t es_hidx(int64_t i, int64_t j, int64_t NX) { return (size_t)((i + ES_BUF - 1) + (NX + 2 * ES_BUF) * (j + ES_BUF - 1)); }
+
+/* One call of loop!(plasma, field::ElectrostaticField, ...)   PIC2D3V.jl:530-581, followed by update! :294-297.
+ * Particles: species one after the other in x,y,vx,vy,vz (SoA image of xyv[5,P]).
+ * Exy: [2][(NX+6)*(NY+6)] halo arrays, in/out.  accumulate = 1 is the reference as written: update! ADDS the new
+ * field to Exy (applyperiodicity!(oa, a) does oa[i,j] += real(a[...]) :21-27 and nothing zeroes Exy for this field
+ * type); accumulate = 0 zeroes Exy first (what the Lorenz-gauge update! does, :475).
+ * Outputs (NX*NY, column-major): rho = reduction!(phi, rhos) before the transform; Ex, Ey = real parts after the inverse
+ * transforms; phir = real(pifft! * phi) of :1326 (phi holds the spectrum of rho with [1,1] zeroed, i.e. rho - mean). */
+ORACLE_API void oracle_es_loop(int nspecies, const int64_t *sP, const int32_t *sshape, const double *scharge,
+                               const double *smass, const double *sweight, double *x, double *y, double *vx, double *vy,
+                               double *vz, int64_t NX, int64_t NY, double Lx, double Ly, double dt, const double *B,
+                               double *Exy, int accumulate, double *rho, double *Ex, double *Ey, double *phir, int nthreads)
+{
+    const size_t n = (size_t)(NX * NY), hn = (size_t)((NX + 2 * ES_BUF) * (NY + 2 * ES_BUF));
+    const double NX_Lx = (double)NX / Lx, NY_Ly = (double)NY / Ly;
+    const double dV = (Lx / (double)NX) * (Ly / (double)NY);
+    if (nthreads < 1) nthreads = 1;
+    double *rhos = (double *)calloc(hn * (size_t)nthreads, sizeof(double));
+    const double *Fx = Exy, *Fy = Exy + hn;
+    for (int k = 0; k < nthreads; ++k) {                                    /* @threads for k in axes(field.rhos, 3) */
+        double *rk = rhos + (size_t)k * hn;
+        int64_t base = 0;
+        for (int s = 0; s < nspecies; ++s) {                                /* for species in plasma */
+            const int64_t P = sP[s];
+            const double qw_dV = scharge[s] * sweight[s] / dV, q_m = scharge[s] / smass[s];
+            const int64_t chunk = (P + nthreads - 1) / nthreads;            /* partition(1:P, ceil(Int, P/nthreads())) */
+            int64_t lo = k * chunk, hi = lo + chunk < P ? lo + chunk : P;
+            for (int64_t i = base + lo; i < base + hi; ++i) {
+                int64_t ix0, iy0; double wx[6], wy[6];
+                int nx = es_shape(sshape[s], x[i], NX_Lx, &ix0, wx), ny = es_shape(sshape[s], y[i], NY_Ly, &iy0, wy);
+                double Exi = 0, Eyi = 0;                                     /* field(shape, x, y) :1217-1229 */
+                for (int b = 0; b < ny; ++b)
+                    for (int a = 0; a < nx; ++a) {
+                        double wxy = wx[a] * wy[b];
+                        Exi = fma(Fx[es_hidx(ix0 + a, iy0 + b, NX)], wxy, Exi);
+                        Eyi = fma(Fy[es_hidx(ix0 + a, iy0 + b, NX)], wxy, Eyi);
+                    }
+                double vxi = vx[i], vyi = vy[i], v[3] = { vx[i], vy[i], vz[i] };
+                oracle_es_boris(v, Exi, Eyi, B, dt, q_m);
+                vx[i] = v[0]; vy[i] = v[1]; vz[i] = v[2];
+                x[i] = es_unimod_d(x[i] + (vxi + vx[i]) / 2 * dt, Lx);
+                y[i] = es_unimod_d(y[i] + (vyi + vy[i]) / 2 * dt, Ly);
+                nx = es_shape(sshape[s], x[i], NX_Lx, &ix0, wx); ny = es_shape(sshape[s], y[i], NY_Ly, &iy0, wy);
+                for (int b = 0; b < ny; ++b)                                 /* deposit! :1246-1253 */
+                    for (int a = 0; a < nx; ++a) rk[es_hidx(ix0 + a, iy0 + b, NX)] += wx[a] * wy[b] * qw_dV;
+            }
+            base += P;
+        }
+    }
+    /* reduction!(field.phi, field.rhos): phi = 0, fold every thread's halo grid with unimod   :485-490, 13-19 */
+    double *pr = (double *)calloc(6 * n, sizeof(double));
+    double *pim = pr + n, *xr = pim + n, *xi = xr + n, *yr = xi + n, *yi = yr + n;
+    for (int k = 0; k < nthreads; ++k)
+        for (int64_t j = -(ES_BUF - 1); j <= NY + ES_BUF; ++j)
+            for (int64_t i = -(ES_BUF - 1); i <= NX + ES_BUF; ++i)
+                pr[(es_unimod_i(i, NX) - 1) + NX * (es_unimod_i(j, NY) - 1)] += rhos[(size_t)k * hn + es_hidx(i, j, NX)];
+    free(rhos);
+    for (size_t k = 0; k < n; ++k) rho[k] = pr[k];
+    fft2(pr, pim, NX, NY, -1);
+    pr[0] = 0.0; pim[0] = 0.0;                                               /* field.phi[1, 1] = 0 */
+    for (int64_t j = 0; j < NY; ++j) {
+        double ky = TWO_PI / Ly * (double)(j < NY / 2 ? j : j - NY);         /* FFTHelper :254-255 */
+        for (int64_t i = 0; i < NX; ++i) {
+            double kx = TWO_PI / Lx * (double)(i < NX / 2 ? i : i - NX);
+            size_t k = (size_t)(i + j * NX);
+            double m = (i == 0 && j == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky); /* im_k^-2 = -im ./ k2, [1,1] = 0 */
+            double a = pr[k], b = pim[k];
+            double tre = a * 0.0 - b * m, tim = a * m + b * 0.0;
+            xr[k] = tre * kx; xi[k] = tim * kx; yr[k] = tre * ky; yi[k] = tim * ky;
+        }
+    }
+    fft2(xr, xi, NX, NY, +1);
+    fft2(yr, yi, NX, NY, +1);
+    fft2(pr, pim, NX, NY, +1);                                               /* diagnose!: real.(pifft! * phi) :1326 */
+    const double inv = (double)(NX * NY);
+    for (size_t k = 0; k < n; ++k) { Ex[k] = xr[k] / inv; Ey[k] = yr[k] / inv; phir[k] = pr[k] / inv; }
+    free(pr);
+    /* update!(field): applyperiodicity!(view(Exy,c,:,:), E) -> oa[i,j] += real(a[unimod(i,NX), unimod(j,NY)]) */
+    double *Gx = Exy, *Gy = Exy + hn;
+    if (!accumulate) memset(Exy, 0, 2 * hn * sizeof(double));
+    for (int64_t j = -(ES_BUF - 1); j <= NY + ES_BUF; ++j)
+        for (int64_t i = -(ES_BUF - 1); i <= NX + ES_BUF; ++i) {
+            size_t src = (size_t)((es_unimod_i(i, NX) - 1) + NX * (es_unimod_i(j, NY) - 1));
+            Gx[es_hidx(i, j, NX)] += Ex[src];
+            Gy[es_hidx(i, j, NX)] += Ey[src];
+        }
+}
+
+/* diagnose!(d, plasma) + the field energy of diagnose!(d::ElectrostaticDiagnostics, f, ...)   PIC2D3V.jl:1301-1321.
+ * out[8] = kineticenergy, fieldenergy, particlemomentum[3], characteristicmomentum[3].
+ * kineticenergy(s) = sum(abs2, velocities(s)) * s.mass / 2 * s.weight  :177; momentum(s, op) :179-187;
+ * fieldenergy = mean(abs2, f.Exy) / 2 over the WHOLE halo array (2 x (NX+6) x (NY+6) elements). */
+ORACLE_API void oracle_es_diagnose(int nspecies, const int64_t *sP, const double *smass, const double *sweight,
+                                   const double *vx, const double *vy, const double *vz, int64_t NX, int64_t NY,
+                                   const double *Exy, double *out)
+{
+    for (int k = 0; k < 8; ++k) out[k] = 0.0;
+    int64_t base = 0;
+    for (int s = 0; s < nspecies; ++s) {
+        double s2 = 0, m[3] = { 0, 0, 0 }, c[3] = { 0, 0, 0 };
+        for (int64_t i = base; i < base + sP[s]; ++i) {
+            s2 += vx[i] * vx[i]; s2 += vy[i] * vy[i]; s2 += vz[i] * vz[i];
+            m[0] += vx[i]; m[1] += vy[i]; m[2] += vz[i];
+            c[0] += fabs(vx[i]); c[1] += fabs(vy[i]); c[2] += fabs(vz[i]);
+        }
+        out[0] += s2 * smass[s] / 2 * sweight[s];
+        for (int k = 0; k < 3; ++k) { out[2 + k] += m[k] * (smass[s] * sweight[s]); out[5 + k] += c[k] * (smass[s] * sweight[s]); }
+        base += sP[s];
+    }
+    const size_t hn = (size_t)((NX + 2 * ES_BUF) * (NY + 2 * ES_BUF));
+    double se = 0;
+    for (size_t k = 0; k < 2 * hn; ++k) se += Exy[k] * Exy[k];
+    out[1] = se / (double)(2 * hn) / 2;
+}
+
+/* Species(P, vth, density, shape; Lx, Ly)   PIC2D3V.jl:194-213: Halton starts (sample(P,i) = halton.(0:P-1, i, 1/sqrt(2))
+ * :191), v = vth * erfinv(2 sample - 1) * vth, mean removed, rescaled to std vth/sqrt(2) (Statistics.std: corrected,
+ * n-1).  erfinv is supplied by the caller's table einv[3*P] = erfinv.(2 .* sample(P, {5,7,9}) .- 1) (scipy in the tests):
+ * the C library has no erfinv.  Returns the weight calculateweight(n0, P, Lx, Ly) = n0*Lx*Ly/P  :189. */
+ORACLE_API double oracle_es_species(int64_t P, double vth, double density, double Lx, double Ly, const double *einv,
+                                    double *x, double *y, double *vx, double *vy, double *vz)
+{
+    const double seed = 1 / sqrt(2.0);
+    double *v[3] = { vx, vy, vz };
+    for (int64_t i = 0; i < P; ++i) { x[i] = Lx * oracle_es_halton(i, 2, seed); y[i] = Ly * oracle_es_halton(i, 3, seed); }
+    for (int c = 0; c < 3; ++c) {
+        double *u = v[c];
+        for (int64_t i = 0; i < P; ++i) u[i] = vth * einv[(size_t)c * P + i] * vth;
+        double mean = 0;
+        for (int64_t i = 0; i < P; ++i) mean += u[i];
+        mean /= (double)P;
+        for (int64_t i = 0; i < P; ++i) u[i] -= mean;
+        double m2 = 0, ss = 0;
+        for (int64_t i = 0; i < P; ++i) m2 += u[i];
+        m2 /= (double)P;
+        for (int64_t i = 0; i < P; ++i) ss += (u[i] - m2) * (u[i] - m2);
+        double sd = sqrt(ss / (double)(P - 1));
+        for (int64_t i = 0; i < P; ++i) u[i] *= (vth / sqrt(2.0)) / sd;
+    }
+    return density * Lx * Ly / (double)P;
+}
+
 ORACLE_API int oracle_max_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);

@@ -9,6 +9,8 @@ like the Julia it replaces:
     src/GaussianFixedPoint.jl    -> gaussian_fixed_point(...)
     src/GaussianFixedPointQuiet.jl -> gaussian_fixed_point_quiet(...)
     src/Electrostatic2D3V.jl     -> electrostatic_2d3v(...)
+    src/PIC2D3V.jl (electrostatic path: Species, shapes, ElectrostaticField, ElectrostaticDiagnostics, loop!, diagnose!)
+                                 -> the pic2d3v submodule
 
 There is no CPU path: importing works anywhere (so the ABI can be checked), but every compute call
 needs a CUDA device and raises PicGolfError otherwise.  Nothing here imports oracle/.
@@ -27,6 +29,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "libpicgolf.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "picgolf.h")
+ES_HEADER_PATH = os.path.join(_ROOT, "include", "picgolf_es.h")
+HEADER_PATHS = [HEADER_PATH, ES_HEADER_PATH]
 
 NGP_LEAPFROG, GAUSS_LEAPFROG, GAUSS_FIXEDPOINT, CIC_BORIS_2D3V, GAUSS_SIMPSON13, AREA_SIMPSON13, GAUSS_BORIS_1D2V = 1, 2, 3, 4, 5, 6, 7
 GAUSS_BORIS_1D2V2S = 8
@@ -47,7 +51,7 @@ class PicGolfError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/picgolf.cu for sm_100a into lib/libpicgolf.so (in-tree, travels with gpurun)."""
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in sorted(os.listdir(src_dir))] + [HEADER_PATH]
+    srcs = [os.path.join(src_dir, f) for f in sorted(os.listdir(src_dir))] + HEADER_PATHS
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
@@ -67,6 +71,18 @@ class Config(C.Structure):
         ("deterministic", C.c_int32), ("sort_every", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
         ("local_first", C.c_int64), ("local_count", C.c_int64), ("mass_ratio", C.c_double),
+    ]
+
+
+class ESConfig(C.Structure):
+    """ctypes image of `picgolf_es_config` (include/picgolf_es.h)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("nspecies", C.c_int32), ("NX", C.c_int64), ("NY", C.c_int64),
+        ("Lx", C.c_double), ("Ly", C.c_double), ("dt", C.c_double), ("B0x", C.c_double), ("B0y", C.c_double), ("B0z", C.c_double),
+        ("NT", C.c_int64), ("ntskip", C.c_int32), ("ngskip", C.c_int32), ("field_accumulate", C.c_int32),
+        ("field_history", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
+        ("species_P", C.c_int64 * 4), ("species_shape", C.c_int32 * 4), ("species_charge", C.c_double * 4),
+        ("species_mass", C.c_double * 4), ("species_weight", C.c_double * 4),
     ]
 
 
@@ -124,6 +140,30 @@ _SIGNATURES = {
     "picgolf_stage_boris": [_dp, _dp, _dp, _dp, _dp, _i64, _d, _d],
     "picgolf_stage_fp64_peak": [C.POINTER(_d)],
     "picgolf_stage_quiet_start": [_i64, _i64, _i64, _dp, _dp],
+    # include/picgolf_es.h (PIC2D3V.jl electrostatic path; host mirror in pic2d3v.py)
+    "picgolf_es_config_default": [C.POINTER(ESConfig)],
+    "picgolf_es_create": [C.POINTER(ESConfig), C.POINTER(_vp)],
+    "picgolf_es_destroy": [_vp],
+    "picgolf_es_local_range": [_vp, _int, C.POINTER(_i64), C.POINTER(_i64)],
+    "picgolf_es_set_species": [_vp, _int, _dp, _dp, _dp, _dp, _dp, _i64],
+    "picgolf_es_get_species": [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64],
+    "picgolf_es_set_species_xyv": [_vp, _int, _dp, _i64],
+    "picgolf_es_get_species_xyv": [_vp, _int, _dp, _i64],
+    "picgolf_es_init_species": [_vp, _int, _d],
+    "picgolf_es_step": [_vp, _i64],
+    "picgolf_es_synchronize": [_vp],
+    "picgolf_es_steps_done": [_vp, C.POINTER(_i64)],
+    "picgolf_es_get_fields": [_vp, _vp, _vp, _vp, _vp, _vp],
+    "picgolf_es_set_field": [_vp, _dp, _dp],
+    "picgolf_es_get_diagnostics": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)],
+    "picgolf_es_get_field_history": [_vp, _int, _vp, _i64, C.POINTER(_i64)],
+    "picgolf_es_spectrum": [_vp, _int, _int, _int, _dp],
+    "picgolf_es_launch_count": [_vp, C.POINTER(_i64)],
+    "picgolf_es_get_stream": [_vp, C.POINTER(_vp)],
+    "picgolf_es_comm_init": [_vp, _vp, _int, _int],
+    "picgolf_es_stage_shape": [_int, _dp, _i64, _d, _ip, _dp],
+    "picgolf_es_stage_boris": [_dp, _dp, _dp, _dp, _dp, _i64, _d, _d, _d, _d, _d],
+    "picgolf_stage_wk_spectrum": [_dp, _i64, _i64, _i64, _int, _int, _dp],
 }
 
 _lib: Optional[C.CDLL] = None

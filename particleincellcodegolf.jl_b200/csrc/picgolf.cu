@@ -1856,3 +1856,6 @@ PG_API int picgolf_stage_quiet_start(int64_t P, int64_t first, int64_t count, do
     PG_TRY(dx.download(x, count * 8));
     return dv.download(v, count * 8);
 }
+
+// ---- PIC2D3V.jl electrostatic path + omega-k post-processing (include/picgolf_es.h) ----
+#include "picgolf_es.inc"

@@ -1,4 +1,4 @@
-"""The C-ABI library loads, exports every symbol include/picgolf.h declares, and refuses to compute
+"""The C-ABI library loads, exports every symbol include/picgolf.h and include/picgolf_es.h declare, and refuses to compute
 without a GPU (no CPU fallback).  No compute calls here."""
 import ctypes as C
 import os
@@ -17,10 +17,10 @@ def _declared(header):
 
 def test_library_exports_every_declared_symbol(pg):
     lib = pg.load()
-    names = _declared(pg.HEADER_PATH)
-    assert len(names) >= 35
+    names = sorted(set(n for hp in pg.HEADER_PATHS for n in _declared(hp)))  # include/picgolf.h + include/picgolf_es.h
+    assert len(names) >= 58
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/picgolf.h but not exported by libpicgolf.so"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported by libpicgolf.so"
     nm = subprocess.run(["nm", "-D", "--defined-only", pg.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (picgolf_\w+)", nm))
     assert set(names) <= exported
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(pg):
 
 
 def test_python_signature_table_matches_header(pg):
-    names = set(_declared(pg.HEADER_PATH))
+    names = set(n for hp in pg.HEADER_PATHS for n in _declared(hp))
     assert set(pg._SIGNATURES) | {"picgolf_last_error"} == names
 
 
