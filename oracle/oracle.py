@@ -390,7 +390,7 @@ class ESField:
         """Exy[c, 1:NX, 1:NY] as two flat column-major NX*NY arrays."""
         NX, NY = self.NX, self.NY
         g = self.Exy.reshape(2, NY + 6, NX + 6)
-        return g[0, 2:NY + 2, 2:NX + 2].ravel().copy(), g[1, 2:NY + 2, 2:NX + 2].ravel().copy()
+        return g[0, 3:NY + 3, 3:NX + 3].ravel().copy(), g[1, 3:NY + 3, 3:NX + 3].ravel().copy()
 
     def step(self):
         """loop!(plasma, field, to, t, _); diagnose!(diagnostics, field, plasma, t, to)   2D3V.jl:123-126"""

@@ -219,22 +219,20 @@ class Simulation:
         return out.reshape((n, self.ND), order="F")
 
     # -- multi-GPU
-    def connect(self, group=None):
-        """One process per GPU: ship the NCCL id over torch.distributed and join (rho is all-reduced every step)."""
-        import torch
+    def connect(self):
+        """One process per GPU: ship the NCCL id over torch.distributed (default group) and join; rho is all-reduced
+        every step.  Then call init_particles()."""
         import torch.distributed as dist
-        nranks, rank = self.cfg.nranks, self.cfg.rank
-        if nranks == 1:
+
+        from . import comm_unique_id
+        from .distributed import broadcast_bytes
+
+        if self.cfg.nranks == 1:
             return
-        buf = (C.c_char * 128)()
-        if rank == 0:
-            _check(self._lib.picgolf_comm_unique_id(buf))
-        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda()
-        dist.broadcast(t, src=0, group=group)
-        raw = bytes(t.cpu().tolist())
-        _check(self._lib.picgolf_es_comm_init(self._h, raw, nranks, rank))
+        uid = comm_unique_id() if dist.get_rank() == 0 else None
+        uid = broadcast_bytes(uid, 128, src=0)
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _check(self._lib.picgolf_es_comm_init(self._h, buf, self.cfg.nranks, self.cfg.rank))
 
 
 # ---- stage-level helpers ------------------------------------------------------------------------------

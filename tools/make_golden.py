@@ -213,6 +213,44 @@ def c5_2d3v(steps=4):
          x=x, y=y, vx=vx, vy=vy, vz=vz, rho=np.array(rhos), Ex=np.array(Exs), Ey=np.array(Eys), K=np.array(Ks))
 
 
+def es_setup(NX=32, NY=16, ppc=6, Lx=2.0, Ly=1.0, shapes=(12, 13)):
+    """Two-species magnetised plasma in the style of src/2D3V.jl:70-116 (electrons + ions of mass 16) at test size, on a
+    non-square box with Lx != Ly, Halton starts of Species(...) (PIC2D3V.jl:194-213)."""
+    P = NX * NY * ppc
+    n0 = 4 * math.pi ** 2
+    dl = min(Lx / NX, Ly / NY)
+    vth = dl * math.sqrt(n0)
+    dt = dl / (6 * vth)
+    B = [math.sqrt(n0) / 4, math.sqrt(n0) / 16, -math.sqrt(n0) / 8]
+    species = []
+    for (q, m), sh in zip(((-1.0, 1.0), (1.0, 16.0)), shapes):
+        x, y, vx, vy, vz, w = o.es_species(P, vth / math.sqrt(m), n0, Lx, Ly)
+        species.append(dict(x=x, y=y, vx=vx, vy=vy, vz=vz, charge=q, mass=m, weight=w, shape=sh, vth=vth / math.sqrt(m)))
+    return dict(NX=NX, NY=NY, P=P, Lx=Lx, Ly=Ly, n0=n0, dt=dt, B=B), species
+
+
+def esfield(NT=12, ntskip=4, ngskip=2):
+    """loop!/diagnose! of PIC2D3V.ElectrostaticField, both readings of update! (accumulate 1 = as written)."""
+    par, species = es_setup()
+    out = dict(NT=NT, ntskip=ntskip, ngskip=ngskip, **{k: np.asarray(v) for k, v in par.items()})
+    for s, sp in enumerate(species):
+        out[f"xyv0_{s}"] = np.stack([sp[k] for k in ("x", "y", "vx", "vy", "vz")], axis=1)  # P x 5 (Julia: xyv[5, P])
+        out[f"spec_{s}"] = np.array([sp["charge"], sp["mass"], sp["weight"], sp["shape"], sp["vth"]])
+    for acc in (1, 0):
+        f = o.ESField(species, par["NX"], par["NY"], par["Lx"], par["Ly"], par["dt"], par["B"], NT=NT, ntskip=ntskip, ngskip=ngskip,
+                      accumulate=bool(acc))
+        rhos, Exs_, Eys_ = [], [], []
+        for _ in range(NT):
+            f.step()
+            rhos.append(f.rho.copy()); Exs_.append(f.Ex.copy()); Eys_.append(f.Ey.copy())
+        gx, gy = f.exy_interior()
+        tag = f"acc{acc}_"
+        out.update({tag + "rho": np.array(rhos), tag + "Ex": np.array(Exs_), tag + "Ey": np.array(Eys_), tag + "Exy_x": gx, tag + "Exy_y": gy,
+                    tag + "scalars": f.scalars.copy(), tag + "Exs": f.Exs.copy(), tag + "Eys": f.Eys.copy(), tag + "phis": f.phis.copy(),
+                    tag + "x": f.x.copy(), tag + "y": f.y.copy(), tag + "vx": f.vx.copy(), tag + "vy": f.vy.copy(), tag + "vz": f.vz.copy()})
+    save("esfield", **out)
+
+
 def stencils():
     """Stage-level vectors: Gaussian stencils at awkward centres for N = 64, 128, 4096."""
     rng = np.random.default_rng(7)
@@ -237,7 +275,7 @@ if __name__ == "__main__":
     if args.only:
         globals()[args.only]()
         sys.exit(0)
-    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils(); ngp1d2v(); ngp1d2v2s()
+    c1_ngp(); gauss_explicit(); c2_fixedpoint(); c5_2d3v(); stencils(); ngp1d2v(); ngp1d2v2s(); esfield()
     if not args.skip_c3:
         c3_quiet()
         simpson13()
