@@ -35,6 +35,16 @@ struct ESParticleArgs {
     int NX, NY;
 };
 
+// 0-based periodic cell of the (1-based, unwrapped) stencil index i: the reference's single-wrap unimod; an index that
+// is still outside 1..N after it (a particle that left the box by more than a period -- the reference would throw a
+// BoundsError on its halo array -- or a NaN position) is folded with a full modulo instead of touching foreign memory.
+__device__ __forceinline__ int es_cell0(int i, int N)
+{
+    int u = es::unimod(i, N) - 1;
+    if ((unsigned)u >= (unsigned)N) { u = (i - 1) % N; if (u < 0) u += N; }
+    return u;
+}
+
 // for i in species.chunks[k] (:546-553): gather -> boris -> move -> deposit, any particle order.
 template <int SHAPE>
 __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs a)
@@ -54,7 +64,7 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs
         es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
         es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { cx[s] = es::unimod(ix0 + s, NX) - 1; cy[s] = (es::unimod(iy0 + s, NY) - 1) * NX; }
+        for (int s = 0; s < S; ++s) { cx[s] = es_cell0(ix0 + s, NX); cy[s] = es_cell0(iy0 + s, NY) * NX; }
         double Exi = 0.0, Eyi = 0.0; // field(species.shape, x[i], y[i])   :1217-1229 (j outer, i inner, @muladd)
 #pragma unroll
         for (int jj = 0; jj < S; ++jj)
@@ -72,7 +82,7 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs
         es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
         es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { cx[s] = es::unimod(ix0 + s, NX) - 1; cy[s] = (es::unimod(iy0 + s, NY) - 1) * NX; }
+        for (int s = 0; s < S; ++s) { cx[s] = es_cell0(ix0 + s, NX); cy[s] = es_cell0(iy0 + s, NY) * NX; }
 #pragma unroll
         for (int jj = 0; jj < S; ++jj)
 #pragma unroll

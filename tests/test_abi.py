@@ -54,6 +54,33 @@ def test_config_struct_layout(pg):
     assert (sp.N, sp.P, sp.T, sp.half_width, sp.scheme) == (64, 2048, 8192, 7, 5) and sp.rtol == 4 * np.finfo(float).eps
 
 
+def test_es_config_struct_layout(pg):
+    """picgolf_es_config (include/picgolf_es.h) and its ctypes image agree; defaults are the set-up of src/2D3V.jl:70-116."""
+    cfg = pg.ESConfig()
+    assert pg.load().picgolf_es_config_default(C.byref(cfg)) == 0
+    assert cfg.struct_size == C.sizeof(pg.ESConfig) == 256
+    assert (cfg.nspecies, cfg.NX, cfg.NY, cfg.NT, cfg.ntskip, cfg.ngskip) == (2, 128, 128, 1024, 4, 2)
+    assert list(cfg.species_P)[:2] == [128 * 128 * 16] * 2 and list(cfg.species_shape)[:2] == [12, 12]
+    assert list(cfg.species_charge)[:2] == [-1.0, 1.0] and list(cfg.species_mass)[:2] == [1.0, 32.0]
+    n0 = 4 * np.pi ** 2
+    assert cfg.species_weight[0] == n0 / (128 * 128 * 16) and abs(cfg.B0x - np.sqrt(n0) / 4) < 1e-15
+    assert abs(cfg.dt - (1 / 128) / (6 * (1 / 128) * np.sqrt(n0))) < 1e-18 and cfg.field_accumulate == 1
+    h = C.c_void_p()
+    bad = pg.ESConfig.from_buffer_copy(cfg)
+    bad.struct_size = 8
+    assert pg.load().picgolf_es_create(C.byref(bad), C.byref(h)) == -1
+    bad = pg.ESConfig.from_buffer_copy(cfg)
+    bad.NX = 100
+    assert pg.load().picgolf_es_create(C.byref(bad), C.byref(h)) == -5
+    bad = pg.ESConfig.from_buffer_copy(cfg)
+    bad.species_shape[1] = 16  # BSplineWeighting{6}: bspline is defined for 0..5 only
+    assert pg.load().picgolf_es_create(C.byref(bad), C.byref(h)) == -1
+    bad = pg.ESConfig.from_buffer_copy(cfg)
+    bad.ngskip = 3  # @assert ispow2(ngskip)
+    assert pg.load().picgolf_es_create(C.byref(bad), C.byref(h)) == -1
+    assert pg.load().picgolf_es_step(None, 1) == -1 and pg.load().picgolf_es_destroy(None) == 0
+
+
 def test_argument_errors_are_codes_not_crashes(pg):
     lib = pg.load()
     cfg = pg.default_config(pg.NGP_LEAPFROG)
