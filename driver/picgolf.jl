@@ -129,4 +129,127 @@ function diagnostics(s::Sim)
     return D[1:rows[], :], sw[1:rows[]]
 end
 
+# ------------------------------------------------------------------------------------------------
+# PIC2D3V.jl electrostatic path (include/picgolf_es.h): Species / shapes / ElectrostaticField / ElectrostaticDiagnostics.
+#
+#     using .PicGolf
+#     es = PicGolf.ESSim(plasma, field, diagnostics)   # PIC2D3V objects: reads charge, mass, weight, shape, xyv, B0, dt, ...
+#     PicGolf.loop!(es, NT)                            # replaces `for t in 0:NT-1; loop!(...); diagnose!(...); end` (src/2D3V.jl:123-126)
+#     PicGolf.fetch!(es, plasma, diagnostics)          # xyv, kineticenergy, fieldenergy, momenta, Exs/Eys/phis back into the PIC2D3V objects
+# ------------------------------------------------------------------------------------------------
+const ES_NGP, ES_AREA, ES_BSPLINE0 = Int32(0), Int32(1), Int32(10)
+
+# Mirror of `picgolf_es_config` (include/picgolf_es.h) -- field order and types must match (256 bytes).
+Base.@kwdef mutable struct ESConfig
+    struct_size::Int32 = 0
+    nspecies::Int32 = 1
+    NX::Int64 = 128
+    NY::Int64 = 128
+    Lx::Float64 = 1.0
+    Ly::Float64 = 1.0
+    dt::Float64 = 0.0
+    B0x::Float64 = 0.0
+    B0y::Float64 = 0.0
+    B0z::Float64 = 0.0
+    NT::Int64 = 1
+    ntskip::Int32 = 1
+    ngskip::Int32 = 1
+    field_accumulate::Int32 = 1      # update! as written (PIC2D3V.jl:294-297)
+    field_history::Int32 = 1
+    device::Int32 = -1
+    rank::Int32 = 0
+    nranks::Int32 = 1
+    reserved_::Int32 = 0
+    species_P::NTuple{4, Int64} = (0, 0, 0, 0)
+    species_shape::NTuple{4, Int32} = (0, 0, 0, 0)
+    species_charge::NTuple{4, Float64} = (0.0, 0.0, 0.0, 0.0)
+    species_mass::NTuple{4, Float64} = (1.0, 1.0, 1.0, 1.0)
+    species_weight::NTuple{4, Float64} = (0.0, 0.0, 0.0, 0.0)
+end
+
+# shape code of a PIC2D3V.AbstractShape, by type name (no dependency on the PIC2D3V module here)
+function shapecode(shape)
+    n = string(nameof(typeof(shape)))
+    n == "NGPWeighting" && return ES_NGP
+    n == "AreaWeighting" && return ES_AREA
+    n == "BSplineWeighting" && return ES_BSPLINE0 + Int32(Int(typeof(shape).parameters[1]))
+    error("no libpicgolf kernel for shape $(typeof(shape))")
+end
+
+pad4(v, z) = ntuple(i -> i <= length(v) ? v[i] : z, 4)
+
+mutable struct ESSim
+    h::Ptr{Cvoid}
+    cfg::ESConfig
+    function ESSim(plasma, field, diagnostics; accumulate=true, history=true, device=-1)
+        g = field.gridparams
+        NT = length(diagnostics.kineticenergy) * diagnostics.ntskip
+        cfg = ESConfig(nspecies=length(plasma), NX=g.NX, NY=g.NY, Lx=g.Lx, Ly=g.Ly, dt=field.boris.dt_2 * 2,
+            B0x=field.B0[1], B0y=field.B0[2], B0z=field.B0[3], NT=NT, ntskip=diagnostics.ntskip, ngskip=diagnostics.ngskip,
+            field_accumulate=accumulate, field_history=history, device=device,
+            species_P=pad4([Int64(size(s.xyv, 2)) for s in plasma], Int64(0)),
+            species_shape=pad4([shapecode(s.shape) for s in plasma], Int32(0)),
+            species_charge=pad4([s.charge for s in plasma], 0.0), species_mass=pad4([s.mass for s in plasma], 1.0),
+            species_weight=pad4([s.weight for s in plasma], 0.0))
+        cfg.struct_size = Int32(sizeof(ESConfig))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:picgolf_es_create, LIB), Cint, (Ref{ESConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        es = new(h[], cfg)
+        finalizer(e -> ccall((:picgolf_es_destroy, LIB), Cint, (Ptr{Cvoid},), e.h), es)
+        for (i, s) in enumerate(plasma)   # Species.xyv is 5 x P column-major: passed as is
+            xyv = s.xyv
+            GC.@preserve xyv check(ccall((:picgolf_es_set_species_xyv, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64),
+                                         es.h, i - 1, xyv, size(xyv, 2)))
+        end
+        return es
+    end
+end
+
+loop!(es::ESSim, n::Integer=1) = check(ccall((:picgolf_es_step, LIB), Cint, (Ptr{Cvoid}, Int64), es.h, n))
+
+function fetch!(es::ESSim, plasma, diagnostics)
+    for (i, s) in enumerate(plasma)
+        xyv = s.xyv
+        GC.@preserve xyv check(ccall((:picgolf_es_get_species_xyv, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64),
+                                     es.h, i - 1, xyv, size(xyv, 2)))
+    end
+    ND = length(diagnostics.kineticenergy)
+    rows = Ref{Int64}(0)
+    pm, cm = zeros(3, ND), zeros(3, ND)
+    check(ccall((:picgolf_es_get_diagnostics, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Int64}),
+                es.h, diagnostics.kineticenergy, diagnostics.fieldenergy, pm, cm, ND, rows))
+    for ti in 1:rows[]
+        diagnostics.particlemomentum[ti] .= pm[:, ti]
+        diagnostics.characteristicmomentum[ti] .= cm[:, ti]
+    end
+    diagnostics.ti[] = rows[]
+    if es.cfg.field_history != 0
+        for (w, F) in enumerate((diagnostics.Exs, diagnostics.Eys, diagnostics.ϕs))   # NX/ngskip x NY/ngskip x ND, column-major
+            n = Ref{Int64}(0)
+            check(ccall((:picgolf_es_get_field_history, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ref{Int64}),
+                        es.h, w - 1, F, size(F, 3), n))
+        end
+    end
+    return nothing
+end
+
+# |fft| omega-k map of a stored history on the GPU (PIC2D3V.jl:1483-1493, Electrostatic2D3V.jl:219-233):
+# which 0/1/2 = Exs/Eys/phis, axis 0/1 = kx/ky, mode 1 = abs.(fft(F))[:, 1, :], mode 0 = sum over lines of abs.(fft(F[:, i, :])).
+function spectrum(es::ESSim, which::Integer, axis::Integer, mode::Integer)
+    n = (axis == 0 ? es.cfg.NX : es.cfg.NY) ÷ es.cfg.ngskip
+    Z = zeros(n, es.cfg.NT ÷ es.cfg.ntskip)
+    check(ccall((:picgolf_es_spectrum, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}), es.h, which, axis, mode, Z))
+    return Z
+end
+
+# the same for a history the driver collected itself, e.g. Exs of src/Electrostatic2D3V.jl:171
+function wk_spectrum(F::Array{Float64, 3}, axis::Integer, mode::Integer)
+    n = size(F, axis + 1)
+    Z = zeros(n, size(F, 3))
+    check(ccall((:picgolf_stage_wk_spectrum, LIB), Cint, (Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Ptr{Float64}),
+                F, size(F, 1), size(F, 2), size(F, 3), axis, mode, Z))
+    return Z
+end
+
 end # module
