@@ -23,11 +23,65 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def check_esfield(rank, world, local):
+    """PIC2D3V.jl electrostatic path (include/picgolf_es.h): two species sharded over the ranks, device-side Halton start
+    (global mean / variance all-reduced), rho all-reduced every step; against the same run on one GPU."""
+    import math
+
+    from particleincellcodegolf.jl_b200 import pic2d3v as es
+
+    NX, NY, Lx, Ly, NT = 64, 32, 2.0, 1.0, 8
+    P = (1 << 18) + 3  # not divisible by the rank count
+    n0 = 4 * math.pi ** 2
+    dl = min(Lx / NX, Ly / NY)
+    vth = dl * math.sqrt(n0)
+
+    def build(r, w):
+        plasma = [es.Species(P, vth, n0, es.BSplineWeighting(2), Lx=Lx, Ly=Ly, charge=-1, mass=1),
+                  es.Species(P, vth / 4, n0, es.AreaWeighting(), Lx=Lx, Ly=Ly, charge=1, mass=16)]
+        sim = es.Simulation(plasma, es.ElectrostaticField(NX, NY, Lx, Ly, dt=dl / (6 * vth), B0x=math.sqrt(n0) / 4, B0z=0.5, accumulate=False),
+                            es.ElectrostaticDiagnostics(NX, NY, NT, 2, 2), device=local, rank=r, nranks=w)
+        if w > 1:
+            sim.connect()
+            sim.init_particles()
+        return sim
+
+    sim, ref = build(rank, world), build(0, 1)
+    good = True
+    for s in range(2):  # the start itself: same particles as the single-GPU start
+        f, c = sim.ranges[s]
+        for a, b in zip(sim.species(s), ref.species(s)):
+            good = good and rel(a, b[f:f + c]) < 1e-12
+    sim.loop(NT); ref.loop(NT)
+    fa, fb = sim.fields(), ref.fields()
+    e = dict(rho=rel(fa["rho"], fb["rho"]), Ex=rel(fa["Ex"], fb["Ex"]), Exy=rel(fa["Exy_y"], fb["Exy_y"]))
+    for s in range(2):
+        f, c = sim.ranges[s]
+        for k, (a, b) in enumerate(zip(sim.species(s), ref.species(s))):
+            e[f"s{s}c{k}"] = rel(a, b[f:f + c])
+    sa, sb = sim.scalars(), ref.scalars()
+    e["ke"] = rel(sa["kineticenergy"], sb["kineticenergy"]); e["fe"] = rel(sa["fieldenergy"], sb["fieldenergy"])
+    e["cmom"] = rel(sa["characteristicmomentum"], sb["characteristicmomentum"])
+    e["Exs"] = rel(sim.history("Exs"), ref.history("Exs"))
+    good = good and max(e.values()) < 1e-10 and len(sa["kineticenergy"]) == NT // 2
+    print(f"[rank {rank}] esfield {e} ok={good}", flush=True)
+    sim.close(); ref.close()
+    return good
+
+
 def main():
     rank, world, local = pgd.env_rank()
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    if os.environ.get("PICGOLF_CHECK_ONLY") == "es":
+        ok = check_esfield(rank, world, local)
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        if rank == 0:
+            print("MULTIGPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+        sys.exit(0 if int(t.item()) == 1 else 1)
     peer_seen = None
     for mode in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO, pg.DEPOSIT_POLY):
         N, P, steps = 4096, 1 << 21, 6
@@ -134,6 +188,7 @@ def main():
     print(f"[rank {rank}] ngp_1d2v_2s bit-identical={good}", flush=True)
     ok &= good
     sim.close(); ref.close()
+    ok &= check_esfield(rank, world, local)
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
