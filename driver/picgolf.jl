@@ -159,7 +159,7 @@ Base.@kwdef mutable struct ESConfig
     device::Int32 = -1
     rank::Int32 = 0
     nranks::Int32 = 1
-    reserved_::Int32 = 0
+    sort_every::Int32 = 0
     species_P::NTuple{4, Int64} = (0, 0, 0, 0)
     species_shape::NTuple{4, Int32} = (0, 0, 0, 0)
     species_charge::NTuple{4, Float64} = (0.0, 0.0, 0.0, 0.0)

@@ -58,7 +58,11 @@ typedef struct picgolf_es_config {
     int32_t field_history;     /* 1: keep Exs, Eys, phis [NX/ngskip, NY/ngskip, NT/ntskip] on the device (:1322-1327) */
     int32_t device;            /* CUDA device ordinal; -1 = current */
     int32_t rank, nranks;      /* particle sharding (every species is split evenly over the ranks) */
-    int32_t reserved_;
+    int32_t sort_every;        /* particle order: 0 = the library decides (shards of >= 2^20 particles with >= 8 per cell are kept
+                                * sorted by 16x16-cell tile, re-sorted every 8 steps, and run through shared-memory windows);
+                                * n > 0 = tile-sorted, re-sorted every n steps; < 0 = never sort (any-order kernel, global atomics).
+                                * The reference sorts for cache locality too (sort!(s::Species, dx, dy) :210-215); getters always
+                                * return the caller's particle order. */
     int64_t species_P[PICGOLF_ES_MAX_SPECIES];       /* GLOBAL particle count of each species */
     int32_t species_shape[PICGOLF_ES_MAX_SPECIES];   /* picgolf_es_shape */
     double species_charge[PICGOLF_ES_MAX_SPECIES];   /* Species.charge */
@@ -120,6 +124,9 @@ int picgolf_es_get_field_history(picgolf_es_handle h, int which, double *out, in
 int picgolf_es_spectrum(picgolf_es_handle h, int which, int axis, int mode, double *out);
 
 int picgolf_es_launch_count(picgolf_es_handle h, int64_t *launches);
+/* Tile-sorted mode: sorts so far, and particle deposits/gathers that fell outside their tile's shared-memory window
+ * (slow path through global memory: a stale-sort indicator). */
+int picgolf_es_sort_stats(picgolf_es_handle h, int64_t *sorts, int64_t *slow_particles);
 int picgolf_es_get_stream(picgolf_es_handle h, void **stream);
 /* One process per GPU: id128 from picgolf_comm_unique_id (picgolf.h); rho is all-reduced once per step. */
 int picgolf_es_comm_init(picgolf_es_handle h, const void *id128, int nranks, int rank);

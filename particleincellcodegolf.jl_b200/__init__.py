@@ -80,7 +80,7 @@ class ESConfig(C.Structure):
         ("struct_size", C.c_int32), ("nspecies", C.c_int32), ("NX", C.c_int64), ("NY", C.c_int64),
         ("Lx", C.c_double), ("Ly", C.c_double), ("dt", C.c_double), ("B0x", C.c_double), ("B0y", C.c_double), ("B0z", C.c_double),
         ("NT", C.c_int64), ("ntskip", C.c_int32), ("ngskip", C.c_int32), ("field_accumulate", C.c_int32),
-        ("field_history", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
+        ("field_history", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("sort_every", C.c_int32),
         ("species_P", C.c_int64 * 4), ("species_shape", C.c_int32 * 4), ("species_charge", C.c_double * 4),
         ("species_mass", C.c_double * 4), ("species_weight", C.c_double * 4),
     ]
@@ -159,6 +159,7 @@ _SIGNATURES = {
     "picgolf_es_get_field_history": [_vp, _int, _vp, _i64, C.POINTER(_i64)],
     "picgolf_es_spectrum": [_vp, _int, _int, _int, _dp],
     "picgolf_es_launch_count": [_vp, C.POINTER(_i64)],
+    "picgolf_es_sort_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "picgolf_es_get_stream": [_vp, C.POINTER(_vp)],
     "picgolf_es_comm_init": [_vp, _vp, _int, _int],
     "picgolf_es_stage_shape": [_int, _dp, _i64, _d, _ip, _dp],

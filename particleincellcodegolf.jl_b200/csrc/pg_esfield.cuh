@@ -14,6 +14,8 @@
 #include "pg_common.cuh"
 #include "pg_es_math.h"
 #include "pg_fft.cuh"
+#include "pg_kernels_2d.cuh"
+#include "pg_sort.cuh"
 
 namespace pg {
 
@@ -33,6 +35,13 @@ struct ESParticleArgs {
     double dep;                     // qw_dV / wref (|dep| <= 1): the solve multiplies by wref
     double fx_scale;
     int NX, NY;
+    // tile-sorted mode (es_particles_tiled): as P2DArgs
+    const unsigned int *tile_start, *tile_end; // particle range of each tile in the sorted arrays
+    const unsigned int *item_off;              // [ntiles+1] prefix of ceil(count/T2_CHUNK): work items per tile
+    unsigned long long *slow_count;
+    double fxw_scale;    // 2^fracw: format of the shared-memory window, which accumulates the UNSIGNED fractions wx*wy
+    double wscale;       // window -> global: dep * 2^(frac - fracw), applied once per window cell at the flush
+    int ntx, ntiles;
 };
 
 // 0-based periodic cell of the (1-based, unwrapped) stencil index i: the reference's single-wrap unimod; an index that
@@ -99,6 +108,133 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs
         const double s = block_sum(sum[k], scratch);
         if (threadIdx.x == 0) a.partials[ES_NSUM * blockIdx.x + k] = s;
     }
+}
+
+// Tile-sorted variant (the scheme of particles_2d3v_tiled, pg_kernels_2d.cuh, for any shape).  The particles of a species
+// are kept sorted by T2_TS x T2_TS-cell tile (pg_sort.cuh, mode 2); a work item is up to T2_CHUNK consecutive particles of
+// ONE tile.  The block stages the T2_WS x T2_WS window of Exy around the tile in shared memory and accumulates the
+// fractions wx*wy of the deposit into a fixed-point window of the same size -- two 32-bit limbs with native shared-memory
+// atomics (64-bit ones are CAS loops on sm_100a); the species' signed weight q*w/dV enters once per window cell when the
+// window is flushed with integer REDs.  So the S^2 gathers and S^2 deposits of a particle never leave the SM.  A stencil
+// that does not fit the window (a particle that drifted more than T2_R - S cells out of its tile since the last sort) goes
+// to global memory and is counted.
+template <int SHAPE>
+__global__ void __launch_bounds__(PG_THREADS) es_particles_tiled(ESParticleArgs a)
+{
+    constexpr int S = es::support(SHAPE);
+    __shared__ double2 Ew[T2_WS * T2_WS];
+    __shared__ unsigned int rlo[T2_WS * T2_WS], rhi[T2_WS * T2_WS];
+    __shared__ double scratch[32];
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double sum[ES_NSUM];
+#pragma unroll
+    for (int k = 0; k < ES_NSUM; ++k) sum[k] = 0.0;
+    unsigned int nslow = 0;
+    const unsigned int nitems = a.item_off[a.ntiles];
+    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int lo = 0, hi = a.ntiles; // tile of this item: last t with item_off[t] <= item
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int tile = lo;
+        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
+        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
+        const int ox = (tile % a.ntx) * T2_TS - T2_R, oy = (tile / a.ntx) * T2_TS - T2_R; // window origin (0-based cells)
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
+            Ew[c] = a.Exy[gx + (size_t)gy * NX];
+            rlo[c] = 0u; rhi[c] = 0u;
+        }
+        __syncthreads();
+        for (long long p = start + threadIdx.x; p < end; p += blockDim.x) {
+            double x = ld_stream(a.x + p), y = ld_stream(a.y + p);
+            double vx = ld_stream(a.vx + p), vy = ld_stream(a.vy + p), vz = ld_stream(a.vz + p);
+            int ix0, iy0;
+            double wx[S], wy[S];
+            es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
+            es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
+            double Exi = 0.0, Eyi = 0.0;
+            {
+                const int rx = (ix0 - 1 - ox) & mx, ry = (iy0 - 1 - oy) & my;
+                if (rx <= T2_WS - S && ry <= T2_WS - S) {
+                    const double2 *e = Ew + rx + ry * T2_WS;
+#pragma unroll
+                    for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < S; ++ii) {
+                            const double wxy = wx[ii] * wy[jj];
+                            const double2 f = e[ii + jj * T2_WS];
+                            Exi = fma(f.x, wxy, Exi);
+                            Eyi = fma(f.y, wxy, Eyi);
+                        }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < S; ++ii) {
+                            const double wxy = wx[ii] * wy[jj];
+                            const double2 f = __ldg(&a.Exy[es_cell0(ix0 + ii, NX) + (size_t)es_cell0(iy0 + jj, NY) * NX]);
+                            Exi = fma(f.x, wxy, Exi);
+                            Eyi = fma(f.y, wxy, Eyi);
+                        }
+                }
+            }
+            const double vxi = vx, vyi = vy;
+            es::boris_push(a.boris, vx, vy, vz, Exi, Eyi, a.q_m);
+            x = es::unimod(x + (vxi + vx) / 2 * a.dt, a.Lx);
+            y = es::unimod(y + (vyi + vy) / 2 * a.dt, a.Ly);
+            es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
+            es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
+            {
+                const int rx = (ix0 - 1 - ox) & mx, ry = (iy0 - 1 - oy) & my;
+                if (rx <= T2_WS - S && ry <= T2_WS - S) {
+                    const int r0 = rx + ry * T2_WS;
+#pragma unroll
+                    for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < S; ++ii) {
+                            // the fractions of the B-splines of order >= 4 can come out as -1e-17 instead of 0 (cancellation in
+                            // the reference's own polynomials): the two-limb add below is exact for either sign (mod 2^64)
+                            const fx_t v = to_fx(wx[ii] * wy[jj], a.fxw_scale);
+                            const unsigned int vlo = (unsigned int)v;
+                            const unsigned int old = atomicAdd(&rlo[r0 + ii + jj * T2_WS], vlo);
+                            const unsigned int carry = (old + vlo) < old ? 1u : 0u;
+                            const unsigned int vhi = (unsigned int)(v >> 32) + carry;
+                            if (vhi) atomicAdd(&rhi[r0 + ii + jj * T2_WS], vhi);
+                        }
+                } else {
+                    ++nslow;
+#pragma unroll
+                    for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                        for (int ii = 0; ii < S; ++ii)
+                            atomicAdd(&a.rho[es_cell0(ix0 + ii, NX) + (size_t)es_cell0(iy0 + jj, NY) * NX],
+                                      to_fx(wx[ii] * wy[jj] * a.dep, a.fx_scale));
+                }
+            }
+            st_stream(a.x + p, x); st_stream(a.y + p, y);
+            st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
+            sum[0] += vx * vx + vy * vy + vz * vz;
+            sum[1] += vx; sum[2] += vy; sum[3] += vz;
+            sum[4] += fabs(vx); sum[5] += fabs(vy); sum[6] += fabs(vz);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            const long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
+            if (v) {
+                int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
+                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)__double2ll_rn((double)v * a.wscale));
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < ES_NSUM; ++k) {
+        const double s = block_sum(sum[k], scratch);
+        if (threadIdx.x == 0) a.partials[ES_NSUM * blockIdx.x + k] = s;
+    }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -28,10 +28,11 @@ struct SortArgs {
     unsigned int *bin_start;  // [nbins] start offsets (kept for the tiled 2D kernel); may be NULL
     long long P;
     int narr, nbins;
-    int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1])
+    int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1]) on the unit box;  2: the same on an Lx x Ly box
     int N, NY;  // grid
     int tshift; // 2D: log2(tile edge in cells)
     int vsplit; // 1D: 1 -> key = 2*cell + (v >= 0): each beam keeps its own bins, so a bin drifts as a whole (pg_kernels_poly.cuh)
+    double kx, ky; // mode 2: cells per unit length NX/Lx, NY/Ly (PIC2D3V GridParameters: positions live in (0, Lx] x (0, Ly])
     int sublg;  // 1D with vsplit: log2 of the position sub-bins per cell (key = ((2*cell + sign) << sublg) + sub): particles of a
                 // bin stay ordered by position, so the rows of 64 particles a warp of fp_pass_poly evaluates lie in ONE cell
                 // except where a cell boundary cuts through the bin
@@ -45,6 +46,11 @@ __device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
         const double d = a.in[0][j] * (double)a.N - (double)c; // offset from the cell centre, [-1/2, 1/2]
         const int sub = min((1 << a.sublg) - 1, max(0, (int)((d + 0.5) * (double)(1 << a.sublg))));
         return (((c & (a.N - 1)) * 2 + (a.in[1][j] >= 0.0 ? 1 : 0)) << a.sublg) + sub;
+    }
+    if (a.mode == 2) {
+        int ex = ((int)ceil(a.in[0][j] * a.kx) - 1) & (a.N - 1);
+        int ey = ((int)ceil(a.in[1][j] * a.ky) - 1) & (a.NY - 1);
+        return (ey >> a.tshift) * max(1, a.N >> a.tshift) + (ex >> a.tshift);
     }
     int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
     int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);

@@ -82,7 +82,7 @@ class Simulation:
     """plasma + field + diagnostics on one GPU (or one shard of the particles per rank)."""
 
     def __init__(self, plasma: Sequence[Species], field: ElectrostaticField, diagnostics: ElectrostaticDiagnostics, *, device=-1,
-                 rank=0, nranks=1):
+                 rank=0, nranks=1, sort_every=0):
         self._lib = load()
         self._h = _vp()
         cfg = ESConfig()
@@ -92,7 +92,7 @@ class Simulation:
         cfg.B0x, cfg.B0y, cfg.B0z = field.B0
         cfg.NT, cfg.ntskip, cfg.ngskip = diagnostics.NT, diagnostics.ntskip, diagnostics.ngskip
         cfg.field_accumulate, cfg.field_history = int(field.accumulate), int(diagnostics.history)
-        cfg.device, cfg.rank, cfg.nranks = device, rank, nranks
+        cfg.device, cfg.rank, cfg.nranks, cfg.sort_every = device, rank, nranks, sort_every
         if len(plasma) > 4:
             raise PicGolfError(-1, "at most 4 species")
         for s, sp in enumerate(plasma):
@@ -180,6 +180,12 @@ class Simulation:
         v = _i64()
         _check(self._lib.picgolf_es_launch_count(self._h, C.byref(v)))
         return v.value
+
+    def sort_stats(self):
+        """(sorts so far, particles that left their tile's shared-memory window) of the tile-sorted mode."""
+        a, b = _i64(), _i64()
+        _check(self._lib.picgolf_es_sort_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- fields and diagnostics
     def fields(self):

@@ -53,12 +53,12 @@ def test_stage_boris_bit_exact(es, oracle):
             assert np.array_equal([a[k], b[k], c[k]], oracle.es_boris(v[:, k], ex[k], ey[k], B, dt, q_m))
 
 
-def _run_against(es, oracle, species_o, NX, NY, Lx, Ly, dt, B, NT, ntskip, ngskip, acc):
+def _run_against(es, oracle, species_o, NX, NY, Lx, Ly, dt, B, NT, ntskip, ngskip, acc, sort_every=-1):
     f = oracle.ESField(species_o, NX, NY, Lx, Ly, dt, B, NT=NT, ntskip=ntskip, ngskip=ngskip, accumulate=bool(acc))
     plasma = [_species_from_arrays(es, np.stack([s[k] for k in ("x", "y", "vx", "vy", "vz")], axis=1), s["charge"], s["mass"], s["weight"],
                                    s["shape"], Lx, Ly) for s in species_o]
     sim = es.Simulation(plasma, es.ElectrostaticField(NX, NY, Lx, Ly, dt=dt, B0x=B[0], B0y=B[1], B0z=B[2], accumulate=bool(acc)),
-                        es.ElectrostaticDiagnostics(NX, NY, NT, ntskip, ngskip))
+                        es.ElectrostaticDiagnostics(NX, NY, NT, ntskip, ngskip), sort_every=sort_every)
     for t in range(NT):
         f.step()
         sim.loop(1)
@@ -132,10 +132,38 @@ def _random_species(shape, NX, NY, Lx, Ly, charge, mass, seed, ppc=5, dt=0.01):
 
 @pytest.mark.parametrize("shapes", [(0, 1), (10, 11), (12, 13), (14, 15), (15, 12)])
 @pytest.mark.parametrize("acc", [1, 0])
-def test_loop_matches_oracle(es, oracle, shapes, acc):
+@pytest.mark.parametrize("sort_every", [-1, 3])  # any-order kernel (global atomics) / tile-sorted kernel (shared-memory windows)
+def test_loop_matches_oracle(es, oracle, shapes, acc, sort_every):
     NX, NY, Lx, Ly = 32, 16, 1.5, 2.0
     sp = [_random_species(shapes[0], NX, NY, Lx, Ly, -1.0, 1.0, 11), _random_species(shapes[1], NX, NY, Lx, Ly, 2.0, 7.0, 12)]
-    _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.9, -0.4, 0.6], NT=9, ntskip=2, ngskip=4, acc=acc)
+    sim, _ = _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.9, -0.4, 0.6], NT=9, ntskip=2, ngskip=4, acc=acc, sort_every=sort_every)
+    assert sim.sort_stats()[0] == (3 if sort_every > 0 else 0)  # sorted before steps 0, 3, 6
+
+
+@pytest.mark.parametrize("shape", [1, 12, 15])
+def test_tiled_path_at_size(es, shape):
+    """2^20 particles per species on a 64 x 128 grid (several tiles, several work items per tile): the tile-sorted kernel
+    against the any-order kernel, particles returned in the caller's order, few window misses."""
+    NX, NY, Lx, Ly, NT = 64, 128, 1.0, 2.0, 10
+    P = 1 << 20
+    n0 = 4 * math.pi ** 2
+    dl = min(Lx / NX, Ly / NY)
+    vth = dl * math.sqrt(n0)
+    out = []
+    for sort_every in (-1, 0):
+        plasma = [es.Species(P, vth, n0, _shape(es, shape), Lx=Lx, Ly=Ly, charge=-1, mass=1),
+                  es.Species(P, vth / 4, n0, _shape(es, shape), Lx=Lx, Ly=Ly, charge=1, mass=16)]
+        sim = es.Simulation(plasma, es.ElectrostaticField(NX, NY, Lx, Ly, dt=dl / (6 * vth), B0x=math.sqrt(n0) / 4, accumulate=False),
+                            es.ElectrostaticDiagnostics(NX, NY, NT, 2, 2), sort_every=sort_every)
+        sim.loop(NT)
+        out.append((sim.fields(), sim.species(0), sim.species(1), sim.scalars(), sim.history("Exs"), sim.sort_stats()))
+    (fa, a0, a1, sa, ha, sta), (fb, b0, b1, sb, hb, stb) = out
+    assert sta == (0, 0) and stb[0] == 2 and stb[1] < 1e-3 * 2 * P * NT  # auto = tiled at this size: sorts before steps 0 and 8
+    assert relnorm(fb["rho"], fa["rho"]) < TOL and relnorm(fb["Ex"], fa["Ex"]) < TOL
+    for x, y in list(zip(a0, b0)) + list(zip(a1, b1)):
+        assert relnorm(y, x) < TOL  # same particle order as the caller's
+    assert relnorm(sb["kineticenergy"], sa["kineticenergy"]) < TOL and relnorm(sb["fieldenergy"], sa["fieldenergy"]) < TOL
+    assert relnorm(hb, ha) < TOL
 
 
 def test_three_species_and_reproducible_charge(es, oracle):
