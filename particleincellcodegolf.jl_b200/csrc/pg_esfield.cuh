@@ -118,8 +118,14 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs
 // window is flushed with integer REDs.  So the S^2 gathers and S^2 deposits of a particle never leave the SM.  A stencil
 // that does not fit the window (a particle that drifted more than T2_R - S cells out of its tile since the last sort) goes
 // to global memory and is counted.
+#ifndef PG_ES_MINBLOCKS
+#define PG_ES_MINBLOCKS 2 // resident blocks per SM the register allocation aims at (A/B builds: tools/build_variants.sh)
+#endif
+#ifndef PG_ES_PREFETCH
+#define PG_ES_PREFETCH 1  // 1: the next particle's five values are loaded before the current one is processed
+#endif
 template <int SHAPE>
-__global__ void __launch_bounds__(PG_THREADS) es_particles_tiled(ESParticleArgs a)
+__global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tiled(ESParticleArgs a)
 {
     constexpr int S = es::support(SHAPE);
     __shared__ double2 Ew[T2_WS * T2_WS];
@@ -147,9 +153,24 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_tiled(ESParticleArgs 
             rlo[c] = 0u; rhi[c] = 0u;
         }
         __syncthreads();
+#if PG_ES_PREFETCH
+        double nx = 0.0, ny = 0.0, nvx = 0.0, nvy = 0.0, nvz = 0.0;
+        if (start + threadIdx.x < end) {
+            const long long p0 = start + threadIdx.x;
+            nx = ld_stream(a.x + p0); ny = ld_stream(a.y + p0); nvx = ld_stream(a.vx + p0); nvy = ld_stream(a.vy + p0); nvz = ld_stream(a.vz + p0);
+        }
+#endif
         for (long long p = start + threadIdx.x; p < end; p += blockDim.x) {
+#if PG_ES_PREFETCH
+            double x = nx, y = ny, vx = nvx, vy = nvy, vz = nvz;
+            {
+                const long long pn = p + blockDim.x;
+                if (pn < end) { nx = ld_stream(a.x + pn); ny = ld_stream(a.y + pn); nvx = ld_stream(a.vx + pn); nvy = ld_stream(a.vy + pn); nvz = ld_stream(a.vz + pn); }
+            }
+#else
             double x = ld_stream(a.x + p), y = ld_stream(a.y + p);
             double vx = ld_stream(a.vx + p), vy = ld_stream(a.vy + p), vz = ld_stream(a.vz + p);
+#endif
             int ix0, iy0;
             double wx[S], wy[S];
             es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
