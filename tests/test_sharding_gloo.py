@@ -90,6 +90,39 @@ def _worker(rank, world, port, out):
         assert sweeps == s_ref == 4
         assert relnorm(E, ref.E) < 1e-12
         assert relnorm(vv, ref.v[f:f + c]) < 1e-12
+
+        # 6. PIC2D3V species (include/picgolf_es.h): the Halton start comes from the GLOBAL particle index, its mean and
+        #    corrected variance from all-reduced shard sums (what picgolf_es_init_species does with NCCL)
+        from scipy.special import erfinv
+        Ps, vth, seed = 1024 + 5, 0.013, 1 / np.sqrt(2.0)
+        f, c = pg.shard_range(Ps, rank, world)
+        xo, yo, vxo, vyo, vzo, wgt = o.es_species(Ps, vth, 4 * np.pi ** 2, 2.0, 0.5)
+        idx = np.arange(f, f + c)
+        assert np.array_equal(2.0 * np.array([o.es_halton(i, 2, seed) for i in idx]), xo[f:f + c])
+        raw = vth * erfinv(2 * np.array([o.es_halton(i, 5, seed) for i in idx]) - 1) * vth
+
+        def gsum(a):
+            t = torch.tensor([float(np.sum(a))], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t.item())
+
+        v = raw - gsum(raw) / Ps
+        m2 = gsum(v) / Ps
+        sd = np.sqrt(gsum((v - m2) ** 2) / (Ps - 1))
+        v = v * ((vth / np.sqrt(2.0)) / sd)
+        assert relnorm(v, vxo[f:f + c]) < 1e-12
+
+        # 7. one sharded step of loop! (first step: Exy = 0): the shard grids sum to the unsharded charge density
+        NXe, NYe, Lxe, Lye = 16, 32, 2.0, 0.5
+        full = dict(x=xo, y=yo, vx=vxo, vy=vyo, vz=vzo, charge=-1.0, mass=1.0, weight=wgt, shape=12)
+        mine = {k: (a[f:f + c].copy() if isinstance(a, np.ndarray) else a) for k, a in full.items()}
+        fa = o.ESField([full], NXe, NYe, Lxe, Lye, 0.01, [0.3, 0.0, 0.1], NT=1)
+        fb = o.ESField([mine], NXe, NYe, Lxe, Lye, 0.01, [0.3, 0.0, 0.1], NT=1)
+        fa.step(); fb.step()
+        r = torch.from_numpy(fb.rho.copy())
+        dist.all_reduce(r)
+        assert relnorm(r.numpy(), fa.rho) < 1e-13
+        assert np.array_equal(fb.x, fa.x[f:f + c]) and np.array_equal(fb.vz, fa.vz[f:f + c])
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
