@@ -166,6 +166,30 @@ def test_tiled_path_at_size(es, shape):
     assert relnorm(hb, ha) < TOL
 
 
+def _species_n(shape, P, NX, NY, Lx, Ly, charge, mass, seed, dt):
+    rng = np.random.default_rng(seed)
+    vth = 0.3 * min(Lx / NX, Ly / NY) / dt
+    return dict(x=Lx * (1 - rng.random(P)), y=Ly * (1 - rng.random(P)), vx=rng.standard_normal(P) * vth, vy=rng.standard_normal(P) * vth,
+                vz=rng.standard_normal(P) * vth, charge=charge, mass=mass, weight=4 * math.pi ** 2 * Lx * Ly / max(P, 64) / abs(charge), shape=shape)
+
+
+@pytest.mark.parametrize("sort_every", [-1, 2])
+def test_smallest_grid_window_wraps_onto_itself(es, oracle, sort_every):
+    """16 x 16 cells: one tile whose 32 x 32 shared-memory window covers the periodic grid four times over."""
+    NX = NY = 16
+    sp = [_species_n(15, 1500, NX, NY, 1.0, 1.0, -1.0, 1.0, 41, 0.02), _species_n(1, 700, NX, NY, 1.0, 1.0, 1.0, 3.0, 42, 0.02)]
+    _run_against(es, oracle, sp, NX, NY, 1.0, 1.0, 0.02, [0.3, 0.2, -0.7], NT=6, ntskip=3, ngskip=1, acc=1, sort_every=sort_every)
+
+
+@pytest.mark.parametrize("sort_every", [-1, 1])
+def test_four_species_ragged_counts(es, oracle, sort_every):
+    """The species limit, counts that are not multiples of anything (1, 31, 257, 1000), a different shape each."""
+    NX, NY, Lx, Ly = 32, 64, 0.5, 3.0
+    sp = [_species_n(sh, P, NX, NY, Lx, Ly, q, m, 50 + k, 0.01)
+          for k, (sh, P, q, m) in enumerate(((12, 1, -1.0, 1.0), (0, 31, 1.0, 2.0), (13, 257, -2.0, 5.0), (14, 1000, 1.0, 11.0)))]
+    _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.0, 1.1, 0.4], NT=5, ntskip=1, ngskip=8, acc=0, sort_every=sort_every)
+
+
 def test_three_species_and_reproducible_charge(es, oracle):
     NX = NY = 16
     sp = [_random_species(12, NX, NY, 1.0, 1.0, -1.0, 1.0, 21, dt=0.02), _random_species(13, NX, NY, 1.0, 1.0, 1.0, 4.0, 22, dt=0.02),
