@@ -51,6 +51,8 @@ Base.@kwdef mutable struct Config
     local_first::Int64 = -1
     local_count::Int64 = -1
     mass_ratio::Float64 = 0.0
+    field_history::Int32 = 0     # 2D3V: keep Exs/Eys/phis (Electrostatic2D3V.jl:171-173) on the device
+    reserved2_::Int32 = 0
 end
 
 struct PicGolfError <: Exception
@@ -115,6 +117,15 @@ function fields2d(s::Sim)
     r, Ex, Ey = (Vector{Float64}(undef, n) for _ in 1:3)
     check(ccall((:picgolf_get_fields_2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s.h, r, Ex, Ey))
     return (reshape(a, s.cfg.N, s.cfg.NY) for a in (r, Ex, Ey))   # column-major, same as Julia
+end
+
+# Exs / Eys / phis of src/Electrostatic2D3V.jl:171-173 (which = 0 / 1 / 2) for a Sim created with field_history=1
+function snapshots(s::Sim, which::Integer)
+    n = Ref{Int64}(0)
+    check(ccall((:picgolf_get_snapshots_2d, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ref{Int64}), s.h, which, C_NULL, 0, n))
+    F = zeros(s.cfg.N, s.cfg.NY, max(n[], 1))
+    check(ccall((:picgolf_get_snapshots_2d, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ref{Int64}), s.h, which, F, size(F, 3), n))
+    return F[:, :, 1:n[]]
 end
 
 function diagnostics(s::Sim)

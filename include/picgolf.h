@@ -96,6 +96,9 @@ typedef struct picgolf_config {
     int64_t local_first;     /* first global particle index owned (0-based); -1 = even split by rank */
     int64_t local_count;     /* particles owned; -1 = even split by rank */
     double mass_ratio;       /* 1D2V2S: M, mass of a species-2 particle in units of species 1 (NGP1D2V2S.jl:13 M=8) */
+    int32_t field_history;   /* 2D3V: 1 = keep the snapshots Exs, Eys, phis [NX, NY, T] of every recorded step on the device
+                              * (Electrostatic2D3V.jl:171-173); read them with picgolf_get_snapshots_2d */
+    int32_t reserved2_;
 } picgolf_config;
 
 typedef struct picgolf_handle_s *picgolf_handle;
@@ -184,6 +187,11 @@ int picgolf_get_diagnostics(picgolf_handle h, double *D, int64_t ld, int32_t *sw
 /* 1D2V: time-averaged field history Es[N, rows] (NGP1D2V.jl:57,64: Es[:,ti] .+= E; Es ./= T/TO), column-major with
  * leading dimension N; cols_out = windows started so far.  Window length = diag_every steps. */
 int picgolf_get_field_history(picgolf_handle h, double *Es, int64_t max_cols, int64_t *cols_out);
+/* 2D3V with field_history = 1: the snapshots of Electrostatic2D3V.jl:171-173, one NX x NY slice per recorded step (every
+ * diag_every = NS steps): which = 0 Exs (real.(Ex)), 1 Eys, 2 phis (real.(pifft * phi): phi is the spectrum of the charge density
+ * with phi[1,1] = 0, so this is rho - mean(rho)).  out is NX x NY x slices column-major, ready for the omega-k maps of lines 219-233
+ * (picgolf_stage_wk_spectrum, picgolf_es.h). */
+int picgolf_get_snapshots_2d(picgolf_handle h, int which, double *out, int64_t max_slices, int64_t *slices_out);
 /* Raw per-step sums (column-major, ld rows): 1D: sum(E.^2), sum(v.^2), sum(v), sweeps;
  * 2D: sum(Ex^2+Ey^2), sum(vx^2+vy^2), sum(vx), sum(vy).  Lets the driver form any K it wants. */
 int picgolf_get_raw_diagnostics(picgolf_handle h, double *raw, int64_t ld, int64_t *rows_out);

@@ -71,6 +71,7 @@ class Config(C.Structure):
         ("deterministic", C.c_int32), ("sort_every", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved_", C.c_int32),
         ("local_first", C.c_int64), ("local_count", C.c_int64), ("mass_ratio", C.c_double),
+        ("field_history", C.c_int32), ("reserved2_", C.c_int32),
     ]
 
 
@@ -104,6 +105,7 @@ _SIGNATURES = {
     "picgolf_set_particles_1d2v": [_vp, _dp, _dp, _dp, _i64],
     "picgolf_get_particles_1d2v": [_vp, _vp, _vp, _vp, _i64],
     "picgolf_get_field_history": [_vp, _vp, _i64, C.POINTER(_i64)],
+    "picgolf_get_snapshots_2d": [_vp, _int, _vp, _i64, C.POINTER(_i64)],
     "picgolf_init_quiet": [_vp],
     "picgolf_init_synthetic": [_vp, C.c_uint64, _d],
     "picgolf_get_particles": [_vp, _vp, _vp, _i64],
@@ -332,6 +334,15 @@ class PIC:
         _check(self._lib.picgolf_get_field_history(self._h, _out_ptr(Es), Es.shape[1], C.byref(cols)))
         return Es[:, : cols.value]
 
+    def snapshots(self, which: str):
+        """2D3V created with field_history=1: Exs / Eys / phis of src/Electrostatic2D3V.jl:171-173 as (NX, NY, slices), Fortran order."""
+        w = {"Ex": 0, "Exs": 0, "Ey": 1, "Eys": 1, "phi": 2, "phis": 2}[which]
+        n = _i64()
+        _check(self._lib.picgolf_get_snapshots_2d(self._h, w, None, 0, C.byref(n)))
+        out = np.zeros(self.ncell * max(n.value, 1))
+        _check(self._lib.picgolf_get_snapshots_2d(self._h, w, _out_ptr(out), max(n.value, 1), C.byref(n)))
+        return out[: self.ncell * n.value].reshape((self.cfg.N, self.cfg.NY, n.value), order="F")
+
     def raw_diagnostics(self):
         rows = _i64()
         _check(self._lib.picgolf_get_raw_diagnostics(self._h, None, 0, C.byref(rows)))
@@ -531,7 +542,8 @@ def ngp_1d2v_2s(N=256, P=None, T=2 ** 16, TO=None, M=8.0, n0=4 * math.pi ** 2, r
 def electrostatic_2d3v(NX=128, NY=None, P=None, T=2 ** 13, NS=2, n0=4 * math.pi ** 2, rank=0, nranks=1, device=-1,
                        **over) -> PIC:
     """src/Electrostatic2D3V.jl:23-25  NX=NY=128;P=NX*NY*2^5;NG=sqrt(NX^2+NY^2);n0=4pi^2;vth=sqrt(n0)/NG;
-    dt=1/NG/6vth;B0=sqrt(n0)/4;NS=2;w=n0/P/(dx*dy).  T here is the number of diagnostics rows kept."""
+    dt=1/NG/6vth;B0=sqrt(n0)/4;NS=2;w=n0/P/(dx*dy).  T here is the number of diagnostics rows kept;
+    field_history=1 also keeps the Exs/Eys/phis snapshots of lines 171-173 on the device (PIC.snapshots)."""
     cfg = default_config(CIC_BORIS_2D3V)
     NY = NX if NY is None else NY
     cfg.N, cfg.NY = NX, NY

@@ -547,4 +547,23 @@ __global__ void split_E2_kernel(const double2 *E2, long long n, double *Ex, doub
     if (k < n) { double2 e = E2[k]; if (Ex) Ex[k] = e.x; if (Ey) Ey[k] = e.y; }
 }
 
+// Exs[:,:,ti] .= real.(Ex); Eys[:,:,ti] .= real.(Ey); phis[:,:,ti] .= real.(pifft * phi)      src/Electrostatic2D3V.jl:171-173.
+// phi holds the spectrum of the charge density with phi[1,1] = 0 (:143-144), so its inverse transform is rho - mean(rho);
+// one block (runs on recorded steps only, and only when the handle keeps snapshots).
+__global__ void __launch_bounds__(1024) snapshot2d_kernel(const double2 *E2, const double *rho, long long n, double *ex, double *ey, double *phi)
+{
+    __shared__ double scratch[32];
+    __shared__ double mean_s;
+    double s = 0.0;
+    for (long long k = threadIdx.x; k < n; k += blockDim.x) s += rho[k];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) mean_s = s / (double)n;
+    __syncthreads();
+    const double mean = mean_s;
+    for (long long k = threadIdx.x; k < n; k += blockDim.x) {
+        const double2 e = E2[k];
+        ex[k] = e.x; ey[k] = e.y; phi[k] = rho[k] - mean;
+    }
+}
+
 } // namespace pg

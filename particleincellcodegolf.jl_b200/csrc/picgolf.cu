@@ -162,6 +162,7 @@ struct picgolf_handle_s {
     int64_t first = 0, count = 0;
     bool is2d = false, fixedpoint = false, ngp = false, simpson = false, b1d2v = false, have_deposit = false;
     double *vy1 = nullptr, *hist = nullptr; // 1D2V: vy array, field history [N x T]
+    double *snap[3] = {nullptr, nullptr, nullptr}; // 2D3V with cfg.field_history: Exs, Eys, phis [NX*NY x T]   Electrostatic2D3V.jl:171-173
     size_t smem_b1 = 0;
     size_t smem_sp1 = 0, smem_spk = 0;
     // particles (1D: xb/vb ping-pong for the fixed point; leapfrog and 2D use index 0)
@@ -363,7 +364,7 @@ static int destroy_impl(picgolf_handle h)
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
-                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg};
+                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2]};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -533,6 +534,11 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         PG_CUDA(cudaMemset(h->rho_fx, 0, h->ncell * sizeof(unsigned long long)));
         PG_CUDA(cudaMemset(h->rho_last, 0, h->ncell * sizeof(double)));
         PG_CUDA(cudaMemset(h->E2, 0, h->ncell * sizeof(double2)));
+        if (c.field_history)
+            for (int w = 0; w < 3; ++w) {
+                PG_TRY(dalloc(&h->snap[w], (size_t)h->ncell * h->T));
+                PG_CUDA(cudaMemset(h->snap[w], 0, (size_t)h->ncell * h->T * sizeof(double)));
+            }
         PG_TRY(make_twiddles(&h->tw, NX)); PG_TRY(make_twiddles(&h->twy, NY));
         PG_TRY(set_smem(solve2d_rows_fwd, (size_t)2 * ROWS_PER_BLOCK * NX * 8));
         PG_TRY(set_smem(solve2d_rows_inv, (size_t)(2 * ROWS_PER_BLOCK * NX + 32) * 8));
@@ -648,6 +654,8 @@ static int reset_run_state(picgolf_handle h)
     h->slow_pending = false; h->steps_at_probe = 0; h->steps_at_probe_prev_steps = 0; h->force_sort = false; h->poly_quiet = false; h->probe_have_prev = false;
     for (auto &ps : h->probe_step) ps = -1;
     if (h->hist) PG_CUDA(cudaMemset(h->hist, 0, (size_t)h->ncell * h->T * sizeof(double)));
+    for (int w = 0; w < 3; ++w)
+        if (h->snap[w]) PG_CUDA(cudaMemset(h->snap[w], 0, (size_t)h->ncell * h->T * sizeof(double)));
     return 0;
 }
 
@@ -1248,6 +1256,14 @@ static int step_2d3v(picgolf_handle h)
     PG_TRY(allreduce_grid(h));
     PG_TRY(launch_solve2d(h));
     bool record = ((h->steps + 1) % c.diag_every) == 0; // if t % NS == 0   :164
+    if (record && h->snap[0]) { // Exs[:,:,ti] .= real.(Ex); Eys ...; phis ...   :171-173, ti = t / NS
+        const int64_t ti = (h->steps + 1) / c.diag_every - 1;
+        if (ti < h->T) {
+            const size_t off = (size_t)ti * h->ncell;
+            snapshot2d_kernel<<<1, 1024, 0, h->stream>>>(h->E2, h->rho_last, h->ncell, h->snap[0] + off, h->snap[1] + off, h->snap[2] + off);
+            h->launches++;
+        }
+    }
     PG_TRY(launch_step_end(h, record));
     h->since_sort++;
     return 0;
@@ -1446,6 +1462,23 @@ PG_API int picgolf_get_field_history(picgolf_handle h, double *Es, int64_t max_c
         if (max_cols < cols) return fail(PICGOLF_ERR_ARG, "max_cols %lld < %lld", (long long)max_cols, (long long)cols);
         PG_CUDA(cudaMemcpy(Es, h->hist, (size_t)cols * c.N * sizeof(double), cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i < cols * c.N; ++i) Es[i] /= (double)c.diag_every; // Es ./= T/TO
+    }
+    return 0;
+}
+
+PG_API int picgolf_get_snapshots_2d(picgolf_handle h, int which, double *out, int64_t max_slices, int64_t *slices_out)
+{
+    if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
+    if (!h->is2d) return fail(PICGOLF_ERR_ARG, "handle is not a 2D3V scheme");
+    if (which < 0 || which > 2) return fail(PICGOLF_ERR_ARG, "which must be 0 (Exs), 1 (Eys) or 2 (phis)");
+    if (!h->snap[0]) return fail(PICGOLF_ERR_STATE, "the handle was created with field_history = 0");
+    PG_TRY(use_device(h));
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t slices = std::min<int64_t>(h->T, h->steps / h->cfg.diag_every);
+    if (slices_out) *slices_out = slices;
+    if (out) {
+        if (max_slices < slices) return fail(PICGOLF_ERR_ARG, "max_slices %lld < %lld", (long long)max_slices, (long long)slices);
+        PG_CUDA(cudaMemcpy(out, h->snap[which], (size_t)slices * h->ncell * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return 0;
 }

@@ -272,6 +272,34 @@ def test_spectrum_of_the_stored_history(es):
         assert relnorm(sim.spectrum(name, axis=0, mode=0), sum(np.abs(np.fft.fft2(H[:, i, :])) for i in range(8))) < 1e-10
 
 
+def test_2d3v_snapshots_on_device(pg, es):
+    """src/Electrostatic2D3V.jl:171-173: Exs, Eys, phis of every NS-th step kept on the device (field_history=1), and their
+    omega-k map (lines 219-233) from the same library."""
+    g = golden("c5_2d3v")
+    NX, NY = int(g["NX"]), int(g["NY"])
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=int(g["P"]), T=8, NS=2, field_history=1)
+    sim.set_particles(g["x0"], g["vx0"], y=g["y0"], vy=g["vy0"], vz=g["vz0"])
+    sim.step(3)
+    assert sim.snapshots("Exs").shape == (NX, NY, 1)  # t = 2 only
+    sim.step(1)
+    Exs, Eys, phis = sim.snapshots("Exs"), sim.snapshots("Eys"), sim.snapshots("phis")
+    assert Exs.shape == (NX, NY, 2)
+    for ti, t in enumerate((1, 3)):  # Julia t = 2, 4
+        assert relnorm(Exs[:, :, ti].ravel(order="F"), g["Ex"][t]) < 1e-11 and relnorm(Eys[:, :, ti].ravel(order="F"), g["Ey"][t]) < 1e-11
+        rk = np.fft.fft2(g["rho"][t].reshape(NY, NX).T)
+        rk[0, 0] = 0  # phi[1, 1] = 0   :144
+        assert relnorm(phis[:, :, ti], np.real(np.fft.ifft2(rk))) < 1e-11
+    K, _ = sim.diagnostics()
+    assert K.shape == (2, 5) and relnorm(K[:, :3], g["K"][[1, 3], :3]) < 1e-10
+    plain = pg.electrostatic_2d3v(NX=NX, NY=NY, P=int(g["P"]), T=8, NS=2)
+    with pytest.raises(pg.PicGolfError):
+        plain.snapshots("Exs")  # not kept unless asked for
+    # the omega-k map of the snapshots: needs power-of-two extents -> repeat the two slices to 4
+    F = np.concatenate([Exs, Exs], axis=2)
+    want = sum(np.abs(np.fft.fft2(F[:, i, :])) for i in range(NY))  # sum(i -> abs.(fft(F[:, i, :])), 1:size(F, 2))   :219
+    assert relnorm(es.wk_spectrum(F, axis=0, mode=0), want) < 1e-10
+
+
 def test_argument_errors(es, pg):
     f = es.ElectrostaticField(16, 16, 1.0, 1.0, dt=0.01)
     d = es.ElectrostaticDiagnostics(16, 16, 4, 1)
