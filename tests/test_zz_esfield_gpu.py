@@ -202,6 +202,32 @@ def test_three_species_and_reproducible_charge(es, oracle):
     assert np.array_equal(a["rho"], b["rho"]) and np.array_equal(a["Ex"], b["Ex"])  # integer charge grid: order-free
 
 
+def test_conservation_at_size(es):
+    """Size-independent properties at 2 x 2^23 particles (128^2 grid, B-spline 2, tile-sorted by default at this size):
+    total charge, momentum without a magnetic field, window misses."""
+    NX = NY = 128
+    P = 1 << 23
+    n0 = 4 * math.pi ** 2
+    dl = 1.0 / NX
+    vth = dl * math.sqrt(n0)
+    plasma = [es.Species(P, vth, n0, es.BSplineWeighting(2), Lx=1.0, Ly=1.0, charge=-1, mass=1),
+              es.Species(P, vth / 4, 2 * n0, es.BSplineWeighting(2), Lx=1.0, Ly=1.0, charge=1, mass=16)]
+    sim = es.Simulation(plasma, es.ElectrostaticField(NX, NY, 1.0, 1.0, dt=dl / (6 * vth), accumulate=False),
+                        es.ElectrostaticDiagnostics(NX, NY, 12, 1, 4))
+    sim.loop(12)
+    rho = sim.fields()["rho"]
+    dV = dl * dl
+    q = [sp.charge * sp.weight * sp.P for sp in plasma]  # -n0 and +2 n0: net charge n0
+    assert abs(rho.sum() * dV - sum(q)) < 1e-12 * sum(abs(v) for v in q)
+    sc = sim.scalars()
+    p, c = sc["particlemomentum"], sc["characteristicmomentum"]
+    assert np.abs(p - p[0]).max() < 1e-11 * c.max()  # same shape for gather and deposit + spectral solve: momentum is conserved
+    tot = sc["kineticenergy"] + sc["fieldenergy"]
+    assert abs(tot[-1] / tot[0] - 1) < 0.05
+    sorts, slow = sim.sort_stats()
+    assert sorts == 2 and slow < 1e-4 * 2 * P * 12
+
+
 def test_species_init_is_the_reference_halton_start(es, oracle):
     P, vth, n0, Lx, Ly = 4096, 0.013, 4 * math.pi ** 2, 2.0, 0.5
     sim = es.Simulation([es.Species(P, vth, n0, es.BSplineWeighting(2), Lx=Lx, Ly=Ly)], es.ElectrostaticField(16, 16, Lx, Ly, dt=0.01),
