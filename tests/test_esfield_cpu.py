@@ -120,6 +120,7 @@ def test_single_mode_solve_with_box_lengths(oracle):
     ii, jj = np.meshgrid(np.arange(1, NX + 1), np.arange(1, NY + 1), indexing="ij")
     xc, yc = (ii - 0.5) * Lx / NX, (jj - 0.5) * Ly / NY
     k = 2 * math.pi * m / Lx
+    cnt = (8 + np.rint(4 * np.cos(k * xc))).astype(int)  # that many NGP particles on every cell centre
     x = np.repeat(xc.ravel(order="F"), cnt.ravel(order="F"))
     y = np.repeat(yc.ravel(order="F"), cnt.ravel(order="F"))
     sp = dict(x=x, y=y, vx=np.zeros(x.size), vy=np.zeros(x.size), vz=np.zeros(x.size), charge=1.0, mass=1.0, weight=1.0, shape=0)
