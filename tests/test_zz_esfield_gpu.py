@@ -4,6 +4,7 @@ Bars: shape fractions, Boris, xyv round trip, repeated runs: bit-exact; rho, E, 
 |d| <= 1e-11 max|.| (fixed-point charge in a different summation order than the reference's thread grids); scalars 1e-11;
 spectra 1e-10 against numpy's FFT."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -164,6 +165,16 @@ def test_tiled_path_at_size(es, shape):
         assert relnorm(y, x) < TOL  # same particle order as the caller's
     assert relnorm(sb["kineticenergy"], sa["kineticenergy"]) < TOL and relnorm(sb["fieldenergy"], sa["fieldenergy"]) < TOL
     assert relnorm(hb, ha) < TOL
+
+
+@pytest.mark.skipif(not os.environ.get("PICGOLF_TEST_EXPERIMENTS"), reason="opt-in experiment (PICGOLF_ES_AGG), not part of the shipped default path")
+@pytest.mark.parametrize("shapes", [(0, 1), (12, 13), (15, 12)])
+def test_experiment_warp_aggregated_deposit(es, oracle, shapes, monkeypatch):
+    """es_particles_tiled_agg (cell order inside the tiles, match.any + redux.sync aggregation): same integer sums, same bars."""
+    monkeypatch.setenv("PICGOLF_ES_AGG", "1")
+    NX, NY, Lx, Ly = 32, 16, 1.5, 2.0
+    sp = [_random_species(shapes[0], NX, NY, Lx, Ly, -1.0, 1.0, 11), _random_species(shapes[1], NX, NY, Lx, Ly, 2.0, 7.0, 12)]
+    _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.9, -0.4, 0.6], NT=9, ntskip=2, ngskip=4, acc=0, sort_every=3)
 
 
 def _species_n(shape, P, NX, NY, Lx, Ly, charge, mass, seed, dt):
