@@ -267,13 +267,6 @@ __global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tile
 // fraction is split into two 24-bit limbs that redux.sync sums over the group without overflow (32 x 2^24 < 2^32), and the
 // group's first lane issues the window adds.  Same integer sums as es_particles_tiled, so the parity tests apply as they are.
 // ---------------------------------------------------------------------------------------------
-__global__ void es_tile_ranges_kernel(const unsigned int *bin_start, const unsigned int *bin_end, int ntiles, int cells_per_tile,
-                                      unsigned int *tile_start, unsigned int *tile_end)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntiles) { tile_start[t] = bin_start[(size_t)t * cells_per_tile]; tile_end[t] = bin_end[(size_t)t * cells_per_tile + cells_per_tile - 1]; }
-}
-
 template <int SHAPE>
 __global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tiled_agg(ESParticleArgs a)
 {
