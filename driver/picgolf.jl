@@ -106,6 +106,29 @@ function particles(s::Sim)
     return x, v
 end
 
+# x, vx, vy of a 1D2V Sim (src/NGP1D2V.jl:30-32; the two-species scheme holds 2P particles, species 1 first)
+function particles_1d2v(s::Sim)
+    x, vx, vy = (Vector{Float64}(undef, s.count) for _ in 1:3)
+    check(ccall((:picgolf_get_particles_1d2v, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64), s.h, x, vx, vy, s.count))
+    return x, vx, vy
+end
+
+function particles_2d3v(s::Sim)
+    a = [Vector{Float64}(undef, s.count) for _ in 1:5]
+    check(ccall((:picgolf_get_particles_2d3v, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                s.h, a[1], a[2], a[3], a[4], a[5], s.count))
+    return a
+end
+
+# Es[N, TO] of src/NGP1D2V.jl:57,64 (time-averaged field of every window of T/TO steps)
+function field_history(s::Sim)
+    n = Ref{Int64}(0)
+    check(ccall((:picgolf_get_field_history, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Int64}), s.h, C_NULL, 0, n))
+    Es = zeros(s.cfg.N, max(n[], 1))
+    check(ccall((:picgolf_get_field_history, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Int64}), s.h, Es, size(Es, 2), n))
+    return Es[:, 1:n[]]
+end
+
 function fields(s::Sim)
     r, E = Vector{Float64}(undef, s.cfg.N), Vector{Float64}(undef, s.cfg.N)
     check(ccall((:picgolf_get_fields, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s.h, r, E))
@@ -132,7 +155,8 @@ function diagnostics(s::Sim)
     rows = Ref{Int64}(0)
     check(ccall((:picgolf_get_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Ref{Int64}),
                 s.h, C_NULL, 0, C_NULL, rows))
-    ncol = s.cfg.scheme == CIC_BORIS_2D3V ? 5 : 4
+    # 5 columns for the 2D3V K[ti,1:5] and for the 1D2V D[ti,1:5] (NGP1D2V.jl:59-61), 4 for the 1D1V scripts
+    ncol = s.cfg.scheme in (CIC_BORIS_2D3V, GAUSS_BORIS_1D2V, GAUSS_BORIS_1D2V2S) ? 5 : 4
     D = zeros(max(rows[], 1), ncol)                 # column-major T x ncol: the ABI's layout IS Julia's
     sw = zeros(Int32, max(rows[], 1))
     check(ccall((:picgolf_get_diagnostics, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Ref{Int64}),

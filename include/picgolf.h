@@ -118,7 +118,7 @@ int picgolf_device_count(void);
  * scheme CIC_BORIS_2D3V -> Electrostatic2D3V.jl:23-25 (NX=NY=128,P=NX*NY*2^5,T=2^13,n0=4pi^2,...)
  * scheme GAUSS_SIMPSON13 -> GaussianFixedPointQuietSimpson13.jl:1-6 (same literals as the quiet fixed point)
  * scheme GAUSS_BORIS_1D2V -> NGP1D2V.jl:22-23 (N=512,P=15N,T=TO=2^14/16 rows,n0=4pi^2,vth,dt,B0,w=n0/P, diag_every=16)
- * scheme GAUSS_BORIS_1D2V2S -> NGP1D2V2S.jl:13-14 (N=256,P=8N per species,M=8,T=TO=32 rows,diag_every=2^16/32,
+ * scheme GAUSS_BORIS_1D2V2S -> NGP1D2V2S.jl:13-14 (N=256,P=8N per species,M=8,T=TO=2^16/32=2048 rows,diag_every=T/TO=32,
  *        vth=sqrt(n0)/N/8,dt=1/N/16vth,B0=sqrt(n0)/8,w=n0/2P) */
 int picgolf_config_default(picgolf_config *cfg, int scheme, int quiet);
 

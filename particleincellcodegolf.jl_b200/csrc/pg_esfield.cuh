@@ -259,144 +259,6 @@ __global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tile
 }
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENT (opt-in: PICGOLF_ES_AGG=1 at handle creation; not measured yet).  es_particles_tiled is bound
-// by the shared-memory pipe: 2 S^2 window atomics per particle plus S^2 16-byte gathers at random window positions.  This
-// variant expects the particles of a tile ordered by CELL (pg_sort.cuh mode 3), so that the 32 particles of a warp share a
-// few cells -- the gathers of a warp then hit a few addresses (broadcasts) -- and aggregates the deposit inside the warp
-// before it touches the window: lanes whose new stencil has the same origin are grouped with match.any, every fixed-point
-// fraction is split into two 24-bit limbs that redux.sync sums over the group without overflow (32 x 2^24 < 2^32), and the
-// group's first lane issues the window adds.  Same integer sums as es_particles_tiled, so the parity tests apply as they are.
-// ---------------------------------------------------------------------------------------------
-template <int SHAPE>
-__global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tiled_agg(ESParticleArgs a)
-{
-    constexpr int S = es::support(SHAPE);
-    __shared__ double2 Ew[T2_WS * T2_WS];
-    __shared__ unsigned int rlo[T2_WS * T2_WS], rhi[T2_WS * T2_WS];
-    __shared__ double scratch[32];
-    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
-    const int lane = threadIdx.x & 31;
-    double sum[ES_NSUM];
-#pragma unroll
-    for (int k = 0; k < ES_NSUM; ++k) sum[k] = 0.0;
-    unsigned int nslow = 0;
-    const unsigned int nitems = a.item_off[a.ntiles];
-    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int lo = 0, hi = a.ntiles;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int tile = lo;
-        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
-        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
-        const int ox = (tile % a.ntx) * T2_TS - T2_R, oy = (tile / a.ntx) * T2_TS - T2_R;
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
-            Ew[c] = a.Exy[gx + (size_t)gy * NX];
-            rlo[c] = 0u; rhi[c] = 0u;
-        }
-        __syncthreads();
-        // whole warps stay in the loop together (the *_sync intrinsics below name all 32 lanes); `live` masks the tail
-        for (long long pb = start + (threadIdx.x & ~31); pb < end; pb += blockDim.x) {
-            const long long p = pb + lane;
-            const bool live = p < end;
-            double x = 0.5 * a.Lx, y = 0.5 * a.Ly, vx = 0.0, vy = 0.0, vz = 0.0;
-            if (live) { x = ld_stream(a.x + p); y = ld_stream(a.y + p); vx = ld_stream(a.vx + p); vy = ld_stream(a.vy + p); vz = ld_stream(a.vz + p); }
-            int ix0, iy0;
-            double wx[S], wy[S];
-            es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
-            es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
-            double Exi = 0.0, Eyi = 0.0;
-            {
-                const int rx = (ix0 - 1 - ox) & mx, ry = (iy0 - 1 - oy) & my;
-                if (rx <= T2_WS - S && ry <= T2_WS - S) {
-                    const double2 *e = Ew + rx + ry * T2_WS;
-#pragma unroll
-                    for (int jj = 0; jj < S; ++jj)
-#pragma unroll
-                        for (int ii = 0; ii < S; ++ii) {
-                            const double wxy = wx[ii] * wy[jj];
-                            const double2 f = e[ii + jj * T2_WS];
-                            Exi = fma(f.x, wxy, Exi);
-                            Eyi = fma(f.y, wxy, Eyi);
-                        }
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < S; ++jj)
-#pragma unroll
-                        for (int ii = 0; ii < S; ++ii) {
-                            const double wxy = wx[ii] * wy[jj];
-                            const double2 f = __ldg(&a.Exy[es_cell0(ix0 + ii, NX) + (size_t)es_cell0(iy0 + jj, NY) * NX]);
-                            Exi = fma(f.x, wxy, Exi);
-                            Eyi = fma(f.y, wxy, Eyi);
-                        }
-                }
-            }
-            const double vxi = vx, vyi = vy;
-            es::boris_push(a.boris, vx, vy, vz, Exi, Eyi, a.q_m);
-            x = es::unimod(x + (vxi + vx) / 2 * a.dt, a.Lx);
-            y = es::unimod(y + (vyi + vy) / 2 * a.dt, a.Ly);
-            es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
-            es::shape_weights<SHAPE>(y, a.NY_Ly, iy0, wy);
-            const int rx = (ix0 - 1 - ox) & mx, ry = (iy0 - 1 - oy) & my;
-            const bool inwin = live && rx <= T2_WS - S && ry <= T2_WS - S;
-            const int key = inwin ? (rx | (ry << 8)) : (-1 - lane);       // lanes outside the window: groups of one
-            const unsigned int grp = __match_any_sync(0xffffffffu, key);
-            if (inwin) {                                                   // every lane of a group takes this branch together
-                const int leader = __ffs(grp) - 1, r0 = rx + ry * T2_WS;
-#pragma unroll
-                for (int jj = 0; jj < S; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii < S; ++ii) {
-                        long long vs = __double2ll_rn(wx[ii] * wy[jj] * a.fxw_scale);
-                        if (vs < 0) vs = 0; // fractions of -1e-17 (cancellation in the reference's polynomials) round to 0 anyway
-                        const unsigned int slo = __reduce_add_sync(grp, (unsigned int)(vs & 0xFFFFFF));
-                        const unsigned int shi = __reduce_add_sync(grp, (unsigned int)(vs >> 24));
-                        if (lane == leader) {
-                            const fx_t v = ((fx_t)shi << 24) + (fx_t)slo;
-                            const unsigned int vlo = (unsigned int)v;
-                            const unsigned int old = atomicAdd(&rlo[r0 + ii + jj * T2_WS], vlo);
-                            const unsigned int carry = (old + vlo) < old ? 1u : 0u;
-                            const unsigned int vhi = (unsigned int)(v >> 32) + carry;
-                            if (vhi) atomicAdd(&rhi[r0 + ii + jj * T2_WS], vhi);
-                        }
-                    }
-            } else if (live) {
-                ++nslow;
-#pragma unroll
-                for (int jj = 0; jj < S; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii < S; ++ii)
-                        atomicAdd(&a.rho[es_cell0(ix0 + ii, NX) + (size_t)es_cell0(iy0 + jj, NY) * NX], to_fx(wx[ii] * wy[jj] * a.dep, a.fx_scale));
-            }
-            if (live) {
-                st_stream(a.x + p, x); st_stream(a.y + p, y);
-                st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
-                sum[0] += vx * vx + vy * vy + vz * vz;
-                sum[1] += vx; sum[2] += vy; sum[3] += vz;
-                sum[4] += fabs(vx); sum[5] += fabs(vy); sum[6] += fabs(vz);
-            }
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            const long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
-            if (v) {
-                int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
-                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)__double2ll_rn((double)v * a.wscale));
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int k = 0; k < ES_NSUM; ++k) {
-        const double s = block_sum(sum[k], scratch);
-        if (threadIdx.x == 0) a.partials[ES_NSUM * blockIdx.x + k] = s;
-    }
-    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Field solve (:562-579): pfft! * phi; phi[1,1] = 0; tmp = phi * im_k^-2; Ex = tmp*kx[i]; Ey = tmp*ky[j]; pifft! both,
 // with FFTHelper's kx = 2pi/Lx * vcat(0:NX/2-1, -NX/2:-1) (:254-258).  Pass A is solve2d_rows_fwd (pg_fft.cuh); these
 // are pass B and C of the same three-kernel transform with the box lengths, and with what update!/diagnose! need.

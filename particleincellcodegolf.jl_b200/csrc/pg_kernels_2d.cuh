@@ -258,141 +258,6 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENT (opt-in: PICGOLF_2D_AGG=1 at handle creation; never measured): particles_2d3v_tiled is bound
-// by the shared-memory pipe (4 sixteen-byte gathers + 8 window atomics per particle at random window positions).  This variant expects
-// the particles of a tile ordered by CELL (pg_sort.cuh mode 3) -- the gathers of a warp then hit a few addresses -- and aggregates the
-// deposit inside the warp: lanes whose new CIC corner is the same cell are grouped with match.any, every fixed-point weight is split
-// into two 24-bit limbs that redux.sync sums over the group (32 x 2^24 < 2^32), and the group's first lane issues the window adds.
-// The integer sums are those of particles_2d3v_tiled.
-// ------------------------------------------------------------------------------------------------
-__global__ void tile_ranges_kernel(const unsigned int *bin_start, const unsigned int *bin_end, int ntiles, int cells_per_tile,
-                                   unsigned int *tile_start, unsigned int *tile_end)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntiles) { tile_start[t] = bin_start[(size_t)t * cells_per_tile]; tile_end[t] = bin_end[(size_t)t * cells_per_tile + cells_per_tile - 1]; }
-}
-
-__global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled_agg(P2DArgs a)
-{
-    __shared__ double2 Ew[T2_WS * T2_WS];
-    __shared__ unsigned int rlo[T2_WS * T2_WS], rhi[T2_WS * T2_WS];
-    __shared__ double scratch[32];
-    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
-    const int lane = threadIdx.x & 31;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    unsigned int nslow = 0;
-    const unsigned int nitems = a.item_off[a.ntiles];
-    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int lo = 0, hi = a.ntiles;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int tile = lo;
-        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
-        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
-        const int ox = (tile % a.ntx) * T2_TS - T2_R, oy = (tile / a.ntx) * T2_TS - T2_R;
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
-            Ew[c] = a.E2[gx + (size_t)gy * NX];
-            rlo[c] = 0u; rhi[c] = 0u;
-        }
-        __syncthreads();
-        // whole warps stay in the loop together (the *_sync intrinsics name all 32 lanes); `live` masks the tail
-        for (long long pb = start + (threadIdx.x & ~31); pb < end; pb += blockDim.x) {
-            const long long p = pb + lane;
-            const bool live = p < end;
-            double x = 0.5, y = 0.5, vx = 0.0, vy = 0.0, vz = 0.0;
-            if (live) { x = ld_stream(a.x + p); y = ld_stream(a.y + p); vx = ld_stream(a.vx + p); vy = ld_stream(a.vy + p); vz = ld_stream(a.vz + p); }
-            Cic4 c;
-            cic4(x, y, NX, NY, c);
-            double ex = 0.0, ey = 0.0;
-            {
-                const int rx = (c.ix[0] - 1 - ox) & mx, ry = (c.iy[0] - 1 - oy) & my;
-                if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
-                    const double2 *e = Ew + rx + ry * T2_WS;
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            double wxy = c.wx[ii] * c.wy[jj];
-                            double2 f = e[ii + jj * T2_WS];
-                            ex = fma(f.x, wxy, ex);
-                            ey = fma(f.y, wxy, ey);
-                        }
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            double wxy = c.wx[ii] * c.wy[jj];
-                            double2 f = __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
-                            ex = fma(f.x, wxy, ex);
-                            ey = fma(f.y, wxy, ey);
-                        }
-                }
-            }
-            boris(vx, vy, vz, ex, ey, a.dt, a.t1, a.tscale);
-            x = unimod(x + vx * a.dt, 1.0);
-            y = unimod(y + vy * a.dt, 1.0);
-            cic4(x, y, NX, NY, c);
-            const int rx = (c.ix[0] - 1 - ox) & mx, ry = (c.iy[0] - 1 - oy) & my;
-            const bool inwin = live && rx <= T2_WS - 2 && ry <= T2_WS - 2;
-            const int key = inwin ? (rx | (ry << 8)) : (-1 - lane); // lanes outside the window: groups of one
-            const unsigned int grp = __match_any_sync(0xffffffffu, key);
-            if (inwin) { // every lane of a group takes this branch together
-                const int leader = __ffs(grp) - 1, r0 = rx + ry * T2_WS;
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii) {
-                        const fx_t vs = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale); // CIC weights are >= 0 and <= 1: vs <= 2^48
-                        const unsigned int slo = __reduce_add_sync(grp, (unsigned int)(vs & 0xFFFFFF));
-                        const unsigned int shi = __reduce_add_sync(grp, (unsigned int)(vs >> 24));
-                        if (lane == leader) {
-                            const fx_t v = ((fx_t)shi << 24) + (fx_t)slo;
-                            const unsigned int vlo = (unsigned int)v;
-                            const unsigned int old = atomicAdd(&rlo[r0 + ii + jj * T2_WS], vlo);
-                            const unsigned int carry = (old + vlo) < old ? 1u : 0u;
-                            const unsigned int vhi = (unsigned int)(v >> 32) + carry;
-                            if (vhi) atomicAdd(&rhi[r0 + ii + jj * T2_WS], vhi);
-                        }
-                    }
-            } else if (live) {
-                ++nslow;
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii)
-                        atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
-            }
-            if (live) {
-                st_stream(a.x + p, x); st_stream(a.y + p, y);
-                st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
-                s0 += vx * vx + vy * vy; s1 += vx; s2 += vy;
-            }
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
-            if (v) {
-                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift;
-                int gx = (ox + (c & (T2_WS - 1))) & mx, gy = (oy + (c >> 5)) & my;
-                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)v);
-            }
-        }
-        __syncthreads();
-    }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
-    s2 = block_sum(s2, scratch);
-    if (threadIdx.x == 0) {
-        a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
-    }
-    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
-}
-
-// ------------------------------------------------------------------------------------------------
 // TMA-staged variant of the tiled kernel (opt-in experiment, PICGOLF_2D_TMA=1: measured slower than
 // particles_2d3v_tiled on B200 because the SM-side work, not the particle streams, limits it; see picgolf.cu).  Same tiles, same windows and
 // the same per-particle arithmetic, but the five particle streams are moved by the copy engine: one persistent

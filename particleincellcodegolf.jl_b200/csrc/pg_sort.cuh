@@ -28,7 +28,7 @@ struct SortArgs {
     unsigned int *bin_start;  // [nbins] start offsets (kept for the tiled 2D kernel); may be NULL
     long long P;
     int narr, nbins;
-    int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1]) on the unit box;  2: the same on an Lx x Ly box;  3: (tile, cell within the tile) on an Lx x Ly box
+    int mode;   // 0: 1D key = cell of in[0];  1: 2D key = tile of (in[0], in[1]) on the unit box;  2: the same on an Lx x Ly box
     int N, NY;  // grid
     int tshift; // 2D: log2(tile edge in cells)
     int vsplit; // 1D: 1 -> key = 2*cell + (v >= 0): each beam keeps its own bins, so a bin drifts as a whole (pg_kernels_poly.cuh)
@@ -47,13 +47,10 @@ __device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
         const int sub = min((1 << a.sublg) - 1, max(0, (int)((d + 0.5) * (double)(1 << a.sublg))));
         return (((c & (a.N - 1)) * 2 + (a.in[1][j] >= 0.0 ? 1 : 0)) << a.sublg) + sub;
     }
-    if (a.mode >= 2) {
+    if (a.mode == 2) {
         int ex = ((int)ceil(a.in[0][j] * a.kx) - 1) & (a.N - 1);
         int ey = ((int)ceil(a.in[1][j] * a.ky) - 1) & (a.NY - 1);
-        const int tile = (ey >> a.tshift) * max(1, a.N >> a.tshift) + (ex >> a.tshift);
-        if (a.mode == 2) return tile;
-        const int m = (1 << a.tshift) - 1; // mode 3: particles of a tile stay contiguous and are ordered by cell inside it
-        return (tile << (2 * a.tshift)) + ((ey & m) << a.tshift) + (ex & m);
+        return (ey >> a.tshift) * max(1, a.N >> a.tshift) + (ex >> a.tshift);
     }
     int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
     int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);

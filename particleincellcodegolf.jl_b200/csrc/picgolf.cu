@@ -189,9 +189,6 @@ struct picgolf_handle_s {
     int pass_blocks = 0; // blocks of the particle pass that wrote this step's partial sums (0: nblocks)
     size_t smem_pass = 0, smem_lf = 0;
     bool ngp_tma = false, tma2d = false;
-    bool agg2d = false;  // PICGOLF_2D_AGG=1: cell order inside the tiles + warp-aggregated deposit (particles_2d3v_tiled_agg, experiment)
-    int ncellbins = 0;
-    unsigned int *tile_lo = nullptr, *tile_hi = nullptr;
     bool have_particles = false;
     int64_t steps = 0, launches = 0;
     nccl::Comm comm = nullptr;
@@ -326,7 +323,7 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
         break;
     }
     case PICGOLF_GAUSS_BORIS_1D2V2S: { // NGP1D2V2S.jl:13-14
-        c->N = 256; c->P = 8 * c->N; c->T = 32; c->diag_every = (1 << 16) / 32; c->half_width = 7; c->mass_ratio = 8;
+        c->N = 256; c->P = 8 * c->N; c->T = (1 << 16) / 32; c->diag_every = 32; c->half_width = 7; c->mass_ratio = 8; // T=2^16; TO=T/32 rows of T/TO=32 steps
         double n0 = 4 * pi * pi, vth = sqrt(n0) / (double)c->N / 8;
         c->W = n0; c->dt = 1 / (double)c->N / (16 * vth); c->B0 = sqrt(n0) / 8; c->w = n0 / (double)(2 * c->P);
         break;
@@ -367,8 +364,7 @@ static int destroy_impl(picgolf_handle h)
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
-                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2],
-                    h->tile_lo, h->tile_hi};
+                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2]};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -566,18 +562,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             h->sort_auto = c.sort_every <= 0;
             for (int q = 0; q < 5; ++q) PG_TRY(dalloc(&h->p2[1][q], n));
             PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
-            h->agg2d = getenv("PICGOLF_2D_AGG") != nullptr;
-            h->ncellbins = h->agg2d ? h->nbins << (2 * T2_SHIFT) : h->nbins; // agg: one bin per (tile, cell of the tile)
-            PG_TRY(dalloc(&h->bin_count, h->ncellbins)); PG_TRY(dalloc(&h->bin_cursor, h->ncellbins));
-            PG_TRY(dalloc(&h->bin_start, h->ncellbins)); PG_TRY(dalloc(&h->item_off, h->nbins + 1));
-            PG_CUDA(cudaMemset(h->bin_count, 0, h->ncellbins * sizeof(unsigned int)));
-            if (h->agg2d) { PG_TRY(dalloc(&h->tile_lo, h->nbins)); PG_TRY(dalloc(&h->tile_hi, h->nbins)); }
+            PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
+            PG_TRY(dalloc(&h->bin_start, h->nbins)); PG_TRY(dalloc(&h->item_off, h->nbins + 1));
+            PG_CUDA(cudaMemset(h->bin_count, 0, h->nbins * sizeof(unsigned int)));
             PG_TRY(dalloc(&h->slow_count, 1));
             PG_CUDA(cudaMemset(h->slow_count, 0, sizeof(unsigned long long)));
-            if (!h->agg2d) {
-                PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
-                PG_TRY(set_smem(sort_scatter_kernel<5>, (size_t)h->nbins * 8));
-            }
+            PG_TRY(set_smem(sort_hist_kernel, (size_t)h->nbins * 4));
+            PG_TRY(set_smem(sort_scatter_kernel<5>, (size_t)h->nbins * 8));
             int64_t items = h->count / T2_CHUNK + h->nbins;
             PG_TRY(occupancy_blocks(particles_2d3v_tiled, PG_THREADS, 0, h->sms, items * PG_THREADS, &h->nblocks_sorted));
             // The TMA-staged variant is correct but measured slower on B200 (6.15 ms vs 4.85 ms per pass at 2^28
@@ -1224,18 +1215,6 @@ static int sort_particles_2d(picgolf_handle h)
     a.pid_out = h->pid[1 - h->pidpar];
     a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor; a.bin_start = h->bin_start;
     a.P = h->count; a.narr = 5; a.nbins = h->nbins; a.mode = 1; a.N = (int)h->cfg.N; a.NY = (int)h->cfg.NY; a.tshift = T2_SHIFT;
-    if (h->agg2d) { // experiment: (tile, cell) keys on the unit box (mode 3 with kx = NX, ky = NY is mode 1's arithmetic), warp-aggregated counting sort
-        a.nbins = h->ncellbins; a.mode = 3; a.kx = (double)a.N; a.ky = (double)a.NY;
-        sort_hist_match_kernel<<<h->sms * 8, SORT_THREADS, 0, h->stream>>>(a);
-        sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->bin_start, h->ncellbins);
-        sort_scatter_match_kernel<5><<<h->sms * 8, SORT_THREADS, 0, h->stream>>>(a);
-        tile_ranges_kernel<<<(h->nbins + 255) / 256, 256, 0, h->stream>>>(h->bin_start, h->bin_cursor, h->nbins, 1 << (2 * T2_SHIFT), h->tile_lo, h->tile_hi);
-        tile_worklist_kernel<<<1, 1024, 0, h->stream>>>(h->tile_lo, h->tile_hi, h->item_off, h->nbins);
-        h->launches += 5;
-        h->timer.end(sp, h->stream);
-        h->par ^= 1; h->pidpar ^= 1; h->pid_valid = true; h->since_sort = 0; h->sorts++;
-        return 0;
-    }
     const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
     int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
@@ -1267,10 +1246,7 @@ static int step_2d3v(picgolf_handle h)
     if (h->use_sorted_now) {
         a.tile_start = h->bin_start; a.tile_end = h->bin_cursor; a.item_off = h->item_off; a.slow_count = h->slow_count;
         a.fxw_scale = h->fxw_scale; a.fx_shift = h->fx_shift; a.ntx = std::max(1, a.NX >> T2_SHIFT); a.ntiles = h->nbins;
-        if (h->agg2d) {
-            a.tile_start = h->tile_lo; a.tile_end = h->tile_hi;
-            particles_2d3v_tiled_agg<<<h->nblocks_sorted, PG_THREADS, 0, h->stream>>>(a);
-        } else if (h->tma2d) particles_2d3v_tma<<<h->nblocks_sorted, T2_TMA_THREADS, T2_TMA_SMEM, h->stream>>>(a);
+        if (h->tma2d) particles_2d3v_tma<<<h->nblocks_sorted, T2_TMA_THREADS, T2_TMA_SMEM, h->stream>>>(a);
         else particles_2d3v_tiled<<<h->nblocks_sorted, PG_THREADS, 0, h->stream>>>(a);
     } else {
         particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);

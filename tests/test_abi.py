@@ -52,6 +52,10 @@ def test_config_struct_layout(pg):
     assert (e.N, e.NY, e.P, e.diag_every) == (128, 128, 128 * 128 * 32, 2)
     sp = pg.default_config(pg.GAUSS_SIMPSON13)  # src/GaussianFixedPointQuietSimpson13.jl:1-6
     assert (sp.N, sp.P, sp.T, sp.half_width, sp.scheme) == (64, 2048, 8192, 7, 5) and sp.rtol == 4 * np.finfo(float).eps
+    b1 = pg.default_config(pg.GAUSS_BORIS_1D2V)  # src/NGP1D2V.jl:22: T=2^14, TO=T/16 rows, windows of T/TO = 16 steps
+    assert (b1.N, b1.P, b1.T, b1.diag_every, b1.half_width) == (512, 15 * 512, 1024, 16, 7)
+    b2 = pg.default_config(pg.GAUSS_BORIS_1D2V2S)  # src/NGP1D2V2S.jl:13: T=2^16, TO=T/32 = 2048 rows, windows of T/TO = 32 steps
+    assert (b2.N, b2.P, b2.T, b2.diag_every, b2.mass_ratio) == (256, 8 * 256, 2048, 32, 8.0)
 
 
 def test_es_config_struct_layout(pg):

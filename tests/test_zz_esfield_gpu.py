@@ -167,43 +167,6 @@ def test_tiled_path_at_size(es, shape):
     assert relnorm(hb, ha) < TOL
 
 
-@pytest.mark.skipif(not os.environ.get("PICGOLF_TEST_EXPERIMENTS"), reason="opt-in experiment (PICGOLF_ES_AGG), not part of the shipped default path")
-@pytest.mark.parametrize("shapes", [(0, 1), (12, 13), (15, 12)])
-def test_experiment_warp_aggregated_deposit(es, oracle, shapes, monkeypatch):
-    """es_particles_tiled_agg (cell order inside the tiles, match.any + redux.sync aggregation): same integer sums, same bars."""
-    monkeypatch.setenv("PICGOLF_ES_AGG", "1")
-    NX, NY, Lx, Ly = 32, 16, 1.5, 2.0
-    sp = [_random_species(shapes[0], NX, NY, Lx, Ly, -1.0, 1.0, 11), _random_species(shapes[1], NX, NY, Lx, Ly, 2.0, 7.0, 12)]
-    _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.9, -0.4, 0.6], NT=9, ntskip=2, ngskip=4, acc=0, sort_every=3)
-
-
-@pytest.mark.skipif(not os.environ.get("PICGOLF_TEST_EXPERIMENTS"), reason="opt-in experiment (PICGOLF_2D_AGG), not part of the shipped default path")
-def test_experiment_warp_aggregated_deposit_config5(pg, monkeypatch):
-    """particles_2d3v_tiled_agg: golden fixture of config 5 with frequent re-sorts, then 2^20 particles against the any-order kernel."""
-    monkeypatch.setenv("PICGOLF_2D_AGG", "1")
-    g = golden("c5_2d3v")
-    NX, NY = int(g["NX"]), int(g["NY"])
-    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=int(g["P"]), T=16, NS=1, deposit_mode=pg.DEPOSIT_SORTED, sort_every=2)
-    sim.set_particles(g["x0"], g["vx0"], y=g["y0"], vy=g["vy0"], vz=g["vz0"])
-    for t in range(4):
-        sim.step(1)
-        rho, Ex, Ey = sim.fields()
-        assert relnorm(rho.reshape(-1, order="F"), g["rho"][t]) < 1e-12 and relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < 1e-11
-    for a, k in zip(sim.particles(), ("x", "y", "vx", "vy", "vz")):
-        assert relnorm(a, g[k]) < 1e-11
-    NX = NY = 128
-    P = 1 << 20
-    rng = np.random.default_rng(31)
-    sims = [pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=16, NS=1, deposit_mode=m, sort_every=5) for m in (pg.DEPOSIT_ATOMIC, pg.DEPOSIT_AUTO)]
-    st = [1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * sims[0].vth / np.sqrt(2) for _ in range(3)]
-    for s_ in sims:
-        s_.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
-        s_.step(12)
-    for a, b in zip(sims[1].particles(), sims[0].particles()):
-        assert relnorm(a, b) < 1e-10
-    assert relnorm(sims[1].fields()[0], sims[0].fields()[0]) < 1e-11
-
-
 def _species_n(shape, P, NX, NY, Lx, Ly, charge, mass, seed, dt):
     rng = np.random.default_rng(seed)
     vth = 0.3 * min(Lx / NX, Ly / NY) / dt
