@@ -28,7 +28,14 @@ struct Ctrl {
     double sp_acc[6];
     unsigned int sp_arrive, pad2_;
     unsigned long long flush_global; // multi-GPU polynomial mode: sum over the ranks of the flush counters (pg_peer.cuh)
+    unsigned long long loop_sweeps;  // sweeps executed inside the device-driven loop since the particles were set (launch accounting)
 };
+
+// Sweep index of a launch.  The fixed schedule (stage timers on, NCCL reduction) passes it as a kernel argument; inside the
+// device-driven loop (a CUDA-graph WHILE node, picgolf.cu) the same kernel nodes run every iteration, so k < 0 means "read it
+// from Ctrl": the solve of an iteration is sweep ctrl->sweeps + 1 and records it, everything after it in the iteration reads
+// ctrl->sweeps.
+__device__ __forceinline__ int sweep_index(int k, const Ctrl *c) { return k >= 0 ? k : c->sweeps; }
 
 // Batched in-place FFT on shared memory.  Element e of batch b lives at [b*bstride + e*estride].
 // tw[k] = exp(-2 pi i k / twN), k < twN/2, n divides twN.  All threads of the block participate.
@@ -191,6 +198,7 @@ struct Solve1DArgs {
     double *hist;     // 1D2V: time-averaged field history column Es[:,ti] += E (NGP1D2V.jl:57), or NULL
     PeerArgs peer;    // multi-GPU: sum the ranks' grids over peer memory here (pg_peer.cuh); nranks <= 1: rho_fx is the sum
     int flush_slot;   // NCCL path, polynomial mode: rho_fx[N] holds the all-reduced flush counter
+    cudaGraphConditionalHandle cond; // device-driven loop: handle of the WHILE node this solve sits in (0: fixed schedule)
 };
 
 // One block.  Dynamic shared memory: 2*N doubles + 32.
@@ -198,23 +206,29 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
 {
     extern __shared__ double smem[];
     double *re = smem, *im = smem + a.N, *scratch = smem + 2 * a.N;
-    if (a.fixedpoint && a.ctrl->final_k >= 0) return; // step already converged: predicated no-op
+    if (a.fixedpoint && a.ctrl->final_k >= 0) { // step already converged: predicated no-op
+        if (a.cond && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);
+        return;
+    }
     const int N = a.N;
+    const int k = a.k >= 0 ? a.k : a.ctrl->sweeps + 1; // read by every thread before thread 0 records it below
     const bool peers = a.peer.nranks > 1 && !a.rho_in;
+    unsigned long long pseq = 0ULL;
     if (peers) {
-        peer_gather_begin(a.peer);
+        pseq = peer_gather_begin(a.peer);
         if (threadIdx.x == 0) a.ctrl->flush_global = peer_flush_sum(a.peer);
     }
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double r;
         if (a.rho_in) r = a.rho_in[n];
-        else if (peers) r = (double)peer_sum(a.peer, n) * a.fx_inv * a.w; // the publish kernel cleared rho_fx
+        else if (peers) r = (double)peer_sum(a.peer, pseq, n) * a.fx_inv * a.w; // the publish kernel cleared rho_fx
         else { r = (double)(long long)a.rho_fx[n] * a.fx_inv * a.w; a.rho_fx[n] = 0ULL; }
         a.rho_last[n] = r;
         re[n] = r; im[n] = 0.0;
     }
     __syncthreads();
-    if (peers) peer_gather_end(a.peer);
+    if (peers) peer_gather_end(a.peer, pseq);
+    const bool peer_failed = peers && *a.peer.error != 0; // a peer never published (pg_peer.cuh): poison the field, end the step
     if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
     fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
@@ -235,6 +249,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     const double dN = (double)N;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double e = re[n] / dN;
+        if (peer_failed) e = __longlong_as_double(0x7ff8000000000000LL);
         double f = a.E[n];
         a.E[n] = e;
         if (a.hist) a.hist[n] += e;
@@ -252,8 +267,11 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
             double d = sqrt(d2);
             double m = fmax(sqrt(f2), sqrt(e2));
             bool conv = isfinite(d) && d <= fmax(a.atol, a.rtol * m);
-            a.ctrl->sweeps = a.k;
-            if (conv || a.k >= a.max_sweeps) a.ctrl->final_k = a.k;
+            const bool last = conv || k >= a.max_sweeps || peer_failed;
+            a.ctrl->sweeps = k;
+            if (a.cond) a.ctrl->loop_sweeps += 1ULL;
+            if (last) a.ctrl->final_k = k;
+            if (a.cond) cudaGraphSetConditional(a.cond, last ? 0u : 1u); // the rest of this iteration still runs (pass k finalises)
         }
     }
 }

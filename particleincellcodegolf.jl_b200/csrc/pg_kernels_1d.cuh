@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(PG_THREADS) fp_pass_atomic(FPArgs a)
     extern __shared__ double smem[];
     double *Es = smem, *scratch = smem + 2 * a.N;
     fx_t *rs = reinterpret_cast<fx_t *>(smem + a.N);
-    const int fk = a.ctrl->final_k;
-    if (!FIRST && fk >= 0 && a.k > fk) return;
-    const bool final = !FIRST && fk == a.k;
-    const bool v0_is_V = FIRST || a.k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
+    const int fk = a.ctrl->final_k, k = FIRST ? 0 : sweep_index(a.k, a.ctrl);
+    if (!FIRST && fk >= 0 && k > fk) return;
+    const bool final = !FIRST && fk == k;
+    const bool v0_is_V = FIRST || k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
     const int N = a.N, Nmask = N - 1;
     const double dN = (double)N, dt = a.dt;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(PG_THREADS, PG_SORTED_MINBLOCKS) fp_pass_sorte
 {
     extern __shared__ double smem[];
     __shared__ double scratch[32];
-    const int fk = a.ctrl->final_k;
-    if (!FIRST && fk >= 0 && a.k > fk) return;
-    const bool final = !FIRST && fk == a.k;
-    const bool v0_is_V = FIRST || a.k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
+    const int fk = a.ctrl->final_k, k = FIRST ? 0 : sweep_index(a.k, a.ctrl);
+    if (!FIRST && fk >= 0 && k > fk) return;
+    const bool final = !FIRST && fk == k;
+    const bool v0_is_V = FIRST || k == 1; // sweep 1 starts from v = V (`V.=v`): the work buffer is stale until pass 1 writes it
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *acc = smem + warp * WIN_WARP_DOUBLES; // [WIN_ALLOC][WIN_LD]
     double *Ew = acc + WIN_ALLOC * WIN_LD;        // [WIN_ROWS]

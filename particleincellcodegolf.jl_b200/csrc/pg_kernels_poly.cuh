@@ -1,52 +1,60 @@
-// pg_kernels_poly.cuh -- cell-polynomial form of the Gaussian fixed-point pass (src/GaussianFixedPoint.jl:6-9,
+// pg_kernels_poly.cuh -- sub-cell polynomial form of the Gaussian fixed-point pass (src/GaussianFixedPoint.jl:6-9,
 // src/GaussianFixedPointQuiet.jl:7-10) for shards with many particles per cell.
 //
-// For a power-of-two grid every weight of the stencil d(c) is a polynomial in t = 2*delta, delta = c*N - round(c*N)
-// (gauss_cellpoly.inc: W_j = sum_n PG_CW[j+6][n] t^n, degree 16, |error| <= 7e-17).  Both particle<->grid maps of a
-// sweep are linear in the weights, so they factor through the powers of t:
-//     gather   sum(k->E[k[1]]*k[2], d(c))  = sum_n t^n G[cell][n],   G[cell][n] = sum_j CW[j][n] E[cell+j]   gpoly_kernel
-//     deposit  r[k[1]] += k[2]             : M[cell][n] += t^n,       rho[i] = sum_j sum_n CW[j][n] M[i-j][n]  mom2rho_kernel
-// A particle-sweep then costs one Horner evaluation (16 DFMA) and 16 power accumulations instead of two 13-weight
-// stencil evaluations (~255 FP64 instructions in fp_pass_sorted), which moves the pass from the FP64 pipe to HBM.
+// For a power-of-two grid every weight of the stencil d(c) is a function of delta = c*N - round(c*N) only.  A cell is cut
+// into CP_NSUB = 8 intervals: y = c*N*8 (exact: a power-of-two scaling of x+X), interval m = round(y), u = y - m.  On the
+// sub-interval s = (m+4)&7 of stencil centre k = (m+4)>>3 each weight is a degree-10 polynomial in u
+// (gauss_cellpoly.inc: W_j = sum_n PG_CWS[s][j+6][n] u^n, |error| <= 9e-17 for |u| <= 1, i.e. twice the interval).
+// Both particle<->grid maps of a sweep are linear in the weights, so they factor through the powers of u:
+//     gather   sum(k->E[k[1]]*k[2], d(c))  = sum_n u^n G[m][n],    G[m][n] = sum_j CWS[s][j][n] E[k+j]              gpoly_kernel
+//     deposit  r[k[1]] += k[2]             : M[m][n] += u^n,        rho[i] = sum_j sum_s sum_n CWS[s][j][n] M[m(i-j,s)][n]   mom2rho_kernel
+// A particle-sweep then costs one Horner evaluation (10 DFMA) and 10 power accumulations -- 47 FP64 instructions instead
+// of the ~255 of the two 13-weight stencil evaluations in fp_pass_sorted, and of the 66 of the one-polynomial-per-cell
+// form (degree 16) that round 1 shipped; that moves the pass from the FP64 pipe to HBM.
 //
-// fp_pass_poly: every warp streams ONE contiguous range of the (cell, sign v)-sorted particle arrays with 128-bit
-// loads (2 particles per lane and row).  Deposit: each lane keeps the moment set of the cell it is currently in in
-// registers and a spare set -- the other cell of the drifting bin, which straddles two neighbouring cells -- in a
-// private shared-memory column; a set is flushed with 17 integer REDs into the fixed-point moment grid Mg only when
-// the lane meets a third cell -- a few times per pass in sorted order, so there are no shared-memory or per-particle
-// atomics at all.
-// Gather: the G rows of the CP_WG cells around the warp's position are staged in shared memory; a particle reads the
-// 17 coefficients of its own cell (lanes in the same cell broadcast).  Any particle order is handled correctly
-// (window reloads, global-memory gather, early flushes); order only decides the speed, and the mid-stream flushes
-// are counted so that the host can re-sort sooner when lanes start to alternate between cells (picgolf_sort_stats).
+// fp_pass_poly: every warp streams ONE contiguous range of the (cell, sign v, sub-cell position)-sorted particle arrays
+// with 128-bit loads (2 particles per lane and row).  Deposit: each lane keeps ONE moment set in registers, that of the
+// interval it is currently in, and keeps adding to it while |u| <= 1 relative to that interval's centre (the polynomials
+// are fitted that far: hysteresis of half an interval on either side), so a sorted bin that straddles an interval edge
+// never makes a lane alternate; the set is flushed with 11 integer REDs into the fixed-point moment grid Mg only when a
+// particle lies a whole interval away -- ~20 times per pass in sorted order -- so there are no shared-memory atomics and
+// no per-particle atomics at all.
+// Gather: the G rows of the CP_WG intervals around the warp's position are staged in shared memory; a particle reads the
+// 11 coefficients of its own interval (lanes in the same interval broadcast).  Any particle order is handled correctly
+// (window reloads, global-memory gather, early flushes); order only decides the speed, and the flushes are counted so
+// that the host can re-sort sooner when the bins shear apart (picgolf_sort_stats).
 #pragma once
 #include "pg_kernels_1d.cuh"
 #include "gauss_cellpoly.inc"
 
 namespace pg {
 
-constexpr int CP_NC = PG_CW_NC; // coefficients / moments per cell (degree 16)
-constexpr int CP_NM = CP_NC - 1; // moments kept as doubles (n = 1..16); n = 0 is an integer count
-constexpr int CP_WG = 8;         // cells in a warp's gather window
-constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned,
-                                 // and two neighbouring rows (144 B apart) never share a bank within one 128-bit access
+constexpr int CP_NSUB = PG_CWS_NSUB; // polynomial intervals per cell
+constexpr int CP_SUBLG = 3;
+static_assert((1 << CP_SUBLG) == CP_NSUB, "CP_NSUB must be 2^CP_SUBLG");
+constexpr int CP_NC = PG_CWS_NC; // coefficients / moments per interval (degree 10)
+constexpr int CP_NM = CP_NC - 1; // moments kept as doubles (n = 1..10); n = 0 is an integer count
+constexpr int CP_WG = 16;        // intervals in a warp's gather window (two cells)
+constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned
+constexpr double CP_UMAX = 1.0;  // a lane stays with its interval while |u| <= CP_UMAX (the range the polynomials are fitted on)
+constexpr double CP_MAGIC = 6755399441055744.0; // 1.5 * 2^52: y + CP_MAGIC rounds y to the nearest integer (ties to even), |y| < 2^51
 
-// 3 blocks of 128 threads per SM (160 registers per thread): 4 x 128 at 128 registers measured the same, 5 x 128 at 96
-// registers 19 % slower -- the compiler needs the registers to overlap the coefficient loads of a lane's two particles.
 #ifndef PG_CP_THREADS
 #define PG_CP_THREADS 128
 #endif
 #ifndef PG_CP_MINBLOCKS
-#define PG_CP_MINBLOCKS 3
+#define PG_CP_MINBLOCKS 4
 #endif
 constexpr int CP_THREADS = PG_CP_THREADS; // threads per block of fp_pass_poly
-constexpr int CP_STAGES = 4;     // rows of particle data in flight per warp (cp.async ring, 1.5 KB per stage)
+#ifndef PG_CP_STAGES
+#define PG_CP_STAGES 4
+#endif
+constexpr int CP_STAGES = PG_CP_STAGES; // rows of particle data in flight per warp (cp.async ring, 1.5 KB per stage)
 constexpr int CP_STAGE_D2 = 96;  // double2 slots per stage: X, V, v pairs of the 32 lanes
 
 __host__ __device__ inline size_t cp_smem_bytes(int threads)
 {
-    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2)) +
-           (size_t)threads * CP_NM * sizeof(double); // + the spare moment set of every lane
+    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2));
 }
 
 // 16-byte asynchronous global -> shared copy (L2 only); each lane later reads back exactly the bytes it copied itself,
@@ -59,12 +67,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// G[z*CP_GS + n] = sum_j CW[j][n] * E[(z+j) mod N]  for the 0-based cell z = mod1(round(c*N),N)-1; also clears the moment
-// grid the previous mom2rho_kernel consumed.  Skipped (like the solve) once the step has converged.
+// Table row of interval m (any sign): m mod (N * CP_NSUB).  Its stencil centre is the Julia cell index k = (m+4)>>3
+// (0-based cell z = k-1), its sub-interval s = (m+4)&7.  Conversely the row of (z, s) is 8z + s + 4.
+__device__ __forceinline__ int cp_row_of(int z, int s, int Mmask) { return (CP_NSUB * z + s + CP_NSUB / 2) & Mmask; }
+
+// G[row(z,s)*CP_GS + n] = sum_j CWS[s][j][n] * E[(z+j) mod N]; also clears the moment grid the previous mom2rho_kernel
+// consumed.  gridDim.y = CP_NSUB: a block serves one sub-interval, so the table index is uniform (constant-bank operands).
+// Skipped (like the solve) once the step has converged.
 struct GPolyArgs {
     const double *E;
-    double *G;   // [N][CP_GS]
-    fx_t *Mg;    // [N][CP_NC]
+    double *G;   // [N*CP_NSUB][CP_GS]
+    fx_t *Mg;    // [N*CP_NSUB][CP_NC]
     const Ctrl *ctrl;
     int N, k;
 };
@@ -72,29 +85,33 @@ struct GPolyArgs {
 __global__ void __launch_bounds__(128) gpoly_kernel(GPolyArgs a)
 {
     const int fk = a.ctrl->final_k;
-    if (fk >= 0 && a.k > fk) return;
-    const int N = a.N, Nmask = N - 1;
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fk >= 0 && sweep_index(a.k, a.ctrl) > fk) return;
+    const int N = a.N, Nmask = N - 1, Mmask = N * CP_NSUB - 1;
+    const int z = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
     if (z < N) {
         double e[GAUSS_NW];
 #pragma unroll
         for (int q = 0; q < GAUSS_NW; ++q) e[q] = a.E[(z + q - 6) & Nmask];
+        double *g = a.G + (size_t)cp_row_of(z, s, Mmask) * CP_GS;
 #pragma unroll
         for (int n = 0; n < CP_NC; ++n) {
-            double g = 0.0;
+            double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < GAUSS_NW; ++q) g = fma(PG_CW[q][n], e[q], g);
-            a.G[(size_t)z * CP_GS + n] = g;
+            for (int q = 0; q < GAUSS_NW; ++q) acc = fma(PG_CWS[s][q][n], e[q], acc);
+            g[n] = acc;
         }
-        a.G[(size_t)z * CP_GS + CP_NC] = 0.0;
+        g[CP_NC] = 0.0;
     }
-    const int lo = blockIdx.x * blockDim.x * CP_NC, hi = min(N * CP_NC, lo + (int)blockDim.x * CP_NC);
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) a.Mg[i] = 0ULL;
+    const int nb = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
+    const long long total = (long long)N * CP_NSUB * CP_NC, per = (total + nb - 1) / nb;
+    const long long lo = (long long)b * per, hi = min(total, lo + per);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) a.Mg[i] = 0ULL;
 }
 
-// rho_fx[i] += fixed( sum_j sum_n CW[j][n] * M[(i-j) mod N][n] ).  One block = CPM_CELLS output cells; the moments of
-// the CPM_CELLS+12 source cells are converted to fp64 once in shared memory; 4 threads share the 13 offsets of a cell
-// and are summed in a fixed order.  Mg is cleared later by gpoly_kernel (other blocks read the halo cells).
+// rho_fx[i] += fixed( sum_j sum_s sum_n CWS[s][j][n] * M[row(i-j, s)][n] ).  One block = CPM_CELLS output cells; the
+// moments of the CPM_CELLS+12 source cells are converted to fp64 once in shared memory (cell stride odd: the lanes of a warp
+// read different banks); warp s sums the contributions of sub-interval s (uniform table index), the 8 partial sums of a
+// cell are added in a fixed order.  Mg is cleared later by gpoly_kernel (other blocks read the halo cells).
 struct Mom2RhoArgs {
     const fx_t *Mg;
     fx_t *rho;
@@ -103,62 +120,63 @@ struct Mom2RhoArgs {
     int N;
     const unsigned long long *flush_src; // NCCL path on several GPUs: this rank's flush counter goes to rho[N] and is summed with the grid
 };
-constexpr int CPM_CELLS = 64;
+constexpr int CPM_CELLS = 32;
+constexpr int CPM_LD = CP_NSUB * CP_NC + 1; // 89 doubles per source cell
 
-__global__ void __launch_bounds__(4 * CPM_CELLS) mom2rho_kernel(Mom2RhoArgs a)
+__global__ void __launch_bounds__(32 * CP_NSUB) mom2rho_kernel(Mom2RhoArgs a)
 {
-    __shared__ double Ms[(CPM_CELLS + 12) * CP_NC];
-    __shared__ double part[4][CPM_CELLS];
+    __shared__ double Ms[(CPM_CELLS + 12) * CPM_LD];
+    __shared__ double part[CP_NSUB][CPM_CELLS];
     if (a.ctrl->final_k >= 0) return; // converged: the moments belong to the next step's first solve
-    const int N = a.N, Nmask = N - 1;
+    const int N = a.N, Nmask = N - 1, Mmask = N * CP_NSUB - 1;
     const int i0 = blockIdx.x * CPM_CELLS;
     if (a.flush_src && blockIdx.x == 0 && threadIdx.x == 0) a.rho[N] = *a.flush_src;
-    for (int t = threadIdx.x; t < (CPM_CELLS + 12) * CP_NC; t += blockDim.x) {
-        const int c = t / CP_NC, n = t - c * CP_NC;
-        Ms[t] = (double)(long long)a.Mg[(size_t)((i0 + c - 6) & Nmask) * CP_NC + n] * a.fx_inv;
+    for (int t = threadIdx.x; t < (CPM_CELLS + 12) * CP_NSUB * CP_NC; t += blockDim.x) {
+        const int c = t / (CP_NSUB * CP_NC), r = t - c * (CP_NSUB * CP_NC); // r = s*CP_NC + n: the rows of a cell are contiguous in Mg
+        const int s = r / CP_NC, n = r - s * CP_NC;
+        Ms[c * CPM_LD + r] = (double)(long long)a.Mg[(size_t)cp_row_of((i0 + c - 6) & Nmask, s, Mmask) * CP_NC + n] * a.fx_inv;
     }
     __syncthreads();
-    const int i = threadIdx.x & (CPM_CELLS - 1), p = threadIdx.x / CPM_CELLS; // offsets q = p, p+4, p+8, (p+12)
-    double s = 0.0;
-    for (int q = p; q < GAUSS_NW; q += 4) {
-        // cell i receives W_j from source cell i - j, j = q - 6; source slot = (i - j) + 6 = i + 12 - q
-        const double *m = Ms + (i + 12 - q) * CP_NC;
+    const int i = threadIdx.x & 31, s = threadIdx.x >> 5;
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int n = 0; n < CP_NC; ++n) s = fma(PG_CW[q][n], m[n], s);
+    for (int q = 0; q < GAUSS_NW; ++q) {
+        // cell i receives W_j from source cell i - j, j = q - 6; source slot = (i - j) + 6 = i + 12 - q
+        const double *m = Ms + (i + 12 - q) * CPM_LD + s * CP_NC;
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < CP_NC; ++n) acc = fma(PG_CWS[s][q][n], m[n], acc);
+        if (q & 1) s1 += acc; else s0 += acc;
     }
-    part[p][i] = s;
+    part[s][i] = s0 + s1;
     __syncthreads();
     if (threadIdx.x < CPM_CELLS && i0 + i < N) {
-        const double r = (part[0][i] + part[1][i]) + (part[2][i] + part[3][i]);
+        const double r = ((part[0][i] + part[1][i]) + (part[2][i] + part[3][i])) + ((part[4][i] + part[5][i]) + (part[6][i] + part[7][i]));
         a.rho[i0 + i] += to_fx(r, a.fx_scale);
     }
 }
 
-// Centre cell Int(round(c*N)) and t = 2*(c*N - round(c*N)) of a stencil at the midpoint c = (x+X)/2, from the sum
-// s = x+X.  N is a power of two, so s*N = 2*c*N exactly; adding 1.5*2^53 (ulp 2) rounds it to the nearest EVEN integer,
-// ties to the even multiple -- exactly 2*rint(c*N) for |c*N| < 2^51 -- and leaves rint(c*N) in the low mantissa word.
-// Same bits as the literal  cn = ((x+X)/2)*N; r = rint(cn); t = 2*(cn-r), without the conversion unit and 3 FP64
-// instructions shorter.
-__device__ __forceinline__ void cp_centre(double s, double dN, int &cell, double &t)
+// Interval m = round(y) (ties to even) of y = c*N*CP_NSUB, as an integer (the low mantissa word of y + 1.5*2^52) and as a
+// double (the interval's centre).  No conversion-unit instructions.
+__device__ __forceinline__ void cp_interval(double y, int &idx, double &centre)
 {
-    const double cn2 = s * dN;
-    const double big = cn2 + 13510798882111488.0;
-    const double r2 = big - 13510798882111488.0;
-    cell = __double2loint(big);
-    t = cn2 - r2;
+    const double big = y + CP_MAGIC;
+    idx = __double2loint(big);
+    centre = big - CP_MAGIC;
 }
 
-// One lane's moment set for the cell it is currently in (n = 0 is an integer count).
+// One lane's moment set for the interval it is currently in (n = 0 is an integer count).
 struct CPSet {
     double m[CP_NM];
-    int cnt, cell;
+    double centre;
+    int cnt, idx;
 };
 
-// Add the set to the fixed-point moment grid (17 integer REDs) and clear it.
-__device__ __forceinline__ void cp_flush(CPSet &s, fx_t *Mg, double fx_scale, int Nmask)
+// Add the set to the fixed-point moment grid (11 integer REDs) and clear it.
+__device__ __forceinline__ void cp_flush(CPSet &s, fx_t *Mg, double fx_scale, int Mmask)
 {
     if (s.cnt) {
-        fx_t *p = Mg + (size_t)((s.cell - 1) & Nmask) * CP_NC; // Julia index -> 0-based cell
+        fx_t *p = Mg + (size_t)(s.idx & Mmask) * CP_NC;
         atomicAdd(p, to_fx((double)s.cnt, fx_scale));
 #pragma unroll
         for (int n = 0; n < CP_NM; ++n) { atomicAdd(p + 1 + n, to_fx(s.m[n], fx_scale)); s.m[n] = 0.0; }
@@ -166,81 +184,51 @@ __device__ __forceinline__ void cp_flush(CPSet &s, fx_t *Mg, double fx_scale, in
     }
 }
 
-// The moment set of the lane's CURRENT cell lives in registers (CPSet); the set of the other cell of the drifting bin
-// (the "spare") in a lane-private shared-memory column col[n*blockDim.x] (conflict-free), exchanged with the register
-// set when the lane changes over.  (Both sets in registers, selected by cell parity: 4 % slower, 32 registers more;
-// a branch-free sum / odd-sum form: another 4 % slower.  Both measured on B200.)
-struct CPSpare { int cnt, cell; };
-
-__device__ __forceinline__ void cp_flush_spare(CPSpare &sp, double *col, int stride, fx_t *Mg, double fx_scale, int Nmask)
+// M[m][n] += u^n for the particle at y.  The lane stays with its interval while |u| <= CP_UMAX (see the header).
+__device__ __forceinline__ void cp_deposit1(double y, CPSet &P, fx_t *Mg, double fx_scale, int Mmask, unsigned int &nflush)
 {
-    if (sp.cnt) {
-        fx_t *p = Mg + (size_t)((sp.cell - 1) & Nmask) * CP_NC;
-        atomicAdd(p, to_fx((double)sp.cnt, fx_scale));
-#pragma unroll
-        for (int n = 0; n < CP_NM; ++n) { atomicAdd(p + 1 + n, to_fx(col[n * stride], fx_scale)); col[n * stride] = 0.0; }
-        sp.cnt = 0;
-    }
-}
-
-__device__ __forceinline__ void cp_deposit1(int cell, double t, CPSet &P, CPSpare &sp, double *col, int stride, fx_t *Mg,
-                                            double fx_scale, int Nmask, unsigned int &nflush)
-{
-    if (cell != P.cell) { // rare in sorted order
-        if (cell == sp.cell) { // change over to the other cell of the bin: exchange the two sets
-#pragma unroll
-            for (int n = 0; n < CP_NM; ++n) { const double m = col[n * stride]; col[n * stride] = P.m[n]; P.m[n] = m; }
-            const int c = sp.cnt; sp.cnt = P.cnt; P.cnt = c;
-            sp.cell = P.cell; P.cell = cell;
-            ++nflush; // exchanges count as well: lanes alternating between the two cells pay 32 shared accesses each time
-        } else {               // a third cell: retire the spare, park the current set
-            nflush += sp.cnt > 0;
-            cp_flush_spare(sp, col, stride, Mg, fx_scale, Nmask);
-#pragma unroll
-            for (int n = 0; n < CP_NM; ++n) { col[n * stride] = P.m[n]; P.m[n] = 0.0; }
-            sp.cnt = P.cnt; sp.cell = P.cell;
-            P.cnt = 0; P.cell = cell;
-        }
+    double u = y - P.centre;
+    if (!(fabs(u) <= CP_UMAX)) { // ~20 times per pass in sorted order (and for the lane's first particle)
+        nflush += P.cnt > 0;
+        cp_flush(P, Mg, fx_scale, Mmask);
+        cp_interval(y, P.idx, P.centre);
+        u = y - P.centre;
     }
     P.cnt++;
-    const double t2 = t * t;
-    double pa = t, pb = t2;
+    const double u2 = u * u;
+    double pa = u, pb = u2;
 #pragma unroll
     for (int n = 0; n < CP_NM; n += 2) {
         P.m[n] += pa; P.m[n + 1] += pb;
-        if (n + 2 < CP_NM) { pa *= t2; pb *= t2; }
+        if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
     }
 }
 
-// Rare path: the particle's cell is outside the warp's gather window.
-__device__ __noinline__ double cp_slow_gather(const double *G, int cell, double t, int N)
+// sum_n u^n g[n] from one row (128-bit loads of the pairs (c_2m, c_2m+1)): even and odd halves as two independent
+// Horner chains in u^2.
+__device__ __forceinline__ double cp_horner(const double *g, double u)
 {
-    const double *g = G + (size_t)((cell - 1) & (N - 1)) * CP_GS;
-    const double t2 = t * t; // same operation order as cp_horner
-    double ge = g[16], go = g[15];
-    for (int n = 14; n >= 0; n -= 2) ge = fma(ge, t2, g[n]);
-    for (int n = 13; n >= 1; n -= 2) go = fma(go, t2, g[n]);
-    return fma(go, t, ge);
-}
-
-// sum_n t^n g[n] from one staged row (128-bit shared loads of the pairs (c_2m, c_2m+1)): even and odd halves as two
-// independent Horner chains in t^2.
-__device__ __forceinline__ double cp_horner(const double *g, double t)
-{
+    static_assert(CP_NC == 11, "cp_horner is written for degree 10");
     const double2 *g2 = reinterpret_cast<const double2 *>(g);
-    const double t2 = t * t;
-    double2 c = g2[8];
-    double ge = c.x; // c_16
-    c = g2[7];
-    ge = fma(ge, t2, c.x);
-    double go = c.y; // c_15
+    const double u2 = u * u;
+    double2 c = g2[5];
+    double ge = c.x; // c_10
+    c = g2[4];
+    ge = fma(ge, u2, c.x);
+    double go = c.y; // c_9
 #pragma unroll
-    for (int m = 6; m >= 0; --m) {
+    for (int m = 3; m >= 0; --m) {
         c = g2[m];
-        ge = fma(ge, t2, c.x);
-        go = fma(go, t2, c.y);
+        ge = fma(ge, u2, c.x);
+        go = fma(go, u2, c.y);
     }
-    return fma(go, t, ge);
+    return fma(go, u, ge);
+}
+
+// Rare path: the particle's interval is outside the warp's gather window (same operation order as cp_horner).
+__device__ __noinline__ double cp_slow_gather(const double *G, int idx, double u, int Mmask)
+{
+    return cp_horner(G + (size_t)(idx & Mmask) * CP_GS, u);
 }
 
 // The last P % 64 particles of a shard (no full row): one thread each, global-memory gather polynomial and direct
@@ -248,13 +236,16 @@ __device__ __forceinline__ double cp_horner(const double *g, double t)
 template <bool FIRST>
 __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, bool final, bool v0_is_V, double &sv2, double &sv)
 {
-    const int N = a.N, Nmask = N - 1;
-    const double dN = (double)N, dt = a.dt;
+    const int Mmask = a.N * CP_NSUB - 1;
+    const double dNs = a.dN, hdt = a.dt / 2;
     double Xj = a.X[j], Vj = a.V[j], vj = v0_is_V ? Vj : a.v[j];
-    double xj = Xj + (vj + Vj) / 2 * dt;
+    double xj = Xj + (vj + Vj) * hdt;
+    int idx;
+    double centre;
     if (!FIRST) {
-        const double cn = ((xj + Xj) / 2) * dN, rr = rint(cn), d = cn - rr;
-        vj = Vj + cp_slow_gather(a.G, (int)rr, d + d, N) * dt;
+        const double y = (xj + Xj) * dNs;
+        cp_interval(y, idx, centre);
+        vj = Vj + cp_slow_gather(a.G, idx, y - centre, Mmask) * a.dt;
         a.v[j] = vj;
         if (final) {
             const double xw = jl_mod1(xj);
@@ -262,29 +253,31 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
             sv2 = fma(vj, vj, sv2); sv += vj;
             Xj = xw; Vj = vj;
         }
-        xj = Xj + (vj + Vj) / 2 * dt;
+        xj = Xj + (vj + Vj) * hdt;
     }
-    const double cn = ((xj + Xj) / 2) * dN, rr = rint(cn), d = cn - rr, t = d + d;
-    fx_t *p = a.Mg + (size_t)(((int)rr - 1) & Nmask) * CP_NC;
+    const double y = (xj + Xj) * dNs;
+    cp_interval(y, idx, centre);
+    const double u = y - centre;
+    fx_t *p = a.Mg + (size_t)(idx & Mmask) * CP_NC;
     double pw = 1.0;
-    for (int n = 0; n < CP_NC; ++n) { atomicAdd(p + n, to_fx(pw, a.fx_scale)); pw *= t; }
+    for (int n = 0; n < CP_NC; ++n) { atomicAdd(p + n, to_fx(pw, a.fx_scale)); pw *= u; }
 }
 
 // Pass k of a step (same contract as fp_pass_sorted / fp_pass_atomic; FPArgs.G / FPArgs.Mg carry the polynomial
-// tables).  Row = 64 consecutive particles; lane l owns particles 2l and 2l+1 of the row.
+// tables, FPArgs.dN = N*CP_NSUB/2 so that y = (x+X)*dN).  Row = 64 consecutive particles; lane l owns particles 2l and 2l+1.
 template <bool FIRST>
 __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPArgs a)
 {
     extern __shared__ double smem[];
     __shared__ double scratch[32];
-    const int fk = a.ctrl->final_k;
-    if (!FIRST && fk >= 0 && a.k > fk) return;
-    const bool final = !FIRST && fk == a.k;
-    const bool v0_is_V = FIRST || a.k == 1; // sweep 1 starts from v = V: the work buffer is stale until pass 1 writes it
+    const int fk = a.ctrl->final_k, k = FIRST ? 0 : sweep_index(a.k, a.ctrl);
+    if (!FIRST && fk >= 0 && k > fk) return;
+    const bool final = !FIRST && fk == k;
+    const bool v0_is_V = FIRST || k == 1; // sweep 1 starts from v = V: the work buffer is stale until pass 1 writes it
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *Gw = smem + warp * (CP_GS * CP_WG); // [CP_WG][CP_GS]
-    const int N = a.N, Nmask = N - 1;
-    const double dN = a.dN, hdt = a.dt / 2; // ((v+V)/2)*dt == (v+V)*(dt/2) bit for bit (exact power-of-two scalings)
+    const int Mmask = a.N * CP_NSUB - 1;
+    const double dNs = a.dN, hdt = a.dt / 2; // ((v+V)/2)*dt == (v+V)*(dt/2) bit for bit (exact power-of-two scalings)
     // full rows only; every warp streams one contiguous range [r0, r1)
     const int rows = (int)(a.P >> 6);
     const int nw = gridDim.x * wpb, gw = blockIdx.x * wpb + warp;
@@ -293,13 +286,10 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     const double2 *X2 = reinterpret_cast<const double2 *>(a.X), *V2 = reinterpret_cast<const double2 *>(a.V);
     double2 *v2 = reinterpret_cast<double2 *>(a.v), *xo2 = reinterpret_cast<double2 *>(a.xout);
     CPSet A;
-    CPSpare spare;
-    double *col = smem + wpb * (CP_GS * CP_WG + 2 * CP_STAGES * CP_STAGE_D2) + threadIdx.x;
-    const int cstride = blockDim.x;
 #pragma unroll
-    for (int n = 0; n < CP_NM; ++n) { A.m[n] = 0.0; col[n * cstride] = 0.0; }
-    A.cnt = 0; A.cell = 0x40000000; spare.cnt = 0; spare.cell = 0x40000001;
-    int gb = 0x40000000; // Julia index of window slot 0; the first row always restages (see `staged`)
+    for (int n = 0; n < CP_NM; ++n) A.m[n] = 0.0;
+    A.cnt = 0; A.idx = 0; A.centre = 1e300; // no interval yet: the first particle opens one
+    int gb = 0x40000000; // interval of window slot 0; the first row always restages (see `staged`)
     bool staged = false;
     double sv2 = 0.0, sv = 0.0;
     unsigned int nflush = 0;
@@ -329,37 +319,40 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
         for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt; // x.=X.+(v.+V)/2*dt
         if (!FIRST) {
-            int cell[2];
-            double t[2];
+            int idx[2];
+            double u[2];
             unsigned int slot[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                cp_centre(xj[q] + Xj[q], dN, cell[q], t[q]);
-                slot[q] = (unsigned int)(cell[q] - gb) & (unsigned int)Nmask;
+                const double y = (xj[q] + Xj[q]) * dNs;
+                double centre;
+                cp_interval(y, idx[q], centre);
+                u[q] = y - centre;
+                slot[q] = (unsigned int)(idx[q] - gb) & (unsigned int)Mmask;
             }
             if (!__all_sync(0xffffffffu, staged && slot[0] < CP_WG && slot[1] < CP_WG)) {
-                // recentre the window one cell below the smallest centre of this row and restage it
-                int cm = min(cell[0], cell[1]);
+                // recentre the window two intervals below the smallest interval of this row and restage it
+                int cm = min(idx[0], idx[1]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) cm = min(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-                gb = cm - 1;
+                gb = cm - 2;
                 staged = true;
                 __syncwarp();
                 for (int i = lane; i < CP_GS * CP_WG; i += 32) {
                     const int s = i / CP_GS, n = i - s * CP_GS;
-                    Gw[i] = a.G[(size_t)((gb + s - 1) & Nmask) * CP_GS + n];
+                    Gw[i] = a.G[(size_t)((gb + s) & Mmask) * CP_GS + n];
                 }
                 __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 2; ++q) slot[q] = (unsigned int)(cell[q] - gb) & (unsigned int)Nmask;
+                for (int q = 0; q < 2; ++q) slot[q] = (unsigned int)(idx[q] - gb) & (unsigned int)Mmask;
             }
             double g[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) g[q] = cp_horner(Gw + (slot[q] < CP_WG ? slot[q] : 0u) * CP_GS, t[q]);
-            if (slot[0] >= CP_WG || slot[1] >= CP_WG) { // rare: a centre more than CP_WG cells above the row's smallest
+            for (int q = 0; q < 2; ++q) g[q] = cp_horner(Gw + (slot[q] < CP_WG ? slot[q] : 0u) * CP_GS, u[q]);
+            if (slot[0] >= CP_WG || slot[1] >= CP_WG) { // rare: an interval more than CP_WG above the row's smallest
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
-                    if (slot[q] >= CP_WG) g[q] = cp_slow_gather(a.G, cell[q], t[q], N);
+                    if (slot[q] >= CP_WG) g[q] = cp_slow_gather(a.G, idx[q], u[q], Mmask);
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) vj[q] = Vj[q] + g[q] * a.dt; // v[j]=V[j]+sum(...)*dt
@@ -378,18 +371,11 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
             for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt;
         }
-        {
-            int cell[2];
-            double t[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) cp_centre(xj[q] + Xj[q], dN, cell[q], t[q]);
-            cp_deposit1(cell[0], t[0], A, spare, col, cstride, a.Mg, a.fx_scale, Nmask, nflush);
-            cp_deposit1(cell[1], t[1], A, spare, col, cstride, a.Mg, a.fx_scale, Nmask, nflush);
-        }
+        for (int q = 0; q < 2; ++q) cp_deposit1((xj[q] + Xj[q]) * dNs, A, a.Mg, a.fx_scale, Mmask, nflush);
     }
     cp_async_wait<0>();
-    cp_flush(A, a.Mg, a.fx_scale, Nmask);
-    cp_flush_spare(spare, col, cstride, a.Mg, a.fx_scale, Nmask);
+    cp_flush(A, a.Mg, a.fx_scale, Mmask);
     // ragged tail of the shard: fewer than 64 particles, first warp of the last block
     if (blockIdx.x == gridDim.x - 1 && warp == 0) {
         const long long j = ((long long)rows << 6) + lane;

@@ -7,33 +7,37 @@
 // every rank waits for the flags and adds up the nranks grids itself with plain loads over NVLink (64-bit integer adds
 // in rank order: bit-identical on all ranks and to the NCCL sum).  A predicated-off sweep costs nothing.
 //
-// Protocol (seq = host-side count of enqueued sweeps, slot = seq & 1):
+// Protocol (seq = number of sweeps published so far, counted ON THE DEVICE in this rank's own header -- the launches of a
+// device-driven loop (picgolf.cu) are the same graph nodes every iteration, so no host-side counter can ride in their
+// arguments; every rank executes the same sweeps, so the counters agree; slot = seq & 1):
 //   publish(seq):  wait until every peer's `done` >= the sequence number this slot last carried (nobody still reads
 //                  it); copy rho -> data[slot], clear rho; fence; ready = seq.
 //   solve(seq):    wait until every peer's `ready` >= seq; rho[n] = sum_q peer[q].data[slot][n]; then done = seq.
 // A rank publishes sweep s+1 only after its own solve(s), and solve(s) needs every peer's publish(s): no rank is ever
-// more than one real sweep ahead, and with the `done` handshake two slots suffice.  Waits give up after ~2 s and raise
-// an error flag instead of hanging the GPU.
+// more than one real sweep ahead, and with the `done` handshake two slots suffice.  A wait gives up only after ~5 minutes
+// (a rank that stalls for seconds -- checkpoint I/O, a re-sort, module load -- is simply waited for, as NCCL would); on
+// time-out the error flag is raised, the solve poisons E with NaN and ends the step, and picgolf_synchronize and the getters
+// return PICGOLF_ERR_NCCL, so a dead peer can neither hang the GPU for ever nor produce a silently wrong field.
 #pragma once
 #include "pg_common.cuh"
 
 namespace pg {
 
 constexpr int PEER_MAX = 16;
-constexpr long long PEER_TIMEOUT_CYCLES = 4000000000LL;
+constexpr long long PEER_TIMEOUT_CYCLES = 600000000000LL; // ~5 min at 1.9 GHz
 
 struct PeerPub {
     unsigned long long ready;       // highest sweep sequence number whose grid this rank has published
     unsigned long long done;        // highest sequence number this rank has finished reading from all peers
     unsigned long long last_pub[2]; // per slot: the sequence number of its content
     unsigned long long flushes;     // this rank's cumulative flush counter (polynomial mode), summed next to the grid
-    unsigned long long pad_[11];    // header = 128 bytes; fx_t data[2][ncell] follows
+    unsigned long long seq;         // sweeps this rank has published (device-side sequence counter; never reset)
+    unsigned long long pad_[10];    // header = 128 bytes; fx_t data[2][ncell] follows
 };
 
 struct PeerArgs {
     PeerPub *peer[PEER_MAX]; // peer[rank] is this rank's own buffer
     int nranks, rank;        // nranks <= 1: not in use
-    unsigned long long seq;
     long long ncell;
     int *error;
     const unsigned long long *flush_src; // this rank's flush counter, or NULL
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rh
 {
     if (fixedpoint && *final_k >= 0) return; // step already converged: predicated no-op, like the solve
     PeerPub *me = p.peer[p.rank];
-    const int slot = (int)(p.seq & 1ULL);
+    const unsigned long long seq = me->seq + 1ULL; // only this kernel writes it, at its very end
+    const int slot = (int)(seq & 1ULL);
     if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->done, me->last_pub[slot], p.error);
     __syncthreads();
     fx_t *dst = peer_data(me, slot, p.ncell);
@@ -80,18 +85,21 @@ __global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rh
     if (threadIdx.x == 0) me->flushes = p.flush_src ? *p.flush_src : 0ULL;
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) { me->last_pub[slot] = p.seq; st_release_sys(&me->ready, p.seq); }
+    if (threadIdx.x == 0) { me->last_pub[slot] = seq; me->seq = seq; st_release_sys(&me->ready, seq); }
 }
 
 // In the solve kernel (one block): wait for all grids of this sweep, then peer_sum(n) for every cell, then peer_done().
-__device__ __forceinline__ void peer_gather_begin(const PeerArgs &p)
+// Returns the sequence number of the sweep being gathered (this rank's latest publish).
+__device__ __forceinline__ unsigned long long peer_gather_begin(const PeerArgs &p)
 {
-    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->ready, p.seq, p.error);
+    const unsigned long long seq = p.peer[p.rank]->seq;
+    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->ready, seq, p.error);
     __syncthreads();
+    return seq;
 }
-__device__ __forceinline__ long long peer_sum(const PeerArgs &p, long long n)
+__device__ __forceinline__ long long peer_sum(const PeerArgs &p, unsigned long long seq, long long n)
 {
-    const int slot = (int)(p.seq & 1ULL);
+    const int slot = (int)(seq & 1ULL);
     unsigned long long s = 0ULL;
     for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(peer_data(p.peer[q], slot, p.ncell) + n);
     return (long long)s;
@@ -102,9 +110,18 @@ __device__ __forceinline__ unsigned long long peer_flush_sum(const PeerArgs &p) 
     for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(&p.peer[q]->flushes);
     return s;
 }
-__device__ __forceinline__ void peer_gather_end(const PeerArgs &p) // after a __syncthreads() that follows the last peer_sum
+__device__ __forceinline__ void peer_gather_end(const PeerArgs &p, unsigned long long seq) // after a __syncthreads() that follows the last peer_sum
 {
-    if (threadIdx.x == 0) st_release_sys(&p.peer[p.rank]->done, p.seq);
+    if (threadIdx.x == 0) st_release_sys(&p.peer[p.rank]->done, seq);
+}
+
+// Touches every peer's header once (picgolf_peer_connect): cudaIpcOpenMemHandle maps peer memory lazily, and the first
+// access over NVLink must not land inside a timed sweep.
+__global__ void peer_touch_kernel(PeerArgs p, unsigned long long *sink)
+{
+    unsigned long long s = 0ULL;
+    for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(&p.peer[q]->ready) + ld_relaxed_sys(peer_data(p.peer[q], 1, p.ncell) + (p.ncell - 1));
+    if (s == 0xFFFFFFFFFFFFFFFFULL) *sink = s;
 }
 
 } // namespace pg

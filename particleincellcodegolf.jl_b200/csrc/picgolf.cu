@@ -197,7 +197,6 @@ struct picgolf_handle_s {
     // the sweep sequence counter, and the device-side time-out flag
     PeerPub *peer_mine = nullptr, *peer_ptr[PEER_MAX] = {};
     bool peer_ok = false, peer_this_solve = false;
-    unsigned long long peer_seq = 0;
     int *peer_err = nullptr;
     StageTimer timer;
     // cell-sorted mode
@@ -226,13 +225,33 @@ struct picgolf_handle_s {
     int64_t probe_step[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     cudaEvent_t run_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // end-of-step markers
     int64_t steps_at_probe = 0, steps_at_probe_prev_steps = 0;
-    // CUDA graphs of one fixed-point step, one per ping-pong parity
+    // Simpson-1/3 schemes: CUDA graphs of one fixed-schedule step, one per ping-pong parity
     cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr}; // [par + 2*have_deposit]
     int64_t graph_launches[4] = {0, 0, 0, 0};
     bool graph_failed = false;
+    // Gaussian fixed point: the device-driven sweep loop.  One graph per (X/V parity, charge-grid parity, kernel family):
+    //   WHILE (not converged) { [moments -> rho] [publish] solve [gather polynomials] particle pass }  ->  step_end
+    // The solve kernel sets the WHILE condition (cudaGraphSetConditional), so exactly S sweeps are launched -- no
+    // predicated-off launches, no host involvement (for _ in 0:9 ... && break, GaussianFixedPoint.jl:7).
+    cudaGraphExec_t loop_graph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t cap_stream = nullptr;
+    bool loop_failed = false, loop_off = false;
+    int loop_launches_per_sweep = 0;
+    int64_t loop_steps = 0;
 };
 
 static int use_device(picgolf_handle h) { PG_CUDA(cudaSetDevice(h->device)); return 0; }
+
+// After a synchronisation: did a peer-memory wait time out (pg_peer.cuh)?  The fields are NaN-poisoned in that case.
+static int check_peer(picgolf_handle h)
+{
+    if (!h->peer_err) return 0;
+    int err = 0;
+    PG_CUDA(cudaMemcpy(&err, h->peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(PICGOLF_ERR_NCCL, "peer-memory reduction: a rank never published its charge grid (timed out); the fields of this run are poisoned with NaN");
+    return 0;
+}
+
 
 template <typename T>
 static int dalloc(T **p, size_t n)
@@ -353,6 +372,8 @@ static int destroy_impl(picgolf_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->timer.destroy();
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
+    for (auto &g : h->loop_graph) if (g) cudaGraphExecDestroy(g);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->slow_host) cudaFreeHost(h->slow_host);
     if (h->slow_ev) cudaEventDestroy(h->slow_ev);
     for (auto &e : h->run_ev) if (e) cudaEventDestroy(e);
@@ -389,6 +410,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     h->sms = prop.multiProcessorCount;
     PG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
+    { const char *e = getenv("PICGOLF_LOOP"); h->loop_off = e && e[0] == '0'; } // A/B: fixed schedule instead of the device-driven loop
     h->is2d = c.scheme == PICGOLF_CIC_BORIS_2D3V;
     h->simpson = c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13;
     h->fixedpoint = c.scheme == PICGOLF_GAUSS_FIXEDPOINT || h->simpson;
@@ -490,9 +512,9 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                     if (c.sort_every <= 0) h->sort_every = 16; // starting point; adapted from the flush counter every step
                     h->smem_poly = cp_smem_bytes(CP_THREADS);
                     PG_TRY(set_smem(fp_pass_poly<true>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false>, h->smem_poly));
-                    PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * N)); PG_TRY(dalloc(&h->Mg, (size_t)CP_NC * N));
-                    PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * N * sizeof(double)));
-                    PG_CUDA(cudaMemset(h->Mg, 0, (size_t)CP_NC * N * sizeof(unsigned long long)));
+                    PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * CP_NSUB * N)); PG_TRY(dalloc(&h->Mg, (size_t)CP_NC * CP_NSUB * N));
+                    PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * CP_NSUB * N * sizeof(double)));
+                    PG_CUDA(cudaMemset(h->Mg, 0, (size_t)CP_NC * CP_NSUB * N * sizeof(unsigned long long)));
                     // one contiguous range of >= 16 rows (of 64 particles) per warp
                     const int64_t rows = (h->count + 63) / 64;
                     PG_TRY(occupancy_blocks(fp_pass_poly<false>, CP_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
@@ -637,8 +659,22 @@ PG_API int picgolf_local_range(picgolf_handle h, int64_t *first, int64_t *count)
 // ------------------------------------------------------------------------------------------
 // particle state
 // ------------------------------------------------------------------------------------------
+// Launches of the device-driven loop are counted on the device (one counter increment per sweep); fold them into the
+// host-side count before Ctrl is cleared.
+static int bank_loop_launches(picgolf_handle h)
+{
+    if (h->loop_steps == 0) return 0;
+    PG_CUDA(cudaStreamSynchronize(h->stream));
+    Ctrl c;
+    PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
+    h->launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep;
+    h->loop_steps = 0;
+    return 0;
+}
+
 static int reset_run_state(picgolf_handle h)
 {
+    PG_TRY(bank_loop_launches(h));
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
@@ -647,7 +683,7 @@ static int reset_run_state(picgolf_handle h)
     if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, ((size_t)h->ncell + 1) * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
-    if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * CP_NSUB * h->ncell * sizeof(unsigned long long), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
@@ -709,7 +745,7 @@ PG_API int picgolf_get_particles_1d2v(picgolf_handle h, double *x, double *vx, d
     if (vx) PG_CUDA(cudaMemcpyAsync(vx, h->vb[0], b, cudaMemcpyDeviceToHost, h->stream));
     if (vy) PG_CUDA(cudaMemcpyAsync(vy, h->vy1, b, cudaMemcpyDeviceToHost, h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer(h);
 }
 
 static int init_grid(picgolf_handle h) { return (int)std::max<int64_t>(1, std::min<int64_t>((h->count + 255) / 256, (int64_t)h->sms * 8)); }
@@ -745,7 +781,7 @@ PG_API int picgolf_synchronize(picgolf_handle h)
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
     PG_TRY(use_device(h));
     PG_CUDA(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer(h);
 }
 
 PG_API int picgolf_get_particles(picgolf_handle h, double *x, double *v, int64_t count)
@@ -767,12 +803,12 @@ PG_API int picgolf_get_particles(picgolf_handle h, double *x, double *v, int64_t
             PG_CUDA(cudaMemcpyAsync(dst[q], tmp, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
         PG_CUDA(cudaStreamSynchronize(h->stream));
-        return 0;
+        return check_peer(h);
     }
     if (x) PG_CUDA(cudaMemcpyAsync(x, h->xb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (v) PG_CUDA(cudaMemcpyAsync(v, h->vb[h->par], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer(h);
 }
 
 PG_API int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, double *vx, double *vy, double *vz,
@@ -808,7 +844,7 @@ static PeerArgs peer_args(picgolf_handle h)
     PeerArgs p;
     memset(&p, 0, sizeof(p));
     for (int q = 0; q < h->nranks; ++q) p.peer[q] = h->peer_ptr[q];
-    p.nranks = h->nranks; p.rank = h->rank; p.seq = h->peer_seq; p.ncell = h->ncell; p.error = h->peer_err;
+    p.nranks = h->nranks; p.rank = h->rank; p.ncell = h->ncell; p.error = h->peer_err;
     p.flush_src = h->slow_count;
     return p;
 }
@@ -820,7 +856,6 @@ static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
     if (h->peer_ok && !h->is2d && !h->simpson && row0 == 0 && nrows == 1) {
         // 1D schemes: publish this rank's grid; the solve kernel that follows adds the ranks' grids up itself
         const int sp = h->timer.begin(ST_REDUCE, h->stream);
-        h->peer_seq++;
         peer_publish_kernel<<<1, 1024, 0, h->stream>>>(peer_args(h), h->rho_fx, &h->ctrl->final_k, h->fixedpoint ? 1 : 0);
         h->timer.end(sp, h->stream);
         h->launches++;
@@ -838,7 +873,7 @@ static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
     return nccl::check(rc, "ncclAllReduce(rho)");
 }
 
-static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
+static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false, cudaGraphConditionalHandle cond = 0)
 {
     const picgolf_config &c = h->cfg;
     Solve1DArgs a;
@@ -847,7 +882,7 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false)
     a.w = c.w; a.fx_inv = h->fx_inv; a.rtol = c.rtol; a.atol = c.atol;
     a.N = (int)c.N; a.lg = ilog2(c.N); a.fixedpoint = (h->fixedpoint && !simpson_e1) ? 1 : 0;
     a.k = k; a.max_sweeps = c.max_sweeps; a.store_normE1 = simpson_e1 ? 1 : 0;
-    a.hist = nullptr;
+    a.hist = nullptr; a.cond = cond;
     if (h->peer_this_solve) a.peer = peer_args(h);
     a.flush_slot = (h->comm && !h->peer_ok && h->poly && h->use_sorted_now) ? 1 : 0;
     if (h->b1d2v) { // Es[:,ti] .+= E with ti = cld(t, T/TO)   NGP1D2V.jl:56-57
@@ -932,10 +967,10 @@ static void probe_poly_flushes(picgolf_handle h)
             const unsigned long long now = h->slow_host[idx];
             if (h->probe_have_prev) {
                 const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during one step
-                // expected in sorted order, per particle and pass: a lane meets ~2 new cells per (cell, sign v) group
-                // (64*groups/P), and inside the one sub-bin of a group that a cell boundary cuts through it alternates
-                // between the two cells on every other particle (1/(2*subbins)); ~4 passes per step
-                const double expect = 4.0 * (64.0 * (double)(h->nbins >> h->sublg) / (double)h->cfg.P + 0.5 / (double)(1 << h->sublg));
+                // expected in sorted order: the warp that streams a (cell, sign v) group walks through its CP_NSUB polynomial
+                // intervals, and each of its 32 lanes flushes once per interval (plus once per warp range); ~4 passes per step
+                const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
+                const double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
                 h->poly_quiet = frac < 5e-5 + 1.5 * expect;
                 if (frac > 1e-3 + 3.0 * expect && h->since_sort >= 2 + POLY_RUNAHEAD) {
                     h->force_sort = true;
@@ -987,72 +1022,118 @@ static int sort_particles_1d(picgolf_handle h)
     return 0;
 }
 
-// Cell-polynomial form of the step (pg_kernels_poly.cuh): per sweep  moments -> rho, [all-reduce], solve, E -> per-cell
-// gather polynomials (+ clear the moments), particle pass.
-static int enqueue_poly_step(picgolf_handle h, FPArgs a)
-{
-    const picgolf_config &c = h->cfg;
-    const int N = (int)c.N;
-    h->pass_blocks = h->nblocks_poly;
-    if (!h->have_deposit) {
-        const int sp = h->timer.begin(ST_PARTICLES, h->stream);
-        fp_pass_poly<true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
-        h->timer.end(sp, h->stream);
-        h->launches++;
-    }
-    Mom2RhoArgs m;
-    m.Mg = h->Mg; m.rho = h->rho_fx; m.ctrl = h->ctrl; m.fx_scale = h->fx_scale; m.fx_inv = h->fx_inv; m.N = N;
-    m.flush_src = (h->comm && !h->peer_ok) ? h->slow_count : nullptr;
-    GPolyArgs g;
-    g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N;
-    for (int k = 1; k <= c.max_sweeps; ++k) {
-        int sp = h->timer.begin(ST_SOLVE, h->stream);
-        mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 4 * CPM_CELLS, 0, h->stream>>>(m);
-        h->timer.end(sp, h->stream);
-        PG_TRY(allreduce_grid(h));
-        PG_TRY(launch_solve1d(h, k));
-        g.k = k;
-        sp = h->timer.begin(ST_SOLVE, h->stream);
-        gpoly_kernel<<<(N + 127) / 128, 128, 0, h->stream>>>(g);
-        h->timer.end(sp, h->stream);
-        a.k = k;
-        sp = h->timer.begin(ST_PARTICLES, h->stream);
-        fp_pass_poly<false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
-        h->timer.end(sp, h->stream);
-        h->launches += 4;
-    }
-    PG_TRY(launch_step_end(h, true));
-    return 0;
-}
-
-static int enqueue_fixedpoint_step(picgolf_handle h)
+static FPArgs fp_args(picgolf_handle h)
 {
     const picgolf_config &c = h->cfg;
     FPArgs a;
     a.X = h->xb[h->par]; a.V = h->vb[h->par]; a.v = h->vb[1 - h->par]; a.xout = h->xb[1 - h->par];
     a.E = h->E; a.rho = h->rho_fx; a.rho_next = h->rho_next; a.partials = h->partials; a.ctrl = h->ctrl;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
-    a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg; a.dN = (double)c.N;
-    h->pass_blocks = h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
-    if (h->use_sorted_now && h->poly) return enqueue_poly_step(h, a);
-    if (!h->have_deposit) { // only the first step after the particles were set: later ones inherit the fused deposit
-        const int sp3_ = h->timer.begin(ST_PARTICLES, h->stream);
-        if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
-        else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-        h->timer.end(sp3_, h->stream);
+    a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg;
+    a.dN = (double)c.N * (CP_NSUB / 2); // polynomial passes: y = (x+X)*dN = c*N*CP_NSUB
+    return a;
+}
+
+static bool poly_now(picgolf_handle h) { return h->use_sorted_now && h->poly; }
+
+// Pass 0 of the first step after the particles were set: later steps inherit the deposit fused into the previous final pass.
+static int enqueue_first_pass(picgolf_handle h)
+{
+    FPArgs a = fp_args(h);
+    const int sp = h->timer.begin(ST_PARTICLES, h->stream);
+    if (poly_now(h)) fp_pass_poly<true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    else if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
+    else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    h->timer.end(sp, h->stream);
+    h->launches++;
+    return 0;
+}
+
+// One sweep: [moments -> rho] [sum over ranks] solve [E -> per-cell gather polynomials (+ clear the moments)] particle pass.
+// k >= 1: fixed schedule, the sweep index is a kernel argument and a sweep after convergence is a predicated no-op.
+// k < 0:  body of the device-driven loop; the kernels read the sweep index from Ctrl and the solve steers the WHILE node `cond`.
+static int enqueue_sweep(picgolf_handle h, int k, cudaGraphConditionalHandle cond)
+{
+    const picgolf_config &c = h->cfg;
+    const int N = (int)c.N;
+    FPArgs a = fp_args(h);
+    a.k = k;
+    const bool poly = poly_now(h);
+    if (poly) { // cell-polynomial form (pg_kernels_poly.cuh)
+        Mom2RhoArgs m;
+        m.Mg = h->Mg; m.rho = h->rho_fx; m.ctrl = h->ctrl; m.fx_scale = h->fx_scale; m.fx_inv = h->fx_inv; m.N = N;
+        m.flush_src = (h->comm && !h->peer_ok) ? h->slow_count : nullptr;
+        const int sp = h->timer.begin(ST_SOLVE, h->stream);
+        mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 32 * CP_NSUB, 0, h->stream>>>(m);
+        h->timer.end(sp, h->stream);
         h->launches++;
     }
-    for (int k = 1; k <= c.max_sweeps; ++k) {
-        PG_TRY(allreduce_grid(h));
-        PG_TRY(launch_solve1d(h, k));
-        a.k = k;
-        const int sp4_ = h->timer.begin(ST_PARTICLES, h->stream);
-        if (h->use_sorted_now) fp_pass_sorted<false, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
-        else fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
-        h->timer.end(sp4_, h->stream);
+    PG_TRY(allreduce_grid(h));
+    PG_TRY(launch_solve1d(h, k, false, cond));
+    if (poly) {
+        GPolyArgs g;
+        g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N; g.k = k;
+        const int sp = h->timer.begin(ST_SOLVE, h->stream);
+        gpoly_kernel<<<dim3((N + 127) / 128, CP_NSUB), 128, 0, h->stream>>>(g);
+        h->timer.end(sp, h->stream);
         h->launches++;
     }
+    const int sp = h->timer.begin(ST_PARTICLES, h->stream);
+    if (poly) fp_pass_poly<false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    else if (h->use_sorted_now) fp_pass_sorted<false, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
+    else fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
+    h->timer.end(sp, h->stream);
+    h->launches++;
+    return 0;
+}
+
+// Fixed schedule: the host enqueues all max_sweeps sweeps; those after convergence are ~3 us predicated no-ops.  Used when
+// the stage timers are on (their events cannot live inside a WHILE node) and when the grid is summed with NCCL.
+static int enqueue_fixed_schedule(picgolf_handle h)
+{
+    for (int k = 1; k <= h->cfg.max_sweeps; ++k) PG_TRY(enqueue_sweep(h, k, 0));
     PG_TRY(launch_step_end(h, true));
+    return 0;
+}
+
+// Device-driven loop: build (once per slot) the graph  WHILE(cond){ sweep } -> step_end.  cond starts at 1 on every launch
+// (cudaGraphCondAssignDefault); the solve kernel clears it when isapprox(F,E) holds or k = max_sweeps, the rest of that
+// iteration (the finalising particle pass) still runs, then the loop exits.
+static int build_loop_graph(picgolf_handle h, cudaGraphExec_t *exec)
+{
+    if (!h->cap_stream) PG_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    PG_CUDA(cudaGraphCreate(&g, 0));
+    struct Guard { cudaGraph_t g; ~Guard() { if (g) cudaGraphDestroy(g); } } guard{g};
+    cudaGraphConditionalHandle cond;
+    PG_CUDA(cudaGraphConditionalHandleCreate(&cond, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = cond; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    PG_CUDA(cudaGraphAddNode(&wnode, g, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    cudaStream_t run = h->stream;
+    const int64_t l0 = h->launches;
+    // the sweep, captured into the body of the WHILE node
+    PG_CUDA(cudaStreamBeginCaptureToGraph(h->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    h->stream = h->cap_stream;
+    int rc = enqueue_sweep(h, -1, cond);
+    h->stream = run;
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, nullptr);
+    h->loop_launches_per_sweep = (int)(h->launches - l0);
+    h->launches = l0;
+    if (rc != 0) return rc;
+    PG_CUDA(e);
+    // step_end, after the loop
+    PG_CUDA(cudaStreamBeginCaptureToGraph(h->cap_stream, g, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+    h->stream = h->cap_stream;
+    rc = launch_step_end(h, true);
+    h->stream = run;
+    e = cudaStreamEndCapture(h->cap_stream, nullptr);
+    h->launches = l0;
+    if (rc != 0) return rc;
+    PG_CUDA(e);
+    PG_CUDA(cudaGraphInstantiate(exec, g, 0));
     return 0;
 }
 
@@ -1098,21 +1179,14 @@ static int enqueue_simpson_step(picgolf_handle h)
     return 0;
 }
 
-// One fixed-point step = 2*max_sweeps + 2 launches, most of them predicated no-ops.  For small problems the
+// Simpson-1/3 schemes: one step = 2*max_sweeps + 4 launches, most of them predicated no-ops.  For small problems the
 // step is launch-bound, so the whole sequence is captured once per ping-pong parity into a CUDA graph and
 // replayed (single GPU, stage timers off; NCCL calls and timing events stay out of graphs).
-static int step_fixedpoint(picgolf_handle h)
+static int step_simpson(picgolf_handle h)
 {
-    // Lazy first sort: the first step after the particles were (re)set runs on the any-order kernels, the
-    // cell sort happens before the second one.  A caller that exchanges the whole state every step (bench.py's
-    // e2e arm) then never pays for a from-scratch sort + unsort that a single step cannot amortise.
-    h->use_sorted_now = h->sorted && (h->pid_valid || h->steps > 0);
-    if (h->use_sorted_now && h->poly && h->pid_valid) probe_poly_flushes(h);
-    if (h->use_sorted_now && (!h->pid_valid || h->since_sort >= h->sort_every || h->force_sort)) PG_TRY(sort_particles_1d(h));
-    int (*enqueue)(picgolf_handle) = h->simpson ? enqueue_simpson_step : enqueue_fixedpoint_step;
-    const bool use_graph = !h->sorted && !h->comm && !h->timer.enabled && h->count <= (1 << 22) && !h->graph_failed;
+    const bool use_graph = !h->comm && !h->timer.enabled && h->count <= (1 << 22) && !h->graph_failed;
     if (!use_graph) {
-        PG_TRY(enqueue(h));
+        PG_TRY(enqueue_simpson_step(h));
     } else {
         const int slot = h->par + 2 * (h->have_deposit ? 1 : 0);
         cudaGraphExec_t &exec = h->step_graph[slot];
@@ -1122,7 +1196,7 @@ static int step_fixedpoint(picgolf_handle h)
             cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
             int rc = 0;
             if (e == cudaSuccess) {
-                rc = enqueue(h);
+                rc = enqueue_simpson_step(h);
                 e = cudaStreamEndCapture(h->stream, &g);
             }
             if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&exec, g, 0);
@@ -1133,9 +1207,8 @@ static int step_fixedpoint(picgolf_handle h)
                 cudaGetLastError();
                 exec = nullptr;
                 h->graph_failed = true;
-                PG_TRY(enqueue(h));
+                PG_TRY(enqueue_simpson_step(h));
                 h->par ^= 1; h->since_sort++;
-                if (!h->simpson) { h->have_deposit = true; std::swap(h->rho_fx, h->rho_next); }
                 return 0;
             }
         }
@@ -1144,10 +1217,52 @@ static int step_fixedpoint(picgolf_handle h)
     }
     h->par ^= 1;
     h->since_sort++;
-    if (!h->simpson) { // the final pass deposited the next step's first rho (atomic / sorted kernels: into rho_next)
-        h->have_deposit = true;
-        std::swap(h->rho_fx, h->rho_next);
+    return 0;
+}
+
+// One step of the Gaussian fixed point (GaussianFixedPoint.jl:7-10).  Default: the device-driven loop (build_loop_graph) --
+// S sweeps cost S x {[mom2rho] [publish] solve [gpoly] pass} + step_end launches and nothing else.  The fixed schedule
+// (all max_sweeps sweeps enqueued, the surplus predicated off) remains for stage timing and for the NCCL reduction.
+static int step_fixedpoint(picgolf_handle h)
+{
+    // Lazy first sort: the first step after the particles were (re)set runs on the any-order kernels, the
+    // cell sort happens before the second one.  A caller that exchanges the whole state every step (bench.py's
+    // e2e arm) then never pays for a from-scratch sort + unsort that a single step cannot amortise.
+    h->use_sorted_now = h->sorted && (h->pid_valid || h->steps > 0);
+    if (h->use_sorted_now && h->poly && h->pid_valid) probe_poly_flushes(h);
+    if (h->use_sorted_now && (!h->pid_valid || h->since_sort >= h->sort_every || h->force_sort)) PG_TRY(sort_particles_1d(h));
+    if (h->simpson) return step_simpson(h);
+    h->pass_blocks = poly_now(h) ? h->nblocks_poly : h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
+    if (!h->have_deposit) PG_TRY(enqueue_first_pass(h));
+    const bool loop = !h->loop_off && !h->loop_failed && !h->timer.enabled && (!h->comm || h->peer_ok);
+    bool done = false;
+    if (loop) {
+        const int slot = h->par + 2 * (h->rho_fx == h->rho_base[1] ? 1 : 0) + 4 * (h->use_sorted_now ? 1 : 0);
+        cudaGraphExec_t &exec = h->loop_graph[slot];
+        if (!exec && build_loop_graph(h, &exec) != 0) { // no conditional nodes on this driver: fixed schedule for good
+            cudaGetLastError();
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            if (h->cap_stream && cudaStreamIsCapturing(h->cap_stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+                cudaGraph_t junk = nullptr;
+                cudaStreamEndCapture(h->cap_stream, &junk);
+                cudaGetLastError();
+            }
+            exec = nullptr;
+            h->loop_failed = true;
+        }
+        if (exec) {
+            PG_CUDA(cudaGraphLaunch(exec, h->stream));
+            h->launches += 1; // step_end; the sweeps are counted on the device (Ctrl.loop_sweeps, picgolf_launch_count)
+            h->loop_steps++;
+            done = true;
+        }
     }
+    if (!done) PG_TRY(enqueue_fixed_schedule(h));
+    h->par ^= 1;
+    h->since_sort++;
+    // the final pass deposited the next step's first rho (atomic / sorted kernels: into rho_next; polynomial: the moment grid)
+    h->have_deposit = true;
+    std::swap(h->rho_fx, h->rho_next);
     if (h->poly && h->sort_auto) { // end-of-step marker for probe_poly_flushes (h->steps is incremented by the caller)
         cudaEvent_t &e = h->run_ev[h->steps & 7];
         if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -1274,6 +1389,8 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
     if (nsteps < 0) return fail(PICGOLF_ERR_ARG, "nsteps < 0");
     if (!h->have_particles) return fail(PICGOLF_ERR_STATE, "set or initialise particles before stepping");
+    if (h->nranks > 1 && !h->comm)
+        return fail(PICGOLF_ERR_STATE, "handle is rank %d of %d but picgolf_comm_init was never called: its shard alone would deposit a wrong charge", h->rank, h->nranks);
     if (nsteps == 0) return 0;
     PG_TRY(use_device(h));
     const int sp8_ = h->timer.begin(ST_TOTAL, h->stream);
@@ -1329,7 +1446,7 @@ PG_API int picgolf_get_fields(picgolf_handle h, double *rho, double *E)
     if (rho) PG_CUDA(cudaMemcpyAsync(rho, h->rho_last, b, cudaMemcpyDeviceToHost, h->stream));
     if (E) PG_CUDA(cudaMemcpyAsync(E, h->E + (size_t)(h->grid_rows - 1) * h->ncell, b, cudaMemcpyDeviceToHost, h->stream)); // E[end,:]
     PG_CUDA(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer(h);
 }
 
 PG_API int picgolf_set_field(picgolf_handle h, const double *E)
@@ -1374,6 +1491,7 @@ static int fetch_raw(picgolf_handle h, std::vector<double> &raw, int64_t *rows)
 {
     PG_TRY(use_device(h));
     PG_CUDA(cudaStreamSynchronize(h->stream));
+    PG_TRY(check_peer(h));
     Ctrl c;
     PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
     *rows = c.rows;
@@ -1507,6 +1625,13 @@ PG_API int picgolf_launch_count(picgolf_handle h, int64_t *launches)
 {
     if (!h || !launches) return fail(PICGOLF_ERR_ARG, "NULL argument");
     *launches = h->launches;
+    if (h->loop_steps > 0) { // + the sweeps the device-driven loop has launched since the particles were set
+        PG_TRY(use_device(h));
+        PG_CUDA(cudaStreamSynchronize(h->stream));
+        Ctrl c;
+        PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
+        *launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep;
+    }
     return 0;
 }
 
@@ -1581,6 +1706,11 @@ PG_API int picgolf_peer_connect(picgolf_handle h, const void *handles, int nrank
         h->peer_ptr[q] = (PeerPub *)p;
     }
     h->peer_ok = true;
+    // map every peer buffer now (cudaIpc maps lazily): the first access over NVLink must not land inside a timed sweep
+    peer_touch_kernel<<<1, 1, 0, h->stream>>>(peer_args(h), (unsigned long long *)h->peer_err);
+    h->launches++;
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -29,8 +29,10 @@ def broadcast_bytes(payload, nbytes: int, src: int = 0) -> bytes:
 
 
 def connect(pic: PIC, peer=None) -> None:
-    """Create the handle's NCCL communicator (collective over all ranks of the default group) and, with peer=True or
-    PICGOLF_PEER=1, the peer-memory reduction of the 1D charge grids (pg_peer.cuh; opt-in for now)."""
+    """Create the handle's NCCL communicator (collective over all ranks of the default group) and the peer-memory reduction
+    of the 1D charge grids (pg_peer.cuh).  peer=None: PICGOLF_PEER=1 / 0 forces it on / off; otherwise it is on for the
+    Gaussian fixed point, whose device-driven sweep loop (a CUDA-graph WHILE node) cannot contain NCCL calls, and off
+    (one ncclAllReduce per step) for the schemes with a single solve per step."""
     import torch.distributed as dist
 
     if pic.cfg.nranks == 1:
@@ -39,8 +41,9 @@ def connect(pic: PIC, peer=None) -> None:
     uid = broadcast_bytes(uid, 128, src=0)
     pic.comm_init(uid)
     if peer is None:
-        peer = os.environ.get("PICGOLF_PEER") is not None
-    if peer:
+        env = os.environ.get("PICGOLF_PEER")
+        peer = (env != "0") if env is not None else pic.cfg.scheme == 3  # GAUSS_FIXEDPOINT
+    if peer and pic.cfg.scheme not in (4, 5, 6):  # 2D3V and the Simpson schemes sum their grids with NCCL
         connect_peers(pic)
 
 

@@ -522,9 +522,10 @@ def test_poly_mode_matches_atomic_mode(pg, oracle, start, N, P):
     sorts, flushes = s.sort_stats()
     assert sorts == 3  # before steps 1, 5, 9 (0-based)
     if P // N >= 4096:
-        # (cell, sign v) bins drift as a whole: a lane changes cell about twice per bin (64/bin_size flushes per
-        # particle and pass); lanes alternating between cells would flush on a large share of their particles
-        assert flushes / (P * float(sws[1:].sum())) < 0.02
+        # (cell, sign v) bins drift as a whole: each lane of the warp that streams a bin flushes once per polynomial interval
+        # (8 per cell and beam: 32 * 16 * N / P = 0.03 flushes per particle and pass here, plus one per warp range);
+        # lanes alternating between intervals would flush on a large share of their particles
+        assert flushes / (P * float(sws[1:].sum())) < 0.1
 
 
 def test_poly_mode_warm_beams_force_resort(pg):
