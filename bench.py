@@ -10,13 +10,15 @@ A "step" is one PIC time step = S fixed-point sweeps (S reported).  One JSON lin
 
 Timing: W untimed warm-up steps, then exactly K steps bracketed by barrier + synchronize; CUDA events
 on the library's own stream; max over ranks.  Inputs (8 GiB of particle state per GPU) exceed L2.
-`value` has the particle state resident in HBM; `e2e` moves the whole particle state host->device and
-device->host through the C ABI every step (pinned host buffers).
+`value` has the particle state resident in HBM; `e2e` pushes the whole particle state host->device and
+device->host through the C ABI every step (picgolf_step_streamed, pinned host buffers, copies overlapped
+with the steps of the neighbouring calls); the serial set/step/get sequence is reported next to it.
 """
 import argparse
 import json
 import math
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -39,42 +41,76 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread every ~5 ms (a 0.1 s timed region
+    still gets ~20 samples), nvidia-smi -lms 100 as the fallback."""
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu):
-        self.gpu, self.proc, self.lines = gpu, None, []
+        self.gpu, self.sm, self.mx, self.reasons, self.stop_flag, self.t, self.proc, self.how = gpu, [], [], set(), False, None, None, None
+
+    def _nvml_loop(self, h, nv):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.how = "nvml, 5 ms"
+            self.t = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.how = "nvidia-smi -lms 100"
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.lines = []
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for l in self.lines:
-            f = [s.strip() for s in l.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+            for l in self.lines:
+                f = [s.strip() for s in l.split(",")]
+                try:
+                    self.sm.append(float(f[1])); self.mx.append(float(f[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+        elif self.t:
+            self.t.join(timeout=1)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0, "how": self.how}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "how": self.how}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -100,8 +136,23 @@ def make_sim(pg, workload, per_gpu, rank, world, device, T, deposit_mode=0):
     return sim, name, bytes_per_unit
 
 
-def init_sim(sim, workload, seed=1234):
-    sim.init_synthetic(seed=seed, vth=getattr(sim, "vth", 0.0))
+def init_sim(sim, workload, seed=1234, vth=None):
+    sim.init_synthetic(seed=seed, vth=getattr(sim, "vth", 0.0) if vth is None else vth)
+
+
+def traffic_of(key):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and FP64 instructions per particle of the dominant
+    kernel, from the committed `ncu --set full` capture of this kernel at 2^28 particles (ncu cannot run inside a timed bench;
+    the file names its capture)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[key]
+            t = dict(t)
+            t["source"] = "profiles/" + name
+            return t
+        except Exception:
+            continue
+    return None
 
 
 def run_gpu(args):
@@ -117,6 +168,8 @@ def run_gpu(args):
     if args.gpus > 1 and world == 1:
         raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local)
+    sampler.start()  # before the warm-up: the timed region of the driver's run is only ~0.1 s long
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, Wm = args.steps, max(args.warmup, 3)
@@ -136,11 +189,17 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     # ---- device-resident timing -------------------------------------------------------------
     sim.step(Wm)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.sm.clear(); sampler.mx.clear(); sampler.reasons.clear()  # keep only what is sampled from here on
     sorts0 = sim.sort_stats()[0]
     l0 = sim.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -148,14 +207,10 @@ def run_gpu(args):
     sim.step(K)  # one C-ABI call enqueues all K steps (no host sync inside)
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     launches = sim.launches - l0
     sorts_timed = sim.sort_stats()[0] - sorts0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     P = sim.cfg.P
     value = P * K / (ms * 1e-3)
     D, sw = sim.diagnostics()
@@ -163,9 +218,11 @@ def run_gpu(args):
     mean_sweeps = float(sweeps.mean())
 
     # ---- roofline of the dominant kernel (the particle pass), timed live with CUDA events ------
+    # (stage timers on: the fixed launch schedule, whose events bracket every kernel -- the kernels are those of the timed region)
     sim.stage_timing(True)
     sim.stage_times(reset=True)
-    nroof = 40 if (args.workload == "gauss_fp" and sim.deposit_path == pg.DEPOSIT_POLY) else 12  # long enough to contain a re-sort
+    poly = args.workload == "gauss_fp" and sim.deposit_path == pg.DEPOSIT_POLY
+    nroof = 40 if poly else 12  # long enough to contain a re-sort
     s0 = sim.sort_stats()[0]
     sim.step(nroof)
     st = sim.stage_times(reset=True)
@@ -174,122 +231,78 @@ def run_gpu(args):
     if args.workload == "gauss_fp":
         passes = float(sw2[Wm + K:Wm + K + nroof].sum())  # S solves -> S particle passes per step (the k=0 pass is fused into the previous step's final pass)
         alg_bytes_launch = 32.0 * per_gpu
-        poly = sim.deposit_path == pg.DEPOSIT_POLY
-        kernel = ("fp_pass_poly<FIRST> (per-cell gather polynomial + implicit-midpoint update + register moment deposit)" if poly else
+        kernel = ("fp_pass_poly<FIRST> (sub-cell gather polynomial + implicit-midpoint update + register moment deposit)" if poly else
                   "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)")
+        tkey = "gauss_fp_poly" if poly else "gauss_fp"
     elif args.workload == "ngp":
         passes = float(nroof + 1)
         alg_bytes_launch = 32.0 * per_gpu
         kernel = "lf_pass_ngp_tma (TMA-staged tiles: drift + kick + drift + NGP deposit)"
+        tkey = "ngp"
     else:
         passes = float(nroof)
         alg_bytes_launch = 80.0 * per_gpu
         kernel = "particles_2d3v_tiled (gather + boris + move + CIC deposit)"
+        tkey = "2d3v"
     launch_ms = st["particles"] / passes
     peak, peak_src = peaks()
     achieved = alg_bytes_launch / (launch_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # per-launch DRAM bytes of the same kernel from the committed ncu --set full capture (only valid at 2^28/GPU)
-        key = "gauss_fp_poly" if args.workload == "gauss_fp" and sim.deposit_path == pg.DEPOSIT_POLY else args.workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[key]
-        if per_gpu == 1 << 28:
-            traffic = tj["traffic_bytes"]
-    except Exception:
-        pass
+    tj = traffic_of(tkey) if per_gpu == 1 << 28 else None  # the capture is of a 2^28-particle launch
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": traffic, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "peak_source": peak_src, "traffic": tj["traffic_bytes"] if tj else None,
+                "traffic_source": (tj["source"] + ": " + tj.get("capture", "")) if tj else None,
+                "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "stage_ms_per_step": {k: v / nroof for k, v in st.items()},
                 "resorts_in_stage_window": sim.sort_stats()[0] - s0, "stage_window_steps": nroof}
 
-    # ---- FP64 pipe view of the same kernel (the binding limit of the erf-shape passes) ----------
+    # ---- FP64 pipe view of the same kernel (the second bound of the erf-shape passes) ----------
     fp64 = None
     if args.workload == "gauss_fp":
         peak_tf = pg.fp64_peak_tflops()
-        # FP64 instructions per particle-pass measured with ncu (profiles/): 255 for a fp_pass_sorted pass with two
-        # stencils (middle passes and the final pass with the fused first deposit of the next step); 68 for fp_pass_poly
-        # (FP64 pipe active 57.6 % of 3.25 M cycles = 132 warp-instructions per row of 64 particles in the first and
-        # middle passes, 144 in the final pass: mean over a 3-sweep step 68 per particle)
-        per_pass = 68 if sim.deposit_path == pg.DEPOSIT_POLY else 255
+        per_pass = (tj or {}).get("fp64_inst_per_particle_pass", 47 if poly else 255)  # ncu: smsp__inst_executed_pipe_fp64.sum * 32 / particles
         fp64_inst = float(sum(per_pass * int(s_) for s_ in sw2[Wm + K:Wm + K + nroof])) * per_gpu
         ach = fp64_inst * 2.0 / (st["particles"] * 1e-3) / 1e12  # counted as 2 flops per lane-instruction (FMA-equivalent)
         fp64 = {"measured_peak_tflops": peak_tf, "achieved_tflops_fma_equiv": ach, "frac": ach / peak_tf,
                 "fp64_instructions_per_particle_pass": per_pass,
-                "note": "FP64 lane-instructions of the pass kernels x2 / kernel time (the second bound of the erf-shape passes besides HBM)"}
+                "note": "FP64 lane-instructions of the pass kernels (ncu count, profiles/) x2 / kernel time measured here"}
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
     e2e = None
     if not args.no_e2e:
-        n = sim.count
-        ncomp = 5 if args.workload == "2d3v" else 2
-        host = [torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for _ in range(ncomp)]
-        got = sim.particles()
-        for h, g in zip(host, got):
-            h[:] = g
-        del got
-        lib, hnd = pg.load(), sim._h
-        import ctypes as C
-        ptr = [h.ctypes.data_as(C.c_void_p) for h in host]
-        Ke = max(1, min(K, args.e2e_steps))
-
-        def one():
-            if ncomp == 2:
-                pg._check(lib.picgolf_set_particles(hnd, host[0], host[1], n))
-                pg._check(lib.picgolf_step(hnd, 1))
-                pg._check(lib.picgolf_get_particles(hnd, ptr[0], ptr[1], n))
-            else:
-                pg._check(lib.picgolf_set_particles_2d3v(hnd, *host, n))
-                pg._check(lib.picgolf_step(hnd, 1))
-                pg._check(lib.picgolf_get_particles_2d3v(hnd, *ptr, n))
-        one()
-        barrier()
-        t0 = time.perf_counter()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(Ke):
-            one()
-        f1.record(stream)
-        barrier()
-        ems = f0.elapsed_time(f1)  # device time between the first H2D and the last D2H on the library's stream
-        wall = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([ems], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        e2e = {"value": P * Ke / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncomp * n, "d2h_bytes_per_step": 8 * ncomp * n,
-               "steps": Ke, "ms_per_step": ems / Ke, "wall_ms_per_step": wall / Ke,
-               "what": "per step: picgolf_set_particles (pinned host -> HBM), picgolf_step(1), picgolf_get_particles (HBM -> host)"}
-        # second reading of "inputs in, result out": the particle state goes in every step, only the step's fields
-        # (rho, E) and its diagnostics row come back
-        def one_fields():
-            if ncomp == 2:
-                pg._check(lib.picgolf_set_particles(hnd, host[0], host[1], n))
-            else:
-                pg._check(lib.picgolf_set_particles_2d3v(hnd, *host, n))
-            pg._check(lib.picgolf_step(hnd, 1))
-            fl = sim.fields()
-            sim.diagnostics()
-            return sum(a.nbytes for a in fl) + 40
-        one_fields()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(Ke):
-            d2h = one_fields()
-        f1.record(stream)
-        barrier()
-        fms = f0.elapsed_time(f1)
-        if world > 1:
-            t = torch.tensor([fms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fms = float(t.item())
-        e2e["state_in_fields_out"] = {"value": P * Ke / (fms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncomp * n,
-                                      "d2h_bytes_per_step": int(d2h), "ms_per_step": fms / Ke,
-                                      "what": "per step: picgolf_set_particles, picgolf_step(1), picgolf_get_fields + picgolf_get_diagnostics"}
+        e2e = run_e2e(args, pg, sim, torch, barrier, max_over_ranks, stream, P, world)
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.workload, args.cpu_log2_particles, args.cpu_steps)
+
+    # ---- the same workload in the warm (saturated two-stream) regime ------------------------------------------
+    warm = None
+    if args.warm and args.workload == "gauss_fp":
+        sim.close()
+        sim, _, _ = make_sim(pg, "gauss_fp", per_gpu, rank, world, local, T=128, deposit_mode=0)
+        if world > 1:
+            pgd.connect(sim)
+        stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local))
+        warm = {}
+        for vth in (0.05, 0.3):
+            init_sim(sim, "gauss_fp", seed=99, vth=vth)
+            sim.step(4)
+            barrier()
+            so, lo_ = sim.sort_stats()[0], sim.launches
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            Kw = 24
+            g0.record(stream)
+            sim.step(Kw)
+            g1.record(stream)
+            barrier()
+            msw = max_over_ranks(g0.elapsed_time(g1))
+            sww = sim.diagnostics()[1][4:4 + Kw].astype(float)
+            warm[f"vth={vth}"] = {"value": P * Kw / (msw * 1e-3), "unit": UNIT, "ms_per_step": msw / Kw, "steps": Kw, "mean_sweeps_per_step": float(sww.mean()),
+                                  "resorts": sim.sort_stats()[0] - so, "hbm_roofline_frac_step": (P / world) * Kw * 32.0 * (float(sww.mean()) + 1) / (msw * 1e-3) / (peak * 1e9),
+                                  "start": f"seeded-uniform x, v = +-1 + {vth}*N(0,1): beams as warm as after saturation (vortices), the bins of the sorted order shear apart within a few steps"}
+        warm["note"] = ("the headline is measured in the cold-beam phase (bins drift rigidly, one re-sort per 16-64 steps); with warm beams the flush "
+                        "probe forces re-sorts every few steps (counted here)")
 
     # ---- the other two scoped workloads, briefly (device-resident, same timing rules) ----------------------
     others = None
@@ -312,16 +325,14 @@ def run_gpu(args):
             s2.step(Ko)
             g1.record(st2)
             s2.synchronize(); torch.cuda.synchronize()
-            mso = g0.elapsed_time(g1)
-            if world > 1:
-                t = torch.tensor([mso], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                mso = float(t.item())
+            mso = max_over_ranks(g0.elapsed_time(g1))
             vo = s2.cfg.P * Ko / (mso * 1e-3)
             others[wl] = {"workload": name2, "value": vo, "unit": UNIT, "steps": Ko, "ms_per_step": mso / Ko,
                           "algorithmic_bytes_per_particle_step": bpu2, "hbm_roofline_frac_step": (vo / world) * bpu2 / (peak * 1e9),
                           "sorts_total_incl_warmup": s2.sort_stats()[0]}
             s2.close()
+            if rank == 0 and world == 1 and not args.no_cpu:
+                others[wl]["cpu_baseline"] = cpu_baseline(wl, args.cpu_log2_particles, args.cpu_steps)
 
     if rank == 0:
         if args.workload == "gauss_fp":
@@ -337,7 +348,7 @@ def run_gpu(args):
             "algorithmic_bytes_per_particle_step": bpu,
             "hbm_roofline_frac_step": (value / world) * bpu / (peak * 1e9),
             "roofline": roofline, "fp64_pipe": fp64, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "sorts_in_timed_region": int(sorts_timed), "other_workloads": others,
+            "sorts_in_timed_region": int(sorts_timed), "warm_regime": warm, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     sim.close()
@@ -346,10 +357,83 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_e2e(args, pg, sim, torch, barrier, max_over_ranks, stream, P, world):
+    """Per step: the whole particle state of the shard goes host -> device and the stepped state comes back device -> host,
+    through the C ABI.  Headline: picgolf_step_streamed (three device buffer sets, copies of neighbouring calls overlap the
+    step; wall clock around Ke back-to-back calls and the final synchronize).  Beside it the serial
+    picgolf_set_particles / picgolf_step(1) / picgolf_get_particles sequence of round 1."""
+    n = sim.count
+    ncomp = 5 if args.workload == "2d3v" else 2
+    K = args.steps
+    host = [torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for _ in range(ncomp)]
+    outs = [[torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for _ in range(ncomp)] for _ in range(2)]
+    got = sim.particles()
+    for h, g in zip(host, got):
+        h[:] = g
+    del got
+    Ke = max(1, args.e2e_steps)
+    for i in range(2):  # builds the ring, touches every buffer
+        sim.step_streamed(host, outs[i & 1])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        sim.step_streamed(host, outs[i & 1])
+    sim.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ems = max_over_ranks(wall)
+    e2e = {"value": P * Ke / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncomp * n, "d2h_bytes_per_step": 8 * ncomp * n,
+           "steps": Ke, "ms_per_step": ems / Ke, "timer": "host wall clock around the calls and the final picgolf_synchronize (three CUDA streams: no single-stream event pair spans it)",
+           "what": "per step: picgolf_step_streamed = upload of the whole shard state from pinned host memory, one PIC step, download of the stepped state; "
+                   "uploads, steps and downloads of neighbouring calls overlap (3 device buffer sets)"}
+    # the serial form: set -> step -> get, one after the other
+    import ctypes as C
+    lib, hnd = pg.load(), sim._h
+    ptr = [h.ctypes.data_as(C.c_void_p) for h in outs[0]]
+    Ks = max(1, min(3, Ke))
+
+    def one():
+        if ncomp == 2:
+            pg._check(lib.picgolf_set_particles(hnd, host[0], host[1], n))
+            pg._check(lib.picgolf_step(hnd, 1))
+            pg._check(lib.picgolf_get_particles(hnd, ptr[0], ptr[1], n))
+        else:
+            pg._check(lib.picgolf_set_particles_2d3v(hnd, *host, n))
+            pg._check(lib.picgolf_step(hnd, 1))
+            pg._check(lib.picgolf_get_particles_2d3v(hnd, *ptr, n))
+    one()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(Ks):
+        one()
+    f1.record(stream)
+    barrier()
+    sms = max_over_ranks(f0.elapsed_time(f1))
+    e2e["serial_set_step_get"] = {"value": P * Ks / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / Ks, "steps": Ks,
+                                  "what": "per step: picgolf_set_particles, picgolf_step(1), picgolf_get_particles, one after the other (CUDA events on the library's stream)"}
+    del host, outs
+    return e2e
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference loop, timed on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(workload, log2p, steps):
+def julia_probe():
+    """Is the reference's own runtime on this box?  (probe before assuming.)"""
+    exe = shutil.which("julia")
+    ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))
+    if exe:
+        try:
+            ver = subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=60).stdout.strip()
+        except Exception as e:  # noqa: BLE001
+            ver = f"not runnable: {e}"
+        return {"julia": exe, "version": ver, "baseline/_ref": ref,
+                "note": "julia is present, but the reference scripts (/root/reference) do not travel to this box and must not be copied into the repo; the C restatement is timed"}
+    return {"julia": None, "baseline/_ref": ref, "note": "no julia executable on PATH and no baseline/_ref: the reference (19 Julia scripts, no package) cannot run here"}
+
+
+def cpu_baseline(workload, log2p, steps, warmup=1):
     from oracle import oracle as o
 
     P = 1 << log2p
@@ -359,17 +443,19 @@ def cpu_baseline(workload, log2p, steps):
         x0 = rng.random(P)
         v0 = np.where(np.arange(1, P + 1) > P / 2, 1.0, -1.0)
         fp = o.FixedPoint(x0, v0, N, 1 / (6 * N), 400.0, hw=6, rtol=1e-8)
-        fp.step()
+        for _ in range(warmup):
+            fp.step()
         t0 = time.perf_counter()
         sw = [fp.step()[2] for _ in range(steps)]
         dt = time.perf_counter() - t0
         cores, extra = 1, {"mean_sweeps_per_step": float(np.mean(sw))}
-        sample = f"N=4096 P=2^{log2p} seeded-uniform two-stream, {steps} steps after 1 warm-up, single thread (the 1D scripts have no threading)"
+        sample = f"N=4096 P=2^{log2p} seeded-uniform two-stream, {steps} steps after {warmup} warm-up, single thread (the 1D scripts have no threading: JULIA_NUM_THREADS=1 is how the reference runs them)"
     elif workload == "ngp":
         N = 4096
         x = rng.random(P)
         v = np.where(np.arange(1, P + 1) > P / 2, 1.0, -1.0)
-        o.ngp_step(x, v, N, 1 / (4 * N), 256.0 / P * N)
+        for _ in range(warmup):
+            o.ngp_step(x, v, N, 1 / (4 * N), 256.0 / P * N)
         t0 = time.perf_counter()
         for _ in range(steps):
             o.ngp_step(x, v, N, 1 / (4 * N), 256.0 / P * N)
@@ -385,31 +471,41 @@ def cpu_baseline(workload, log2p, steps):
         Ex, Ey = np.zeros(NX * NY), np.zeros(NX * NY)
         cores = o.max_threads()
         args = (NX, NY, 1 / NG / (6 * vth), math.sqrt(n0) / 4, n0 / P * NX * NY)
-        o.step_2d3v(*st, *args, Ex, Ey, nthreads=cores)
+        for _ in range(warmup):
+            o.step_2d3v(*st, *args, Ex, Ey, nthreads=cores)
         t0 = time.perf_counter()
         for _ in range(steps):
             o.step_2d3v(*st, *args, Ex, Ey, nthreads=cores)
         dt = time.perf_counter() - t0
         extra = {}
-        sample = f"256x256 P=2^{log2p}, {steps} steps, {cores} threads with per-thread grids (Electrostatic2D3V.jl:114,126-141)"
+        sample = f"256x256 P=2^{log2p}, {steps} steps, {cores} threads with per-thread grids (Electrostatic2D3V.jl:114,126-141: Threads.nthreads() = all host cores)"
     out = {"value": P * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sample_ms_per_step": dt / steps * 1e3,
-           "note": "C restatement of the Julia loop (oracle/picgolf_oracle.c, gcc -O2), not Julia: julia is not installed"}
+           "sample_particles": P, "sample_steps": steps,
+           "note": "C restatement of the Julia loop (oracle/picgolf_oracle.c, gcc -O2), not Julia", "reference_runtime_probe": julia_probe()}
     out.update(extra)
     return out
 
 
 def run_reference(args):
+    """The reference arm: the CPU implementation of the same path on this box's host cores.  It runs EXACTLY the requested
+    `--warmup` + `--steps` steps, on a bounded sample of the workload: the particle count is cut (calibrated on one step so that
+    the whole run takes ~30 s), every other parameter is the GPU arm's.  particle-steps/s is size-independent for these O(P)
+    loops (the grid work is < 1 % at >= 16 particles per cell), and the line says what was run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    K, Wm = args.steps, max(args.warmup, 1)
-    cpu = cpu_baseline(args.workload, args.cpu_log2_particles, max(1, min(K, args.cpu_steps)))
+    K, Wm = max(1, args.steps), max(0, args.warmup)
+    cal = cpu_baseline(args.workload, 16, 1, warmup=1)  # calibration: seconds per particle-step on this box
+    per = 1.0 / cal["value"]
+    log2p = int(max(14, min(22, math.floor(math.log2(30.0 / ((K + Wm) * per))))))
+    cpu = cpu_baseline(args.workload, log2p, K, warmup=Wm)
     per_gpu = 1 << args.log2_particles_per_gpu
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
             "ms_per_step": cpu["sample_ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: same configuration as the GPU arm ({per_gpu * max(world, args.gpus)} particles), timed on a bounded sample",
-                       "sample": cpu["sample"]},
+            "config": {"workload": f"{args.workload}: bounded sample of the GPU arm's configuration -- 2^{log2p} particles instead of {per_gpu * max(world, args.gpus)}, "
+                                   f"same grid, time step, stencil and tolerance; {K} timed steps after {Wm} warm-up steps on the host cores; {cpu['sample']}",
+                       "sample_particles": cpu["sample_particles"], "sample_steps": K},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -418,17 +514,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200, help="timed steps (default: ~1 s of device time at 2^28 particles)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gauss_fp", choices=["gauss_fp", "ngp", "2d3v"])
     ap.add_argument("--log2-particles-per-gpu", type=int, default=28)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--deposit-mode", default="auto", choices=["auto", "atomic", "sorted", "poly"],
                     help="gauss_fp only: force a deposit path (A/B runs); auto = what a caller gets")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", dest="others", action="store_false", help="skip the brief NGP and 2D3V runs")
+    ap.add_argument("--no-warm", dest="warm", action="store_false", help="skip the warm-beam (saturated regime) run of config 4")
     ap.add_argument("--cpu-log2-particles", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=3)
     args = ap.parse_args()

@@ -147,7 +147,8 @@ int picgolf_init_quiet(picgolf_handle h);
 /* Seeded synthetic two-stream start on device (counter-based splitmix64, NOT Julia's rand):
  * x ~ U[0,1), v = -1 for global j <= P/2 else +1 (the NGPFourier.jl:2 pattern).  For 2D3V:
  * x,y ~ U(0,1], v Maxwellian with per-component std vth/sqrt(2) (Electrostatic2D3V.jl:45-55
- * without the sample-mean correction).  vth is ignored in 1D. */
+ * without the sample-mean correction).  1D: vth > 0 warms the beams, v = +-1 + vth*N(0,1) (the velocity spread of the
+ * saturated two-stream state); vth = 0 is the cold start of the scripts. */
 int picgolf_init_synthetic(picgolf_handle h, uint64_t seed, double vth);
 /* Copy the local shard back in the caller's original particle order. */
 int picgolf_get_particles(picgolf_handle h, double *x, double *v, int64_t count);
@@ -165,6 +166,17 @@ int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, double *v
  * any getter or picgolf_synchronize() waits. */
 int picgolf_step(picgolf_handle h, int64_t nsteps);
 int picgolf_synchronize(picgolf_handle h);
+/* Streaming form of  picgolf_set_particles(x_in, v_in) -> picgolf_step(1) -> picgolf_get_particles(x_out, v_out)  for a driver
+ * that pushes a sequence of particle states through the device (ensembles, parameter scans, a host-side outer loop around
+ * the loop body of NGPFourier.jl:5-6 / GaussianFixedPoint.jl:7-10).  Same result as the three calls, but ASYNCHRONOUS and
+ * pipelined: the library keeps three device buffer sets and two copy streams, so the upload of call n+1, the step of call n
+ * and the download of call n-1 overlap (PCIe is full duplex) -- use pinned host memory (cudaHostRegister / cudaMallocHost),
+ * pageable buffers serialise the copies.  x_in/v_in must stay untouched and x_out/v_out are valid only after
+ * picgolf_synchronize() (or any later getter on the handle).  The field of the step starts from E = 0 like after
+ * picgolf_set_particles; the diagnostics trace keeps growing by one row per call.  x_out / v_out may be NULL.
+ * 2D3V: arrays in the order x, y, vx, vy, vz (Electrostatic2D3V.jl:125-138); a row is recorded when diag_every == 1. */
+int picgolf_step_streamed(picgolf_handle h, const double *x_in, const double *v_in, double *x_out, double *v_out, int64_t count);
+int picgolf_step_streamed_2d3v(picgolf_handle h, const double *const in[5], double *const out[5], int64_t count);
 /* Steps completed since the particles were last set. */
 int picgolf_steps_done(picgolf_handle h, int64_t *steps);
 

@@ -100,6 +100,8 @@ _SIGNATURES = {
     "picgolf_create": [C.POINTER(Config), C.POINTER(_vp)],
     "picgolf_destroy": [_vp],
     "picgolf_local_range": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "picgolf_step_streamed": [_vp, _vp, _vp, _vp, _vp, _i64],
+    "picgolf_step_streamed_2d3v": [_vp, C.POINTER(_vp), C.POINTER(_vp), _i64],
     "picgolf_set_particles": [_vp, _dp, _dp, _i64],
     "picgolf_set_particles_2d3v": [_vp, _dp, _dp, _dp, _dp, _dp, _i64],
     "picgolf_set_particles_1d2v": [_vp, _dp, _dp, _dp, _i64],
@@ -266,6 +268,21 @@ class PIC:
         else:
             x, v = _f64(x), _f64(v)
             _check(self._lib.picgolf_set_particles(self._h, x, v, x.size))
+
+    def step_streamed(self, inputs, outputs):
+        """picgolf_step_streamed: upload `inputs` (x, v) or (x, y, vx, vy, vz), one step, download into `outputs`, all
+        asynchronous and pipelined over three device buffer sets.  The arrays are contiguous float64 numpy arrays (pinned host
+        memory for the copies to overlap) that must stay alive, and `outputs` are valid only after synchronize()."""
+        n = self.count
+        for a in list(inputs) + list(outputs):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == n
+        if self.is2d:
+            pin = (_vp * 5)(*[a.ctypes.data for a in inputs])
+            pout = (_vp * 5)(*[a.ctypes.data for a in outputs])
+            _check(self._lib.picgolf_step_streamed_2d3v(self._h, pin, pout, n))
+        else:
+            _check(self._lib.picgolf_step_streamed(self._h, inputs[0].ctypes.data, inputs[1].ctypes.data,
+                                                   outputs[0].ctypes.data, outputs[1].ctypes.data, n))
 
     def init_quiet(self):
         _check(self._lib.picgolf_init_quiet(self._h))

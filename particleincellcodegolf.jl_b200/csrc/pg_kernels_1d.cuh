@@ -694,14 +694,21 @@ __global__ void quiet_start_kernel(double *x, double *v, long long count, long l
     }
 }
 
-// Seeded synthetic two-stream start (the NGPFourier.jl:2 pattern with a counter-based generator).
-__global__ void synthetic_1d_kernel(double *x, double *v, long long count, long long first, long long P, uint64_t seed)
+// Seeded synthetic two-stream start (the NGPFourier.jl:2 pattern with a counter-based generator).  vth > 0 warms the
+// beams: v = +-1 + vth * N(0,1) (Box-Muller on two more draws) -- the velocity spread of the saturated two-stream state
+// that the cold start only reaches after ~10 plasma periods (bench.py's warm-regime line).
+__global__ void synthetic_1d_kernel(double *x, double *v, long long count, long long first, long long P, uint64_t seed, double vth)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < count; n += stride) {
         uint64_t g = (uint64_t)(first + n);
         x[n] = u01(splitmix64(seed ^ (g * 0xD1342543DE82EF95ULL)));
-        v[n] = ((double)(first + n + 1) > (double)P / 2) ? 1.0 : -1.0;
+        double vn = ((double)(first + n + 1) > (double)P / 2) ? 1.0 : -1.0;
+        if (vth > 0.0) {
+            const double u1 = u01(splitmix64(seed ^ ((g * 4 + 1) * 0x9E3779B97F4A7C15ULL))), u2 = u01(splitmix64(seed ^ ((g * 4 + 2) * 0xC2B2AE3D27D4EB4FULL)));
+            vn += vth * sqrt(-2.0 * log(1.0 - u1)) * cospi(2.0 * u2);
+        }
+        v[n] = vn;
     }
 }
 

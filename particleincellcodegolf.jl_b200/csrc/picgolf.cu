@@ -233,9 +233,18 @@ struct picgolf_handle_s {
     //   WHILE (not converged) { [moments -> rho] [publish] solve [gather polynomials] particle pass }  ->  step_end
     // The solve kernel sets the WHILE condition (cudaGraphSetConditional), so exactly S sweeps are launched -- no
     // predicated-off launches, no host involvement (for _ in 0:9 ... && break, GaussianFixedPoint.jl:7).
-    cudaGraphExec_t loop_graph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaGraphExec_t loop_graph[24] = {}; // [buffer set of the streamed ring][sorted kernels][charge-grid parity][X/V parity]
     cudaStream_t cap_stream = nullptr;
     bool loop_failed = false, loop_off = false;
+    // picgolf_step_streamed: a ring of three particle buffer sets (set 0 = the handle's own arrays) and two copy streams,
+    // so that the upload of call n+1, the step of call n and the download of call n-1 overlap (PCIe is full duplex)
+    struct BufSet { double *a[10]; };  // 1D: xb[0], xb[1], vb[0], vb[1];  2D: p2[0][0..4]
+    BufSet sset[3] = {};
+    int sset_n = 0, sset_cur = 0;      // arrays per set (0: ring not built yet); set currently installed in xb/vb/p2
+    bool sset_used[3] = {false, false, false};
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr}, ev_down[3] = {nullptr, nullptr, nullptr};
+    int64_t stream_calls = 0;
     int loop_launches_per_sweep = 0;
     int64_t loop_steps = 0;
 };
@@ -365,11 +374,21 @@ PG_API int picgolf_config_default(picgolf_config *c, int scheme, int quiet)
 // ------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------
+static void install_set(picgolf_handle h, int s);
+
 static int destroy_impl(picgolf_handle h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamSynchronize(h->down_stream); }
+    if (h->sset_n) { // the ring of picgolf_step_streamed: set 0 is freed below with the handle's own arrays
+        install_set(h, 0);
+        for (int q = 1; q < 3; ++q) for (int i = 0; i < h->sset_n; ++i) if (h->sset[q].a[i]) cudaFree(h->sset[q].a[i]);
+        for (int q = 0; q < 3; ++q) { if (h->ev_up[q]) cudaEventDestroy(h->ev_up[q]); if (h->ev_comp[q]) cudaEventDestroy(h->ev_comp[q]); if (h->ev_down[q]) cudaEventDestroy(h->ev_down[q]); }
+    }
+    if (h->up_stream) cudaStreamDestroy(h->up_stream);
+    if (h->down_stream) cudaStreamDestroy(h->down_stream);
     h->timer.destroy();
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
     for (auto &g : h->loop_graph) if (g) cudaGraphExecDestroy(g);
@@ -675,6 +694,11 @@ static int bank_loop_launches(picgolf_handle h)
 static int reset_run_state(picgolf_handle h)
 {
     PG_TRY(bank_loop_launches(h));
+    if (h->sset_n) { // back from picgolf_step_streamed to the plain calls: drain the copy streams (the caller has just enqueued
+                     // its upload into the installed set on h->stream, which is ordered after that set's last step)
+        PG_CUDA(cudaStreamSynchronize(h->up_stream)); PG_CUDA(cudaStreamSynchronize(h->down_stream));
+        for (auto &u : h->sset_used) u = false;
+    }
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpyAsync(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, h->stream));
     PG_CUDA(cudaMemsetAsync(h->rho_last, 0, h->ncell * sizeof(double), h->stream));
@@ -770,7 +794,7 @@ PG_API int picgolf_init_synthetic(picgolf_handle h, uint64_t seed, double vth)
         synthetic_2d3v_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->p2[0][0], h->p2[0][1], h->p2[0][2], h->p2[0][3], h->p2[0][4], h->count,
                                                                    h->first, seed, vth);
     else
-        synthetic_1d_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P, seed);
+        synthetic_1d_kernel<<<init_grid(h), 256, 0, h->stream>>>(h->xb[0], h->vb[0], h->count, h->first, h->cfg.P, seed, vth);
     h->launches++;
     PG_CUDA(cudaGetLastError());
     return reset_run_state(h);
@@ -780,7 +804,9 @@ PG_API int picgolf_synchronize(picgolf_handle h)
 {
     if (!h) return fail(PICGOLF_ERR_ARG, "NULL handle");
     PG_TRY(use_device(h));
+    if (h->up_stream) { PG_CUDA(cudaStreamSynchronize(h->up_stream)); }
     PG_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->down_stream) { PG_CUDA(cudaStreamSynchronize(h->down_stream)); }
     return check_peer(h);
 }
 
@@ -1237,7 +1263,7 @@ static int step_fixedpoint(picgolf_handle h)
     const bool loop = !h->loop_off && !h->loop_failed && !h->timer.enabled && (!h->comm || h->peer_ok);
     bool done = false;
     if (loop) {
-        const int slot = h->par + 2 * (h->rho_fx == h->rho_base[1] ? 1 : 0) + 4 * (h->use_sorted_now ? 1 : 0);
+        const int slot = h->par + 2 * (h->rho_fx == h->rho_base[1] ? 1 : 0) + 4 * (h->use_sorted_now ? 1 : 0) + 8 * h->sset_cur;
         cudaGraphExec_t &exec = h->loop_graph[slot];
         if (!exec && build_loop_graph(h, &exec) != 0) { // no conditional nodes on this driver: fixed schedule for good
             cudaGetLastError();
@@ -1425,6 +1451,120 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
     PG_CUDA(cudaGetLastError());
     if (h->timer.enabled && h->timer.open.size() > 4096) h->timer.drain();
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// streamed step: set_particles -> step(1) -> get_particles as ONE asynchronous call, pipelined over three buffer sets
+// ------------------------------------------------------------------------------------------
+static void install_set(picgolf_handle h, int s)
+{
+    if (!h->sset_n || s == h->sset_cur) return;
+    double **b = h->sset[s].a;
+    if (h->is2d) for (int q = 0; q < 5; ++q) h->p2[0][q] = b[q];
+    else { h->xb[0] = b[0]; h->xb[1] = b[1]; h->vb[0] = b[2]; h->vb[1] = b[3]; }
+    h->sset_cur = s;
+}
+
+static int build_stream_ring(picgolf_handle h)
+{
+    if (h->sset_n) return 0;
+    const size_t n = (size_t)h->count;
+    double **b0 = h->sset[0].a;
+    int na;
+    if (h->is2d) { na = 5; for (int q = 0; q < 5; ++q) b0[q] = h->p2[0][q]; }
+    else { na = 4; b0[0] = h->xb[0]; b0[1] = h->xb[1]; b0[2] = h->vb[0]; b0[3] = h->vb[1]; }
+    for (int s = 1; s < 3; ++s)
+        for (int i = 0; i < na; ++i)
+            if (b0[i]) PG_TRY(dalloc(&h->sset[s].a[i], n)); // leapfrog schemes have no xb[1] / vb[1]
+    PG_CUDA(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 3; ++s) {
+        PG_CUDA(cudaEventCreateWithFlags(&h->ev_up[s], cudaEventDisableTiming));
+        PG_CUDA(cudaEventCreateWithFlags(&h->ev_comp[s], cudaEventDisableTiming));
+        PG_CUDA(cudaEventCreateWithFlags(&h->ev_down[s], cudaEventDisableTiming));
+    }
+    h->sset_n = na; h->sset_cur = 0;
+    return 0;
+}
+
+__global__ void stream_reset_kernel(Ctrl *c) { c->final_k = -1; c->sweeps = 0; }
+
+// in[]/out[]: x, v (1D1V) or x, y, vx, vy, vz (2D3V) host arrays of the local shard.
+static int step_streamed_impl(picgolf_handle h, const double *const *in, double *const *out, int narr, int64_t count)
+{
+    if (count != h->count) return fail(PICGOLF_ERR_ARG, "count %lld != local shard %lld", (long long)count, (long long)h->count);
+    if (h->nranks > 1 && !h->comm) return fail(PICGOLF_ERR_STATE, "sharded handle without a communicator (picgolf_comm_init)");
+    PG_TRY(use_device(h));
+    if (!h->sset_n) { // first streamed call: the handle may hold a running simulation -- finish it, then build the ring
+        PG_CUDA(cudaStreamSynchronize(h->stream));
+        PG_TRY(bank_loop_launches(h));
+        PG_TRY(build_stream_ring(h));
+    }
+    const int s = (int)(h->stream_calls % 3);
+    const size_t bytes = (size_t)count * sizeof(double);
+    double **b = h->sset[s].a;
+    // upload: wait until the previous occupant of this set has been downloaded (which implies its step has finished)
+    if (h->sset_used[s]) PG_CUDA(cudaStreamWaitEvent(h->up_stream, h->ev_down[s], 0));
+    if (h->is2d) for (int q = 0; q < 5; ++q) PG_CUDA(cudaMemcpyAsync(b[q], in[q], bytes, cudaMemcpyHostToDevice, h->up_stream));
+    else { PG_CUDA(cudaMemcpyAsync(b[0], in[0], bytes, cudaMemcpyHostToDevice, h->up_stream)); PG_CUDA(cudaMemcpyAsync(b[2], in[1], bytes, cudaMemcpyHostToDevice, h->up_stream)); }
+    PG_CUDA(cudaEventRecord(h->ev_up[s], h->up_stream));
+    // step: the state of reset_run_state(), enqueued instead of synchronised; the diagnostics trace keeps growing
+    PG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up[s], 0));
+    install_set(h, s);
+    if (h->rho_base[0]) { h->rho_fx = h->rho_base[0]; h->rho_next = h->rho_base[1]; }
+    PG_CUDA(cudaMemsetAsync(h->rho_fx, 0, (size_t)h->grid_rows * h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, ((size_t)h->ncell + 1) * sizeof(unsigned long long), h->stream));
+    if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
+    else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
+    stream_reset_kernel<<<1, 1, 0, h->stream>>>(h->ctrl);
+    h->launches++;
+    h->par = 0; h->steps = 0; h->have_particles = true; h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
+    h->slow_pending = false; h->force_sort = false; h->poly_quiet = false; h->probe_have_prev = false;
+    for (auto &ps : h->probe_step) ps = -1;
+    int rc = 0;
+    if (h->fixedpoint) rc = step_fixedpoint(h);
+    else if (h->is2d) rc = step_2d3v(h);
+    else {
+        rc = lf_launch(h, 0, 1);
+        if (rc == 0) rc = allreduce_grid(h);
+        if (rc == 0) rc = launch_solve1d(h, 1);
+        if (rc == 0) rc = lf_launch(h, 1, 0);
+        if (rc == 0) rc = launch_step_end(h, true);
+    }
+    h->steps++;
+    if (rc != 0) return rc;
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaEventRecord(h->ev_comp[s], h->stream));
+    // download of the stepped state (1D fixed point: the other half of the set's ping-pong pair)
+    PG_CUDA(cudaStreamWaitEvent(h->down_stream, h->ev_comp[s], 0));
+    if (h->is2d) for (int q = 0; q < 5; ++q) { if (out[q]) PG_CUDA(cudaMemcpyAsync(out[q], h->p2[h->par][q], bytes, cudaMemcpyDeviceToHost, h->down_stream)); }
+    else {
+        if (out[0]) PG_CUDA(cudaMemcpyAsync(out[0], h->xb[h->par], bytes, cudaMemcpyDeviceToHost, h->down_stream));
+        if (out[1]) PG_CUDA(cudaMemcpyAsync(out[1], h->vb[h->par], bytes, cudaMemcpyDeviceToHost, h->down_stream));
+    }
+    PG_CUDA(cudaEventRecord(h->ev_down[s], h->down_stream));
+    h->sset_used[s] = true;
+    h->stream_calls++;
+    (void)narr;
+    return 0;
+}
+
+PG_API int picgolf_step_streamed(picgolf_handle h, const double *x_in, const double *v_in, double *x_out, double *v_out, int64_t count)
+{
+    if (!h || !x_in || !v_in) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (h->is2d) return fail(PICGOLF_ERR_ARG, "use picgolf_step_streamed_2d3v for the 2D3V scheme");
+    if (h->b1d2v || h->simpson) return fail(PICGOLF_ERR_UNSUPPORTED, "the streamed step is built for the 1D1V leapfrog / fixed-point schemes and for 2D3V");
+    const double *in[2] = {x_in, v_in};
+    double *out[2] = {x_out, v_out};
+    return step_streamed_impl(h, in, out, 2, count);
+}
+
+PG_API int picgolf_step_streamed_2d3v(picgolf_handle h, const double *const in[5], double *const out[5], int64_t count)
+{
+    if (!h || !in || !out) return fail(PICGOLF_ERR_ARG, "NULL argument");
+    if (!h->is2d) return fail(PICGOLF_ERR_ARG, "handle is not a 2D3V scheme");
+    for (int q = 0; q < 5; ++q) if (!in[q]) return fail(PICGOLF_ERR_ARG, "NULL input array %d", q);
+    return step_streamed_impl(h, in, out, 5, count);
 }
 
 PG_API int picgolf_steps_done(picgolf_handle h, int64_t *steps)

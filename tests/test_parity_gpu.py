@@ -165,7 +165,7 @@ def test_c1_ngp_steps(pg, oracle):
         assert relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
         assert np.array_equal(pg.ngp_index(xg, N), oracle.ngp_index(x, N))
     R = sim.raw_diagnostics()
-    assert R.shape == (8, 4) and relnorm(R[:, :3], g["raw"]) < 1e-11
+    assert R.shape == (8, 4) and relnorm(R[:, :3], g["raw"]) < TOL
     # stepping 8 at once (fused kick + next deposit passes) gives the same state as 8 single steps
     sim2 = pg.ngp_fourier(N=N, NT=64)
     sim2.set_particles(g["x0"], g["v0"])
@@ -187,7 +187,7 @@ def test_explicit_gaussian_steps(pg, oracle):
         assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-11
     x, v = sim.particles()
     assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
-    assert relnorm(sim.raw_diagnostics()[:, :3], g["raw"]) < 1e-10
+    assert relnorm(sim.raw_diagnostics()[:, :3], g["raw"]) < TOL
 
 
 def test_c2_fixed_point_steps(pg, oracle):
@@ -206,12 +206,12 @@ def test_c2_fixed_point_steps(pg, oracle):
     sim.step(15)
     D, sw = sim.diagnostics()
     assert D.shape == (16, 4) and np.array_equal(sw, g["sweeps"]) and np.all(sw == 4)
-    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    assert relnorm(D[:, :3], g["D"][:, :3]) < TOL
     assert np.abs(D[:, 3] - g["D"][:, 3]).max() < 1e-13
     x, v = sim.particles()
-    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10  # 16 steps of error growth
+    assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL  # 16 steps of error growth
     rho, E = sim.fields()
-    assert relnorm(E, g["E"][15]) < 1e-10
+    assert relnorm(E, g["E"][15]) < TOL
 
 
 def test_c2_against_live_oracle_other_seed(pg, oracle):
@@ -226,7 +226,7 @@ def test_c2_against_live_oracle_other_seed(pg, oracle):
         D4, raw, s = fp.step()
         x, v = sim.particles()
         rho, E = sim.fields()
-        assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(E, fp.E) < 1e-11
+        assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL and relnorm(E, fp.E) < TOL
         assert relnorm(rho, fp.r) < TOL
     D, sw = sim.diagnostics()
     assert list(sw) == [4, 4, 4]
@@ -288,13 +288,13 @@ def test_c5_2d3v_steps(pg, oracle):
         sim.step(1)
         rho, Ex, Ey = sim.fields()
         assert relnorm(rho.reshape(-1, order="F"), g["rho"][t]) < TOL
-        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < 1e-11 and relnorm(Ey.reshape(-1, order="F"), g["Ey"][t]) < 1e-11
+        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < TOL and relnorm(Ey.reshape(-1, order="F"), g["Ey"][t]) < TOL
     x, y, vx, vy, vz = sim.particles()
     for a, k in ((x, "x"), (y, "y"), (vx, "vx"), (vy, "vy"), (vz, "vz")):
-        assert relnorm(a, g[k]) < 1e-11
+        assert relnorm(a, g[k]) < TOL
     assert x.min() > 0 and x.max() <= 1 and y.min() > 0 and y.max() <= 1
     K, _ = sim.diagnostics()
-    assert K.shape == (4, 5) and relnorm(K[:, :3], g["K"][:, :3]) < 1e-10
+    assert K.shape == (4, 5) and relnorm(K[:, :3], g["K"][:, :3]) < TOL
     assert np.abs(K[:, 3:] - g["K"][:, 3:]).max() < 1e-14
 
 
@@ -384,6 +384,89 @@ def test_scaled_ngp_properties(pg, oracle):
     assert relnorm(E, Eo) < TOL and relnorm(x, x0) < TOL and relnorm(v, v0) < TOL
 
 
+@pytest.mark.parametrize("mode", ["anyorder", "tiled"])
+def test_c5_full_step_on_its_own_grid(pg, oracle, mode):
+    """BASELINE.json config 5 on its own 256 x 256 grid (src/Electrostatic2D3V.jl:23 shape, 2^21 particles, Maxwellian start
+    passed in): three full steps through the any-order kernel and through the tile-sorted kernel (first step any-order, sort,
+    two tiled steps) against the multi-threaded oracle -- rho, Ex, Ey, the five particle arrays and K, at the 1e-12 bar."""
+    NX = NY = 256
+    P = 1 << 21
+    rng = np.random.default_rng(55)
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=8, NS=1, deposit_mode=pg.DEPOSIT_ATOMIC if mode == "anyorder" else pg.DEPOSIT_SORTED,
+                                sort_every=2)
+    st = [1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * sim.vth / math.sqrt(2) for _ in range(3)]
+    sim.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
+    so = [a.copy() for a in st]
+    Ex, Ey = np.zeros(NX * NY), np.zeros(NX * NY)
+    nthreads = oracle.max_threads()
+    for t in range(3):
+        sim.step(1)
+        ro = oracle.step_2d3v(*so, NX, NY, sim.cfg.dt, sim.cfg.B0, sim.cfg.w, Ex, Ey, nthreads=nthreads)
+        rho, ex, ey = sim.fields()
+        assert relnorm(rho.reshape(-1, order="F"), ro) < TOL
+        assert relnorm(ex.reshape(-1, order="F"), Ex) < TOL and relnorm(ey.reshape(-1, order="F"), Ey) < TOL
+    got = sim.particles()  # caller's order, whatever the tile sort did
+    for a, b in zip(got, so):
+        assert relnorm(a, b) < TOL
+    K, _ = sim.diagnostics()
+    k1 = float(np.mean(Ex ** 2 + Ey ** 2))
+    k2 = float(np.sum(so[2] ** 2 + so[3] ** 2) * sim.cfg.w)
+    assert relnorm(K[2, :2], np.array([k1, k2])) < TOL
+    if mode == "tiled":
+        assert sim.sort_stats()[0] >= 1 and sim.sort_stats()[1] == 0  # sorted once, nothing left its window
+
+
+def test_config5_full_size_properties(pg):
+    """BASELINE.json config 5 at its full single-GPU size (256 x 256, 2^28 particles) through the path a caller gets
+    (AUTO -> tile-sorted kernel): size-independent properties of Electrostatic2D3V.jl's loop."""
+    NX = NY = 256
+    P = 1 << 28
+    sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=8, NS=1)
+    sim.init_synthetic(seed=11, vth=sim.vth)
+    sim.step(4)
+    rho, Ex, Ey = sim.fields()
+    K, _ = sim.diagnostics()
+    n0 = 4 * math.pi ** 2
+    assert abs(rho.mean() / n0 - 1) < 1e-12                       # charge conservation: mean(rho) == n0 (w = n0/P/(dx*dy))
+    assert abs(Ex.sum()) < 1e-9 * np.abs(Ex).max() * NX * NY      # phi[1,1] = 0: zero-mean field
+    assert abs(Ey.sum()) < 1e-9 * np.abs(Ey).max() * NX * NY
+    assert abs(K[-1, 3] - K[0, 3]) < 1e-12 * sim.vth              # mean x momentum: CIC gather/deposit are adjoint (B0 || x rotates vy, vz only)
+    assert abs(K[-1, 2] / K[0, 2] - 1) < 1e-3                     # total energy over 4 steps of a quiet thermal plasma
+    assert sim.sort_stats()[0] >= 1 and sim.sort_stats()[1] < 1e-6 * P * 4
+    x, y, vx, vy, vz = sim.particles()
+    assert x.min() > 0 and x.max() <= 1 and y.min() > 0 and y.max() <= 1  # unimod keeps (0, 1]
+    # K[:,2] = sum((vx^2+vy^2) w), K[:,4:5] = sum(v)/P of the state that came back in the caller's order
+    assert abs(float(np.sum(vx ** 2 + vy ** 2)) * sim.cfg.w / K[-1, 1] - 1) < 1e-11
+    assert abs(float(vx.sum()) / P - K[-1, 3]) < 1e-14
+    del x, y, vx, vy, vz
+    sim.close()
+
+
+def test_ngp_full_size_properties(pg, oracle):
+    """Config-1-scaled NGP at the benchmark's size (N=4096, 2^28 particles, TMA-staged pass): rho is an exact histogram of
+    the half-drifted positions whatever the size (dyadic w), checked against numpy on the full population."""
+    N, P = 4096, 1 << 28
+    sim = pg.ngp_fourier(N=N, P=P, NT=8, W=256.0)  # w = 256 * 4096 / 2^28 = 2^-8
+    sim.init_synthetic(seed=7)
+    x0, v0 = sim.particles()
+    sim.step(1)
+    rho, E = sim.fields()
+    xh = np.mod(x0 + v0 / 2 * sim.cfg.dt, 1)      # u(): first half drift (v = +-1: no negative zero / 1.0 corner here)
+    cells = (np.rint(xh * N).astype(np.int64) - 1) % N  # f(x) = mod1(round(x*N), N), 0-based
+    del xh
+    counts = np.bincount(cells, minlength=N)
+    del cells
+    assert np.array_equal(rho, counts * sim.cfg.w) and rho.sum() == P * sim.cfg.w
+    assert abs(E.sum()) < 1e-9 * np.abs(E).max() * N
+    x, v = sim.particles()
+    assert 0 <= x.min() and x.max() <= 1
+    # second half drift + kick with the library's own E (NGPFourier.jl:6): v += E[f(x)]*dt at the full-step position
+    assert np.array_equal(v, v0 + E[(np.rint(x * N).astype(np.int64) - 1) % N] * sim.cfg.dt)
+    D, _ = sim.diagnostics()
+    assert abs(D[0, 3]) < 1e-12                    # momentum of the symmetric beams after one kick
+    sim.close()
+
+
 # =============================================================================================
 # cell-sorted deposit mode (pg_sort.cuh + fp_pass_sorted): same results, caller's particle order
 # =============================================================================================
@@ -399,9 +482,9 @@ def test_sorted_mode_c2_golden(pg, oracle):
     sim.step(15)
     D, sw = sim.diagnostics()
     assert np.array_equal(sw, g["sweeps"])
-    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    assert relnorm(D[:, :3], g["D"][:, :3]) < TOL
     x, v = sim.particles()
-    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10
+    assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
     sorts, slow = sim.sort_stats()
     assert sorts == 5  # lazy first sort: before steps 1,4,7,10,13 (the first step runs on the any-order kernel)
 
@@ -439,12 +522,12 @@ def test_sorted_mode_matches_atomic_mode(pg, oracle, start):
     a.step(11); s.step(11)
     xa, va = a.particles()
     xs, vs = s.particles()
-    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    assert relnorm(xs, xa) < TOL and relnorm(vs, va) < TOL
     Da, swa = a.diagnostics()
     Ds, sws = s.diagnostics()
     if start == "uniform":
         assert np.array_equal(swa, sws)
-    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < TOL
     sorts, slow = s.sort_stats()
     assert sorts == 3 and slow < P // 100  # before steps 1,5,9; almost everything stays inside its window
 
@@ -468,9 +551,9 @@ def test_poly_mode_c2_golden(pg, oracle):
     sim.step(14)
     D, sw = sim.diagnostics()
     assert np.array_equal(sw, g["sweeps"])
-    assert relnorm(D[:, :3], g["D"][:, :3]) < 1e-10
+    assert relnorm(D[:, :3], g["D"][:, :3]) < TOL
     x, v = sim.particles()
-    assert relnorm(x, g["x"]) < 1e-10 and relnorm(v, g["v"]) < 1e-10
+    assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
     assert sim.sort_stats()[0] == 5
 
 
@@ -513,12 +596,12 @@ def test_poly_mode_matches_atomic_mode(pg, oracle, start, N, P):
     a.step(10); s.step(10)
     xa, va = a.particles()
     xs, vs = s.particles()
-    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    assert relnorm(xs, xa) < TOL and relnorm(vs, va) < TOL
     Da, swa = a.diagnostics()
     Ds, sws = s.diagnostics()
     if start == "uniform":
         assert np.array_equal(swa, sws)
-    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < TOL
     sorts, flushes = s.sort_stats()
     assert sorts == 3  # before steps 1, 5, 9 (0-based)
     if P // N >= 4096:
@@ -543,10 +626,10 @@ def test_poly_mode_warm_beams_force_resort(pg):
         sim.step(24)
     xa, va = a.particles()
     xs, vs = s.particles()
-    assert relnorm(xs, xa) < 1e-10 and relnorm(vs, va) < 1e-10
+    assert relnorm(xs, xa) < TOL and relnorm(vs, va) < TOL
     Da, swa = a.diagnostics()
     Ds, sws = s.diagnostics()
-    assert np.array_equal(swa, sws) and relnorm(Ds[:, 1:3], Da[:, 1:3]) < 1e-11
+    assert np.array_equal(swa, sws) and relnorm(Ds[:, 1:3], Da[:, 1:3]) < TOL
     sorts, flushes = s.sort_stats()
     assert sorts >= 3  # the starting interval alone (16 steps) would give 2
 
@@ -577,12 +660,12 @@ def test_2d3v_tile_sorted_mode(pg, oracle):
         sim.step(1)
         rho, Ex, Ey = sim.fields()
         assert relnorm(rho.reshape(-1, order="F"), g["rho"][t]) < TOL
-        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < 1e-11
+        assert relnorm(Ex.reshape(-1, order="F"), g["Ex"][t]) < TOL
     got = sim.particles()  # caller's order
     for a, k in zip(got, ("x", "y", "vx", "vy", "vz")):
-        assert relnorm(a, g[k]) < 1e-11
+        assert relnorm(a, g[k]) < TOL
     K, _ = sim.diagnostics()
-    assert relnorm(K[:, :3], g["K"][:, :3]) < 1e-10
+    assert relnorm(K[:, :3], g["K"][:, :3]) < TOL
     assert sim.sort_stats()[0] == 2
     # larger: sorted (AUTO) vs any-order
     NX = NY = 128
@@ -596,7 +679,7 @@ def test_2d3v_tile_sorted_mode(pg, oracle):
         s.step(12)
     pa, ps = sims[0].particles(), sims[1].particles()
     for a, b in zip(ps, pa):
-        assert relnorm(a, b) < 1e-10
+        assert relnorm(a, b) < TOL
     fa, fs = sims[0].fields(), sims[1].fields()
     assert relnorm(fs[0], fa[0]) < TOL  # both fixed point; the tiled path quantises per work item, not per deposit
     assert relnorm(fs[1], fa[1]) < 1e-10
@@ -690,7 +773,7 @@ def test_extreme_grid_sizes(pg, oracle, N):
         ro, Eo, _ = oracle.ngp_step(xo, vo, N, ng.cfg.dt, ng.cfg.w)
     rho, E = ng.fields()
     xg, vg = ng.particles()
-    assert np.array_equal(rho, ro) and relnorm(E, Eo) < 1e-10 and relnorm(xg, xo) < TOL and relnorm(vg, vo) < TOL
+    assert np.array_equal(rho, ro) and relnorm(E, Eo) < TOL and relnorm(xg, xo) < TOL and relnorm(vg, vo) < TOL
 
 
 def test_sweep_cap_is_not_an_error(pg, oracle):
@@ -707,7 +790,7 @@ def test_sweep_cap_is_not_an_error(pg, oracle):
     x, v = sim.particles()
     assert list(sw) == sw_o
     assert sw.max() <= 10
-    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11
+    assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL
     few = pg.gaussian_fixed_point(T=4, max_sweeps=2)
     few.set_particles(x0, v0)
     few.step(1)
@@ -783,9 +866,9 @@ def test_simpson13_steps(pg, oracle):
     x, v = sim.particles()
     rho, E = sim.fields()  # rho(x,x) and E[end,:]
     assert np.array_equal(sw, g["swn"])
-    assert relnorm(D[:, :3], g["Dn"][:, :3]) < 1e-10 and np.abs(D[:, 3] - g["Dn"][:, 3]).max() < 1e-13
-    assert relnorm(x, g["xn"]) < 1e-10 and relnorm(v, g["vn"]) < 1e-10
-    assert relnorm(rho, g["rn"]) < 1e-10 and relnorm(E, g["En"][2 * 128:]) < 1e-10
+    assert relnorm(D[:, :3], g["Dn"][:, :3]) < TOL and np.abs(D[:, 3] - g["Dn"][:, 3]).max() < 1e-13
+    assert relnorm(x, g["xn"]) < TOL and relnorm(v, g["vn"]) < TOL
+    assert relnorm(rho, g["rn"]) < TOL and relnorm(E, g["En"][2 * 128:]) < TOL
     # one step against the live oracle at 1e-12
     one = pg.gaussian_fixed_point_quiet_simpson13(N=128, P=4096, T=4, W=400.0, l=1e-8, half_width=6)
     one.set_particles(g["xr"], g["vr"])
@@ -830,9 +913,9 @@ def test_area_simpson13(pg, oracle):
     x, v = sim.particles()
     rho, E = sim.fields()
     assert np.array_equal(sw, g["swn"])
-    assert relnorm(D[:, :3], g["Dn"][:, :3]) < 1e-10
-    assert relnorm(x, g["xn"]) < 1e-10 and relnorm(v, g["vn"]) < 1e-10 and relnorm(rho, g["rn"]) < 1e-10
-    assert relnorm(E, g["En"][256:]) < 1e-10
+    assert relnorm(D[:, :3], g["Dn"][:, :3]) < TOL
+    assert relnorm(x, g["xn"]) < TOL and relnorm(v, g["vn"]) < TOL and relnorm(rho, g["rn"]) < TOL
+    assert relnorm(E, g["En"][256:]) < TOL
     T, dt, W = int(g["T"]), float(g["dt"]), float(g["W"])
     q = pg.area_fixed_point_quiet_simpson13(T=T)
     assert q.cfg.rtol == 1e-14 and (q.cfg.N, q.cfg.P) == (64, 2048)
@@ -864,7 +947,7 @@ def test_ngp1d2v_steps(pg, oracle):
         rho, E = sim.fields()
         assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-10
     x, vx, vy = sim.particles()
-    assert relnorm(x, g["x"]) < 1e-11 and relnorm(vx, g["vx"]) < 1e-11 and relnorm(vy, g["vy"]) < 1e-11
+    assert relnorm(x, g["x"]) < TOL and relnorm(vx, g["vx"]) < TOL and relnorm(vy, g["vy"]) < TOL
     assert 0 <= x.min() and x.max() <= 1
     # diagnostics: one row per window, formed as NGP1D2V.jl:59-61,64 from the sums at the window's last step
     D, _ = sim.diagnostics()
@@ -874,10 +957,10 @@ def test_ngp1d2v_steps(pg, oracle):
         se, s0, s1, s2 = g["raw"][t]
         d1, d2 = (se / N) / 2, (s0 * n0 / P) / 2
         want = np.array([d1 * 2 / n0, d2 * 2 / n0, (d1 + d2) * 2 / n0, s1 / P, s2 / P]) / 4
-        assert relnorm(D[ti], want) < 1e-10
+        assert relnorm(D[ti], want) < TOL
     Es = sim.field_history()  # Es[:,ti] = mean of E over the window
     assert Es.shape == (N, 2)
-    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < 1e-10 and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < 1e-10
+    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < TOL and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < TOL
     # stepping in one call gives the same state
     s2_ = pg.ngp_1d2v(T=64, TO=16)
     s2_.set_particles(g["x0"], g["vx0"], vy=g["vy0"])
@@ -906,7 +989,7 @@ def test_ngp1d2v2s_steps(pg, oracle):
         assert np.abs(rho - g["rho"][t]).max() < TOL * float(g["n0"])
         assert np.abs(E - g["E"][t]).max() < max(1e-10 * np.abs(g["E"][t]).max(), 1e-13 * float(g["n0"]))
     x, vx, vy = sim.particles()
-    assert relnorm(x, g["x"]) < 1e-11 and relnorm(vx, g["vx"]) < 1e-11 and relnorm(vy, g["vy"]) < 1e-11
+    assert relnorm(x, g["x"]) < TOL and relnorm(vx, g["vx"]) < TOL and relnorm(vy, g["vy"]) < TOL
     D, _ = sim.diagnostics()
     assert D.shape == (2, 5)
     n0 = float(g["n0"])
@@ -929,7 +1012,7 @@ def test_ngp1d2v2s_steps(pg, oracle):
         ro, Eo, _ = oracle.step_1d2v2s(xo, vxo, vyo, N2, 7, s2_.cfg.dt, s2_.cfg.B0, s2_.cfg.w, M2)
     xs, vxs, vys = s2_.particles()
     rs, Es2 = s2_.fields()
-    assert relnorm(xs, xo) < 1e-11 and relnorm(vxs, vxo) < 1e-11 and relnorm(vys, vyo) < 1e-11 and relnorm(Es2, Eo) < 1e-10
+    assert relnorm(xs, xo) < TOL and relnorm(vxs, vxo) < TOL and relnorm(vys, vyo) < TOL and relnorm(Es2, Eo) < TOL
     assert np.abs(rs - ro).max() < TOL * n0
 
 
@@ -952,6 +1035,63 @@ def test_2d3v_tma_variant_matches(pg, oracle, monkeypatch):
         sim.step(7)
         res.append((sim.particles(), sim.fields(), sim.diagnostics()[0]))
     for a, b in zip(res[0][0], res[1][0]):
-        assert relnorm(b, a) < 1e-10
+        assert relnorm(b, a) < TOL
     assert relnorm(res[1][1][0], res[0][1][0]) < TOL and relnorm(res[1][1][1], res[0][1][1]) < 1e-10
-    assert relnorm(res[1][2][:, :3], res[0][2][:, :3]) < 1e-11
+    assert relnorm(res[1][2][:, :3], res[0][2][:, :3]) < TOL
+
+
+# =============================================================================================
+# picgolf_step_streamed: the pipelined set -> step -> get
+# =============================================================================================
+@pytest.mark.parametrize("scheme", ["fixedpoint", "fixedpoint_big", "ngp", "gauss_leapfrog", "2d3v"])
+def test_step_streamed_matches_plain_calls(pg, scheme):
+    """Seven different particle states pushed back to back through picgolf_step_streamed (three buffer sets, upload / step /
+    download on three streams) give bit for bit what set_particles -> step(1) -> get_particles gives one state at a time,
+    diagnostics rows included; afterwards the handle still serves the plain calls."""
+    rng = np.random.default_rng(77)
+    if scheme == "fixedpoint":
+        mk = lambda: pg.gaussian_fixed_point(N=128, P=4096, T=16, W=400.0)
+        P, ncomp = 4096, 2
+    elif scheme == "fixedpoint_big":  # AUTO resolves to the sorted / polynomial path: a single step from a fresh state runs any-order
+        mk = lambda: pg.gaussian_fixed_point(N=256, P=1 << 22, T=16, W=400.0)
+        P, ncomp = 1 << 22, 2
+    elif scheme == "ngp":
+        mk = lambda: pg.ngp_fourier(N=4096, P=(1 << 21) + 5, NT=16, W=256.0)
+        P, ncomp = (1 << 21) + 5, 2
+    elif scheme == "gauss_leapfrog":
+        mk = lambda: pg.gaussian(NX=128, NP=8192, NT=16)
+        P, ncomp = 8192, 2
+    else:
+        mk = lambda: pg.electrostatic_2d3v(NX=64, NY=128, P=1 << 18, T=16, NS=1)
+        P, ncomp = 1 << 18, 5
+    a, b = mk(), mk()
+    states = []
+    for i in range(7):
+        if ncomp == 2:
+            states.append([rng.random(P), np.where(rng.random(P) < 0.5, -1.0, 1.0) + 0.01 * rng.standard_normal(P)])
+        else:
+            states.append([1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * a.vth / math.sqrt(2) for _ in range(3)])
+    outs = [[np.full(P, np.nan) for _ in range(ncomp)] for _ in states]
+    for st, out in zip(states, outs):
+        b.step_streamed(st, out)
+    b.synchronize()
+    for st, out in zip(states, outs):
+        if ncomp == 2:
+            a.set_particles(st[0], st[1])
+        else:
+            a.set_particles(st[0], st[2], y=st[1], vy=st[3], vz=st[4])
+        a.step(1)
+        for got, want in zip(out, a.particles()):
+            assert np.array_equal(got, want)
+    for fa, fb in zip(a.fields(), b.fields()):  # fields of the last state
+        assert np.array_equal(fa, fb)
+    Da, Db = a.diagnostics()[0], b.diagnostics()[0]
+    assert Db.shape[0] == 7 and np.array_equal(Db[-1], Da[-1])  # one row per streamed call; the plain handle restarts its trace at every set
+    # back to the plain calls on the streamed handle
+    if ncomp == 2:
+        b.set_particles(states[0][0], states[0][1])
+    else:
+        b.set_particles(states[0][0], states[0][2], y=states[0][1], vy=states[0][3], vz=states[0][4])
+    b.step(1)
+    for got, want in zip(b.particles(), outs[0]):
+        assert np.array_equal(got, want)
