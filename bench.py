@@ -41,25 +41,24 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread every ~5 ms (a 0.1 s timed region
-    still gets ~20 samples), nvidia-smi -lms 100 as the fallback."""
+    """SM clock and throttle reasons sampled from before the warm-up to the end of the timed region (NVML from a thread, as
+    fast as NVML answers; nvidia-smi -lms 100 as the fallback).  Every sample carries a time stamp, so the report gives the
+    samples that fell INSIDE the timed region and, because the driver's 20-step run lasts only ~0.1 s, also everything
+    sampled under load since the warm-up began."""
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu):
-        self.gpu, self.sm, self.mx, self.reasons, self.stop_flag, self.t, self.proc, self.how = gpu, [], [], set(), False, None, None, None
+        self.gpu, self.rows, self.mx, self.stop_flag, self.t, self.proc, self.how = gpu, [], None, False, None, None, None
 
     def _nvml_loop(self, h, nv):
         while not self.stop_flag:
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in self.BITS.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.rows.append((time.perf_counter(), sm, frozenset(n for n, b in self.BITS.items() if r & b)))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def start(self):
         try:
@@ -73,43 +72,49 @@ class ClockSampler:
                 except Exception:
                     pass
             h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.how = "nvml, 5 ms"
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml thread"
             self.t = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
             self.t.start()
             return
         except Exception:
             self.how = "nvidia-smi -lms 100"
         try:
-            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.lines = []
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+
+            def pump():
+                for l in self.proc.stdout:
+                    f = [x.strip() for x in l.split(",")]
+                    try:
+                        self.mx = float(f[1])
+                        self.rows.append((time.perf_counter(), float(f[0]), frozenset(
+                            n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]) if v.lower().startswith("active"))))
+                    except (ValueError, IndexError):
+                        continue
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         self.stop_flag = True
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
+        if self.t:
             self.t.join(timeout=2)
-            for l in self.lines:
-                f = [s.strip() for s in l.split(",")]
-                try:
-                    self.sm.append(float(f[1])); self.mx.append(float(f[2]))
-                except (ValueError, IndexError):
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if val.lower().startswith("active"):
-                        self.reasons.add(name)
-        elif self.t:
-            self.t.join(timeout=1)
-        if not self.sm:
+        rows = list(self.rows)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0, "how": self.how}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons), "samples": len(self.sm),
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        use = inside if len(inside) >= 3 else rows
+        reasons = sorted(set().union(*[r[2] for r in use]))
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(use),
+                "samples_inside_timed_region": len(inside), "samples_since_warmup_began": len(rows),
+                "window": "timed region" if use is inside else "warm-up + timed region (under load throughout; the timed region alone held fewer than 3 samples)",
                 "how": self.how}
 
 
@@ -197,18 +202,20 @@ def run_gpu(args):
         return ms
 
     # ---- device-resident timing -------------------------------------------------------------
+    sampler.rows.clear()  # samples from here on: warm-up and timed region, both under load
     sim.step(Wm)
     barrier()
-    sampler.sm.clear(); sampler.mx.clear(); sampler.reasons.clear()  # keep only what is sampled from here on
     sorts0 = sim.sort_stats()[0]
     l0 = sim.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     sim.step(K)  # one C-ABI call enqueues all K steps (no host sync inside)
     e1.record(stream)
     barrier()
+    tw1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
+    clocks = sampler.stop(tw0, tw1)
     launches = sim.launches - l0
     sorts_timed = sim.sort_stats()[0] - sorts0
     P = sim.cfg.P

@@ -650,12 +650,29 @@ struct StepEndArgs {
     double *raw;            // [4*T]
     Ctrl *ctrl;
     int nblocks, npart, neblocks, T, record, is2d;
+    int det; // deterministic polynomial passes: partials holds four 64-bit integers per block (pg_kernels_poly.cuh)
 };
 
 __global__ void __launch_bounds__(256) step_end_kernel(StepEndArgs a)
 {
     __shared__ double scratch[32];
     double s[3] = {0.0, 0.0, 0.0};
+    if (a.det) { // exact integer sums: the same bits whatever particles each block summed
+        __shared__ long long isum[4];
+        if (threadIdx.x < 4) isum[threadIdx.x] = 0;
+        __syncthreads();
+        const long long *pp = reinterpret_cast<const long long *>(a.partials);
+        long long q[4] = {0, 0, 0, 0};
+        for (int b = threadIdx.x; b < a.nblocks; b += blockDim.x)
+            for (int c = 0; c < 4; ++c) q[c] += pp[4 * b + c];
+        for (int c = 0; c < 4; ++c) atomicAdd(reinterpret_cast<unsigned long long *>(&isum[c]), (unsigned long long)q[c]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double sc = 1.0 / (double)(1LL << 40); // CP_DETV_FRAC
+            s[0] = ((double)isum[1] * 4294967296.0 + (double)isum[0]) * sc;
+            s[1] = ((double)isum[3] * 4294967296.0 + (double)isum[2]) * sc;
+        }
+    } else
     for (int b = threadIdx.x; b < a.nblocks; b += blockDim.x)
         for (int c = 0; c < a.npart; ++c) s[c] += a.partials[a.npart * b + c];
     double e = 0.0;

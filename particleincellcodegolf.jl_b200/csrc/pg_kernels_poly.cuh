@@ -23,9 +23,21 @@
 // 11 coefficients of its own interval (lanes in the same interval broadcast).  Any particle order is handled correctly
 // (window reloads, global-memory gather, early flushes); order only decides the speed, and the flushes are counted so
 // that the host can re-sort sooner when the bins shear apart (picgolf_sort_stats).
+//
+// DET = true (picgolf_config.deterministic = 1): the same pass, bit-reproducible from run to run.  The counting sort ranks
+// the particles of a bin with atomics, so WHICH lane sums which particles changes between runs.  Two things follow.  The
+// interval a particle deposits into must not depend on the lane's history: no hysteresis, always m = round(y); a lane
+// that sits on an interval edge then alternates between two sets, so the second one (the "spare") lives in a lane-private
+// shared-memory column and is exchanged with the register set on a change-over (a third interval retires the spare).
+// And the lane sums integers: u^n + 1.5*2^2 has the fixed-point value of u^n (50 fractional bits) in its low mantissa bits, and the raw 64-bit
+// patterns are added with integer adds (the offset, count * bits(6.0), is taken off at the flush) -- exact, associative,
+// order-free, and more accurate than a running fp64 sum.  A set is flushed as two 64-bit words per moment (low 32 bits,
+// high part) so the grid-wide integer sums cannot overflow; mom2rho_kernel puts them together.  The diagnostics sums
+// (sum v^2, sum v) use the same trick with 40 fractional bits.
 #pragma once
 #include "pg_kernels_1d.cuh"
 #include "gauss_cellpoly.inc"
+#include <type_traits>
 
 namespace pg {
 
@@ -54,7 +66,8 @@ constexpr int CP_STAGE_D2 = 96;  // double2 slots per stage: X, V, v pairs of th
 
 __host__ __device__ inline size_t cp_smem_bytes(int threads)
 {
-    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2));
+    return (size_t)(threads / 32) * (CP_GS * CP_WG * sizeof(double) + (size_t)CP_STAGES * CP_STAGE_D2 * sizeof(double2)) +
+           (size_t)threads * CP_NM * sizeof(double); // + the spare moment set of every lane (deterministic mode)
 }
 
 // 16-byte asynchronous global -> shared copy (L2 only); each lane later reads back exactly the bytes it copied itself,
@@ -80,6 +93,7 @@ struct GPolyArgs {
     fx_t *Mg;    // [N*CP_NSUB][CP_NC]
     const Ctrl *ctrl;
     int N, k;
+    int det;     // deterministic mode: Mg holds two words per moment
 };
 
 __global__ void __launch_bounds__(128) gpoly_kernel(GPolyArgs a)
@@ -103,7 +117,7 @@ __global__ void __launch_bounds__(128) gpoly_kernel(GPolyArgs a)
         g[CP_NC] = 0.0;
     }
     const int nb = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
-    const long long total = (long long)N * CP_NSUB * CP_NC, per = (total + nb - 1) / nb;
+    const long long total = (long long)N * CP_NSUB * CP_NC * (a.det ? 2 : 1), per = (total + nb - 1) / nb;
     const long long lo = (long long)b * per, hi = min(total, lo + per);
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) a.Mg[i] = 0ULL;
 }
@@ -119,8 +133,14 @@ struct Mom2RhoArgs {
     double fx_scale, fx_inv;
     int N;
     const unsigned long long *flush_src; // NCCL path on several GPUs: this rank's flush counter goes to rho[N] and is summed with the grid
+    int det;     // deterministic mode: Mg[row][n] = (low 32-bit sums, high-part sums) of 50-fractional-bit integers
 };
 constexpr int CPM_CELLS = 32;
+constexpr int CP_DET_FRAC = 50;                      // fractional bits of a lane's integer moment sums
+constexpr double CP_DET_MAGIC = 6.0;                 // 1.5 * 2^(52-50): |u^n| <= 1 keeps u^n + 6 inside [4, 8), where ulp = 2^-50
+constexpr int CP_DET_MAXCNT = 2048;                  // particles per set before a forced flush: |sum| < 2^11 * 2^50 < 2^62
+constexpr int CP_DETV_FRAC = 40;                     // the same for the diagnostics sums: v^2, v in (-2048, 2048)
+constexpr double CP_DETV_MAGIC = 6144.0;             // 1.5 * 2^(52-40)
 constexpr int CPM_LD = CP_NSUB * CP_NC + 1; // 89 doubles per source cell
 
 __global__ void __launch_bounds__(32 * CP_NSUB) mom2rho_kernel(Mom2RhoArgs a)
@@ -134,7 +154,11 @@ __global__ void __launch_bounds__(32 * CP_NSUB) mom2rho_kernel(Mom2RhoArgs a)
     for (int t = threadIdx.x; t < (CPM_CELLS + 12) * CP_NSUB * CP_NC; t += blockDim.x) {
         const int c = t / (CP_NSUB * CP_NC), r = t - c * (CP_NSUB * CP_NC); // r = s*CP_NC + n: the rows of a cell are contiguous in Mg
         const int s = r / CP_NC, n = r - s * CP_NC;
-        Ms[c * CPM_LD + r] = (double)(long long)a.Mg[(size_t)cp_row_of((i0 + c - 6) & Nmask, s, Mmask) * CP_NC + n] * a.fx_inv;
+        const size_t g = (size_t)cp_row_of((i0 + c - 6) & Nmask, s, Mmask) * CP_NC + n;
+        if (a.det) // exact integers, put together in a fixed order: the same bits whatever order the lanes flushed in
+            Ms[c * CPM_LD + r] = ((double)(long long)a.Mg[2 * g + 1] * 4294967296.0 + (double)a.Mg[2 * g]) * (1.0 / (double)(1LL << CP_DET_FRAC));
+        else
+            Ms[c * CPM_LD + r] = (double)(long long)a.Mg[g] * a.fx_inv;
     }
     __syncthreads();
     const int i = threadIdx.x & 31, s = threadIdx.x >> 5;
@@ -165,41 +189,115 @@ __device__ __forceinline__ void cp_interval(double y, int &idx, double &centre)
     centre = big - CP_MAGIC;
 }
 
-// One lane's moment set for the interval it is currently in (n = 0 is an integer count).
+// One lane's moment set for the interval it is currently in (n = 0 is an integer count).  DET: integer sums of the raw
+// bit patterns of u^n + CP_DET_MAGIC.
+template <bool DET>
 struct CPSet {
-    double m[CP_NM];
+    typename std::conditional<DET, unsigned long long, double>::type m[CP_NM];
     double centre;
     int cnt, idx;
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int n = 0; n < CP_NM; ++n) m[n] = 0;
+        cnt = 0;
+    }
 };
 
-// Add the set to the fixed-point moment grid (11 integer REDs) and clear it.
-__device__ __forceinline__ void cp_flush(CPSet &s, fx_t *Mg, double fx_scale, int Mmask)
+// One moment value (fixed point, CP_DET_FRAC fractional bits) into the two-word deterministic grid.
+__device__ __forceinline__ void cp_det_red(fx_t *p2, long long val)
+{
+    atomicAdd(p2, (fx_t)(val & 0xFFFFFFFFLL));
+    atomicAdd(p2 + 1, (fx_t)(val >> 32));
+}
+
+// Add the set to the fixed-point moment grid (11 integer REDs; DET: 22) and clear it.
+template <bool DET>
+__device__ __forceinline__ void cp_flush(CPSet<DET> &s, fx_t *Mg, double fx_scale, int Mmask)
 {
     if (s.cnt) {
-        fx_t *p = Mg + (size_t)(s.idx & Mmask) * CP_NC;
-        atomicAdd(p, to_fx((double)s.cnt, fx_scale));
+        if (DET) {
+            fx_t *p = Mg + (size_t)(s.idx & Mmask) * (2 * CP_NC);
+            cp_det_red(p, (long long)s.cnt << CP_DET_FRAC);
+            const unsigned long long off = (unsigned long long)s.cnt * (unsigned long long)__double_as_longlong(CP_DET_MAGIC);
 #pragma unroll
-        for (int n = 0; n < CP_NM; ++n) { atomicAdd(p + 1 + n, to_fx(s.m[n], fx_scale)); s.m[n] = 0.0; }
-        s.cnt = 0;
+            for (int n = 0; n < CP_NM; ++n) cp_det_red(p + 2 * (1 + n), (long long)((unsigned long long)s.m[n] - off));
+        } else {
+            fx_t *p = Mg + (size_t)(s.idx & Mmask) * CP_NC;
+            atomicAdd(p, to_fx((double)s.cnt, fx_scale));
+#pragma unroll
+            for (int n = 0; n < CP_NM; ++n) atomicAdd(p + 1 + n, to_fx((double)s.m[n], fx_scale));
+        }
+        s.clear();
     }
 }
 
-// M[m][n] += u^n for the particle at y.  The lane stays with its interval while |u| <= CP_UMAX (see the header).
-__device__ __forceinline__ void cp_deposit1(double y, CPSet &P, fx_t *Mg, double fx_scale, int Mmask, unsigned int &nflush)
+// The spare set of the deterministic mode: count and interval in registers, the sums in the lane's shared-memory column.
+struct CPSpare { int cnt, idx; };
+
+__device__ __forceinline__ void cp_flush_spare(CPSpare &sp, unsigned long long *col, int stride, fx_t *Mg, int Mmask)
 {
-    double u = y - P.centre;
-    if (!(fabs(u) <= CP_UMAX)) { // ~20 times per pass in sorted order (and for the lane's first particle)
-        nflush += P.cnt > 0;
-        cp_flush(P, Mg, fx_scale, Mmask);
-        cp_interval(y, P.idx, P.centre);
+    if (sp.cnt) {
+        fx_t *p = Mg + (size_t)(sp.idx & Mmask) * (2 * CP_NC);
+        cp_det_red(p, (long long)sp.cnt << CP_DET_FRAC);
+        const unsigned long long off = (unsigned long long)sp.cnt * (unsigned long long)__double_as_longlong(CP_DET_MAGIC);
+#pragma unroll
+        for (int n = 0; n < CP_NM; ++n) { cp_det_red(p + 2 * (1 + n), (long long)(col[n * stride] - off)); col[n * stride] = 0ULL; }
+        sp.cnt = 0;
+    }
+}
+
+// M[m][n] += u^n for the particle at y.  Default: the lane stays with its interval while |u| <= CP_UMAX (see the header).
+// DET: the interval is round(y) whatever the lane did before; `col` / `sp` hold the other interval of an alternating lane.
+template <bool DET>
+__device__ __forceinline__ void cp_deposit1(double y, CPSet<DET> &P, CPSpare &sp, unsigned long long *col, int stride, fx_t *Mg,
+                                            double fx_scale, int Mmask, unsigned int &nflush)
+{
+    double u;
+    if (DET) {
+        int idx;
+        double centre;
+        cp_interval(y, idx, centre);
+        u = y - centre;
+        if (idx != P.idx || P.cnt >= CP_DET_MAXCNT) {
+            if (idx == sp.idx && idx != P.idx) { // change over to the other interval: exchange the two sets
+#pragma unroll
+                for (int n = 0; n < CP_NM; ++n) { const unsigned long long m = col[n * stride]; col[n * stride] = (unsigned long long)P.m[n]; P.m[n] = m; }
+                const int c = sp.cnt; sp.cnt = P.cnt; P.cnt = c;
+                sp.idx = P.idx; P.idx = idx;
+                ++nflush;
+                if (P.cnt >= CP_DET_MAXCNT) cp_flush<DET>(P, Mg, fx_scale, Mmask);
+            } else if (idx == P.idx) {           // full set
+                cp_flush<DET>(P, Mg, fx_scale, Mmask);
+            } else {                             // a third interval: retire the spare, park the current set
+                nflush += sp.cnt > 0;
+                cp_flush_spare(sp, col, stride, Mg, Mmask);
+#pragma unroll
+                for (int n = 0; n < CP_NM; ++n) { col[n * stride] = (unsigned long long)P.m[n]; P.m[n] = 0; }
+                sp.cnt = P.cnt; sp.idx = P.idx;
+                P.cnt = 0; P.idx = idx;
+            }
+        }
+    } else {
         u = y - P.centre;
+        if (!(fabs(u) <= CP_UMAX)) { // ~20 times per pass in sorted order (and for the lane's first particle)
+            nflush += P.cnt > 0;
+            cp_flush<DET>(P, Mg, fx_scale, Mmask);
+            cp_interval(y, P.idx, P.centre);
+            u = y - P.centre;
+        }
     }
     P.cnt++;
     const double u2 = u * u;
     double pa = u, pb = u2;
 #pragma unroll
     for (int n = 0; n < CP_NM; n += 2) {
-        P.m[n] += pa; P.m[n + 1] += pb;
+        if (DET) {
+            P.m[n] += (unsigned long long)__double_as_longlong(pa + CP_DET_MAGIC);
+            P.m[n + 1] += (unsigned long long)__double_as_longlong(pb + CP_DET_MAGIC);
+        } else {
+            P.m[n] += pa; P.m[n + 1] += pb;
+        }
         if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
     }
 }
@@ -231,10 +329,48 @@ __device__ __noinline__ double cp_slow_gather(const double *G, int idx, double u
     return cp_horner(G + (size_t)(idx & Mmask) * CP_GS, u);
 }
 
+// Diagnostics sums of the final pass: sum(v.^2), sum(v) (GaussianFixedPoint.jl:10).  DET: integer sums of the raw patterns of
+// v^2 + 6144 and v + 6144 (CP_DETV_FRAC fractional bits), order-free like the moments.
+template <bool DET>
+struct CPVSum {
+    double s2 = 0.0, s1 = 0.0;
+    unsigned long long i2 = 0ULL, i1 = 0ULL;
+    long long n = 0;
+    __device__ __forceinline__ void add(double v)
+    {
+        if (DET) {
+            i2 += (unsigned long long)__double_as_longlong(v * v + CP_DETV_MAGIC);
+            i1 += (unsigned long long)__double_as_longlong(v + CP_DETV_MAGIC);
+            ++n;
+        } else {
+            s2 = fma(v, v, s2); s1 += v;
+        }
+    }
+};
+
+// Block-wide sum of 64-bit integers; result valid in thread 0.  scratch: >= 32 x 8 bytes.
+__device__ __forceinline__ long long block_sum_ll(long long v, double *scratch)
+{
+    long long *sc = reinterpret_cast<long long *>(scratch);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sc[wid] = v;
+    __syncthreads();
+    long long r = 0;
+    if (wid == 0) {
+        r = lane < nw ? sc[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;
+}
+
 // The last P % 64 particles of a shard (no full row): one thread each, global-memory gather polynomial and direct
 // moment REDs.  Same arithmetic as the streaming loop below.
-template <bool FIRST>
-__device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, bool final, bool v0_is_V, double &sv2, double &sv)
+template <bool FIRST, bool DET>
+__device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, bool final, bool v0_is_V, CPVSum<DET> &vs)
 {
     const int Mmask = a.N * CP_NSUB - 1;
     const double dNs = a.dN, hdt = a.dt / 2;
@@ -250,7 +386,7 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
         if (final) {
             const double xw = jl_mod1(xj);
             a.xout[j] = xw;
-            sv2 = fma(vj, vj, sv2); sv += vj;
+            vs.add(vj);
             Xj = xw; Vj = vj;
         }
         xj = Xj + (vj + Vj) * hdt;
@@ -258,14 +394,20 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
     const double y = (xj + Xj) * dNs;
     cp_interval(y, idx, centre);
     const double u = y - centre;
-    fx_t *p = a.Mg + (size_t)(idx & Mmask) * CP_NC;
-    double pw = 1.0;
-    for (int n = 0; n < CP_NC; ++n) { atomicAdd(p + n, to_fx(pw, a.fx_scale)); pw *= u; }
+    CPSet<DET> one; // the streaming loop's own arithmetic (same powers, same rounding) for a set of one particle
+    one.clear(); one.centre = 1e300;
+    unsigned int nf = 0;
+    CPSpare nosp; nosp.cnt = 0; nosp.idx = 0x40000001;
+    one.idx = 0x40000000; // DET: not an interval any particle can be in
+    unsigned long long dummy[CP_NM];
+    cp_deposit1<DET>(y, one, nosp, dummy, 1, a.Mg, a.fx_scale, Mmask, nf);
+    cp_flush<DET>(one, a.Mg, a.fx_scale, Mmask);
+    (void)u;
 }
 
 // Pass k of a step (same contract as fp_pass_sorted / fp_pass_atomic; FPArgs.G / FPArgs.Mg carry the polynomial
 // tables, FPArgs.dN = N*CP_NSUB/2 so that y = (x+X)*dN).  Row = 64 consecutive particles; lane l owns particles 2l and 2l+1.
-template <bool FIRST>
+template <bool FIRST, bool DET>
 __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPArgs a)
 {
     extern __shared__ double smem[];
@@ -285,13 +427,18 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     const int r0 = min(rows, gw * rpw), r1 = min(rows, r0 + rpw);
     const double2 *X2 = reinterpret_cast<const double2 *>(a.X), *V2 = reinterpret_cast<const double2 *>(a.V);
     double2 *v2 = reinterpret_cast<double2 *>(a.v), *xo2 = reinterpret_cast<double2 *>(a.xout);
-    CPSet A;
+    CPSet<DET> A;
+    A.clear(); A.idx = 0x40000000; A.centre = 1e300; // no interval yet: the first particle opens one
+    CPSpare spare; spare.cnt = 0; spare.idx = 0x40000001;
+    unsigned long long *col = reinterpret_cast<unsigned long long *>(smem + wpb * (CP_GS * CP_WG + 2 * CP_STAGES * CP_STAGE_D2)) + threadIdx.x;
+    const int cstride = blockDim.x;
+    if (DET) {
 #pragma unroll
-    for (int n = 0; n < CP_NM; ++n) A.m[n] = 0.0;
-    A.cnt = 0; A.idx = 0; A.centre = 1e300; // no interval yet: the first particle opens one
+        for (int n = 0; n < CP_NM; ++n) col[n * cstride] = 0ULL;
+    }
     int gb = 0x40000000; // interval of window slot 0; the first row always restages (see `staged`)
     bool staged = false;
-    double sv2 = 0.0, sv = 0.0;
+    CPVSum<DET> vs;
     unsigned int nflush = 0;
     // particle rows arrive through a per-warp cp.async ring: no registers are held while a row is in flight
     double2 *ring = reinterpret_cast<double2 *>(smem + wpb * (CP_GS * CP_WG)) + warp * (CP_STAGES * CP_STAGE_D2) + lane;
@@ -363,7 +510,7 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     Xj[q] = jl_mod1(xj[q]);
-                    sv2 = fma(vj[q], vj[q], sv2); sv += vj[q];
+                    vs.add(vj[q]);
                     Vj[q] = vj[q];
                 }
                 __stcs(xo2 + j2, make_double2(Xj[0], Xj[1]));
@@ -372,20 +519,31 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt;
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) cp_deposit1((xj[q] + Xj[q]) * dNs, A, a.Mg, a.fx_scale, Mmask, nflush);
+        for (int q = 0; q < 2; ++q) cp_deposit1<DET>((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, a.fx_scale, Mmask, nflush);
     }
     cp_async_wait<0>();
-    cp_flush(A, a.Mg, a.fx_scale, Mmask);
+    cp_flush<DET>(A, a.Mg, a.fx_scale, Mmask);
+    if (DET) cp_flush_spare(spare, col, cstride, a.Mg, Mmask);
     // ragged tail of the shard: fewer than 64 particles, first warp of the last block
     if (blockIdx.x == gridDim.x - 1 && warp == 0) {
         const long long j = ((long long)rows << 6) + lane;
-        if (j < a.P) cp_tail_particle<FIRST>(a, j, final, v0_is_V, sv2, sv);
-        if (j + 32 < a.P) cp_tail_particle<FIRST>(a, j + 32, final, v0_is_V, sv2, sv);
+        if (j < a.P) cp_tail_particle<FIRST, DET>(a, j, final, v0_is_V, vs);
+        if (j + 32 < a.P) cp_tail_particle<FIRST, DET>(a, j + 32, final, v0_is_V, vs);
     }
     if (final) {
-        sv2 = block_sum(sv2, scratch);
-        sv = block_sum(sv, scratch);
-        if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
+        if (DET) { // four integers per block: low 32 bits and high part of the two fixed-point sums (step_end_kernel adds them up)
+            const unsigned long long off = (unsigned long long)vs.n * (unsigned long long)__double_as_longlong(CP_DETV_MAGIC);
+            const long long v2 = (long long)(vs.i2 - off), v1 = (long long)(vs.i1 - off);
+            const long long q0 = block_sum_ll(v2 & 0xFFFFFFFFLL, scratch), q1 = block_sum_ll(v2 >> 32, scratch);
+            const long long q2 = block_sum_ll(v1 & 0xFFFFFFFFLL, scratch), q3 = block_sum_ll(v1 >> 32, scratch);
+            if (threadIdx.x == 0) {
+                long long *pp = reinterpret_cast<long long *>(a.partials) + 4 * blockIdx.x;
+                pp[0] = q0; pp[1] = q1; pp[2] = q2; pp[3] = q3;
+            }
+        } else {
+            const double sv2 = block_sum(vs.s2, scratch), sv = block_sum(vs.s1, scratch);
+            if (threadIdx.x == 0) { a.partials[2 * blockIdx.x] = sv2; a.partials[2 * blockIdx.x + 1] = sv; }
+        }
     }
     if (nflush && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nflush);
 }

@@ -211,6 +211,7 @@ struct picgolf_handle_s {
     size_t smem_sorted = 0;
     // cell-polynomial mode (pg_kernels_poly.cuh): per-cell gather polynomials and fixed-point moment grid
     bool poly = false;
+    bool det = false; // deterministic = 1 on the polynomial path: integer moment / diagnostics sums (fp_pass_poly<., true>)
     double *Gpoly = nullptr;
     unsigned long long *Mg = nullptr;
     int nblocks_poly = 1, sublg = 0;
@@ -503,9 +504,10 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             if (c.deterministic) h->sorted = false;
             else if (c.deposit_mode == PICGOLF_DEPOSIT_SORTED) h->sorted = true;
             else if (c.deposit_mode == PICGOLF_DEPOSIT_AUTO) h->sorted = h->count >= (1 << 18) && ppc >= 64;
-            // many particles per cell: cell-polynomial passes (HBM-bound instead of FP64-bound)
-            if (!c.deterministic && (c.deposit_mode == PICGOLF_DEPOSIT_POLY || (c.deposit_mode == PICGOLF_DEPOSIT_AUTO && h->count >= (1 << 22) && ppc >= 1024))) {
-                h->sorted = true; h->poly = true;
+            // many particles per cell: sub-cell polynomial passes (HBM-bound instead of FP64-bound); with deterministic = 1
+            // their lanes sum integers, so the fast path stays bit-reproducible (the windowed fp_pass_sorted does not)
+            if (c.deposit_mode == PICGOLF_DEPOSIT_POLY || (c.deposit_mode == PICGOLF_DEPOSIT_AUTO && h->count >= (1 << 22) && ppc >= 1024)) {
+                h->sorted = true; h->poly = true; h->det = c.deterministic != 0;
             }
             if (h->sorted) {
                 h->K = (int)std::max<int64_t>(1, std::min<int64_t>(64, ppc / 16));
@@ -530,13 +532,14 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                 if (h->poly) {
                     if (c.sort_every <= 0) h->sort_every = 16; // starting point; adapted from the flush counter every step
                     h->smem_poly = cp_smem_bytes(CP_THREADS);
-                    PG_TRY(set_smem(fp_pass_poly<true>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false>, h->smem_poly));
-                    PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * CP_NSUB * N)); PG_TRY(dalloc(&h->Mg, (size_t)CP_NC * CP_NSUB * N));
+                    PG_TRY(set_smem(fp_pass_poly<true, false>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false, false>, h->smem_poly));
+                    PG_TRY(set_smem(fp_pass_poly<true, true>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false, true>, h->smem_poly));
+                    PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * CP_NSUB * N)); PG_TRY(dalloc(&h->Mg, (size_t)2 * CP_NC * CP_NSUB * N)); // x2: deterministic mode
                     PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * CP_NSUB * N * sizeof(double)));
-                    PG_CUDA(cudaMemset(h->Mg, 0, (size_t)CP_NC * CP_NSUB * N * sizeof(unsigned long long)));
+                    PG_CUDA(cudaMemset(h->Mg, 0, (size_t)2 * CP_NC * CP_NSUB * N * sizeof(unsigned long long)));
                     // one contiguous range of >= 16 rows (of 64 particles) per warp
                     const int64_t rows = (h->count + 63) / 64;
-                    PG_TRY(occupancy_blocks(fp_pass_poly<false>, CP_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
+                    PG_TRY(occupancy_blocks(fp_pass_poly<false, true>, CP_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
                     h->nblocks = std::max(h->nblocks, h->nblocks_poly);
                 }
                 PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
@@ -626,8 +629,8 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
     PG_TRY(dalloc(&h->ctrl, 1));
     Ctrl c0; memset(&c0, 0, sizeof(c0)); c0.final_k = -1;
     PG_CUDA(cudaMemcpy(h->ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice));
-    PG_TRY(dalloc(&h->partials, (size_t)3 * h->nblocks));
-    PG_CUDA(cudaMemset(h->partials, 0, (size_t)3 * h->nblocks * sizeof(double)));
+    PG_TRY(dalloc(&h->partials, (size_t)4 * h->nblocks)); // up to 3 doubles per block; 4 integers in deterministic polynomial mode
+    PG_CUDA(cudaMemset(h->partials, 0, (size_t)4 * h->nblocks * sizeof(double)));
     PG_TRY(dalloc(&h->raw, (size_t)4 * h->T));
     PG_CUDA(cudaMemset(h->raw, 0, (size_t)4 * h->T * sizeof(double)));
     (void)cfg;
@@ -707,7 +710,7 @@ static int reset_run_state(picgolf_handle h)
     if (h->rho_next) PG_CUDA(cudaMemsetAsync(h->rho_next, 0, ((size_t)h->ncell + 1) * sizeof(unsigned long long), h->stream));
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
-    if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)CP_NC * CP_NSUB * h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)2 * CP_NC * CP_NSUB * h->ncell * sizeof(unsigned long long), h->stream));
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
@@ -923,12 +926,14 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false, cuda
     return 0;
 }
 
+static bool poly_now(picgolf_handle h);
 static int launch_step_end(picgolf_handle h, bool record)
 {
     StepEndArgs a;
     a.partials = h->partials; a.epartials = h->is2d ? h->epartials : nullptr; a.raw = h->raw; a.ctrl = h->ctrl;
     a.nblocks = h->pass_blocks > 0 ? h->pass_blocks : h->nblocks; a.npart = h->npart; a.neblocks = h->is2d ? (int)(h->cfg.NY / ROWS_PER_BLOCK) : 0;
     a.T = (int)h->T; a.record = record ? 1 : 0; a.is2d = h->npart == 3 ? 1 : 0;
+    a.det = (h->det && h->fixedpoint && !h->simpson && poly_now(h)) ? 1 : 0;
     step_end_kernel<<<1, 256, 0, h->stream>>>(a);
     h->launches++;
     return 0;
@@ -996,7 +1001,10 @@ static void probe_poly_flushes(picgolf_handle h)
                 // expected in sorted order: the warp that streams a (cell, sign v) group walks through its CP_NSUB polynomial
                 // intervals, and each of its 32 lanes flushes once per interval (plus once per warp range); ~4 passes per step
                 const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
-                const double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
+                double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
+                // deterministic mode has no hysteresis: in the sub-bin that an interval edge cuts through (one in 2^sublg / CP_NSUB)
+                // a lane changes over between its two sets on up to every other particle, and the change-overs are counted too
+                if (h->det) expect += std::min(1.0, (double)CP_NSUB / (double)(1 << h->sublg));
                 h->poly_quiet = frac < 5e-5 + 1.5 * expect;
                 if (frac > 1e-3 + 3.0 * expect && h->since_sort >= 2 + POLY_RUNAHEAD) {
                     h->force_sort = true;
@@ -1067,7 +1075,8 @@ static int enqueue_first_pass(picgolf_handle h)
 {
     FPArgs a = fp_args(h);
     const int sp = h->timer.begin(ST_PARTICLES, h->stream);
-    if (poly_now(h)) fp_pass_poly<true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    if (poly_now(h) && h->det) fp_pass_poly<true, true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    else if (poly_now(h)) fp_pass_poly<true, false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
     else if (h->use_sorted_now) fp_pass_sorted<true, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
     else fp_pass_atomic<true><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
     h->timer.end(sp, h->stream);
@@ -1089,6 +1098,7 @@ static int enqueue_sweep(picgolf_handle h, int k, cudaGraphConditionalHandle con
         Mom2RhoArgs m;
         m.Mg = h->Mg; m.rho = h->rho_fx; m.ctrl = h->ctrl; m.fx_scale = h->fx_scale; m.fx_inv = h->fx_inv; m.N = N;
         m.flush_src = (h->comm && !h->peer_ok) ? h->slow_count : nullptr;
+        m.det = h->det ? 1 : 0;
         const int sp = h->timer.begin(ST_SOLVE, h->stream);
         mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 32 * CP_NSUB, 0, h->stream>>>(m);
         h->timer.end(sp, h->stream);
@@ -1098,14 +1108,15 @@ static int enqueue_sweep(picgolf_handle h, int k, cudaGraphConditionalHandle con
     PG_TRY(launch_solve1d(h, k, false, cond));
     if (poly) {
         GPolyArgs g;
-        g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N; g.k = k;
+        g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N; g.k = k; g.det = h->det ? 1 : 0;
         const int sp = h->timer.begin(ST_SOLVE, h->stream);
         gpoly_kernel<<<dim3((N + 127) / 128, CP_NSUB), 128, 0, h->stream>>>(g);
         h->timer.end(sp, h->stream);
         h->launches++;
     }
     const int sp = h->timer.begin(ST_PARTICLES, h->stream);
-    if (poly) fp_pass_poly<false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    if (poly && h->det) fp_pass_poly<false, true><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
+    else if (poly) fp_pass_poly<false, false><<<h->nblocks_poly, CP_THREADS, h->smem_poly, h->stream>>>(a);
     else if (h->use_sorted_now) fp_pass_sorted<false, SORTED_NP><<<h->nblocks_sorted, PG_THREADS, h->smem_sorted, h->stream>>>(a);
     else fp_pass_atomic<false><<<h->nblocks, PG_THREADS, h->smem_pass, h->stream>>>(a);
     h->timer.end(sp, h->stream);

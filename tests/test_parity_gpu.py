@@ -2,7 +2,8 @@
 committed golden fixtures.  Bars (BASELINE.json north_star):
   * NGP cell indices f(x), Julia mod, quiet start, NGP rho with dyadic w: BIT-EXACT;
   * rho, E, x, v after a step: |delta| <= 1e-12 * max|.| (norm-wise; SURVEY.md 7.4 explains why
-    element-wise rtol is meaningless at zero crossings);
+    element-wise rtol is meaningless at zero crossings) -- at every size tested, N = 4096 and 256 x 256 included; the
+    measured error of every comparison is written to PARITY.json (conftest.py), typically 1e-15 ... 5e-13;
   * diagnostics traces within 1e-9 relative over the short horizon before two-stream chaos diverges;
   * long horizon: growth rate of log10 D[:,1] within 1% of the analytic 2*gamma line."""
 import math
@@ -184,7 +185,7 @@ def test_explicit_gaussian_steps(pg, oracle):
     for t in range(8):
         sim.step(1)
         rho, E = sim.fields()
-        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-11
+        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < TOL
     x, v = sim.particles()
     assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
     assert relnorm(sim.raw_diagnostics()[:, :3], g["raw"]) < TOL
@@ -329,7 +330,7 @@ def test_scaled_config4_properties(pg, oracle):
     rho, E = sim.fields()
     _, sw = sim.diagnostics()
     assert sw[0] == s
-    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-11
+    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < TOL
     assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL
 
 
@@ -364,7 +365,7 @@ def test_config4_full_size_properties(pg):
         s2.close()
     (ra, Ea, xa, va, swa), (rb, Eb, xb, vb, swb) = out
     assert np.array_equal(swa, swb)
-    assert relnorm(ra, rb) < TOL and relnorm(Ea, Eb) < 1e-10 and relnorm(xa, xb) < TOL and relnorm(va, vb) < TOL
+    assert relnorm(ra, rb) < TOL and relnorm(Ea, Eb) < 5e-12 and relnorm(xa, xb) < TOL and relnorm(va, vb) < TOL  # two algorithms, 5 steps, 2^26 particles: measured 5.7e-13
 
 
 def test_scaled_ngp_properties(pg, oracle):
@@ -682,7 +683,7 @@ def test_2d3v_tile_sorted_mode(pg, oracle):
         assert relnorm(a, b) < TOL
     fa, fs = sims[0].fields(), sims[1].fields()
     assert relnorm(fs[0], fa[0]) < TOL  # both fixed point; the tiled path quantises per work item, not per deposit
-    assert relnorm(fs[1], fa[1]) < 1e-10
+    assert relnorm(fs[1], fa[1]) < TOL
     sorts, slow = sims[1].sort_stats()
     assert sorts == 3 and slow < P // 1000
     # one step vs the oracle
@@ -693,7 +694,7 @@ def test_2d3v_tile_sorted_mode(pg, oracle):
     sim.step(1)
     ro = oracle.step_2d3v(*so, NX, NY, sim.cfg.dt, sim.cfg.B0, sim.cfg.w, Ex, Ey, nthreads=4)
     rho, ex, ey = sim.fields()
-    assert relnorm(rho.reshape(-1, order="F"), ro) < TOL and relnorm(ex.reshape(-1, order="F"), Ex) < 1e-11
+    assert relnorm(rho.reshape(-1, order="F"), ro) < TOL and relnorm(ex.reshape(-1, order="F"), Ex) < TOL
     got = sim.particles()
     assert relnorm(got[0], so[0]) < TOL and relnorm(got[2], so[2]) < TOL
 
@@ -712,7 +713,7 @@ def test_ngp_odd_particle_count(pg, oracle):
         ro, Eo, _ = oracle.ngp_step(x, v, N, sim.cfg.dt, sim.cfg.w)
     rho, E = sim.fields()
     xg, vg = sim.particles()
-    assert relnorm(rho, ro) < 1e-13 and relnorm(E, Eo) < 1e-11 and relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
+    assert relnorm(rho, ro) < 1e-13 and relnorm(E, Eo) < TOL and relnorm(xg, x) < TOL and relnorm(vg, v) < TOL
 
 
 # =============================================================================================
@@ -732,7 +733,7 @@ def test_ragged_particle_counts_atomic(pg, oracle, P):
     rho, E = sim.fields()
     D, sw = sim.diagnostics()
     assert list(sw) == sw_o
-    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10
+    assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < TOL
 
 
 def test_ragged_particle_count_sorted(pg, oracle):
@@ -748,7 +749,7 @@ def test_ragged_particle_count_sorted(pg, oracle):
     x, v = sim.particles()
     rho, E = sim.fields()
     assert list(sim.diagnostics()[1]) == sw_o
-    assert relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11 and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10
+    assert relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL and relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < TOL
 
 
 @pytest.mark.parametrize("N", [16, 8192])
@@ -764,7 +765,7 @@ def test_extreme_grid_sizes(pg, oracle, N):
     x, v = sim.particles()
     rho, E = sim.fields()
     assert sim.diagnostics()[1][0] == s
-    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < 1e-10 and relnorm(x, fp.x) < 1e-11 and relnorm(v, fp.v) < 1e-11
+    assert relnorm(rho, fp.r) < TOL and relnorm(E, fp.E) < TOL and relnorm(x, fp.x) < TOL and relnorm(v, fp.v) < TOL
     ng = pg.ngp_fourier(N=N, P=P, NT=4, W=float(N))  # w = N*N/P dyadic
     ng.set_particles(x0, v0)
     ng.step(2)
@@ -853,6 +854,36 @@ def test_deterministic_flag_bit_reproducible(pg):
     assert np.array_equal(res[1][1][0], res[0][1][0][perm])
 
 
+@pytest.mark.parametrize("N,P", [(1024, 1 << 22), (256, (1 << 22) + 77)])
+def test_deterministic_fast_path_bit_reproducible(pg, N, P):
+    """deterministic=1 at a size where AUTO picks the polynomial passes: the handle STAYS on fp_pass_poly (lanes sum integers,
+    pg_kernels_poly.cuh DET) and rho, E, x, v and the diagnostics are bit-identical from run to run and for any order in which
+    the caller hands the particles over -- although the counting sort ranks the particles of a bin with atomics, so the lanes
+    sum different particles every run.  Against the default (fp64 lane sums) path the results agree to round-off."""
+    rng = np.random.default_rng(19)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0) + 1e-3 * rng.standard_normal(P)
+    perm = rng.permutation(P)
+    res = []
+    for xs, vs, det in ((x0, v0, 1), (x0, v0, 1), (x0[perm], v0[perm], 1), (x0, v0, 0)):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=400.0, deterministic=det, sort_every=3)
+        assert sim.deposit_path == pg.DEPOSIT_POLY
+        sim.set_particles(xs, vs)
+        sim.step(7)  # step 1 any-order, sorts before steps 2 and 5, five polynomial steps
+        res.append(sim.fields() + sim.particles() + (sim.raw_diagnostics(), sim.diagnostics()[1]))
+        assert sim.sort_stats()[0] == 2
+        sim.close()
+    a, b, c, d = res
+    for u, w in zip(a, b):
+        assert np.array_equal(u, w)                       # run to run
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])  # rho, E: any particle order
+    assert np.array_equal(c[2], a[2][perm]) and np.array_equal(c[3], a[3][perm])
+    # sum E^2, sum v^2, sum v, sweeps of the polynomial steps (row 0 is the any-order first step, whose fp64 block sums of v follow the caller's order)
+    assert np.array_equal(a[4][1:], c[4][1:]) and np.array_equal(a[4][0, 0], c[4][0, 0]) and np.array_equal(a[5], c[5])
+    assert relnorm(a[0], d[0]) < TOL and relnorm(a[2], d[2]) < TOL and relnorm(a[3], d[3]) < TOL  # vs the default path
+    assert relnorm(a[4][:, :2], d[4][:, :2]) < TOL and np.array_equal(a[5], d[5])
+
+
 # =============================================================================================
 # SURVEY 8f rank 1: Simpson-1/3 fixed point (src/GaussianFixedPointQuietSimpson13.jl)
 # =============================================================================================
@@ -878,7 +909,7 @@ def test_simpson13_steps(pg, oracle):
     x, v = one.particles()
     rho, E = one.fields()
     assert one.diagnostics()[1][0] == s
-    assert relnorm(x, o1.x) < TOL and relnorm(v, o1.v) < TOL and relnorm(rho, o1.r) < TOL and relnorm(E, o1.E[256:]) < 1e-11
+    assert relnorm(x, o1.x) < TOL and relnorm(v, o1.v) < TOL and relnorm(rho, o1.r) < TOL and relnorm(E, o1.E[256:]) < TOL
 
 
 def test_simpson13_quiet_growth(pg, oracle):
@@ -945,7 +976,7 @@ def test_ngp1d2v_steps(pg, oracle):
     for t in range(8):
         sim.step(1)
         rho, E = sim.fields()
-        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < 1e-10
+        assert relnorm(rho, g["rho"][t]) < TOL and relnorm(E, g["E"][t]) < TOL
     x, vx, vy = sim.particles()
     assert relnorm(x, g["x"]) < TOL and relnorm(vx, g["vx"]) < TOL and relnorm(vy, g["vy"]) < TOL
     assert 0 <= x.min() and x.max() <= 1
@@ -999,7 +1030,7 @@ def test_ngp1d2v2s_steps(pg, oracle):
         want = np.array([d1 * 2 / n0, d2 * 2 / n0, (d1 + d2) * 2 / n0, s1 / P, s2 / P]) / 4
         assert np.abs(D[ti] - want).max() < 1e-10 * np.abs(want).max()
     Es = sim.field_history()
-    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < 1e-10 and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < 1e-10
+    assert relnorm(Es[:, 0], g["E"][:4].mean(axis=0)) < TOL and relnorm(Es[:, 1], g["E"][4:8].mean(axis=0)) < TOL
     # another mass ratio and size against the live oracle
     rng = np.random.default_rng(4)
     N2, P2, M2 = 128, 3000, 100.0
@@ -1036,7 +1067,7 @@ def test_2d3v_tma_variant_matches(pg, oracle, monkeypatch):
         res.append((sim.particles(), sim.fields(), sim.diagnostics()[0]))
     for a, b in zip(res[0][0], res[1][0]):
         assert relnorm(b, a) < TOL
-    assert relnorm(res[1][1][0], res[0][1][0]) < TOL and relnorm(res[1][1][1], res[0][1][1]) < 1e-10
+    assert relnorm(res[1][1][0], res[0][1][0]) < TOL and relnorm(res[1][1][1], res[0][1][1]) < TOL
     assert relnorm(res[1][2][:, :3], res[0][2][:, :3]) < TOL
 
 

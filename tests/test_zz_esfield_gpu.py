@@ -13,7 +13,9 @@ from conftest import golden, relnorm
 pytestmark = pytest.mark.gpu
 
 SHAPES = [0, 1, 10, 11, 12, 13, 14, 15]
-TOL = 1e-11
+TOL = 1e-12
+TOL_TILED = 3e-11  # tile-sorted vs any-order kernel: two fixed-point formats (per deposit / per window), measured against the NET charge of two
+                   # opposite species (a few % of one species' density): measured 2e-12 ... 9e-12, see PARITY.json
 
 
 @pytest.fixture(scope="module")
@@ -160,11 +162,11 @@ def test_tiled_path_at_size(es, shape):
         out.append((sim.fields(), sim.species(0), sim.species(1), sim.scalars(), sim.history("Exs"), sim.sort_stats()))
     (fa, a0, a1, sa, ha, sta), (fb, b0, b1, sb, hb, stb) = out
     assert sta == (0, 0) and stb[0] == 2 and stb[1] < 1e-3 * 2 * P * NT  # auto = tiled at this size: sorts before steps 0 and 8
-    assert relnorm(fb["rho"], fa["rho"]) < TOL and relnorm(fb["Ex"], fa["Ex"]) < TOL
+    assert relnorm(fb["rho"], fa["rho"]) < TOL_TILED and relnorm(fb["Ex"], fa["Ex"]) < TOL_TILED
     for x, y in list(zip(a0, b0)) + list(zip(a1, b1)):
-        assert relnorm(y, x) < TOL  # same particle order as the caller's
-    assert relnorm(sb["kineticenergy"], sa["kineticenergy"]) < TOL and relnorm(sb["fieldenergy"], sa["fieldenergy"]) < TOL
-    assert relnorm(hb, ha) < TOL
+        assert relnorm(y, x) < TOL_TILED  # same particle order as the caller's
+    assert relnorm(sb["kineticenergy"], sa["kineticenergy"]) < TOL_TILED and relnorm(sb["fieldenergy"], sa["fieldenergy"]) < TOL_TILED
+    assert relnorm(hb, ha) < TOL_TILED
 
 
 def _species_n(shape, P, NX, NY, Lx, Ly, charge, mass, seed, dt):
