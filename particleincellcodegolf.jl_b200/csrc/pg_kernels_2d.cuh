@@ -258,17 +258,20 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged variant of the tiled kernel (opt-in experiment, PICGOLF_2D_TMA=1: measured slower than
-// particles_2d3v_tiled on B200 because the SM-side work, not the particle streams, limits it; see picgolf.cu).  Same tiles, same windows and
-// the same per-particle arithmetic, but the five particle streams are moved by the copy engine: one persistent
-// 512-thread block per SM owns a contiguous range of work items and streams them in sub-tiles of T2_SUB particles
-// through a T2_STAGES-deep shared-memory ring (`cp.async.bulk` loads completing on mbarriers, in-place update,
-// bulk stores).  Bulk copies need 16-byte alignment, so a sub-tile [a,b) is split into its even-aligned interior
-// (staged) and at most two edge particles (plain global accesses).  The E / deposit window is kept across the
-// consecutive items of a tile and flushed only when the tile changes.
+// Ring variant of the tiled kernel.  Same tiles, windows and per-particle arithmetic, but the five particle
+// streams reach the SM through a per-warp `cp.async` ring (LDGSTS, R2_STAGES rows of 32 particles, one particle
+// per lane and array) instead of plain loads: the tiled kernel's warps spend 10.8 of every 15.8 stall cycles per
+// issue waiting for their five global loads (ncu, profiles/r1_d_ncu_particles_2d3v_tiled.txt: long_scoreboard)
+// with DRAM 55 % and the shared-memory pipe ~50 % busy -- it is bound by bytes in flight, not by a unit.  Here
+// R2_STAGES-1 rows (3 x 1280 B per warp, 90 KB per SM) are in flight while a row is processed and no register
+// is held for them.  A lane reads back only the bytes it copied itself, so `cp.async.wait_group` is the only
+// synchronisation; the first rows of an item are requested before the block stages its window.
 // ------------------------------------------------------------------------------------------------
-constexpr int T2_SUB = 1024, T2_STAGES = 3, T2_TMA_THREADS = 512;
-constexpr size_t T2_TMA_SMEM = (size_t)T2_STAGES * 5 * T2_SUB * 8 + (size_t)T2_WS * T2_WS * (16 + 8) + 256 + 64;
+constexpr int R2_ROW = 5 * 32; // doubles per ring stage of one warp
+__host__ __device__ constexpr size_t r2_smem_bytes(int threads, int stages)
+{
+    return (size_t)T2_WS * T2_WS * (16 + 8) + 32 * 8 + (size_t)(threads / 32) * stages * R2_ROW * 8;
+}
 
 struct P2DWindow {
     const double2 *Ew;
@@ -276,200 +279,305 @@ struct P2DWindow {
     int ox, oy;
 };
 
-// gather (old position) -> boris -> move -> deposit (new position) for one particle; window or global fallback
-__device__ __forceinline__ void p2d_particle(const P2DArgs &a, const P2DWindow &w, double &x, double &y, double &vx, double &vy,
-                                             double &vz, double &s0, double &s1, double &s2, unsigned int &nslow)
+// One particle in two halves, so that a lane holding two particles can overlap their shared-memory latencies:
+// p2d_push = gather (old position) -> boris -> move, returns the CIC corners/weights of the new position;
+// p2d_deposit = the four window adds (or the global fallback).
+// G, D: replicas per window cell of the field / of the deposit limbs (w.Ew, w.rlo, w.rhi already point at this lane's replica).
+template <int G>
+__device__ __forceinline__ void p2d_push(const P2DArgs &a, const P2DWindow &w, double &x, double &y, double &vx, double &vy,
+                                         double &vz, double &s0, double &s1, double &s2, Cic4 &c)
 {
     const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
-    Cic4 c;
     cic4(x, y, NX, NY, c);
     double ex = 0.0, ey = 0.0;
     {
         const int rx = (c.ix[0] - 1 - w.ox) & mx, ry = (c.iy[0] - 1 - w.oy) & my;
-        const bool in = rx <= T2_WS - 2 && ry <= T2_WS - 2;
+        if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
+            const double2 *e = w.Ew + (rx + ry * T2_WS) * G;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-                double wxy = c.wx[ii] * c.wy[jj];
-                double2 f = in ? w.Ew[rx + ii + (ry + jj) * T2_WS] : __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
-                ex = fma(f.x, wxy, ex);
-                ey = fma(f.y, wxy, ey);
-            }
+                for (int ii = 0; ii < 2; ++ii) {
+                    double wxy = c.wx[ii] * c.wy[jj];
+                    double2 f = e[(ii + jj * T2_WS) * G];
+                    ex = fma(f.x, wxy, ex);
+                    ey = fma(f.y, wxy, ey);
+                }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    double wxy = c.wx[ii] * c.wy[jj];
+                    double2 f = __ldg(&a.E2[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX]);
+                    ex = fma(f.x, wxy, ex);
+                    ey = fma(f.y, wxy, ey);
+                }
+        }
     }
     boris(vx, vy, vz, ex, ey, a.dt, a.t1, a.tscale);
     x = unimod(x + vx * a.dt, 1.0);
     y = unimod(y + vy * a.dt, 1.0);
     cic4(x, y, NX, NY, c);
-    {
-        const int rx = (c.ix[0] - 1 - w.ox) & mx, ry = (c.iy[0] - 1 - w.oy) & my;
-        if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
-            const int r0 = rx + ry * T2_WS;
-            unsigned int lo[4], old[4];
-            fx_t v[4];
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const int k = ii + 2 * jj;
-                    v[k] = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale);
-                    lo[k] = (unsigned int)v[k];
-                    old[k] = atomicAdd(&w.rlo[r0 + ii + jj * T2_WS], lo[k]);
-                }
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii) {
-                    const int k = ii + 2 * jj;
-                    const unsigned int carry = (old[k] + lo[k]) < old[k] ? 1u : 0u;
-                    const unsigned int hi = (unsigned int)(v[k] >> 32) + carry;
-                    if (hi) atomicAdd(&w.rhi[r0 + ii + jj * T2_WS], hi);
-                }
-        } else {
-            ++nslow;
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                for (int ii = 0; ii < 2; ++ii)
-                    atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
-        }
-    }
     s0 += vx * vx + vy * vy; s1 += vx; s2 += vy;
 }
 
-// Walks the sub-tiles of a contiguous range of work items (uniform across the block).
-struct SubTileCursor {
-    unsigned int item, item_end;
-    int tile;
-    long long pos, end; // next particle to hand out / end of the current item
-    __device__ __forceinline__ void open_item(const P2DArgs &a)
-    {
-        int lo = 0, hi = a.ntiles;
+template <int D>
+__device__ __forceinline__ void p2d_deposit(const P2DArgs &a, const P2DWindow &w, const Cic4 &c, unsigned int &nslow)
+{
+    const int NX = a.NX, mx = NX - 1, my = a.NY - 1;
+    const int rx = (c.ix[0] - 1 - w.ox) & mx, ry = (c.iy[0] - 1 - w.oy) & my;
+    if (rx <= T2_WS - 2 && ry <= T2_WS - 2) {
+        const int r0 = (rx + ry * T2_WS) * D;
+        unsigned int lo[4], old[4];
+        fx_t v[4];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const int k = ii + 2 * jj;
+                v[k] = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale);
+                lo[k] = (unsigned int)v[k];
+                old[k] = atomicAdd(&w.rlo[r0 + (ii + jj * T2_WS) * D], lo[k]);
+            }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const int k = ii + 2 * jj;
+                const unsigned int carry = (old[k] + lo[k]) < old[k] ? 1u : 0u;
+                const unsigned int hi = (unsigned int)(v[k] >> 32) + carry;
+                if (hi) atomicAdd(&w.rhi[r0 + (ii + jj * T2_WS) * D], hi);
+            }
+    } else {
+        ++nslow;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+                atomicAdd(&a.rho[(c.ix[ii] - 1) + (size_t)(c.iy[jj] - 1) * NX], to_fx(c.wx[ii] * c.wy[jj], a.fx_scale));
+    }
+}
+
+template <int G, int D>
+__device__ __forceinline__ void p2d_particle(const P2DArgs &a, const P2DWindow &w, double &x, double &y, double &vx, double &vy,
+                                             double &vz, double &s0, double &s1, double &s2, unsigned int &nslow)
+{
+    Cic4 c;
+    p2d_push<G>(a, w, x, y, vx, vy, vz, s0, s1, s2, c);
+    p2d_deposit<D>(a, w, c, nslow);
+}
+
+template <int R2_STAGES, int MINB>
+__global__ void __launch_bounds__(PG_THREADS, MINB) particles_2d3v_ring(P2DArgs a)
+{
+    static_assert((R2_STAGES & (R2_STAGES - 1)) == 0, "ring depth must be a power of two");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Ew = reinterpret_cast<double2 *>(smem_raw);
+    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + T2_WS * T2_WS), *rhi = rlo + T2_WS * T2_WS;
+    double *scratch = reinterpret_cast<double *>(rhi + T2_WS * T2_WS);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *const mine = scratch + 32 + (size_t)wid * R2_STAGES * R2_ROW + lane; // this lane's column of its warp's ring
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    unsigned int nslow = 0;
+    P2DWindow w;
+    w.Ew = Ew; w.rlo = rlo; w.rhi = rhi;
+    const unsigned int nitems = a.item_off[a.ntiles];
+    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int lo = 0, hi = a.ntiles; // tile of this item: last t with item_off[t] <= item
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
             if (a.item_off[mid] <= item) lo = mid; else hi = mid;
         }
-        tile = lo;
-        pos = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
-        end = min(pos + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
-    }
-    __device__ __forceinline__ void init(const P2DArgs &a, unsigned int i0, unsigned int i1)
-    {
-        item = i0; item_end = i1; tile = -1; pos = end = 0;
-        if (item < item_end) open_item(a);
-    }
-    // next sub-tile [sa, sb) of tile t; false when the range is exhausted
-    __device__ __forceinline__ bool next(const P2DArgs &a, long long &sa, long long &sb, int &t)
-    {
-        while (item < item_end && pos >= end) {
-            ++item;
-            if (item < item_end) open_item(a);
+        const int tile = lo;
+        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
+        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
+        // row k of this warp = particles start + (wid + k*nw)*32 + lane; stage k % R2_STAGES (always commits: uniform group count)
+        auto issue = [&](int k) {
+            const long long p = start + ((long long)(wid + k * nw) << 5) + lane;
+            if (p < end) {
+                double *st = mine + (k & (R2_STAGES - 1)) * R2_ROW;
+                cp_async8(st, a.x + p); cp_async8(st + 32, a.y + p);
+                cp_async8(st + 64, a.vx + p); cp_async8(st + 96, a.vy + p); cp_async8(st + 128, a.vz + p);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < R2_STAGES - 1; ++k) issue(k);
+        w.ox = (tile % a.ntx) * T2_TS - T2_R; w.oy = (tile / a.ntx) * T2_TS - T2_R; // window origin (0-based cells)
+        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
+            int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
+            Ew[c] = a.E2[gx + (size_t)gy * NX];
+            rlo[c] = 0u; rhi[c] = 0u;
         }
-        if (item >= item_end) return false;
-        sa = pos; sb = min(pos + (long long)T2_SUB, end); t = tile;
-        pos = sb;
-        return true;
-    }
-};
-
-__global__ void __launch_bounds__(T2_TMA_THREADS, 1) particles_2d3v_tma(P2DArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *ring = reinterpret_cast<double *>(smem_raw);                       // [STAGES][5][T2_SUB]
-    double2 *Ew = reinterpret_cast<double2 *>(ring + (size_t)T2_STAGES * 5 * T2_SUB);
-    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + T2_WS * T2_WS), *rhi = rlo + T2_WS * T2_WS;
-    double *scratch = reinterpret_cast<double *>(rhi + T2_WS * T2_WS);
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 32);
-    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
-    double *const gp[5] = {a.x, a.y, a.vx, a.vy, a.vz};
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < T2_STAGES; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const unsigned int nitems = a.item_off[a.ntiles];
-    const unsigned int i0 = (unsigned int)((unsigned long long)nitems * blockIdx.x / gridDim.x);
-    const unsigned int i1 = (unsigned int)((unsigned long long)nitems * (blockIdx.x + 1) / gridDim.x);
-    SubTileCursor prod, cons;
-    prod.init(a, i0, i1);
-    cons.init(a, i0, i1);
-    long long issued = 0;
-    auto issue_load = [&]() { // thread 0: next sub-tile of the producer cursor into stage issued % STAGES
-        long long sa, sb; int t;
-        if (!prod.next(a, sa, sb, t)) return;
-        const int s = (int)(issued % T2_STAGES);
-        const long long a2 = sa + (sa & 1), b2 = sb - (sb & 1);
-        const uint32_t bytes = b2 > a2 ? (uint32_t)((b2 - a2) * 8) : 0u;
-        mbar_arrive_expect_tx(&full[s], 5 * bytes);
-        if (bytes)
-            for (int q = 0; q < 5; ++q) bulk_load(ring + ((size_t)s * 5 + q) * T2_SUB, gp[q] + a2, bytes, &full[s]);
-        ++issued;
-    };
-    if (threadIdx.x == 0)
-        for (int k = 0; k < T2_STAGES - 1; ++k) issue_load();
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    unsigned int nslow = 0;
-    P2DWindow w;
-    w.Ew = Ew; w.rlo = rlo; w.rhi = rhi; w.ox = 0; w.oy = 0;
-    int cur_tile = -1;
-    auto flush_window = [&]() {
+        __syncthreads();
+        const int nrows = (int)((end - start + 31) >> 5);
+        for (int k = 0; wid + k * nw < nrows; ++k) {
+            issue(k + R2_STAGES - 1);
+            cp_async_wait<R2_STAGES - 1>(); // row k has landed
+            const long long p = start + ((long long)(wid + k * nw) << 5) + lane;
+            if (p < end) {
+                const double *st = mine + (k & (R2_STAGES - 1)) * R2_ROW;
+                double x = st[0], y = st[32], vx = st[64], vy = st[96], vz = st[128];
+                p2d_particle<1, 1>(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
+                st_stream(a.x + p, x); st_stream(a.y + p, y);
+                st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
         for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
             long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
             if (v) {
-                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift;
+                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift; // rounded: weights are >= 0
                 int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
                 atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)v);
             }
         }
-    };
-    long long sa, sb, q = 0;
-    int t;
-    while (cons.next(a, sa, sb, t)) {
-        if (t != cur_tile) { // (re)build the window: E2 slice in, deposit limbs flushed and cleared
-            if (cur_tile >= 0) flush_window();
-            __syncthreads();
-            w.ox = (t % a.ntx) * T2_TS - T2_R; w.oy = (t / a.ntx) * T2_TS - T2_R;
-            for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
-                Ew[c] = a.E2[gx + (size_t)gy * NX];
-                rlo[c] = 0u; rhi[c] = 0u;
-            }
-            cur_tile = t;
-            __syncthreads();
-        }
-        const int s = (int)(q % T2_STAGES);
-        double *st = ring + (size_t)s * 5 * T2_SUB;
-        const long long a2 = sa + (sa & 1), b2 = sb - (sb & 1);
-        mbar_wait(&full[s], (uint32_t)((q / T2_STAGES) & 1));
-        for (long long i = threadIdx.x; i < b2 - a2; i += blockDim.x) { // staged interior
-            double x = st[i], y = st[T2_SUB + i], vx = st[2 * T2_SUB + i], vy = st[3 * T2_SUB + i], vz = st[4 * T2_SUB + i];
-            p2d_particle(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
-            st[i] = x; st[T2_SUB + i] = y; st[2 * T2_SUB + i] = vx; st[3 * T2_SUB + i] = vy; st[4 * T2_SUB + i] = vz;
-        }
-        // unaligned edge particles straight from/to global memory (threads of two different warps)
-        long long edge = -1; // an odd start and an odd end can never be the same particle
-        if (threadIdx.x == 0 && (sa & 1)) edge = sa;
-        if (threadIdx.x == 32 && (sb & 1)) edge = sb - 1;
-        if (edge >= 0) {
-            double x = a.x[edge], y = a.y[edge], vx = a.vx[edge], vy = a.vy[edge], vz = a.vz[edge];
-            p2d_particle(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
-            a.x[edge] = x; a.y[edge] = y; a.vx[edge] = vx; a.vy[edge] = vy; a.vz[edge] = vz;
-        }
-        fence_proxy_async();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (b2 > a2) {
-                const uint32_t bytes = (uint32_t)((b2 - a2) * 8);
-                for (int k = 0; k < 5; ++k) bulk_store(gp[k] + a2, st + (size_t)k * T2_SUB, bytes);
-            }
-            bulk_commit();
-            bulk_wait_read<1>(); // the stage stored one iteration ago is free again
-            issue_load();
-        }
-        ++q;
     }
-    if (cur_tile >= 0) { __syncthreads(); flush_window(); }
-    if (threadIdx.x == 0) bulk_wait_all<0>();
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    s2 = block_sum(s2, scratch);
+    if (threadIdx.x == 0) {
+        a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
+    }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slice-streaming kernel (default of the tile-sorted path).  ncu of the ring kernel above (profiles/r2_e_*): once the global
+// loads are hidden, the shared-memory data pipe is the limit (80 % busy): per row of 32 particles 43 wavefronts for the four
+// 16-byte field gathers (10.8 per LDS.128: eight lanes of a quarter-warp hit eight 16-byte bank groups at random), 41 for the
+// eight limb atomics (5.1 per ATOMS) and 23 for the ring -- 113 where 41 would do without bank conflicts.  This kernel removes
+// most of the conflicts by REPLICATING the windows: lane l reads the field from replica l % G (cell c, replica r at
+// 16-byte slot c*G + r, so lanes of one quarter-warp collide only when they share r) and adds into deposit replica l % D
+// (word c*D + r); the flush sums the D replicas of a cell.  The replicas fill the SM's shared memory (G = 4, D = 8: 64 + 64 KB
+// for the 32 x 32-cell window), so ONE block of 512 threads runs per SM, and to keep it busy the work is no longer cut into
+// 8192-particle items with a window rebuild each: a block owns a contiguous slice of the tile-sorted arrays (P / gridDim.x
+// particles) and walks through it tile segment by tile segment -- at 2^28 particles 2-3 window builds per block and launch.
+// The deposit window is flushed every S2_FLUSH particles (its high limb must not overflow) and at every tile change.
+// Rows are 64 particles (two per lane, 16-byte cp.async.cg -> LDGSTS.128 that bypass L1, 128-bit stores), S2_STAGES per warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int S2_FLUSH = 1 << 16, S2_STAGES = 2, S2_ROW = 5 * 32; // double2 slots per ring stage of one warp
+__host__ __device__ constexpr size_t s2_smem_bytes(int G, int D, int threads)
+{
+    return (size_t)T2_WS * T2_WS * (16 * G + 8 * D) + 32 * 8 + (size_t)(threads / 32) * S2_STAGES * S2_ROW * 16;
+}
+
+template <int G, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) particles_2d3v_stream(P2DArgs a)
+{
+    constexpr int NC = T2_WS * T2_WS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Ew = reinterpret_cast<double2 *>(smem_raw);                  // [cell][G]
+    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + NC * G), *rhi = rlo + NC * D; // [cell][D]
+    double *scratch = reinterpret_cast<double *>(rhi + NC * D);
+    double2 *ring = reinterpret_cast<double2 *>(scratch + 32);            // [warp][stage][array][lane]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int nw = THREADS / 32;
+    double2 *const mine = ring + (size_t)wid * S2_STAGES * S2_ROW + lane;
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double *const gp[5] = {a.x, a.y, a.vx, a.vy, a.vz};
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    unsigned int nslow = 0;
+    P2DWindow w;
+    w.Ew = Ew + (lane & (G - 1)); w.rlo = rlo + (lane & (D - 1)); w.rhi = rhi + (lane & (D - 1)); w.ox = 0; w.oy = 0;
+    for (int c = threadIdx.x; c < NC * D; c += THREADS) { rlo[c] = 0u; rhi[c] = 0u; }
+    // this block's slice [s_lo, s_hi) of the sorted arrays (row aligned) and the tile its first particle lies in
+    const long long per = (((a.P + gridDim.x - 1) / gridDim.x) + 63) & ~63LL;
+    const long long s_lo = min(a.P, per * (long long)blockIdx.x), s_hi = min(a.P, s_lo + per);
+    int tile = 0;
+    {
+        int lo = 0, hi = a.ntiles; // last t with tile_start[t] <= s_lo
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((long long)a.tile_start[mid] <= s_lo) lo = mid; else hi = mid;
+        }
+        tile = lo;
+    }
+    int cur_tile = -1;
+    for (long long pos = s_lo; pos < s_hi;) {
+        while (tile < a.ntiles - 1 && (long long)a.tile_end[tile] <= pos) ++tile;
+        const long long seg_hi = min(min(s_hi, (long long)a.tile_end[tile]), pos + S2_FLUSH);
+        // rows of this segment: 64 particles from the even base; row k of this warp is row wid + k*nw
+        const long long base = pos & ~63LL;
+        const int nrows = (int)((seg_hi - base + 63) >> 6);
+        auto issue = [&](int k) { // lane copies the pair (p0, p0+1) of each array; always commits (uniform group count)
+            const int r = wid + k * nw;
+            const long long p0 = base + ((long long)r << 6) + 2 * lane;
+            if (r < nrows && p0 + 1 >= pos && p0 < seg_hi) {
+                double2 *st = mine + (k % S2_STAGES) * S2_ROW;
+                if (p0 + 1 < a.P) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) cp_async16(st + 32 * q, gp[q] + p0);
+                } else { // the very last particle of an odd-sized shard
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) cp_async8(st + 32 * q, gp[q] + p0);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < S2_STAGES - 1; ++k) issue(k);
+        if (tile != cur_tile) { // (re)build the field window around this tile, all replicas
+            w.ox = (tile % a.ntx) * T2_TS - T2_R; w.oy = (tile / a.ntx) * T2_TS - T2_R;
+            for (int c = threadIdx.x; c < NC * G; c += THREADS) {
+                const int cell = c / G;
+                int gx = (w.ox + (cell & (T2_WS - 1))) & mx, gy = (w.oy + (cell >> 5)) & my;
+                Ew[c] = a.E2[gx + (size_t)gy * NX];
+            }
+            cur_tile = tile;
+        }
+        __syncthreads();
+        for (int k = 0; wid + k * nw < nrows; ++k) {
+            issue(k + S2_STAGES - 1);
+            cp_async_wait<S2_STAGES - 1>(); // row k has landed
+            const long long p0 = base + ((long long)(wid + k * nw) << 6) + 2 * lane;
+            const bool v0 = p0 >= pos && p0 < seg_hi, v1 = p0 + 1 >= pos && p0 + 1 < seg_hi;
+            if (v0 || v1) {
+                const double2 *st = mine + (k % S2_STAGES) * S2_ROW;
+                double2 X = st[0], Y = st[32], VX = st[64], VY = st[96], VZ = st[128];
+                if (v0 && v1) { // the two pushes are independent: their gathers overlap; then the eight + eight window adds
+                    Cic4 c0, c1;
+                    p2d_push<G>(a, w, X.x, Y.x, VX.x, VY.x, VZ.x, s0, s1, s2, c0);
+                    p2d_push<G>(a, w, X.y, Y.y, VX.y, VY.y, VZ.y, s0, s1, s2, c1);
+                    p2d_deposit<D>(a, w, c0, nslow);
+                    p2d_deposit<D>(a, w, c1, nslow);
+                } else if (v0) p2d_particle<G, D>(a, w, X.x, Y.x, VX.x, VY.x, VZ.x, s0, s1, s2, nslow);
+                else p2d_particle<G, D>(a, w, X.y, Y.y, VX.y, VY.y, VZ.y, s0, s1, s2, nslow);
+                if (v0 && v1) {
+                    __stcs(reinterpret_cast<double2 *>(a.x + p0), X); __stcs(reinterpret_cast<double2 *>(a.y + p0), Y);
+                    __stcs(reinterpret_cast<double2 *>(a.vx + p0), VX); __stcs(reinterpret_cast<double2 *>(a.vy + p0), VY);
+                    __stcs(reinterpret_cast<double2 *>(a.vz + p0), VZ);
+                } else if (v0) {
+                    st_stream(a.x + p0, X.x); st_stream(a.y + p0, Y.x);
+                    st_stream(a.vx + p0, VX.x); st_stream(a.vy + p0, VY.x); st_stream(a.vz + p0, VZ.x);
+                } else {
+                    st_stream(a.x + p0 + 1, X.y); st_stream(a.y + p0 + 1, Y.y);
+                    st_stream(a.vx + p0 + 1, VX.y); st_stream(a.vy + p0 + 1, VY.y); st_stream(a.vz + p0 + 1, VZ.y);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int c = threadIdx.x; c < NC; c += THREADS) { // flush: sum the D replicas of each window cell, clear them
+            unsigned long long v = 0ULL;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                v += ((fx_t)rhi[c * D + r] << 32) + (fx_t)rlo[c * D + r];
+                rlo[c * D + r] = 0u; rhi[c * D + r] = 0u;
+            }
+            if (v) {
+                long long sv = (long long)v;
+                if (a.fx_shift > 0) sv = (sv + (1LL << (a.fx_shift - 1))) >> a.fx_shift; // rounded: weights are >= 0
+                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
+                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)sv);
+            }
+        }
+        pos = seg_hi; // the __syncthreads() at the top of the next segment orders the clears before its deposits
+    }
     s0 = block_sum(s0, scratch);
     s1 = block_sum(s1, scratch);
     s2 = block_sum(s2, scratch);

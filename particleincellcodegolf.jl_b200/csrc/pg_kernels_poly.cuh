@@ -70,16 +70,6 @@ __host__ __device__ inline size_t cp_smem_bytes(int threads)
            (size_t)threads * CP_NM * sizeof(double); // + the spare moment set of every lane (deterministic mode)
 }
 
-// 16-byte asynchronous global -> shared copy (L2 only); each lane later reads back exactly the bytes it copied itself,
-// so cp.async.wait_group alone orders the accesses.
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // Table row of interval m (any sign): m mod (N * CP_NSUB).  Its stencil centre is the Julia cell index k = (m+4)>>3
 // (0-based cell z = k-1), its sub-interval s = (m+4)&7.  Conversely the row of (z, s) is 8z + s + 4.
 __device__ __forceinline__ int cp_row_of(int z, int s, int Mmask) { return (CP_NSUB * z + s + CP_NSUB / 2) & Mmask; }

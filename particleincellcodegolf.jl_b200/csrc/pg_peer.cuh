@@ -24,7 +24,7 @@
 namespace pg {
 
 constexpr int PEER_MAX = 16;
-constexpr long long PEER_TIMEOUT_CYCLES = 600000000000LL; // ~5 min at 1.9 GHz
+constexpr long long PEER_TIMEOUT_CYCLES = 600000000000LL; // default: ~5 min at 1.9 GHz (PICGOLF_PEER_TIMEOUT_S overrides, picgolf.cu)
 
 struct PeerPub {
     unsigned long long ready;       // highest sweep sequence number whose grid this rank has published
@@ -41,6 +41,7 @@ struct PeerArgs {
     long long ncell;
     int *error;
     const unsigned long long *flush_src; // this rank's flush counter, or NULL
+    long long timeout_cycles;            // a wait gives up after this many SM cycles
 };
 
 __device__ __forceinline__ fx_t *peer_data(PeerPub *p, int slot, long long ncell) { return reinterpret_cast<fx_t *>(p + 1) + (size_t)slot * ncell; }
@@ -62,11 +63,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     return v;
 }
 
-__device__ __forceinline__ void peer_wait(const unsigned long long *flag, unsigned long long need, int *error)
+__device__ __forceinline__ void peer_wait(const unsigned long long *flag, unsigned long long need, int *error, long long timeout_cycles)
 {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < need) {
-        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) { *error = 1; return; }
+        if (clock64() - t0 > timeout_cycles) { *error = 1; return; }
         __nanosleep(64);
     }
 }
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rh
     PeerPub *me = p.peer[p.rank];
     const unsigned long long seq = me->seq + 1ULL; // only this kernel writes it, at its very end
     const int slot = (int)(seq & 1ULL);
-    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->done, me->last_pub[slot], p.error);
+    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->done, me->last_pub[slot], p.error, p.timeout_cycles);
     __syncthreads();
     fx_t *dst = peer_data(me, slot, p.ncell);
     for (long long n = threadIdx.x; n < p.ncell; n += blockDim.x) { dst[n] = rho[n]; rho[n] = 0ULL; }
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(1024) peer_publish_kernel(PeerArgs p, fx_t *rh
 __device__ __forceinline__ unsigned long long peer_gather_begin(const PeerArgs &p)
 {
     const unsigned long long seq = p.peer[p.rank]->seq;
-    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->ready, seq, p.error);
+    if (threadIdx.x < p.nranks) peer_wait(&p.peer[threadIdx.x]->ready, seq, p.error, p.timeout_cycles);
     __syncthreads();
     return seq;
 }

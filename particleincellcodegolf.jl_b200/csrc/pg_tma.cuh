@@ -56,4 +56,20 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // Make generic-proxy writes to shared memory visible to the async proxy (the copy engine) before a bulk store.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (L2 only); each lane later reads back exactly the bytes it copied itself,
+// so cp.async.wait_group alone orders the accesses.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 8-byte form (only .ca exists below 16 bytes): one particle per lane, no alignment requirement beyond the double itself.
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
 } // namespace pg

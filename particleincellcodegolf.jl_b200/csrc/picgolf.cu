@@ -188,7 +188,9 @@ struct picgolf_handle_s {
     int nblocks = 1, npart = 2;
     int pass_blocks = 0; // blocks of the particle pass that wrote this step's partial sums (0: nblocks)
     size_t smem_pass = 0, smem_lf = 0;
-    bool ngp_tma = false, tma2d = false;
+    bool ngp_tma = false;
+    int k2d = 0, k2d_a = 0, k2d_b = 0, k2d_c = 0; // 2D tile-sorted particle kernel: 0 = particles_2d3v_tiled, 1 = particles_2d3v_ring<a, b>, 2 = particles_2d3v_stream<a, b, c>
+    size_t smem_ring = 0;
     bool have_particles = false;
     int64_t steps = 0, launches = 0;
     nccl::Comm comm = nullptr;
@@ -287,6 +289,28 @@ static int set_smem(K kernel, size_t bytes)
 {
     if (bytes > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return 0;
+}
+
+// instantiated variants of the ring kernel (stages, resident blocks per SM the register budget is cut for)
+typedef void (*p2d_kernel_t)(P2DArgs);
+static p2d_kernel_t ring_kernel(int stages, int minb)
+{
+    if (stages == 4 && minb == 3) return particles_2d3v_ring<4, 3>;
+    if (stages == 2 && minb == 3) return particles_2d3v_ring<2, 3>;
+    if (stages == 4 && minb == 2) return particles_2d3v_ring<4, 2>;
+    return nullptr;
+}
+// ... and of the slice-streaming kernel: field replicas G, deposit replicas D, threads of the one block per SM
+static p2d_kernel_t stream_kernel(int G, int D, int threads)
+{
+    if (G == 4 && D == 8 && threads == 512) return particles_2d3v_stream<4, 8, 512>;
+    if (G == 4 && D == 4 && threads == 512) return particles_2d3v_stream<4, 4, 512>;
+    if (G == 8 && D == 2 && threads == 512) return particles_2d3v_stream<8, 2, 512>;
+    if (G == 2 && D == 8 && threads == 512) return particles_2d3v_stream<2, 8, 512>;
+    if (G == 1 && D == 1 && threads == 512) return particles_2d3v_stream<1, 1, 512>;
+    if (G == 4 && D == 4 && threads == 768) return particles_2d3v_stream<4, 4, 768>;
+    if (G == 2 && D == 4 && threads == 1024) return particles_2d3v_stream<2, 4, 1024>;
+    return nullptr;
 }
 
 template <typename K>
@@ -589,8 +613,10 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         PG_TRY(set_smem(solve2d_cols, (size_t)2 * COLS_PER_BLOCK * (NY + 1) * 8));
         h->npart = 3;
         PG_TRY(occupancy_blocks(particles_2d3v_kernel, PG_THREADS, 0, h->sms, h->count, &h->nblocks));
+        int ilog2f = 0;
         {   // fixed-point formats: CIC weights are <= 1 and sum to 1 per particle (no overflow possible)
             int frac = std::max(8, std::min(60, 62 - ilog2(c.P + 1)));
+            ilog2f = frac;
             h->fx_scale = ldexp(1.0, frac); h->fx_inv = ldexp(1.0, -frac);
             int fracw = std::max(frac, 62 - ilog2((int64_t)T2_CHUNK + 1)); // a window only sees T2_CHUNK particles
             h->fxw_scale = ldexp(1.0, fracw); h->fx_shift = fracw - frac;
@@ -615,13 +641,30 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             PG_TRY(set_smem(sort_scatter_kernel<5>, (size_t)h->nbins * 8));
             int64_t items = h->count / T2_CHUNK + h->nbins;
             PG_TRY(occupancy_blocks(particles_2d3v_tiled, PG_THREADS, 0, h->sms, items * PG_THREADS, &h->nblocks_sorted));
-            // The TMA-staged variant is correct but measured slower on B200 (6.15 ms vs 4.85 ms per pass at 2^28
-            // particles: at 105 registers only 16 warps/SM remain to hide the shared-memory gather/atomic latency),
-            // so it stays an opt-in experiment (PICGOLF_2D_TMA=1) until its SM-side loop is restructured.
-            h->tma2d = getenv("PICGOLF_2D_TMA") != nullptr;
-            if (h->tma2d) {
-                PG_TRY(set_smem(particles_2d3v_tma, T2_TMA_SMEM));
-                h->nblocks_sorted = h->sms;
+            // particle kernel of the tile-sorted path (PICGOLF_2D_KERNEL): "stream" (default: slice streaming with replicated
+            // windows; stream<G><D>_<threads> picks a measured variant, e.g. stream48_512), "ring<stages><blocks/SM>" (per-warp
+            // cp.async ring over 8192-particle work items) or "tiled" (plain loads)
+            const char *kv = getenv("PICGOLF_2D_KERNEL");
+            h->k2d = 2; h->k2d_a = 4; h->k2d_b = 8; h->k2d_c = 512;
+            if (kv && !strcmp(kv, "tiled")) h->k2d = 0;
+            else if (kv && !strncmp(kv, "ring", 4) && strlen(kv) == 6) { h->k2d = 1; h->k2d_a = kv[4] - '0'; h->k2d_b = kv[5] - '0'; }
+            else if (kv && !strncmp(kv, "stream", 6) && strlen(kv) > 9) { h->k2d_a = kv[6] - '0'; h->k2d_b = kv[7] - '0'; h->k2d_c = atoi(kv + 9); }
+            else if (kv && strcmp(kv, "stream")) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such kernel", kv);
+            if (h->k2d == 1) {
+                p2d_kernel_t kern = ring_kernel(h->k2d_a, h->k2d_b);
+                if (!kern) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such variant", kv);
+                h->smem_ring = r2_smem_bytes(PG_THREADS, h->k2d_a);
+                PG_TRY(set_smem(kern, h->smem_ring));
+                PG_TRY(occupancy_blocks(kern, PG_THREADS, h->smem_ring, h->sms, items * PG_THREADS, &h->nblocks_sorted));
+            } else if (h->k2d == 2) {
+                p2d_kernel_t kern = stream_kernel(h->k2d_a, h->k2d_b, h->k2d_c);
+                if (!kern) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such variant", kv);
+                h->smem_ring = s2_smem_bytes(h->k2d_a, h->k2d_b, h->k2d_c);
+                PG_TRY(set_smem(kern, h->smem_ring));
+                h->nblocks_sorted = h->sms; // one block per SM, each streams a contiguous slice of the sorted arrays
+                // its deposit window is flushed every S2_FLUSH particles instead of every T2_CHUNK
+                int fracs = std::max(ilog2f, 62 - ilog2((int64_t)S2_FLUSH + 1));
+                h->fxw_scale = ldexp(1.0, fracs); h->fx_shift = fracs - ilog2f;
             }
             h->nblocks = std::max(h->nblocks, h->nblocks_sorted);
         }
@@ -875,6 +918,9 @@ static PeerArgs peer_args(picgolf_handle h)
     for (int q = 0; q < h->nranks; ++q) p.peer[q] = h->peer_ptr[q];
     p.nranks = h->nranks; p.rank = h->rank; p.ncell = h->ncell; p.error = h->peer_err;
     p.flush_src = h->slow_count;
+    p.timeout_cycles = PEER_TIMEOUT_CYCLES;
+    if (const char *ts = getenv("PICGOLF_PEER_TIMEOUT_S")) // test runs: give up quickly instead of holding a GPU box for minutes
+        if (atof(ts) > 0) p.timeout_cycles = (long long)(atof(ts) * 1.9e9);
     return p;
 }
 
@@ -1398,7 +1444,8 @@ static int step_2d3v(picgolf_handle h)
     if (h->use_sorted_now) {
         a.tile_start = h->bin_start; a.tile_end = h->bin_cursor; a.item_off = h->item_off; a.slow_count = h->slow_count;
         a.fxw_scale = h->fxw_scale; a.fx_shift = h->fx_shift; a.ntx = std::max(1, a.NX >> T2_SHIFT); a.ntiles = h->nbins;
-        if (h->tma2d) particles_2d3v_tma<<<h->nblocks_sorted, T2_TMA_THREADS, T2_TMA_SMEM, h->stream>>>(a);
+        if (h->k2d == 2) stream_kernel(h->k2d_a, h->k2d_b, h->k2d_c)<<<h->nblocks_sorted, h->k2d_c, h->smem_ring, h->stream>>>(a);
+        else if (h->k2d == 1) ring_kernel(h->k2d_a, h->k2d_b)<<<h->nblocks_sorted, PG_THREADS, h->smem_ring, h->stream>>>(a);
         else particles_2d3v_tiled<<<h->nblocks_sorted, PG_THREADS, 0, h->stream>>>(a);
     } else {
         particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);

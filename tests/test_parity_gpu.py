@@ -1047,18 +1047,19 @@ def test_ngp1d2v2s_steps(pg, oracle):
     assert np.abs(rs - ro).max() < TOL * n0
 
 
-def test_2d3v_tma_variant_matches(pg, oracle, monkeypatch):
-    """The opt-in TMA-staged 2D kernel (PICGOLF_2D_TMA=1) must give the same physics as the default tiled kernel
-    (odd work-item boundaries exercise its unaligned edge particles)."""
+@pytest.mark.parametrize("variant", ["stream", "stream48_512", "stream44_512", "stream82_512", "stream28_512", "stream11_512", "stream44_768", "stream24_1024", "ring43", "ring23", "ring42"])
+def test_2d3v_kernel_variants_match(pg, oracle, monkeypatch, variant):
+    """The tile-sorted 2D path has three particle kernels -- particles_2d3v_stream (slice streaming through per-warp cp.async
+    rings with replicated shared-memory windows, the default), particles_2d3v_ring (the same ring over 8192-particle work
+    items) and particles_2d3v_tiled (plain loads, PICGOLF_2D_KERNEL=tiled) -- the first two in several builds:
+    all must give the same physics (to round-off: the counting sort ranks with atomics, so the split of a tile into work
+    items, and with it the rounding of the window sums, differs from run to run).  P is odd so that work items end in ragged rows."""
     NX = NY = 64
     P = (1 << 18) + 3
     rng = np.random.default_rng(51)
     res = []
-    for tma in (False, True):
-        if tma:
-            monkeypatch.setenv("PICGOLF_2D_TMA", "1")
-        else:
-            monkeypatch.delenv("PICGOLF_2D_TMA", raising=False)
+    for kern in ("tiled", variant):
+        monkeypatch.setenv("PICGOLF_2D_KERNEL", kern)
         sim = pg.electrostatic_2d3v(NX=NX, NY=NY, P=P, T=8, NS=1, deposit_mode=pg.DEPOSIT_SORTED, sort_every=3)
         if not res:
             st = [1 - rng.random(P), 1 - rng.random(P)] + [rng.standard_normal(P) * sim.vth / np.sqrt(2) for _ in range(3)]
