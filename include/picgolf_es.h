@@ -59,7 +59,8 @@ typedef struct picgolf_es_config {
     int32_t device;            /* CUDA device ordinal; -1 = current */
     int32_t rank, nranks;      /* particle sharding (every species is split evenly over the ranks) */
     int32_t sort_every;        /* particle order: 0 = the library decides (shards of >= 2^20 particles with >= 8 per cell are kept
-                                * sorted by 16x16-cell tile, re-sorted every 8 steps, and run through shared-memory windows);
+                                * sorted by 16x16-cell tile and run through shared-memory windows; re-sorted every 16 steps to begin with, then
+                                * every 2...64 steps following the counted window misses -- fixed 16 on several GPUs);
                                 * n > 0 = tile-sorted, re-sorted every n steps; < 0 = never sort (any-order kernel, global atomics).
                                 * The reference sorts for cache locality too (sort!(s::Species, dx, dy) :210-215); getters always
                                 * return the caller's particle order. */

@@ -58,6 +58,13 @@ __device__ __forceinline__ int unimod(int x, int n) { return (0 < x && x <= n) ?
 // the grid is bit-identical whatever the order of the atomics (see pg_kernels_1d.cuh).
 typedef unsigned long long fx_t;
 __device__ __forceinline__ fx_t to_fx(double v, double fx_scale) { return (fx_t)__double2ll_rn(v * fx_scale); }
+// The same rounding (to nearest, ties to even) for |v * fx_scale| < 2^51 without the conversion instruction (F2I.S64.F64 runs
+// on the quarter-rate XU pipe): adding 1.5 * 2^52 leaves the rounded integer in the low mantissa bits.
+__device__ __forceinline__ fx_t to_fx_small(double v, double fx_scale)
+{
+    const double M = 6755399441055744.0;
+    return (fx_t)(__double_as_longlong(v * fx_scale + M) - __double_as_longlong(M));
+}
 
 // ---- reductions -------------------------------------------------------------------------
 

@@ -106,19 +106,34 @@ PG_HD int shape_weights_rt(int shape, double z, double NZ_Lz, int &j0, double *w
 
 // ElectrostaticBoris: t = B*dt/2, t2 = dot(t,t), dt_2 = dt/2 (:44-48); the push (:49-54) as written, including its
 // use of q_m (E impulse scaled by q_m, rotation about the UNSCALED t with the factor q_m^2*2/(1+q_m^2*t2)).
+// The three divisions `... * 2 / (1 + q_m^2 t2)` of a push have the same divisor for every particle of a species, so the
+// species' Boris carries den = 1 + q_m^2 t2 and rden = RN(1/den), and the quotient is formed as
+//   q0 = x*rden;  e = fma(-den, q0, x);  q = fma(e, rden, q0)
+// which is the correctly rounded x/den (Markstein's theorem: q0 is within an ulp of the quotient, e is exact, and rden is
+// the correctly rounded reciprocal) -- the same bits as the IEEE division the reference performs, for a third of the
+// instructions of a double-precision divide.  tests/test_esfield_cpu.py checks it bit for bit against the oracle's `/`.
 struct Boris {
     double t[3], t2, dt_2;
+    double q_m, q2, den, rden; // of the species this push is for
 };
-PG_HD Boris make_boris(double B0x, double B0y, double B0z, double dt)
+PG_HD Boris make_boris(double B0x, double B0y, double B0z, double dt, double q_m)
 {
     Boris b;
     b.t[0] = B0x * dt / 2; b.t[1] = B0y * dt / 2; b.t[2] = B0z * dt / 2;
     b.t2 = b.t[0] * b.t[0] + b.t[1] * b.t[1] + b.t[2] * b.t[2];
     b.dt_2 = dt / 2;
+    b.q_m = q_m; b.q2 = q_m * q_m; b.den = 1 + b.q2 * b.t2; b.rden = 1 / b.den;
     return b;
 }
-PG_HD void boris_push(const Boris &b, double &vx, double &vy, double &vz, double Ex, double Ey, double q_m)
+PG_HD double div_by_den(double x, const Boris &b)
 {
+    const double q0 = x * b.rden;
+    const double e = fma(-b.den, q0, x);
+    return fma(e, b.rden, q0);
+}
+PG_HD void boris_push(const Boris &b, double &vx, double &vy, double &vz, double Ex, double Ey)
+{
+    const double q_m = b.q_m;
     const double e0 = Ex * b.dt_2 * q_m, e1 = Ey * b.dt_2 * q_m, e2 = 0.0 * b.dt_2 * q_m; // E2 = [Ex, Ey, 0.0] * dt_2 * q_m
     const double m0 = vx + e0, m1 = vy + e1, m2 = vz + e2;                                 // v- = v + E2
     // cross(a, b) = (a2*b3 - a3*b2, a3*b1 - a1*b3, a1*b2 - a2*b1)
@@ -126,10 +141,10 @@ PG_HD void boris_push(const Boris &b, double &vx, double &vy, double &vz, double
     const double s1 = m1 + (m2 * b.t[0] - m0 * b.t[2]);
     const double s2 = m2 + (m0 * b.t[1] - m1 * b.t[0]);                                    // v- + cross(v-, t)
     const double c0 = s1 * b.t[2] - s2 * b.t[1], c1 = s2 * b.t[0] - s0 * b.t[2], c2 = s0 * b.t[1] - s1 * b.t[0];
-    const double q2 = q_m * q_m, den = 1 + q2 * b.t2;
-    vx = (m0 + c0 * q2 * 2 / den) + e0;                                                    // v+ + E2
-    vy = (m1 + c1 * q2 * 2 / den) + e1;
-    vz = (m2 + c2 * q2 * 2 / den) + e2;
+    const double q2 = b.q2;                                                                // den = 1 + q2 * t2
+    vx = (m0 + div_by_den(c0 * q2 * 2, b)) + e0;                                           // v+ + E2
+    vy = (m1 + div_by_den(c1 * q2 * 2, b)) + e1;
+    vz = (m2 + div_by_den(c2 * q2 * 2, b)) + e2;
 }
 
 // halton(i, base, seed) (:29-37) and sample(P, i) = halton.(0:P-1, i, 1/sqrt(2)) (:191): the quiet start of Species(...)

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(PG_THREADS) es_particles_kernel(ESParticleArgs
                 Eyi = fma(f.y, wxy, Eyi);
             }
         const double vxi = vx, vyi = vy;
-        es::boris_push(a.boris, vx, vy, vz, Exi, Eyi, a.q_m);
+        es::boris_push(a.boris, vx, vy, vz, Exi, Eyi);
         x = es::unimod(x + (vxi + vx) / 2 * a.dt, a.Lx);
         y = es::unimod(y + (vyi + vy) / 2 * a.dt, a.Ly);
         es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tile
                 }
             }
             const double vxi = vx, vyi = vy;
-            es::boris_push(a.boris, vx, vy, vz, Exi, Eyi, a.q_m);
+            es::boris_push(a.boris, vx, vy, vz, Exi, Eyi);
             x = es::unimod(x + (vxi + vx) / 2 * a.dt, a.Lx);
             y = es::unimod(y + (vyi + vy) / 2 * a.dt, a.Ly);
             es::shape_weights<SHAPE>(x, a.NX_Lx, ix0, wx);
@@ -249,6 +249,217 @@ __global__ void __launch_bounds__(PG_THREADS, PG_ES_MINBLOCKS) es_particles_tile
             }
         }
         __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < ES_NSUM; ++k) {
+        const double s = block_sum(sum[k], scratch);
+        if (threadIdx.x == 0) a.partials[ES_NSUM * blockIdx.x + k] = s;
+    }
+    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slice-streaming variant (the scheme of particles_2d3v_stream, pg_kernels_2d.cuh, for any shape; default of the tile-sorted
+// path).  One block of 512 threads per SM owns a contiguous slice of a species' tile-sorted arrays and walks through it tile
+// segment by tile segment; rows of 64 particles (two per lane) arrive through per-warp 16-byte cp.async rings and leave with
+// 128-bit stores; the field and deposit windows are replicated (lane l gathers from replica l % G and adds into replica
+// l % D), which removes most of the bank conflicts of the S^2 gathers and 2 S^2 limb adds per particle.  The two particles
+// of a lane are pushed together (independent gathers overlap) for supports up to 3; wider stencils run one after the other.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+struct ESStencil { int ix0, iy0; double wx[S], wy[S]; };
+
+struct ESWindow {
+    const double2 *Ew;
+    unsigned int *rlo, *rhi;
+    int ox, oy;
+};
+
+template <int SHAPE, int G>
+__device__ __forceinline__ void es_push(const ESParticleArgs &a, const ESWindow &w, double &x, double &y, double &vx, double &vy,
+                                        double &vz, double *sum, ESStencil<es::support(SHAPE)> &st)
+{
+    constexpr int S = es::support(SHAPE);
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    es::shape_weights<SHAPE>(x, a.NX_Lx, st.ix0, st.wx);
+    es::shape_weights<SHAPE>(y, a.NY_Ly, st.iy0, st.wy);
+    double Exi = 0.0, Eyi = 0.0;
+    {
+        const int rx = (st.ix0 - 1 - w.ox) & mx, ry = (st.iy0 - 1 - w.oy) & my;
+        if (rx <= T2_WS - S && ry <= T2_WS - S) {
+            const double2 *e = w.Ew + (rx + ry * T2_WS) * G;
+#pragma unroll
+            for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < S; ++ii) {
+                    const double wxy = st.wx[ii] * st.wy[jj];
+                    const double2 f = e[(ii + jj * T2_WS) * G];
+                    Exi = fma(f.x, wxy, Exi);
+                    Eyi = fma(f.y, wxy, Eyi);
+                }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < S; ++ii) {
+                    const double wxy = st.wx[ii] * st.wy[jj];
+                    const double2 f = __ldg(&a.Exy[es_cell0(st.ix0 + ii, NX) + (size_t)es_cell0(st.iy0 + jj, NY) * NX]);
+                    Exi = fma(f.x, wxy, Exi);
+                    Eyi = fma(f.y, wxy, Eyi);
+                }
+        }
+    }
+    const double vxi = vx, vyi = vy;
+    es::boris_push(a.boris, vx, vy, vz, Exi, Eyi);
+    x = es::unimod(x + (vxi + vx) / 2 * a.dt, a.Lx);
+    y = es::unimod(y + (vyi + vy) / 2 * a.dt, a.Ly);
+    es::shape_weights<SHAPE>(x, a.NX_Lx, st.ix0, st.wx);
+    es::shape_weights<SHAPE>(y, a.NY_Ly, st.iy0, st.wy);
+    sum[0] += vx * vx + vy * vy + vz * vz;
+    sum[1] += vx; sum[2] += vy; sum[3] += vz;
+    sum[4] += fabs(vx); sum[5] += fabs(vy); sum[6] += fabs(vz);
+}
+
+template <int S, int D>
+__device__ __forceinline__ void es_deposit(const ESParticleArgs &a, const ESWindow &w, const ESStencil<S> &st, unsigned int &nslow)
+{
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    const int rx = (st.ix0 - 1 - w.ox) & mx, ry = (st.iy0 - 1 - w.oy) & my;
+    if (rx <= T2_WS - S && ry <= T2_WS - S) {
+        const int r0 = (rx + ry * T2_WS) * D;
+#pragma unroll
+        for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < S; ++ii) { // two-limb add, exact for either sign (mod 2^64); see es_particles_tiled
+                const fx_t v = to_fx_small(st.wx[ii] * st.wy[jj], a.fxw_scale); // fractions <= 1, fxw_scale <= 2^48
+                const unsigned int vlo = (unsigned int)v;
+                const unsigned int old = atomicAdd(&w.rlo[r0 + (ii + jj * T2_WS) * D], vlo);
+                const unsigned int carry = (old + vlo) < old ? 1u : 0u;
+                const unsigned int vhi = (unsigned int)(v >> 32) + carry;
+                if (vhi) atomicAdd(&w.rhi[r0 + (ii + jj * T2_WS) * D], vhi);
+            }
+    } else {
+        ++nslow;
+#pragma unroll
+        for (int jj = 0; jj < S; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < S; ++ii)
+                atomicAdd(&a.rho[es_cell0(st.ix0 + ii, NX) + (size_t)es_cell0(st.iy0 + jj, NY) * NX],
+                          to_fx(st.wx[ii] * st.wy[jj] * a.dep, a.fx_scale));
+    }
+}
+
+template <int SHAPE, int G, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) es_particles_stream(ESParticleArgs a)
+{
+    constexpr int S = es::support(SHAPE), NC = T2_WS * T2_WS, nw = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *Ew = reinterpret_cast<double2 *>(smem_raw);                  // [cell][G]
+    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + NC * G), *rhi = rlo + NC * D; // [cell][D]
+    double *scratch = reinterpret_cast<double *>(rhi + NC * D);
+    double2 *ring = reinterpret_cast<double2 *>(scratch + 32);            // [warp][stage][array][lane]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double2 *const mine = ring + (size_t)wid * S2_STAGES * S2_ROW + lane;
+    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
+    double *const gp[5] = {a.x, a.y, a.vx, a.vy, a.vz};
+    double sum[ES_NSUM];
+#pragma unroll
+    for (int k = 0; k < ES_NSUM; ++k) sum[k] = 0.0;
+    unsigned int nslow = 0;
+    ESWindow w;
+    w.Ew = Ew + (lane & (G - 1)); w.rlo = rlo + (lane & (D - 1)); w.rhi = rhi + (lane & (D - 1)); w.ox = 0; w.oy = 0;
+    for (int c = threadIdx.x; c < NC * D; c += THREADS) { rlo[c] = 0u; rhi[c] = 0u; }
+    const long long per = (((a.P + gridDim.x - 1) / gridDim.x) + 63) & ~63LL;
+    const long long s_lo = min(a.P, per * (long long)blockIdx.x), s_hi = min(a.P, s_lo + per);
+    int tile = 0;
+    {
+        int lo = 0, hi = a.ntiles; // last t with tile_start[t] <= s_lo
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if ((long long)a.tile_start[mid] <= s_lo) lo = mid; else hi = mid;
+        }
+        tile = lo;
+    }
+    int cur_tile = -1;
+    for (long long pos = s_lo; pos < s_hi;) {
+        while (tile < a.ntiles - 1 && (long long)a.tile_end[tile] <= pos) ++tile;
+        const long long seg_hi = min(min(s_hi, (long long)a.tile_end[tile]), pos + S2_FLUSH);
+        const long long base = pos & ~63LL;
+        const int nrows = (int)((seg_hi - base + 63) >> 6);
+        auto issue = [&](int k) { // lane copies the pair (p0, p0+1) of each array; always commits (uniform group count)
+            const int r = wid + k * nw;
+            const long long p0 = base + ((long long)r << 6) + 2 * lane;
+            if (r < nrows && p0 + 1 >= pos && p0 < seg_hi) {
+                double2 *st = mine + (k % S2_STAGES) * S2_ROW;
+                if (p0 + 1 < a.P) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) cp_async16(st + 32 * q, gp[q] + p0);
+                } else { // the very last particle of an odd-sized shard
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) cp_async8(st + 32 * q, gp[q] + p0);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < S2_STAGES - 1; ++k) issue(k);
+        if (tile != cur_tile) { // (re)build the field window around this tile, all replicas
+            w.ox = (tile % a.ntx) * T2_TS - T2_R; w.oy = (tile / a.ntx) * T2_TS - T2_R;
+            for (int c = threadIdx.x; c < NC * G; c += THREADS) {
+                const int cell = c / G;
+                int gx = (w.ox + (cell & (T2_WS - 1))) & mx, gy = (w.oy + (cell >> 5)) & my;
+                Ew[c] = a.Exy[gx + (size_t)gy * NX];
+            }
+            cur_tile = tile;
+        }
+        __syncthreads();
+        for (int k = 0; wid + k * nw < nrows; ++k) {
+            issue(k + S2_STAGES - 1);
+            cp_async_wait<S2_STAGES - 1>(); // row k has landed
+            const long long p0 = base + ((long long)(wid + k * nw) << 6) + 2 * lane;
+            const bool v0 = p0 >= pos && p0 < seg_hi, v1 = p0 + 1 >= pos && p0 + 1 < seg_hi;
+            if (v0 || v1) {
+                const double2 *st = mine + (k % S2_STAGES) * S2_ROW;
+                double2 X = st[0], Y = st[32], VX = st[64], VY = st[96], VZ = st[128];
+                if (S <= 3 && v0 && v1) { // the two pushes are independent: their gathers overlap
+                    ESStencil<S> c0, c1;
+                    es_push<SHAPE, G>(a, w, X.x, Y.x, VX.x, VY.x, VZ.x, sum, c0);
+                    es_push<SHAPE, G>(a, w, X.y, Y.y, VX.y, VY.y, VZ.y, sum, c1);
+                    es_deposit<S, D>(a, w, c0, nslow);
+                    es_deposit<S, D>(a, w, c1, nslow);
+                } else {
+                    ESStencil<S> c;
+                    if (v0) { es_push<SHAPE, G>(a, w, X.x, Y.x, VX.x, VY.x, VZ.x, sum, c); es_deposit<S, D>(a, w, c, nslow); }
+                    if (v1) { es_push<SHAPE, G>(a, w, X.y, Y.y, VX.y, VY.y, VZ.y, sum, c); es_deposit<S, D>(a, w, c, nslow); }
+                }
+                if (v0 && v1) {
+                    __stcs(reinterpret_cast<double2 *>(a.x + p0), X); __stcs(reinterpret_cast<double2 *>(a.y + p0), Y);
+                    __stcs(reinterpret_cast<double2 *>(a.vx + p0), VX); __stcs(reinterpret_cast<double2 *>(a.vy + p0), VY);
+                    __stcs(reinterpret_cast<double2 *>(a.vz + p0), VZ);
+                } else if (v0) {
+                    st_stream(a.x + p0, X.x); st_stream(a.y + p0, Y.x);
+                    st_stream(a.vx + p0, VX.x); st_stream(a.vy + p0, VY.x); st_stream(a.vz + p0, VZ.x);
+                } else {
+                    st_stream(a.x + p0 + 1, X.y); st_stream(a.y + p0 + 1, Y.y);
+                    st_stream(a.vx + p0 + 1, VX.y); st_stream(a.vy + p0 + 1, VY.y); st_stream(a.vz + p0 + 1, VZ.y);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int c = threadIdx.x; c < NC; c += THREADS) { // flush: sum the D replicas of each window cell, clear them
+            unsigned long long v = 0ULL;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                v += ((fx_t)rhi[c * D + r] << 32) + (fx_t)rlo[c * D + r];
+                rlo[c * D + r] = 0u; rhi[c * D + r] = 0u;
+            }
+            if (v) { // the species' signed weight enters here, once per window cell
+                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
+                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)__double2ll_rn((double)(long long)v * a.wscale));
+            }
+        }
+        pos = seg_hi; // the __syncthreads() at the top of the next segment orders the clears before its deposits
     }
 #pragma unroll
     for (int k = 0; k < ES_NSUM; ++k) {
@@ -468,12 +679,12 @@ __global__ void es_stage_shape_kernel(int shape, const double *z, long long coun
 }
 
 __global__ void es_stage_boris_kernel(double *vx, double *vy, double *vz, const double *Ex, const double *Ey, long long count,
-                                      es::Boris b, double q_m)
+                                      es::Boris b)
 {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
     double a = vx[p], c = vy[p], d = vz[p];
-    es::boris_push(b, a, c, d, Ex[p], Ey[p], q_m);
+    es::boris_push(b, a, c, d, Ex[p], Ey[p]);
     vx[p] = a; vy[p] = c; vz[p] = d;
 }
 

@@ -258,21 +258,8 @@ __global__ void __launch_bounds__(PG_THREADS) particles_2d3v_tiled(P2DArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ring variant of the tiled kernel.  Same tiles, windows and per-particle arithmetic, but the five particle
-// streams reach the SM through a per-warp `cp.async` ring (LDGSTS, R2_STAGES rows of 32 particles, one particle
-// per lane and array) instead of plain loads: the tiled kernel's warps spend 10.8 of every 15.8 stall cycles per
-// issue waiting for their five global loads (ncu, profiles/r1_d_ncu_particles_2d3v_tiled.txt: long_scoreboard)
-// with DRAM 55 % and the shared-memory pipe ~50 % busy -- it is bound by bytes in flight, not by a unit.  Here
-// R2_STAGES-1 rows (3 x 1280 B per warp, 90 KB per SM) are in flight while a row is processed and no register
-// is held for them.  A lane reads back only the bytes it copied itself, so `cp.async.wait_group` is the only
-// synchronisation; the first rows of an item are requested before the block stages its window.
+// Shared pieces of the streaming kernel below: the block's windows and one particle's work in two halves.
 // ------------------------------------------------------------------------------------------------
-constexpr int R2_ROW = 5 * 32; // doubles per ring stage of one warp
-__host__ __device__ constexpr size_t r2_smem_bytes(int threads, int stages)
-{
-    return (size_t)T2_WS * T2_WS * (16 + 8) + 32 * 8 + (size_t)(threads / 32) * stages * R2_ROW * 8;
-}
-
 struct P2DWindow {
     const double2 *Ew;
     unsigned int *rlo, *rhi;
@@ -336,7 +323,7 @@ __device__ __forceinline__ void p2d_deposit(const P2DArgs &a, const P2DWindow &w
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
                 const int k = ii + 2 * jj;
-                v[k] = to_fx(c.wx[ii] * c.wy[jj], a.fxw_scale);
+                v[k] = to_fx_small(c.wx[ii] * c.wy[jj], a.fxw_scale); // weights <= 1, fxw_scale <= 2^48
                 lo[k] = (unsigned int)v[k];
                 old[k] = atomicAdd(&w.rlo[r0 + (ii + jj * T2_WS) * D], lo[k]);
             }
@@ -368,89 +355,14 @@ __device__ __forceinline__ void p2d_particle(const P2DArgs &a, const P2DWindow &
     p2d_deposit<D>(a, w, c, nslow);
 }
 
-template <int R2_STAGES, int MINB>
-__global__ void __launch_bounds__(PG_THREADS, MINB) particles_2d3v_ring(P2DArgs a)
-{
-    static_assert((R2_STAGES & (R2_STAGES - 1)) == 0, "ring depth must be a power of two");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *Ew = reinterpret_cast<double2 *>(smem_raw);
-    unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + T2_WS * T2_WS), *rhi = rlo + T2_WS * T2_WS;
-    double *scratch = reinterpret_cast<double *>(rhi + T2_WS * T2_WS);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double *const mine = scratch + 32 + (size_t)wid * R2_STAGES * R2_ROW + lane; // this lane's column of its warp's ring
-    const int NX = a.NX, NY = a.NY, mx = NX - 1, my = NY - 1;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    unsigned int nslow = 0;
-    P2DWindow w;
-    w.Ew = Ew; w.rlo = rlo; w.rhi = rhi;
-    const unsigned int nitems = a.item_off[a.ntiles];
-    for (unsigned int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int lo = 0, hi = a.ntiles; // tile of this item: last t with item_off[t] <= item
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int tile = lo;
-        const long long start = (long long)a.tile_start[tile] + (long long)(item - a.item_off[tile]) * T2_CHUNK;
-        const long long end = min(start + (long long)T2_CHUNK, (long long)a.tile_end[tile]);
-        // row k of this warp = particles start + (wid + k*nw)*32 + lane; stage k % R2_STAGES (always commits: uniform group count)
-        auto issue = [&](int k) {
-            const long long p = start + ((long long)(wid + k * nw) << 5) + lane;
-            if (p < end) {
-                double *st = mine + (k & (R2_STAGES - 1)) * R2_ROW;
-                cp_async8(st, a.x + p); cp_async8(st + 32, a.y + p);
-                cp_async8(st + 64, a.vx + p); cp_async8(st + 96, a.vy + p); cp_async8(st + 128, a.vz + p);
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int k = 0; k < R2_STAGES - 1; ++k) issue(k);
-        w.ox = (tile % a.ntx) * T2_TS - T2_R; w.oy = (tile / a.ntx) * T2_TS - T2_R; // window origin (0-based cells)
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
-            Ew[c] = a.E2[gx + (size_t)gy * NX];
-            rlo[c] = 0u; rhi[c] = 0u;
-        }
-        __syncthreads();
-        const int nrows = (int)((end - start + 31) >> 5);
-        for (int k = 0; wid + k * nw < nrows; ++k) {
-            issue(k + R2_STAGES - 1);
-            cp_async_wait<R2_STAGES - 1>(); // row k has landed
-            const long long p = start + ((long long)(wid + k * nw) << 5) + lane;
-            if (p < end) {
-                const double *st = mine + (k & (R2_STAGES - 1)) * R2_ROW;
-                double x = st[0], y = st[32], vx = st[64], vy = st[96], vz = st[128];
-                p2d_particle<1, 1>(a, w, x, y, vx, vy, vz, s0, s1, s2, nslow);
-                st_stream(a.x + p, x); st_stream(a.y + p, y);
-                st_stream(a.vx + p, vx); st_stream(a.vy + p, vy); st_stream(a.vz + p, vz);
-            }
-        }
-        cp_async_wait<0>();
-        __syncthreads();
-        for (int c = threadIdx.x; c < T2_WS * T2_WS; c += blockDim.x) {
-            long long v = (long long)(((fx_t)rhi[c] << 32) | (fx_t)rlo[c]);
-            if (v) {
-                if (a.fx_shift > 0) v = (v + (1LL << (a.fx_shift - 1))) >> a.fx_shift; // rounded: weights are >= 0
-                int gx = (w.ox + (c & (T2_WS - 1))) & mx, gy = (w.oy + (c >> 5)) & my;
-                atomicAdd(&a.rho[gx + (size_t)gy * NX], (fx_t)v);
-            }
-        }
-        __syncthreads();
-    }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
-    s2 = block_sum(s2, scratch);
-    if (threadIdx.x == 0) {
-        a.partials[3 * blockIdx.x] = s0; a.partials[3 * blockIdx.x + 1] = s1; a.partials[3 * blockIdx.x + 2] = s2;
-    }
-    if (nslow && a.slow_count) atomicAdd(a.slow_count, (unsigned long long)nslow);
-}
-
 // ------------------------------------------------------------------------------------------------
-// Slice-streaming kernel (default of the tile-sorted path).  ncu of the ring kernel above (profiles/r2_e_*): once the global
-// loads are hidden, the shared-memory data pipe is the limit (80 % busy): per row of 32 particles 43 wavefronts for the four
-// 16-byte field gathers (10.8 per LDS.128: eight lanes of a quarter-warp hit eight 16-byte bank groups at random), 41 for the
-// eight limb atomics (5.1 per ATOMS) and 23 for the ring -- 113 where 41 would do without bank conflicts.  This kernel removes
+// Slice-streaming kernel (default of the tile-sorted path).  particles_2d3v_tiled above is bound by bytes in flight: its warps
+// spend 10.8 of every 15.8 stall cycles per issue waiting for their five plain global loads (ncu, profiles/r1_d_*: DRAM 55 %,
+// shared-memory pipe ~50 %).  A first rewrite that fed the same 8192-particle work items through per-warp cp.async rings
+// (measured: 4.05 ms instead of 4.79, profiles/r2_e_*; since deleted) moved the limit to the shared-memory data pipe (80 %
+// busy): per row of 32 particles 43 wavefronts for the four 16-byte field gathers (10.8 per LDS.128: eight lanes of a
+// quarter-warp hit eight 16-byte bank groups at random), 41 for the eight limb atomics (5.1 per ATOMS) and 23 for the ring --
+// 113 where 41 would do without bank conflicts.  This kernel streams the particles the same way and removes
 // most of the conflicts by REPLICATING the windows: lane l reads the field from replica l % G (cell c, replica r at
 // 16-byte slot c*G + r, so lanes of one quarter-warp collide only when they share r) and adds into deposit replica l % D
 // (word c*D + r); the flush sums the D replicas of a cell.  The replicas fill the SM's shared memory (G = 4, D = 8: 64 + 64 KB
@@ -470,7 +382,7 @@ template <int G, int D, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) particles_2d3v_stream(P2DArgs a)
 {
     constexpr int NC = T2_WS * T2_WS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *Ew = reinterpret_cast<double2 *>(smem_raw);                  // [cell][G]
     unsigned int *rlo = reinterpret_cast<unsigned int *>(Ew + NC * G), *rhi = rlo + NC * D; // [cell][D]
     double *scratch = reinterpret_cast<double *>(rhi + NC * D);

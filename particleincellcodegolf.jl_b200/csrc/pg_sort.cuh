@@ -118,9 +118,21 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
             long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
             key[i] = j < a.P ? sort_key(a, j) : -1;
         }
+        // ranks inside the tile: lanes of a warp holding the same key are grouped (match.any) and their leader reserves the
+        // group's slots with ONE shared-memory atomic -- on the nearly sorted arrays of a re-sort a whole warp row has one
+        // key, and 2048 same-address atomics per tile were what the scatter spent its time on (8.6 ms per re-sort of 2^28
+        // particles in the 2D path, profiles/r2_k_launches_2d3v.csv)
+        const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; ++i)
-            if (key[i] >= 0) rank[i] = atomicAdd(&cnt[key[i]], 1u);
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int k = key[i] >= 0 ? key[i] : -1 - lane; // dead lanes: unique negative keys
+            const unsigned int grp = __match_any_sync(0xffffffffu, k);
+            const int leader = __ffs(grp) - 1;
+            unsigned int r = 0;
+            if (k >= 0 && lane == leader) r = atomicAdd(&cnt[k], (unsigned int)__popc(grp));
+            r = __shfl_sync(0xffffffffu, r, leader);
+            rank[i] = r + (unsigned int)__popc(grp & ((1u << lane) - 1u));
+        }
         __syncthreads();
         for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
             unsigned int c = cnt[b];

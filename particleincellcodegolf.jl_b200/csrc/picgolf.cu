@@ -189,7 +189,7 @@ struct picgolf_handle_s {
     int pass_blocks = 0; // blocks of the particle pass that wrote this step's partial sums (0: nblocks)
     size_t smem_pass = 0, smem_lf = 0;
     bool ngp_tma = false;
-    int k2d = 0, k2d_a = 0, k2d_b = 0, k2d_c = 0; // 2D tile-sorted particle kernel: 0 = particles_2d3v_tiled, 1 = particles_2d3v_ring<a, b>, 2 = particles_2d3v_stream<a, b, c>
+    int k2d = 0, k2d_a = 0, k2d_b = 0, k2d_c = 0; // 2D tile-sorted particle kernel: 0 = particles_2d3v_tiled, 2 = particles_2d3v_stream<a, b, c>
     size_t smem_ring = 0;
     bool have_particles = false;
     int64_t steps = 0, launches = 0;
@@ -291,25 +291,12 @@ static int set_smem(K kernel, size_t bytes)
     return 0;
 }
 
-// instantiated variants of the ring kernel (stages, resident blocks per SM the register budget is cut for)
+// instantiated variants of the slice-streaming 2D kernel: field replicas G, deposit replicas D, threads of the one block per SM
 typedef void (*p2d_kernel_t)(P2DArgs);
-static p2d_kernel_t ring_kernel(int stages, int minb)
-{
-    if (stages == 4 && minb == 3) return particles_2d3v_ring<4, 3>;
-    if (stages == 2 && minb == 3) return particles_2d3v_ring<2, 3>;
-    if (stages == 4 && minb == 2) return particles_2d3v_ring<4, 2>;
-    return nullptr;
-}
-// ... and of the slice-streaming kernel: field replicas G, deposit replicas D, threads of the one block per SM
 static p2d_kernel_t stream_kernel(int G, int D, int threads)
 {
     if (G == 4 && D == 8 && threads == 512) return particles_2d3v_stream<4, 8, 512>;
-    if (G == 4 && D == 4 && threads == 512) return particles_2d3v_stream<4, 4, 512>;
-    if (G == 8 && D == 2 && threads == 512) return particles_2d3v_stream<8, 2, 512>;
-    if (G == 2 && D == 8 && threads == 512) return particles_2d3v_stream<2, 8, 512>;
-    if (G == 1 && D == 1 && threads == 512) return particles_2d3v_stream<1, 1, 512>;
-    if (G == 4 && D == 4 && threads == 768) return particles_2d3v_stream<4, 4, 768>;
-    if (G == 2 && D == 4 && threads == 1024) return particles_2d3v_stream<2, 4, 1024>;
+    if (G == 1 && D == 1 && threads == 512) return particles_2d3v_stream<1, 1, 512>; // measurement: what the replicas buy
     return nullptr;
 }
 
@@ -642,21 +629,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             int64_t items = h->count / T2_CHUNK + h->nbins;
             PG_TRY(occupancy_blocks(particles_2d3v_tiled, PG_THREADS, 0, h->sms, items * PG_THREADS, &h->nblocks_sorted));
             // particle kernel of the tile-sorted path (PICGOLF_2D_KERNEL): "stream" (default: slice streaming with replicated
-            // windows; stream<G><D>_<threads> picks a measured variant, e.g. stream48_512), "ring<stages><blocks/SM>" (per-warp
-            // cp.async ring over 8192-particle work items) or "tiled" (plain loads)
+            // windows), "stream11_512" (the same without replicas) or "tiled" (8192-particle work items, plain loads)
             const char *kv = getenv("PICGOLF_2D_KERNEL");
             h->k2d = 2; h->k2d_a = 4; h->k2d_b = 8; h->k2d_c = 512;
             if (kv && !strcmp(kv, "tiled")) h->k2d = 0;
-            else if (kv && !strncmp(kv, "ring", 4) && strlen(kv) == 6) { h->k2d = 1; h->k2d_a = kv[4] - '0'; h->k2d_b = kv[5] - '0'; }
             else if (kv && !strncmp(kv, "stream", 6) && strlen(kv) > 9) { h->k2d_a = kv[6] - '0'; h->k2d_b = kv[7] - '0'; h->k2d_c = atoi(kv + 9); }
             else if (kv && strcmp(kv, "stream")) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such kernel", kv);
-            if (h->k2d == 1) {
-                p2d_kernel_t kern = ring_kernel(h->k2d_a, h->k2d_b);
-                if (!kern) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such variant", kv);
-                h->smem_ring = r2_smem_bytes(PG_THREADS, h->k2d_a);
-                PG_TRY(set_smem(kern, h->smem_ring));
-                PG_TRY(occupancy_blocks(kern, PG_THREADS, h->smem_ring, h->sms, items * PG_THREADS, &h->nblocks_sorted));
-            } else if (h->k2d == 2) {
+            if (h->k2d == 2) {
                 p2d_kernel_t kern = stream_kernel(h->k2d_a, h->k2d_b, h->k2d_c);
                 if (!kern) return fail(PICGOLF_ERR_ARG, "PICGOLF_2D_KERNEL=%s: no such variant", kv);
                 h->smem_ring = s2_smem_bytes(h->k2d_a, h->k2d_b, h->k2d_c);
@@ -1445,7 +1424,6 @@ static int step_2d3v(picgolf_handle h)
         a.tile_start = h->bin_start; a.tile_end = h->bin_cursor; a.item_off = h->item_off; a.slow_count = h->slow_count;
         a.fxw_scale = h->fxw_scale; a.fx_shift = h->fx_shift; a.ntx = std::max(1, a.NX >> T2_SHIFT); a.ntiles = h->nbins;
         if (h->k2d == 2) stream_kernel(h->k2d_a, h->k2d_b, h->k2d_c)<<<h->nblocks_sorted, h->k2d_c, h->smem_ring, h->stream>>>(a);
-        else if (h->k2d == 1) ring_kernel(h->k2d_a, h->k2d_b)<<<h->nblocks_sorted, PG_THREADS, h->smem_ring, h->stream>>>(a);
         else particles_2d3v_tiled<<<h->nblocks_sorted, PG_THREADS, 0, h->stream>>>(a);
     } else {
         particles_2d3v_kernel<<<h->nblocks, PG_THREADS, 0, h->stream>>>(a);

@@ -15,8 +15,8 @@ int h_shape(int shape, double z, double NZ_Lz, int *j0, double *w6) { return sha
 
 void h_boris(double *v, double Ex, double Ey, const double *B, double dt, double q_m)
 {
-    Boris b = make_boris(B[0], B[1], B[2], dt);
-    boris_push(b, v[0], v[1], v[2], Ex, Ey, q_m);
+    Boris b = make_boris(B[0], B[1], B[2], dt, q_m);
+    boris_push(b, v[0], v[1], v[2], Ex, Ey);
 }
 
 double h_halton(long long i, int base, double seed) { return halton(i, base, seed); }
@@ -27,7 +27,7 @@ void h_emulate_particles(int shape, long long P, double *x, double *y, double *v
                          long long *rho_fx, int NX, int NY, double Lx, double Ly, double dt, const double *B, double q_m, double dep,
                          double fx_scale, double *sums)
 {
-    const Boris boris = make_boris(B[0], B[1], B[2], dt);
+    const Boris boris = make_boris(B[0], B[1], B[2], dt, q_m);
     const double NX_Lx = (double)NX / Lx, NY_Ly = (double)NY / Ly;
     const int S = support(shape);
     for (int k = 0; k < 7; ++k) sums[k] = 0.0;
@@ -45,7 +45,7 @@ void h_emulate_particles(int shape, long long P, double *x, double *y, double *v
                 Eyi = fma(Exy2[2 * (cx[ii] + cy[jj]) + 1], wxy, Eyi);
             }
         const double vxi = vx[p], vyi = vy[p];
-        boris_push(boris, vx[p], vy[p], vz[p], Exi, Eyi, q_m);
+        boris_push(boris, vx[p], vy[p], vz[p], Exi, Eyi);
         x[p] = unimod(x[p] + (vxi + vx[p]) / 2 * dt, Lx);
         y[p] = unimod(y[p] + (vyi + vy[p]) / 2 * dt, Ly);
         shape_weights_rt(shape, x[p], NX_Lx, ix0, wx);

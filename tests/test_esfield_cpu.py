@@ -239,10 +239,13 @@ def test_device_header_shapes_bit_exact(oracle, harness, shape):
 
 def test_device_header_boris_and_halton_bit_exact(oracle, harness):
     rng = np.random.default_rng(7)
-    for _ in range(300):
-        v = rng.standard_normal(3)
-        B = rng.standard_normal(3)
-        ex, ey, dt, q_m = rng.standard_normal(), rng.standard_normal(), 0.01 + rng.random() * 0.1, rng.choice([-1.0, 1.0, 1 / 16, -0.25])
+    # (the header divides by the species-wide 1 + q_m^2 t2 through its precomputed reciprocal and an FMA correction: must be the
+    # same bits as the oracle's IEEE division for any charge-to-mass ratio, field strength and velocity scale)
+    for n in range(20000):
+        v = rng.standard_normal(3) * 10.0 ** rng.integers(-6, 7)
+        B = rng.standard_normal(3) * 10.0 ** rng.integers(-3, 4)
+        q_m = rng.choice([-1.0, 1.0, 1 / 16, -0.25]) if n % 2 else rng.standard_normal() * 10.0 ** rng.integers(-2, 3)
+        ex, ey, dt = rng.standard_normal(), rng.standard_normal(), 0.01 + rng.random() * 0.1
         a = v.copy()
         harness.h_boris(a, ex, ey, np.ascontiguousarray(B), dt, q_m)
         assert np.array_equal(a, oracle.es_boris(v, ex, ey, B, dt, q_m))
