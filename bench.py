@@ -160,6 +160,32 @@ def traffic_of(key):
     return None
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any pinned host buffer
+    is allocated, so that the e2e arm's staging memory is first-touched on the GPU's own NUMA node and the eight ranks of a box
+    do not all stream through one socket.  Returns a short description for the JSON line; harmless where it cannot apply."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = open(dev + "/numa_node").read().strip()
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "bound": False, "why": "no local CPU in this process's affinity mask"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # no NVML / no sysfs entry: leave the affinity alone
+        return {"bound": False, "why": type(e).__name__}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -172,6 +198,8 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if args.gpus > 1 and world == 1:
         raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    # several ranks on one box: each next to its own GPU (a single rank keeps all host cores for the CPU baseline's threads)
+    numa = bind_to_gpu_numa(local) if world > 1 else {"bound": False, "why": "single rank"}
     torch.cuda.set_device(local)
     sampler = ClockSampler(local)
     sampler.start()  # before the warm-up: the timed region of the driver's run is only ~0.1 s long
@@ -278,6 +306,7 @@ def run_gpu(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, pg, sim, torch, barrier, max_over_ranks, stream, P, world)
+        e2e["host_affinity"] = numa
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------
     cpu = None

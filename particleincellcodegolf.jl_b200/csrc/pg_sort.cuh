@@ -15,7 +15,7 @@
 namespace pg {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 8;  // particles per thread in a scatter tile
+constexpr int SORT_ITEMS = 4;  // particles per thread in a scatter tile (their whole payload is held in registers)
 constexpr int SORT_MAX_ARR = 5;
 
 struct SortArgs {
@@ -38,23 +38,28 @@ struct SortArgs {
                 // except where a cell boundary cuts through the bin
 };
 
-__device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
+// Bin of a particle from its first two payload values (1D: x and v; 2D: x and y).
+__device__ __forceinline__ int sort_key_of(const SortArgs &a, double p0, double p1)
 {
     if (a.mode == 0) {
-        int c = (int)rint(a.in[0][j] * (double)a.N); // the stencil centre Int(round(x*N)): a bin shares its window rows
+        int c = (int)rint(p0 * (double)a.N); // the stencil centre Int(round(x*N)): a bin shares its window rows
         if (!a.vsplit) return c & (a.N - 1);
-        const double d = a.in[0][j] * (double)a.N - (double)c; // offset from the cell centre, [-1/2, 1/2]
+        const double d = p0 * (double)a.N - (double)c; // offset from the cell centre, [-1/2, 1/2]
         const int sub = min((1 << a.sublg) - 1, max(0, (int)((d + 0.5) * (double)(1 << a.sublg))));
-        return (((c & (a.N - 1)) * 2 + (a.in[1][j] >= 0.0 ? 1 : 0)) << a.sublg) + sub;
+        return (((c & (a.N - 1)) * 2 + (p1 >= 0.0 ? 1 : 0)) << a.sublg) + sub;
     }
     if (a.mode == 2) {
-        int ex = ((int)ceil(a.in[0][j] * a.kx) - 1) & (a.N - 1);
-        int ey = ((int)ceil(a.in[1][j] * a.ky) - 1) & (a.NY - 1);
+        int ex = ((int)ceil(p0 * a.kx) - 1) & (a.N - 1);
+        int ey = ((int)ceil(p1 * a.ky) - 1) & (a.NY - 1);
         return (ey >> a.tshift) * max(1, a.N >> a.tshift) + (ex >> a.tshift);
     }
-    int cx = ((int)ceil(a.in[0][j] * (double)a.N) - 1) & (a.N - 1);
-    int cy = ((int)ceil(a.in[1][j] * (double)a.NY) - 1) & (a.NY - 1);
+    int cx = ((int)ceil(p0 * (double)a.N) - 1) & (a.N - 1);
+    int cy = ((int)ceil(p1 * (double)a.NY) - 1) & (a.NY - 1);
     return (cy >> a.tshift) * (a.N >> a.tshift) + (cx >> a.tshift);
+}
+__device__ __forceinline__ int sort_key(const SortArgs &a, long long j)
+{
+    return sort_key_of(a, a.in[0][j], (a.mode != 0 || a.vsplit) ? a.in[1][j] : 0.0);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortArgs a)
@@ -98,33 +103,42 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count
     }
 }
 
-// Dynamic shared memory: 2*nbins u32.  NARR is a template parameter so that the payload loads of a particle
-// (and of the SORT_ITEMS particles of a thread) are independent and all in flight together.
+// Dynamic shared memory: 2*nbins u32.  A block takes tiles of SORT_THREADS * SORT_ITEMS particles: every thread first
+// requests the whole payload of its SORT_ITEMS particles (NARR doubles + the id each, all loads independent and in flight
+// together -- the bin is computed from the loaded x, y / x, v, nothing is read twice), then the tile is ranked (lanes of a warp
+// with the same key are grouped with match.any and reserve their slots with one shared-memory atomic per group: on the
+// nearly sorted arrays of a re-sort a whole warp row has one key), one global reservation per (tile, bin) follows, and the
+// payload is scattered.  Round 1's form (keys read first, payload re-read later in groups of four, one shared atomic per
+// particle) moved 3.1 TB/s on a re-sort of the 2D arrays; it waited on four dependent memory round trips per tile.
 template <int NARR>
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
 {
+    static_assert(NARR >= 2, "the bin is computed from the first two payload arrays");
     extern __shared__ unsigned int sh[];
     unsigned int *cnt = sh, *base = sh + a.nbins;
     const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     const long long ntiles = (a.P + tile - 1) / tile;
+    const int lane = threadIdx.x & 31;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long j0 = t * tile;
+        double val[SORT_ITEMS][NARR];
+        unsigned int id[SORT_ITEMS], rank[SORT_ITEMS];
+        int key[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
+            if (j < a.P) {
+#pragma unroll
+                for (int q = 0; q < NARR; ++q) val[i][q] = __ldcs(a.in[q] + j);
+                id[i] = a.pid_in ? __ldcs(a.pid_in + j) : (unsigned int)j;
+            }
+        }
         for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) cnt[b] = 0u;
         __syncthreads();
-        const long long j0 = t * tile;
-        int key[SORT_ITEMS];
-        unsigned int rank[SORT_ITEMS];
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; ++i) {
-            long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
-            key[i] = j < a.P ? sort_key(a, j) : -1;
-        }
-        // ranks inside the tile: lanes of a warp holding the same key are grouped (match.any) and their leader reserves the
-        // group's slots with ONE shared-memory atomic -- on the nearly sorted arrays of a re-sort a whole warp row has one
-        // key, and 2048 same-address atomics per tile were what the scatter spent its time on (8.6 ms per re-sort of 2^28
-        // particles in the 2D path, profiles/r2_k_launches_2d3v.csv)
-        const int lane = threadIdx.x & 31;
-#pragma unroll
-        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const long long j = j0 + (long long)i * SORT_THREADS + threadIdx.x;
+            key[i] = j < a.P ? sort_key_of(a, val[i][0], val[i][1]) : -1;
             const int k = key[i] >= 0 ? key[i] : -1 - lane; // dead lanes: unique negative keys
             const unsigned int grp = __match_any_sync(0xffffffffu, k);
             const int leader = __ffs(grp) - 1;
@@ -140,26 +154,12 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(SortArgs a)
         }
         __syncthreads();
 #pragma unroll
-        for (int i0 = 0; i0 < SORT_ITEMS; i0 += 4) {
-            double val[4][NARR];
-            unsigned int id[4];
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            if (key[i] >= 0) {
+                const long long d = (long long)base[key[i]] + rank[i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                long long j = j0 + (long long)(i0 + u) * SORT_THREADS + threadIdx.x;
-                if (key[i0 + u] >= 0) {
-#pragma unroll
-                    for (int q = 0; q < NARR; ++q) val[u][q] = __ldcs(a.in[q] + j);
-                    id[u] = a.pid_in ? __ldcs(a.pid_in + j) : (unsigned int)j;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (key[i0 + u] >= 0) {
-                    long long d = (long long)base[key[i0 + u]] + rank[i0 + u];
-#pragma unroll
-                    for (int q = 0; q < NARR; ++q) a.out[q][d] = val[u][q];
-                    a.pid_out[d] = id[u];
-                }
+                for (int q = 0; q < NARR; ++q) a.out[q][d] = val[i][q];
+                a.pid_out[d] = id[i];
             }
         }
         __syncthreads();
@@ -211,6 +211,20 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_match_kernel(SortAr
             a.pid_out[d] = id;
         }
     }
+}
+
+// Grid of the scatter: as many blocks as are resident (the kernel loops over its tiles), never more than there are tiles.
+template <int NARR>
+static inline int sort_scatter_grid(int sms, long long count, int nbins)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_scatter_kernel<NARR>, SORT_THREADS, (size_t)nbins * 8) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
+    const long long ntiles = (count + tile - 1) / tile;
+    return (int)(ntiles < 1 ? 1 : (ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm));
 }
 
 // out[pid[i]] = in[i]: back to the caller's particle order.

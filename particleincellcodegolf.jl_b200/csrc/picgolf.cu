@@ -1063,9 +1063,8 @@ static int sort_particles_1d(picgolf_handle h)
     a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor;
     a.P = h->count; a.narr = 2; a.nbins = h->nbins; a.mode = 0; a.N = (int)h->cfg.N; a.NY = 1; a.tshift = 0;
     a.vsplit = h->poly ? 1 : 0; a.sublg = h->sublg;
-    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
-    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 8));
+    const int gs = h->poly ? 0 : sort_scatter_grid<2>(h->sms, h->count, h->nbins);
     if (h->poly) { // too many bins for shared-memory tables: warp-aggregated global atomics
         sort_hist_match_kernel<<<h->sms * 8, SORT_THREADS, 0, h->stream>>>(a);
         sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, nullptr, h->nbins);
@@ -1392,9 +1391,8 @@ static int sort_particles_2d(picgolf_handle h)
     a.pid_out = h->pid[1 - h->pidpar];
     a.bin_count = h->bin_count; a.bin_cursor = h->bin_cursor; a.bin_start = h->bin_start;
     a.P = h->count; a.narr = 5; a.nbins = h->nbins; a.mode = 1; a.N = (int)h->cfg.N; a.NY = (int)h->cfg.NY; a.tshift = T2_SHIFT;
-    const long long tile = (long long)SORT_THREADS * SORT_ITEMS;
     int gh = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + SORT_THREADS - 1) / SORT_THREADS, (int64_t)h->sms * 8));
-    int gs = (int)std::max<int64_t>(1, std::min<int64_t>((h->count + tile - 1) / tile, (int64_t)h->sms * 4));
+    const int gs = sort_scatter_grid<5>(h->sms, h->count, h->nbins);
     sort_hist_kernel<<<gh, SORT_THREADS, (size_t)h->nbins * 4, h->stream>>>(a);
     sort_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bin_count, h->bin_cursor, h->bin_start, h->nbins);
     sort_scatter_kernel<5><<<gs, SORT_THREADS, (size_t)h->nbins * 8, h->stream>>>(a);
