@@ -37,7 +37,7 @@ typedef enum picgolf_status {
     PICGOLF_ERR_CUDA = -2,        /* CUDA runtime error (see picgolf_last_error) */
     PICGOLF_ERR_NCCL = -3,        /* NCCL error or NCCL not loadable */
     PICGOLF_ERR_STATE = -4,       /* call order (e.g. step before particles were set) */
-    PICGOLF_ERR_UNSUPPORTED = -5  /* valid in the reference, not built here (e.g. N not a power of 2) */
+    PICGOLF_ERR_UNSUPPORTED = -5  /* valid in the reference, not built here (e.g. an erf-shape scheme on a grid that is not 2^k) */
 } picgolf_status;
 
 /* Which reference script's loop body the handle runs. */
@@ -71,7 +71,8 @@ typedef enum picgolf_deposit_mode {
 typedef struct picgolf_config {
     int32_t struct_size;
     int32_t scheme;          /* picgolf_scheme */
-    int64_t N;               /* 1D: grid cells N (power of two, 8..4096*4).  2D: NX */
+    int64_t N;               /* 1D: grid cells N, 16..8192: a power of two, or -- NGP_LEAPFROG only, NGPFourier.jl's fft takes
+                              * any N -- any even number (direct transforms instead of the radix FFT).  2D: NX (power of two) */
     int64_t NY;              /* 2D only */
     int64_t P;               /* GLOBAL particle count (all ranks); 1D2V2S: per species (the handle holds 2P particles) */
     int64_t T;               /* capacity of the diagnostics trace in rows (steps recorded) */

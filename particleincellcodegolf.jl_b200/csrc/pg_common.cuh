@@ -29,8 +29,9 @@ __device__ __forceinline__ double jl_mod1(double a)
 __device__ __forceinline__ int ngp_cell0(double x, int N)
 {
     long long r = __double2ll_rn(x * (double)N); // rint, ties to even
-    long long m = (r - 1) % (long long)N;
-    if (m < 0) m += N;
+    long long m = r - 1;
+    if (m == -1) return N - 1;                                 // mod1(0, N) = N
+    if (m < 0 || m >= N) { m %= (long long)N; if (m < 0) m += N; } // x outside [0, 1]: never on the stepping path (x = mod(x, 1))
     return (int)m;
 }
 

@@ -277,6 +277,119 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grids that are not a power of two (NGP leapfrog only: `fft` in src/NGPFourier.jl:3-5 takes any N, and its ik vector is
+// well formed for every EVEN N).  The same solve as solve1d_kernel, as two direct O(N^2) transforms: N <= 8192, so
+// 2 x 67 M complex multiply-adds at most, spread over all SMs -- one WARP per output element (the lanes split the sum and
+// combine with a fixed shuffle tree), 32 outputs per block (the block's copy of the tables is what a block pays for).  Twiddles e^{2 pi i m/N}, m < N, come from a table the host
+// computed in long double (make_dft_twiddles), indexed with the exact (k n) mod N, so every term is accurate to an ulp
+// whatever N is.
+//   pass 1 (solve1d_dft_fwd): xi_k = (sum_n rho_n e^{-2 pi i k n/N}) / ik_k, xi_0 = 0           -> spec[k]
+//   pass 2 (solve1d_dft_inv): E_n = (1/N) Re sum_k xi_k e^{+2 pi i k n/N}; clears the deposit grid; sum(E.^2) by the last block
+// Shared memory of both: N double2 twiddles + 2 N doubles (rho / spectrum planes) + reduction scratch.
+// ---------------------------------------------------------------------------------------------
+struct SolveDftArgs {
+    const double *rho_in;       // stage entry only
+    unsigned long long *rho_fx; // [N] integer deposit grid summed over ranks; zeroed by pass 2
+    double *rho_last, *E;
+    const double2 *tw;          // [N] (cos, sin)(2 pi m / N)
+    double2 *spec;              // [N] xi
+    double *part;               // [gridDim.x] partial sums of E^2
+    unsigned int *arrive;       // [1] blocks of pass 2 that have finished (reset by the last one)
+    Ctrl *ctrl;
+    double w, fx_inv;
+    int N;
+};
+constexpr int DFT_THREADS = 256, DFT_OUT = 32; // outputs per block: each of the 8 warps takes four, one after the other
+__host__ __device__ inline size_t dft_smem_bytes(int N) { return (size_t)N * (8 + 8 + 16) + 256; }
+__host__ __device__ inline int dft_blocks(int N) { return (N + DFT_OUT - 1) / DFT_OUT; }
+
+__global__ void __launch_bounds__(DFT_THREADS) solve1d_dft_fwd(SolveDftArgs a)
+{
+    extern __shared__ __align__(16) unsigned char dft_raw[];
+    double2 *tw = reinterpret_cast<double2 *>(dft_raw);
+    double *rho = reinterpret_cast<double *>(tw + a.N);
+    const int N = a.N, lane = threadIdx.x & 31;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        tw[n] = a.tw[n];
+        const double r = a.rho_in ? a.rho_in[n] : (double)(long long)a.rho_fx[n] * a.fx_inv * a.w;
+        rho[n] = r;
+        if (blockIdx.x == 0) a.rho_last[n] = r;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x >> 5; o < DFT_OUT; o += DFT_THREADS / 32) {
+        const int k = blockIdx.x * DFT_OUT + o;
+        if (k >= N) return;
+        double sr = 0.0, si = 0.0;
+        int idx = (int)(((long long)k * lane) % N);          // (k n) mod N for n = lane, lane + 32, ...
+        const int step = (int)(((long long)k * 32) % N);
+        for (int n = lane; n < N; n += 32) {
+            const double2 t = tw[idx]; // e^{-i theta} = (cos, -sin)
+            sr = fma(rho[n], t.x, sr);
+            si = fma(-rho[n], t.y, si);
+            idx += step; if (idx >= N) idx -= N;
+        }
+        sr = warp_sum(sr); si = warp_sum(si);
+        if (lane == 0) {
+            // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk,  kk = vcat(1, 1:N/2, -N/2+1:-1)[k+1]
+            double2 xi = make_double2(0.0, 0.0);
+            if (k > 0) {
+                const double kk = (k <= N / 2) ? (double)k : (double)(k - N);
+                const double b = TWO_PI * kk;
+                xi = make_double2(si / b, -sr / b);
+            }
+            a.spec[k] = xi;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DFT_THREADS) solve1d_dft_inv(SolveDftArgs a)
+{
+    extern __shared__ __align__(16) unsigned char dft_raw[];
+    double2 *tw = reinterpret_cast<double2 *>(dft_raw);
+    double *xr = reinterpret_cast<double *>(tw + a.N), *xi = xr + a.N;
+    double *scratch = xi + a.N;
+    __shared__ bool last;
+    const int N = a.N, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) { tw[k] = a.tw[k]; const double2 z = a.spec[k]; xr[k] = z.x; xi[k] = z.y; }
+    __syncthreads();
+    double e2 = 0.0;
+    for (int o = threadIdx.x >> 5; o < DFT_OUT; o += DFT_THREADS / 32) {
+        const int n = blockIdx.x * DFT_OUT + o;
+        if (n >= N) break;
+        double s = 0.0, u = 0.0; // two independent chains
+        int idx = (int)(((long long)n * lane) % N);      // (k n) mod N for k = lane, lane + 32, ...
+        const int step = (int)(((long long)n * 32) % N);
+        for (int k = lane; k < N; k += 32) {
+            const double2 t = tw[idx];
+            s = fma(xr[k], t.x, s);  // Re (xr + i xi)(cos + i sin)
+            u = fma(-xi[k], t.y, u);
+            idx += step; if (idx >= N) idx -= N;
+        }
+        s = warp_sum(s + u);
+        if (lane == 0) {
+            const double e = s / (double)N;
+            a.E[n] = e;
+            if (!a.rho_in) a.rho_fx[n] = 0ULL;
+            e2 += e * e;
+        }
+    }
+    e2 = block_sum(e2, scratch);
+    if (threadIdx.x == 0) {
+        a.part[blockIdx.x] = e2;
+        __threadfence();
+        last = atomicAdd(a.arrive, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) { // fixed summation order: the same bits whichever block finishes last
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += a.part[b];
+        a.ctrl->sumE2 = t;
+        *a.arrive = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 2D solve: three kernels (x-rows forward, y-columns forward+invert+inverse, x-rows inverse).
 // Z holds the complex spectrum with x in bit-reversed order after pass A.
 // real(ifft(S)) only sees the Hermitian part of S; for real rho that makes Ex on the kx-Nyquist row

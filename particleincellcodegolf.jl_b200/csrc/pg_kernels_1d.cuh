@@ -364,6 +364,7 @@ struct LFArgs {
     long long P;
     double dt, fx_scale;
     int N, do_kick, do_deposit;
+    int pow2;                    // N is a power of two: the cell index is a mask instead of Julia's mod1 division
 };
 
 // One particle of a leapfrog pass (shared by the vectorised and the scalar loops).
@@ -376,7 +377,7 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
     if (a.do_kick) {
         xj = jl_mod1(xj + vj / 2 * dt);
         double e;
-        if (SHAPE == 0) e = Es[ngp_cell0_pow2(xj, N)];
+        if (SHAPE == 0) e = Es[a.pow2 ? ngp_cell0_pow2(xj, N) : ngp_cell0(xj, N)];
         else {
             int ibase; double W[GAUSS_NW];
             gauss_weights(xj, dN, ibase, W);
@@ -388,7 +389,7 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
     }
     if (a.do_deposit) {
         xj = jl_mod1(xj + vj / 2 * dt);
-        if (SHAPE == 0) atomicAdd(&cs[ngp_cell0_pow2(xj, N)], 1u);
+        if (SHAPE == 0) atomicAdd(&cs[a.pow2 ? ngp_cell0_pow2(xj, N) : ngp_cell0(xj, N)], 1u);
         else {
             int ibase; double W[GAUSS_NW];
             gauss_weights(xj, dN, ibase, W);

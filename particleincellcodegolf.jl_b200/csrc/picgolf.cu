@@ -189,6 +189,8 @@ struct picgolf_handle_s {
     int pass_blocks = 0; // blocks of the particle pass that wrote this step's partial sums (0: nblocks)
     size_t smem_pass = 0, smem_lf = 0;
     bool ngp_tma = false;
+    bool dft = false;            // grid is not a power of two (NGP leapfrog): solve1d_dft_fwd / solve1d_dft_inv instead of solve1d_kernel
+    double2 *dft_spec = nullptr, *dft_tw = nullptr; double *dft_part = nullptr; unsigned int *dft_arrive = nullptr;
     int k2d = 0, k2d_a = 0, k2d_b = 0, k2d_c = 0; // 2D tile-sorted particle kernel: 0 = particles_2d3v_tiled, 2 = particles_2d3v_stream<a, b, c>
     size_t smem_ring = 0;
     bool have_particles = false;
@@ -278,6 +280,19 @@ static int make_twiddles(double2 **dst, int n)
     for (int k = 0; k < n / 2; ++k) {
         long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
         t[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    PG_TRY(dalloc(dst, t.size()));
+    PG_CUDA(cudaMemcpy(*dst, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// (cos, sin)(2 pi m / n), m < n: the full circle for the direct transforms of grids that are not a power of two
+static int make_dft_twiddles(double2 **dst, int n)
+{
+    std::vector<double2> t((size_t)std::max(n, 1));
+    for (int m = 0; m < n; ++m) {
+        long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)n;
+        t[m] = make_double2((double)cosl(ang), (double)sinl(ang));
     }
     PG_TRY(dalloc(dst, t.size()));
     PG_CUDA(cudaMemcpy(*dst, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice));
@@ -416,7 +431,8 @@ static int destroy_impl(picgolf_handle h)
                     h->p2[1][0], h->p2[1][1], h->p2[1][2], h->p2[1][3], h->p2[1][4], h->bin_start, h->item_off, h->vy1, h->hist,
                     h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
-                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2]};
+                    h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2],
+                    h->dft_spec, h->dft_part, h->dft_arrive, h->dft_tw};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -489,6 +505,13 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
         h->npart = 2;
         PG_TRY(set_smem(solve1d_kernel, h->smem_pass));
+        h->dft = !is_pow2(N); // NGP leapfrog on a grid that is not 2^k (validated in picgolf_create): direct transforms
+        if (h->dft) {
+            PG_TRY(dalloc(&h->dft_spec, (size_t)N)); PG_TRY(dalloc(&h->dft_part, (size_t)dft_blocks((int)N))); PG_TRY(dalloc(&h->dft_arrive, 1));
+            PG_TRY(make_dft_twiddles(&h->dft_tw, (int)N));
+            PG_CUDA(cudaMemset(h->dft_arrive, 0, sizeof(unsigned int)));
+            PG_TRY(set_smem(solve1d_dft_fwd, dft_smem_bytes((int)N))); PG_TRY(set_smem(solve1d_dft_inv, dft_smem_bytes((int)N)));
+        }
         if (h->b1d2v) {
             PG_TRY(dalloc(&h->vy1, n));
             PG_TRY(dalloc(&h->hist, (size_t)N * h->T));
@@ -676,7 +699,10 @@ PG_API int picgolf_create(const picgolf_config *cfg, picgolf_handle *out)
             return fail(PICGOLF_ERR_UNSUPPORTED, "NX=%lld NY=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N, (long long)c.NY);
     } else {
         if (c.N < 16 || c.N > 8192) return fail(PICGOLF_ERR_ARG, "N must be in 16..8192");
-        if (!is_pow2(c.N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built (radix-2 shared-memory FFT)", (long long)c.N);
+        // grids that are not 2^k: the NGP leapfrog only (NGPFourier.jl's fft takes any N; its ik vector needs an even one) -- direct
+        // transforms (solve1d_dft_*).  The erf-shape kernels rest on delta = c*N - round(c*N) being exact, which needs N = 2^k.
+        if (!is_pow2(c.N) && (c.scheme != PICGOLF_NGP_LEAPFROG || (c.N & 1)))
+            return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: grids that are not a power of two are built for the NGP leapfrog and even N only", (long long)c.N);
         if (c.scheme != PICGOLF_NGP_LEAPFROG && c.scheme != PICGOLF_AREA_SIMPSON13 && c.half_width != 6 && c.half_width != 7)
             return fail(PICGOLF_ERR_ARG, "half_width must be 6 or 7");
         if ((c.scheme == PICGOLF_GAUSS_SIMPSON13 || c.scheme == PICGOLF_AREA_SIMPSON13) && c.N > 4096) return fail(PICGOLF_ERR_ARG, "Simpson-1/3 scheme: N must be <= 4096");
@@ -907,7 +933,7 @@ static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
 {
     h->peer_this_solve = false;
     if (!h->comm) return 0;
-    if (h->peer_ok && !h->is2d && !h->simpson && row0 == 0 && nrows == 1) {
+    if (h->peer_ok && !h->is2d && !h->simpson && !h->dft && row0 == 0 && nrows == 1) {
         // 1D schemes: publish this rank's grid; the solve kernel that follows adds the ranks' grids up itself
         const int sp = h->timer.begin(ST_REDUCE, h->stream);
         peer_publish_kernel<<<1, 1024, 0, h->stream>>>(peer_args(h), h->rho_fx, &h->ctrl->final_k, h->fixedpoint ? 1 : 0);
@@ -930,6 +956,20 @@ static int allreduce_grid(picgolf_handle h, int row0 = 0, int nrows = 1)
 static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false, cudaGraphConditionalHandle cond = 0)
 {
     const picgolf_config &c = h->cfg;
+    if (h->dft) {
+        SolveDftArgs d;
+        memset(&d, 0, sizeof(d));
+        d.rho_fx = h->rho_fx; d.rho_last = h->rho_last; d.E = h->E; d.spec = h->dft_spec; d.part = h->dft_part; d.arrive = h->dft_arrive;
+        d.ctrl = h->ctrl; d.w = c.w; d.fx_inv = h->fx_inv; d.N = (int)c.N; d.tw = h->dft_tw;
+        const int nb = dft_blocks((int)c.N);
+        const size_t sm = dft_smem_bytes((int)c.N);
+        const int sp = h->timer.begin(ST_SOLVE, h->stream);
+        solve1d_dft_fwd<<<nb, DFT_THREADS, sm, h->stream>>>(d);
+        solve1d_dft_inv<<<nb, DFT_THREADS, sm, h->stream>>>(d);
+        h->timer.end(sp, h->stream);
+        h->launches += 2;
+        return 0;
+    }
     Solve1DArgs a;
     memset(&a, 0, sizeof(a));
     a.rho_in = nullptr; a.rho_fx = h->rho_fx; a.rho_last = h->rho_last; a.E = h->E; a.tw = h->tw; a.ctrl = h->ctrl;
@@ -1338,6 +1378,7 @@ static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
     LFArgs a;
     a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
+    a.pow2 = h->dft ? 0 : 1;
     const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
     if (h->ngp_tma) lf_pass_ngp_tma<<<h->nblocks, LF_TMA_THREADS, h->smem_lf, h->stream>>>(a);
     else if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
@@ -1953,6 +1994,13 @@ static int check_grid1d(int64_t N)
     if (!is_pow2(N)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: only power-of-two grids are built", (long long)N);
     return 0;
 }
+// the NGP stages (deposit, solve) also take even grids that are not a power of two, like the NGP leapfrog itself
+static int check_grid1d_ngp(int64_t N)
+{
+    if (N < 16 || N > 8192) return fail(PICGOLF_ERR_ARG, "N must be in 16..8192");
+    if (!is_pow2(N) && (N & 1)) return fail(PICGOLF_ERR_UNSUPPORTED, "N=%lld: grids that are not a power of two must be even", (long long)N);
+    return 0;
+}
 
 PG_API int picgolf_stage_ngp_index(const double *x, int64_t count, int64_t N, int32_t *idx1)
 {
@@ -1993,7 +2041,7 @@ PG_API int picgolf_stage_gauss_stencil(const double *c, int64_t count, int64_t N
 PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, double w, double *rho)
 {
     if (!x || !rho || count < 0) return fail(PICGOLF_ERR_ARG, "bad argument");
-    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    PG_TRY(check_grid1d_ngp(N)); PG_TRY(stage_ready());
     // Runs the production pass (deposit half only) and the production solve's count->rho conversion.
     DevBuf dx, dv, dcnt, dpart;
     std::vector<double> zeros((size_t)count, 0.0);
@@ -2004,6 +2052,7 @@ PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, 
     LFArgs a;
     a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = dcnt.as<unsigned long long>();
     a.partials = dpart.as<double>(); a.P = count; a.dt = 0.0; a.fx_scale = 1.0; a.N = (int)N; a.do_kick = 0; a.do_deposit = 1;
+    a.pow2 = is_pow2(N) ? 1 : 0;
     // with v = 0 and dt = 0 the half drift is x = mod(x + 0, 1): positions in [0,1) are unchanged
     lf_pass<0><<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(a);
     PG_TRY(finish());
@@ -2050,10 +2099,29 @@ PG_API int picgolf_stage_gauss_gather(const double *E, int64_t N, int hw, const 
 PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
 {
     if (!rho || !E) return fail(PICGOLF_ERR_ARG, "bad argument");
-    PG_TRY(check_grid1d(N)); PG_TRY(stage_ready());
+    PG_TRY(check_grid1d_ngp(N)); PG_TRY(stage_ready());
     DevBuf dr, dl, dE, dctrl;
     double2 *tw = nullptr;
     PG_TRY(dr.upload(rho, N * 8)); PG_TRY(dl.alloc(N * 8)); PG_TRY(dE.zero(N * 8)); PG_TRY(dctrl.zero(sizeof(Ctrl)));
+    if (!is_pow2(N)) { // direct transforms (solve1d_dft_*)
+        DevBuf dspec, dpart, darr;
+        const int nb = dft_blocks((int)N);
+        PG_TRY(dspec.alloc(N * 16)); PG_TRY(dpart.zero((size_t)nb * 8)); PG_TRY(darr.zero(8));
+        double2 *dtw = nullptr;
+        PG_TRY(make_dft_twiddles(&dtw, (int)N));
+        struct FreeTw { double2 *p; ~FreeTw() { if (p) cudaFree(p); } } free_tw{dtw};
+        SolveDftArgs d;
+        memset(&d, 0, sizeof(d));
+        d.tw = dtw;
+        d.rho_in = dr.as<double>(); d.rho_last = dl.as<double>(); d.E = dE.as<double>(); d.spec = dspec.as<double2>();
+        d.part = dpart.as<double>(); d.arrive = darr.as<unsigned int>(); d.ctrl = dctrl.as<Ctrl>(); d.w = 1.0; d.fx_inv = 1.0; d.N = (int)N;
+        const size_t sm = dft_smem_bytes((int)N);
+        PG_TRY(set_smem(solve1d_dft_fwd, sm)); PG_TRY(set_smem(solve1d_dft_inv, sm));
+        solve1d_dft_fwd<<<nb, DFT_THREADS, sm>>>(d);
+        solve1d_dft_inv<<<nb, DFT_THREADS, sm>>>(d);
+        PG_TRY(finish());
+        return dE.download(E, N * 8);
+    }
     PG_TRY(make_twiddles(&tw, (int)N));
     Solve1DArgs a;
     memset(&a, 0, sizeof(a));

@@ -94,8 +94,13 @@ def test_argument_errors_are_codes_not_crashes(pg):
     assert lib.picgolf_create(C.byref(bad), C.byref(h)) == -1
     assert b"struct_size" in lib.picgolf_last_error()
     bad = pg.Config.from_buffer_copy(cfg)
-    bad.N = 100  # valid in the reference (FFTW takes any N), not built here
+    bad.N = 101  # an odd grid: the reference's ik vector (NGPFourier.jl:3) is malformed there, not built here
     assert lib.picgolf_create(C.byref(bad), C.byref(h)) == -5
+    bad.N = 100  # even, not a power of two: valid for the NGP leapfrog (direct transforms) -> stops only at the missing device
+    assert lib.picgolf_create(C.byref(bad), C.byref(h)) == -2
+    gfp = pg.default_config(pg.GAUSS_FIXEDPOINT)
+    gfp.N = 100  # ... but not for the erf-shape schemes
+    assert lib.picgolf_create(C.byref(gfp), C.byref(h)) == -5
     bad = pg.Config.from_buffer_copy(cfg)
     bad.scheme = 9
     assert lib.picgolf_create(C.byref(bad), C.byref(h)) == -1

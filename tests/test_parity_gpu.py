@@ -118,9 +118,55 @@ def test_solve1d_parity(pg, oracle, N):
 
 
 def test_unsupported_grid_is_an_error(pg):
+    """Odd grids (the reference's own ik vector is malformed there) and erf-shape schemes on grids that are not 2^k."""
     with pytest.raises(pg.PicGolfError) as e:
-        pg.solve1d(np.ones(100))
+        pg.solve1d(np.ones(101))
     assert e.value.code == -5
+    with pytest.raises(pg.PicGolfError) as e:
+        pg.gaussian_fixed_point(N=100, P=3200, T=4)
+    assert e.value.code == -5
+    with pytest.raises(pg.PicGolfError) as e:
+        pg.ngp_fourier(N=101, P=6464, NT=4)
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("N", [18, 100, 250, 1000, 6000])
+def test_solve1d_any_even_grid(pg, oracle, N):
+    """`fft` in NGPFourier.jl:3-5 takes any N: grids that are not a power of two go through direct transforms
+    (solve1d_dft_fwd / solve1d_dft_inv) and must give the oracle's field (its O(N^2) long-double DFT)."""
+    rng = np.random.default_rng(N)
+    rho = rng.standard_normal(N)
+    rho[0] += 3.0  # a DC component that xi[1] *= 0 must remove
+    E = pg.solve1d(rho)
+    Eo = oracle.solve1d(rho)
+    assert relnorm(E, Eo) < TOL
+    k = 3  # single mode in closed form: rho = cos(2 pi k x)  ->  E = sin(2 pi k x) / (2 pi k)
+    x = np.arange(N) / N
+    Em = pg.solve1d(np.cos(2 * np.pi * k * x))
+    assert np.abs(Em - np.sin(2 * np.pi * k * x) / (2 * np.pi * k)).max() < 1e-13
+
+
+@pytest.mark.parametrize("N,P", [(100, 6400), (96, 1 << 16), (1000, (1 << 21) + 7)])
+def test_ngp_steps_on_grids_that_are_not_a_power_of_two(pg, oracle, N, P):
+    """NGPFourier.jl:1-6 with N = 100, 96, 1000: the cell index goes through Julia's mod1 (no mask), the solve through the direct
+    transforms; rho, E, x, v to 1e-12 over 6 steps, cell indices bit-exact.  The largest case takes
+    the TMA-staged kernel of big shards."""
+    rng = np.random.default_rng(N + 1)
+    sim = pg.ngp_fourier(N=N, P=P, NT=8)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(1, P + 1) > P / 2, 1.0, -1.0)
+    sim.set_particles(x0, v0)
+    xo, vo = x0.copy(), v0.copy()
+    for _ in range(6):
+        sim.step(1)
+        ro, Eo, _ = oracle.ngp_step(xo, vo, N, sim.cfg.dt, sim.cfg.w)
+        rho, E = sim.fields()
+        assert relnorm(rho, ro) < TOL
+        assert relnorm(E, Eo) < TOL
+    x, v = sim.particles()
+    assert relnorm(x, xo) < TOL
+    assert relnorm(v, vo) < TOL
+    assert np.array_equal(pg.ngp_index(x0, N), oracle.ngp_index(x0, N))
 
 
 def test_2d_stage_parity(pg, oracle):

@@ -143,6 +143,19 @@ def test_loop_matches_oracle(es, oracle, shapes, acc, sort_every):
     assert sim.sort_stats()[0] == (3 if sort_every > 0 else 0)  # sorted before steps 0, 3, 6
 
 
+@pytest.mark.parametrize("kernel", ["tiled", "stream11"])
+@pytest.mark.parametrize("shapes", [(0, 1), (12, 13), (15, 11), (14, 10)])
+def test_tile_sorted_kernel_variants_match_oracle(es, oracle, monkeypatch, kernel, shapes):
+    """The tile-sorted path has three particle kernels: es_particles_stream with replicated windows (the default, exercised by
+    every sort_every > 0 test above), the same without replicas (PICGOLF_ES_KERNEL=stream11) and es_particles_tiled
+    (work items, plain loads: PICGOLF_ES_KERNEL=tiled).  All shapes of the other two against the oracle as well."""
+    monkeypatch.setenv("PICGOLF_ES_KERNEL", kernel)
+    NX, NY, Lx, Ly = 32, 16, 1.5, 2.0
+    sp = [_random_species(shapes[0], NX, NY, Lx, Ly, -1.0, 1.0, 21), _random_species(shapes[1], NX, NY, Lx, Ly, 2.0, 7.0, 22)]
+    sim, _ = _run_against(es, oracle, sp, NX, NY, Lx, Ly, 0.01, [0.9, -0.4, 0.6], NT=7, ntskip=2, ngskip=4, acc=1, sort_every=2)
+    assert sim.sort_stats()[0] == 4
+
+
 @pytest.mark.parametrize("shape", [1, 12, 15])
 def test_tiled_path_at_size(es, shape):
     """2^20 particles per species on a 64 x 128 grid (several tiles, several work items per tile): the tile-sorted kernel
