@@ -201,6 +201,13 @@ struct Solve1DArgs {
     cudaGraphConditionalHandle cond; // device-driven loop: handle of the WHILE node this solve sits in (0: fixed schedule)
 };
 
+#ifdef PG_SOLVE_PROF // measurement builds only (tools/solve_prof.py): SM clock at the phase boundaries of the latest solve
+__device__ long long g_solve_prof[8];
+#define PG_PROF(i) do { __syncthreads(); if (threadIdx.x == 0) g_solve_prof[i] = clock64(); } while (0)
+#else
+#define PG_PROF(i) do { } while (0)
+#endif
+
 // One block.  Dynamic shared memory: 2*N doubles + 32.
 __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
 {
@@ -211,6 +218,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         return;
     }
     const int N = a.N;
+    PG_PROF(0);
     const int k = a.k >= 0 ? a.k : a.ctrl->sweeps + 1; // read by every thread before thread 0 records it below
     const bool peers = a.peer.nranks > 1 && !a.rho_in;
     unsigned long long pseq = 0ULL;
@@ -230,7 +238,9 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     if (peers) peer_gather_end(a.peer, pseq);
     const bool peer_failed = peers && *a.peer.error != 0; // a peer never published (pg_peer.cuh): poison the field, end the step
     if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
+    PG_PROF(1);
     fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
+    PG_PROF(2);
     // xi = fft(rho)./ik ; xi[1] *= 0.   z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
         int s = bitrev(p, a.lg); // frequency slot held at position p
@@ -244,7 +254,9 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         }
     }
     __syncthreads();
+    PG_PROF(3);
     fft_smem4<true>(re, im, N, 1, 1, 0, a.tw, N);
+    PG_PROF(4);
     double d2 = 0.0, f2 = 0.0, e2 = 0.0;
     const double dN = (double)N;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -256,9 +268,11 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         double d = f - e;
         d2 = fma(d, d, d2); f2 = fma(f, f, f2); e2 = fma(e, e, e2);
     }
+    PG_PROF(5);
     d2 = block_sum(d2, scratch);
     f2 = block_sum(f2, scratch);
     e2 = block_sum(e2, scratch);
+    PG_PROF(6);
     if (threadIdx.x == 0) {
         a.ctrl->sumE2 = e2;
         if (a.store_normE1) a.ctrl->normE1sq = e2;

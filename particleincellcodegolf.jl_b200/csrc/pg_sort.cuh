@@ -76,30 +76,51 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(SortArgs a)
     }
 }
 
-// One block of 1024 threads; any number of bins (each thread scans a contiguous run).
+// Exclusive scan of the bin counts -> start offsets; one block of 1024 threads, any number of bins.  Warp w owns the contiguous
+// run [w*per, (w+1)*per) and walks it in coalesced chunks of 32 bins (lane-consecutive loads, shuffle scan, running carry): first
+// to total its run, then -- after the 32 run totals have been scanned -- to write the offsets and clear the counts for the next
+// sort.  (Round 1 gave every THREAD a contiguous run: uncoalesced, 0.63 ms for the 2^18 bins of the polynomial mode; now 0.09 ms in the ncu launch list.)
 __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned int *bin_count, unsigned int *bin_cursor,
                                                         unsigned int *bin_start, int nbins)
 {
-    __shared__ unsigned int part[1024];
-    const int per = (nbins + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, nbins);
+    __shared__ unsigned int wtot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per = ((nbins + 31) / 32 + 31) & ~31; // bins per warp, a multiple of 32
+    const int lo = wid * per, hi = min(lo + per, nbins);
     unsigned int s = 0;
-    for (int b = lo; b < hi; ++b) s += bin_count[b];
-    part[threadIdx.x] = s;
+    for (int b = lo + lane; b < hi; b += 32) s += bin_count[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wtot[wid] = s;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan
-        unsigned int t = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += t;
-        __syncthreads();
+    if (wid == 0) { // exclusive scan of the 32 run totals
+        const unsigned int t = wtot[lane];
+        unsigned int inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        wtot[lane] = inc - t;
     }
-    unsigned int run = part[threadIdx.x] - s; // exclusive
-    for (int b = lo; b < hi; ++b) {
-        unsigned int c = bin_count[b];
-        bin_cursor[b] = run;
-        if (bin_start) bin_start[b] = run;
-        bin_count[b] = 0u; // ready for the next sort
-        run += c;
+    __syncthreads();
+    unsigned int run = wtot[wid];
+    for (int b0 = lo; b0 < hi; b0 += 32) {
+        const int b = b0 + lane;
+        const unsigned int c = b < hi ? bin_count[b] : 0u;
+        unsigned int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (b < hi) {
+            const unsigned int off = run + inc - c; // exclusive
+            bin_cursor[b] = off;
+            if (bin_start) bin_start[b] = off;
+            bin_count[b] = 0u; // ready for the next sort
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 

@@ -2139,6 +2139,10 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     return rc;
 }
 
+#ifdef PG_SOLVE_PROF
+PG_API int picgolf_debug_solve_prof(long long *out8) { return cudaMemcpyFromSymbol(out8, g_solve_prof, 8 * sizeof(long long)) == cudaSuccess ? 0 : -3; }
+#endif
+
 PG_API int picgolf_stage_solve2d(const double *rho, int64_t NX, int64_t NY, double *Ex, double *Ey)
 {
     if (!rho || !Ex || !Ey) return fail(PICGOLF_ERR_ARG, "bad argument");
