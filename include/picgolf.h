@@ -221,6 +221,9 @@ int picgolf_launch_count(picgolf_handle h, int64_t *launches);
  * outside their warp's shared-memory window (slow path) -- a stale-sort indicator.
  * In polynomial mode (PICGOLF_DEPOSIT_POLY) the second number counts mid-stream flushes of a lane's moment set. */
 int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_particles);
+/* How many of those sorts were fused into the particle passes of a step (polynomial mode: the final pass of the step writes
+ * its results straight to their slots in the order of the next step's mid-points, no separate pass over the particles). */
+int picgolf_fused_sorts(picgolf_handle h, int64_t *n);
 /* Which deposit path the handle runs (a picgolf_deposit_mode other than AUTO: what AUTO resolved to). */
 int picgolf_deposit_path(picgolf_handle h, int *mode);
 /* The cudaStream_t the handle enqueues on (for CUDA-event timing by the caller). */

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "picgolf_stage_times": [_vp, C.POINTER(_d * 5), _int],
     "picgolf_launch_count": [_vp, C.POINTER(_i64)],
     "picgolf_sort_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "picgolf_fused_sorts": [_vp, C.POINTER(_i64)],
     "picgolf_deposit_path": [_vp, C.POINTER(C.c_int)],
     "picgolf_get_stream": [_vp, C.POINTER(_vp)],
     "picgolf_comm_unique_id": [_vp],
@@ -389,6 +390,13 @@ class PIC:
         a, b = _i64(), _i64()
         _check(self._lib.picgolf_sort_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    @property
+    def fused_sorts(self) -> int:
+        """How many of the sorts were fused into the particle passes of a step (polynomial mode)."""
+        n = _i64()
+        _check(self._lib.picgolf_fused_sorts(self._h, C.byref(n)))
+        return n.value
 
     @property
     def deposit_path(self) -> int:

@@ -20,13 +20,14 @@ struct Ctrl {
     int final_k;     // fixed point: sweep index whose pass finalises the step (-1: still iterating)
     int sweeps;      // solves executed in the current step
     int rows;        // diagnostics rows recorded so far
-    int pad_;
+    int last_sweeps; // sweeps of the previous step
     long long step;  // steps completed
     double sumE2;    // sum(E.^2) of the latest solve (2D: sum(Ex^2+Ey^2))
     // Simpson-1/3 variant: ||E1||^2 of the step, per-row norm partials of the E2/E3 solve, arrival counter
     double normE1sq;
     double sp_acc[6];
-    unsigned int sp_arrive, pad2_;
+    unsigned int sp_arrive;
+    int fs_pred;     // fused re-sort (pg_kernels_poly.cuh): the passes k with k + 1 >= fs_pred count their bins; min of the last two steps' sweeps
     unsigned long long flush_global; // multi-GPU polynomial mode: sum over the ranks of the flush counters (pg_peer.cuh)
     unsigned long long loop_sweeps;  // sweeps executed inside the device-driven loop since the particles were set (launch accounting)
 };

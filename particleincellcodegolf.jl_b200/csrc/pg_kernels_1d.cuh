@@ -68,6 +68,13 @@ struct FPArgs {
     const double *G;     // polynomial mode: per-cell gather polynomials [N][18] (pg_kernels_poly.cuh)
     fx_t *Mg;            // polynomial mode: fixed-point moment grid [N][17]
     double dN;           // (double)N
+    // polynomial mode, re-sort fused into the passes of this step (pg_kernels_poly.cuh); fs_hist == NULL: off
+    unsigned int *fs_hist, *fs_cursor; // bin counts written by the passes k >= 1, slot cursors scanned from them before a final pass
+    double *fs_vout;                   // the final pass writes v to its slot here (the work buffer is still being read in place)
+    const unsigned int *fs_pid_in;     // original index of every particle (picgolf_get_particles un-sorts with it)
+    unsigned int *fs_pid_out;
+    double fs_scale, fs_hs, fs_magic;  // N * 2^sublg, dt/2 * fs_scale, 1.5 * 2^52 + 2^(sublg-1) - 1/2
+    int fs_sublg;
 };
 
 template <bool FIRST>
@@ -693,6 +700,8 @@ __global__ void __launch_bounds__(256) step_end_kernel(StepEndArgs a)
         }
         c->step += 1;
         c->final_k = -1;
+        c->fs_pred = c->last_sweeps > 0 ? min(c->last_sweeps, c->sweeps) : c->sweeps;
+        c->last_sweeps = c->sweeps;
         c->sweeps = 0;
     }
 }

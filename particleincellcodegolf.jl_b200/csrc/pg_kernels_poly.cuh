@@ -34,6 +34,18 @@
 // order-free, and more accurate than a running fp64 sum.  A set is flushed as two 64-bit words per moment (low 32 bits,
 // high part) so the grid-wide integer sums cannot overflow; mom2rho_kernel puts them together.  The diagnostics sums
 // (sum v^2, sum v) use the same trick with 40 fractional bits.
+//
+// Re-sort fused into the passes (FPArgs.fs_hist != NULL, one step at a time, chosen by the host): the particles are kept in the
+// order of the NEXT step's first mid-point x + v*dt/2, binned by (cell centre, sign v, sub-cell position) -- the position every
+// sweep of that step deposits and gathers at, up to E*dt^2/4, whatever the velocity spread.  A final pass k writes
+// x = X + (v_{k-1}+V)/2*dt and v_k, and x depends on the OUTPUT of pass k-1 only, so the bin of (x, v_{k-1}) is known exactly one
+// pass early: every pass k >= 1 that is not final counts these bins (runs of equal keys in a warp row share one RED);
+// cp_fs_scan_kernel turns the counts into slot cursors if the solve declared sweep k+1 final (and clears them otherwise); the
+// final pass recomputes the same key from the same operands (bit-identical: -fmad=false, the key's own fma is explicit),
+// reserves its slots from the cursors (one atomic per run) and writes x, v and the particle's original index there -- into
+// the other halves of the ping-pong buffers (v: a third buffer, the work buffer is read in place), so the sort adds no pass over the particles:
+// 8 B of ids per particle and scattered instead of streaming stores.  A step that ends at sweep 1 has no counting pass before it
+// and writes to the same buffers unpermuted, so the host's buffer rotation never depends on the sweep count.
 #pragma once
 #include "pg_kernels_1d.cuh"
 #include "gauss_cellpoly.inc"
@@ -357,6 +369,164 @@ __device__ __forceinline__ long long block_sum_ll(long long v, double *scratch)
     return r;
 }
 
+// ---- fused re-sort (see the header) ----------------------------------------------------------------------------------------
+// Bin of the particle that ends the step at x = xn (not yet wrapped) with velocity vb: position xn + vb*dt/2 rounded to
+// 1/2^sublg of a cell (offset by half a cell: bins are centred on the stencil centres, like sort_key_of), wrapped; sign of vb.
+__device__ __forceinline__ int cp_fs_key(const FPArgs &a, double xn, double vb)
+{
+    const double big = fma(vb, a.fs_hs, xn * a.fs_scale) + a.fs_magic;
+    const int I = __double2loint(big);
+    const int c = (I >> a.fs_sublg) & (a.N - 1);
+    return (((c << 1) | (vb >= 0.0 ? 1 : 0)) << a.fs_sublg) | (I & ((1 << a.fs_sublg) - 1));
+}
+
+// Counting costs a pass ~25 % more instructions, so only the passes that may precede the final one count: pass k does if
+// k + 1 >= the smaller sweep count of the last two steps (Ctrl.fs_pred, set by step_end_kernel; 0 after a reset: every pass
+// counts).  A step that ends earlier than that finds no counts and writes unpermuted (one re-sort is skipped, nothing else).
+__device__ __forceinline__ bool cp_fs_counts(int k, const Ctrl *c) { return k >= 1 && k + 1 >= c->fs_pred; }
+
+// Lanes holding equal keys next to each other form a run: its first lane and its length (the whole warp calls this).
+__device__ __forceinline__ void cp_fs_runs(int key, int lane, int &head, int &len)
+{
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned int H = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    head = 31 - __clz(H & (0xffffffffu >> (31 - lane)));
+    const unsigned int above = H & ~((2u << head) - 1u);
+    len = (above ? __ffs(above) - 1 : 32) - head;
+}
+
+// Count the two particles of every lane of a row.  In sorted order a lane's pair shares its bin (the warp votes): then runs are
+// taken over the lanes and count double; otherwise the even and the odd particles of the row form runs of their own.
+__device__ __forceinline__ void cp_fs_count(const FPArgs &a, const double (&xn)[2], const double (&vb)[2], int lane)
+{
+    const int k0 = cp_fs_key(a, xn[0], vb[0]), k1 = cp_fs_key(a, xn[1], vb[1]);
+    const bool pairs = __all_sync(0xffffffffu, k0 == k1);
+    int head, len;
+    cp_fs_runs(k0, lane, head, len);
+    if (lane == head) atomicAdd(&a.fs_hist[k0], (unsigned int)(pairs ? 2 * len : len));
+    if (!pairs) {
+        cp_fs_runs(k1, lane, head, len);
+        if (lane == head) atomicAdd(&a.fs_hist[k1], (unsigned int)len);
+    }
+}
+
+// Slot reservation of a row, in two halves so that the atomics are in flight while the row's gather is evaluated: reserve()
+// right after the row is read, slots() just before the stores.
+struct CPFsRes {
+    unsigned int base[2];
+    int head[2];
+    bool pairs;
+};
+__device__ __forceinline__ void cp_fs_reserve(const FPArgs &a, const double (&xn)[2], const double (&vb)[2], int lane, CPFsRes &r)
+{
+    const int k0 = cp_fs_key(a, xn[0], vb[0]), k1 = cp_fs_key(a, xn[1], vb[1]);
+    r.pairs = __all_sync(0xffffffffu, k0 == k1);
+    int len;
+    cp_fs_runs(k0, lane, r.head[0], len);
+    r.base[0] = r.base[1] = 0u;
+    if (lane == r.head[0]) r.base[0] = atomicAdd(&a.fs_cursor[k0], (unsigned int)(r.pairs ? 2 * len : len));
+    r.head[1] = r.head[0];
+    if (!r.pairs) {
+        cp_fs_runs(k1, lane, r.head[1], len);
+        if (lane == r.head[1]) r.base[1] = atomicAdd(&a.fs_cursor[k1], (unsigned int)len);
+    }
+}
+__device__ __forceinline__ void cp_fs_slots(const CPFsRes &r, int lane, long long (&dst)[2])
+{
+    const unsigned int b0 = __shfl_sync(0xffffffffu, r.base[0], r.head[0]);
+    if (r.pairs) {
+        dst[0] = (long long)b0 + 2 * (lane - r.head[0]);
+        dst[1] = dst[0] + 1;
+    } else {
+        const unsigned int b1 = __shfl_sync(0xffffffffu, r.base[1], r.head[1]);
+        dst[0] = (long long)b0 + (lane - r.head[0]);
+        dst[1] = (long long)b1 + (lane - r.head[1]);
+    }
+}
+
+// Between the solve of sweep k and its pass: sweep k final -> exclusive scan of the bin counts of pass k-1 into the slot cursors;
+// otherwise the counts are stale (pass k counts afresh).  Leaves the counts zero either way.  One block per chunk of 16384 bins
+// (16 per thread: 4 x 128-bit loads); a block publishes its total as (epoch, total) in one 64-bit word and adds up the words
+// of the blocks below it -- at most FS_MAXBLOCKS blocks, all resident, lower blocks never wait for higher ones.  The epoch is
+// unique per (step, sweep) since the last reset (which clears the words).
+struct FsScanArgs {
+    unsigned int *hist, *cursor;
+    unsigned long long *sync; // [FS_MAXBLOCKS]
+    const Ctrl *ctrl;
+    int nbins, k;
+};
+constexpr int FS_CHUNK = 1024 * 16;
+constexpr int FS_MAXBLOCKS = 32;
+
+__global__ void __launch_bounds__(1024) cp_fs_scan_kernel(FsScanArgs a)
+{
+    __shared__ unsigned int wsum[32];
+    __shared__ unsigned int carry_s;
+    const int fk = a.ctrl->final_k, k = sweep_index(a.k, a.ctrl);
+    if (k < 2 || (fk >= 0 && k > fk)) return; // pass 0 does not count: at sweep 1 the counts are still zero
+    if (!cp_fs_counts(k - 1, a.ctrl)) return; // neither did pass k-1 (the step was expected to take more sweeps)
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, b = blockIdx.x;
+    const int nbins = a.nbins, base = b * FS_CHUNK; // nbins: a multiple of 4
+    uint4 c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = base + 16 * t + 4 * i;
+        if (idx < nbins) {
+            if (fk == k) c[i] = *reinterpret_cast<const uint4 *>(a.hist + idx);
+            *reinterpret_cast<uint4 *>(a.hist + idx) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            c[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (fk != k) return;
+    unsigned int s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { // exclusive scan of the thread's 16 counts, in place
+        unsigned int v;
+        v = c[i].x; c[i].x = s; s += v;
+        v = c[i].y; c[i].y = s; s += v;
+        v = c[i].z; c[i].z = s; s += v;
+        v = c[i].w; c[i].w = s; s += v;
+    }
+    unsigned int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned int w = wsum[lane];
+        unsigned int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        wsum[lane] = wi - w;
+        const unsigned long long epoch = (unsigned long long)((unsigned int)(a.ctrl->step * 64 + k) + 1u) << 32;
+        volatile unsigned long long *sync = a.sync;
+        if (lane == 31) sync[b] = epoch | wi; // this block's total
+        unsigned int below = 0;
+        if (lane < b) {
+            unsigned long long w64;
+            do { w64 = sync[lane]; } while ((w64 >> 32) != (epoch >> 32));
+            below = (unsigned int)w64;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0) carry_s = below;
+    }
+    __syncthreads();
+    const unsigned int off = carry_s + wsum[wid] + inc - s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = base + 16 * t + 4 * i;
+        if (idx < nbins) *reinterpret_cast<uint4 *>(a.cursor + idx) = make_uint4(off + c[i].x, off + c[i].y, off + c[i].z, off + c[i].w);
+    }
+}
+
 // The last P % 64 particles of a shard (no full row): one thread each, global-memory gather polynomial and direct
 // moment REDs.  Same arithmetic as the streaming loop below.
 template <bool FIRST, bool DET>
@@ -369,17 +539,23 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
     int idx;
     double centre;
     if (!FIRST) {
+        const bool fs = a.fs_hist != nullptr;
+        long long dst = j; // fused re-sort: slot of this particle's end-of-step state (counted by the previous pass from the same operands)
+        const int k = sweep_index(a.k, a.ctrl);
+        if (fs && final && k >= 2 && cp_fs_counts(k - 1, a.ctrl)) dst = (long long)atomicAdd(&a.fs_cursor[cp_fs_key(a, xj, vj)], 1u);
         const double y = (xj + Xj) * dNs;
         cp_interval(y, idx, centre);
         vj = Vj + cp_slow_gather(a.G, idx, y - centre, Mmask) * a.dt;
-        a.v[j] = vj;
+        if (final && fs) { a.fs_vout[dst] = vj; a.fs_pid_out[dst] = a.fs_pid_in[j]; }
+        else a.v[j] = vj;
         if (final) {
             const double xw = jl_mod1(xj);
-            a.xout[j] = xw;
+            a.xout[dst] = xw;
             vs.add(vj);
             Xj = xw; Vj = vj;
         }
         xj = Xj + (vj + Vj) * hdt;
+        if (fs && !final && cp_fs_counts(k, a.ctrl)) atomicAdd(&a.fs_hist[cp_fs_key(a, xj, vj)], 1u);
     }
     const double y = (xj + Xj) * dNs;
     cp_interval(y, idx, centre);
@@ -406,6 +582,8 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     if (!FIRST && fk >= 0 && k > fk) return;
     const bool final = !FIRST && fk == k;
     const bool v0_is_V = FIRST || k == 1; // sweep 1 starts from v = V: the work buffer is stale until pass 1 writes it
+    const bool fs = !FIRST && a.fs_hist != nullptr; // re-sort fused into this step's passes
+    const bool fs_final = fs && final, fs_scatter = fs_final && k >= 2 && cp_fs_counts(k - 1, a.ctrl), fs_count = fs && !final && cp_fs_counts(k, a.ctrl);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *Gw = smem + warp * (CP_GS * CP_WG); // [CP_WG][CP_GS]
     const int Mmask = a.N * CP_NSUB - 1;
@@ -456,6 +634,12 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
         for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt; // x.=X.+(v.+V)/2*dt
         if (!FIRST) {
+            uint2 ids = make_uint2(0u, 0u);
+            CPFsRes res;
+            if (fs_final) { // fused re-sort: reserve this row's slots early, the atomics return while the gather is evaluated
+                ids = __ldcs(reinterpret_cast<const uint2 *>(a.fs_pid_in) + j2);
+                if (fs_scatter) cp_fs_reserve(a, xj, vj, lane, res);
+            }
             int idx[2];
             double u[2];
             unsigned int slot[2];
@@ -493,7 +677,7 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) vj[q] = Vj[q] + g[q] * a.dt; // v[j]=V[j]+sum(...)*dt
-            __stcs(v2 + j2, make_double2(vj[0], vj[1]));
+            if (!fs_final) __stcs(v2 + j2, make_double2(vj[0], vj[1]));
             if (final) {
                 // end of step: x.=mod.(x,1), diagnostics sums -- and the first pass of the NEXT step fused in
                 // (X.=x; V.=v; x = X + (V+V)/2*dt; deposit at (x+X)/2)
@@ -503,10 +687,22 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
                     vs.add(vj[q]);
                     Vj[q] = vj[q];
                 }
-                __stcs(xo2 + j2, make_double2(Xj[0], Xj[1]));
+                if (fs) { // to the slots of the re-sorted arrays (runs of a row are contiguous)
+                    long long dst[2] = {2 * j2, 2 * j2 + 1};
+                    if (fs_scatter) cp_fs_slots(res, lane, dst);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        a.xout[dst[q]] = Xj[q];
+                        a.fs_vout[dst[q]] = vj[q];
+                        a.fs_pid_out[dst[q]] = q ? ids.y : ids.x;
+                    }
+                } else {
+                    __stcs(xo2 + j2, make_double2(Xj[0], Xj[1]));
+                }
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt;
+            if (fs_count) cp_fs_count(a, xj, vj, lane); // the bins this row is written to if the next sweep is the final one
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) cp_deposit1<DET>((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, a.fx_scale, Mmask, nflush);

@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <vector>
 
 #include "pg_common.cuh"
@@ -220,6 +222,14 @@ struct picgolf_handle_s {
     unsigned long long *Mg = nullptr;
     int nblocks_poly = 1, sublg = 0;
     size_t smem_poly = 0;
+    // re-sort fused into the passes of a step (pg_kernels_poly.cuh): third velocity buffer (the final pass writes v to its slot
+    // there while the work buffer is read in place; the two swap roles afterwards), whether this step is such a step
+    double *vspare = nullptr;
+    unsigned long long *fs_sync = nullptr; // (epoch, total) words of the multi-block bin scan
+    bool fs_enabled = false, fs_now = false;
+    int64_t fused_sorts = 0;
+    int probe_age[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // steps since the last sort at the start of the probed step
+    int grow_hold = 0;
     // adaptive re-sort interval (cfg.sort_every == 0): the slow-path counter is copied to pinned memory at every
     // sort and looked at, without synchronising, at the next one
     bool sort_auto = false;
@@ -238,7 +248,8 @@ struct picgolf_handle_s {
     //   WHILE (not converged) { [moments -> rho] [publish] solve [gather polynomials] particle pass }  ->  step_end
     // The solve kernel sets the WHILE condition (cudaGraphSetConditional), so exactly S sweeps are launched -- no
     // predicated-off launches, no host involvement (for _ in 0:9 ... && break, GaussianFixedPoint.jl:7).
-    cudaGraphExec_t loop_graph[24] = {}; // [buffer set of the streamed ring][sorted kernels][charge-grid parity][X/V parity]
+    // keyed by everything a captured launch bakes in: the particle buffers in their current roles, the charge grid, the kernel family
+    std::map<std::array<uintptr_t, 8>, cudaGraphExec_t> loop_graph;
     cudaStream_t cap_stream = nullptr;
     bool loop_failed = false, loop_off = false;
     // picgolf_step_streamed: a ring of three particle buffer sets (set 0 = the handle's own arrays) and two copy streams,
@@ -418,7 +429,7 @@ static int destroy_impl(picgolf_handle h)
     if (h->down_stream) cudaStreamDestroy(h->down_stream);
     h->timer.destroy();
     for (auto &g : h->step_graph) if (g) cudaGraphExecDestroy(g);
-    for (auto &g : h->loop_graph) if (g) cudaGraphExecDestroy(g);
+    for (auto &g : h->loop_graph) if (g.second) cudaGraphExecDestroy(g.second);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->slow_host) cudaFreeHost(h->slow_host);
     if (h->slow_ev) cudaEventDestroy(h->slow_ev);
@@ -432,7 +443,7 @@ static int destroy_impl(picgolf_handle h)
                     h->rho_last, h->E, h->rho_base[0] ? nullptr : (void *)h->rho_fx, h->rho_base[0], h->rho_base[1],
                     h->tw, h->twy, h->Z, h->E2, h->epartials, h->ctrl, h->partials, h->raw,
                     h->pid[0], h->pid[1], h->bin_count, h->bin_cursor, h->slow_count, h->Gpoly, h->Mg, h->snap[0], h->snap[1], h->snap[2],
-                    h->dft_spec, h->dft_part, h->dft_arrive, h->dft_tw};
+                    h->dft_spec, h->dft_part, h->dft_arrive, h->dft_tw, h->vspare, h->fs_sync};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -575,6 +586,14 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                     const int64_t rows = (h->count + 63) / 64;
                     PG_TRY(occupancy_blocks(fp_pass_poly<false, true>, CP_THREADS, h->smem_poly, h->sms, (rows + 15) / 16 * 32, &h->nblocks_poly));
                     h->nblocks = std::max(h->nblocks, h->nblocks_poly);
+                    const char *fsenv = getenv("PICGOLF_FUSED_SORT"); // 0: every re-sort is the stand-alone counting sort (measurement / fallback)
+                    h->fs_enabled = !(fsenv && atoi(fsenv) == 0) && (((int64_t)N << h->sublg) < ((int64_t)1 << 30));
+                    if ((h->nbins + FS_CHUNK - 1) / FS_CHUNK > FS_MAXBLOCKS || h->nbins % 4) h->fs_enabled = false;
+                    if (h->fs_enabled) {
+                        PG_TRY(dalloc(&h->vspare, n));
+                        PG_TRY(dalloc(&h->fs_sync, FS_MAXBLOCKS));
+                        PG_CUDA(cudaMemset(h->fs_sync, 0, FS_MAXBLOCKS * sizeof(unsigned long long)));
+                    }
                 }
                 PG_TRY(dalloc(&h->pid[0], n)); PG_TRY(dalloc(&h->pid[1], n));
                 PG_TRY(dalloc(&h->bin_count, h->nbins)); PG_TRY(dalloc(&h->bin_cursor, h->nbins));
@@ -759,6 +778,10 @@ static int reset_run_state(picgolf_handle h)
     if (h->is2d) PG_CUDA(cudaMemsetAsync(h->E2, 0, h->ncell * sizeof(double2), h->stream));
     else PG_CUDA(cudaMemsetAsync(h->E, 0, (size_t)h->grid_rows * h->ncell * sizeof(double), h->stream));
     if (h->Mg) PG_CUDA(cudaMemsetAsync(h->Mg, 0, (size_t)2 * CP_NC * CP_NSUB * h->ncell * sizeof(unsigned long long), h->stream));
+    if (h->fs_sync) { // the epochs of the bin scan start over with the step counter; the bin counts are zero between steps
+        PG_CUDA(cudaMemsetAsync(h->fs_sync, 0, FS_MAXBLOCKS * sizeof(unsigned long long), h->stream));
+        PG_CUDA(cudaMemsetAsync(h->bin_count, 0, (size_t)h->nbins * sizeof(unsigned int), h->stream));
+    }
     PG_CUDA(cudaStreamSynchronize(h->stream));
     h->par = 0; h->steps = 0; h->have_particles = true;
     h->pid_valid = false; h->pidpar = 0; h->since_sort = 0; h->have_deposit = false;
@@ -1061,7 +1084,23 @@ static void probe_poly_flushes(picgolf_handle h)
         const int idx = (int)((s - POLY_RUNAHEAD) & 7);
         if (h->probe_step[idx] == s - POLY_RUNAHEAD) {
             const unsigned long long now = h->slow_host[idx];
-            if (h->probe_have_prev) {
+            if (h->probe_have_prev && h->fs_enabled && h->sset_n == 0) {
+                // the re-sort is fused into a step's passes and nearly free (picgolf: step_fixedpoint), so the interval may go down to
+                // every step: never let the order get as old again as it was in a step that flushed a lot; grow (by half, up to
+                // 64) only when the oldest order the interval allows was still quiet, and not for 32 steps after a cut
+                const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during step s - RUNAHEAD - 1
+                const int age = h->probe_age[(s - POLY_RUNAHEAD - 1) & 7];
+                const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
+                double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
+                if (h->det) expect += std::min(1.0, (double)CP_NSUB / (double)(1 << h->sublg));
+                h->poly_quiet = frac < 5e-5 + 1.5 * expect;
+                if (frac > 1e-3 + 3.0 * expect) {
+                    if (age < h->sort_every) { h->sort_every = std::max(1, age); h->grow_hold = 32; }
+                } else if (h->poly_quiet && age + 1 >= h->sort_every && h->grow_hold == 0) {
+                    h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
+                }
+                if (h->grow_hold > 0) --h->grow_hold;
+            } else if (h->probe_have_prev) {
                 const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during one step
                 // expected in sorted order: the warp that streams a (cell, sign v) group walks through its CP_NSUB polynomial
                 // intervals, and each of its 32 lanes flushes once per interval (plus once per warp range); ~4 passes per step
@@ -1085,13 +1124,14 @@ static void probe_poly_flushes(picgolf_handle h)
     const void *src = h->comm ? (const void *)&h->ctrl->flush_global : (const void *)h->slow_count;
     cudaMemcpyAsync(&h->slow_host[s & 7], src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
     h->probe_step[s & 7] = s;
+    h->probe_age[s & 7] = (int)std::min<int64_t>(h->since_sort, 1 << 20);
 }
 
 // Counting sort of the step-start state (xb[par], vb[par]) by cell into the other ping-pong buffers.
 static int sort_particles_1d(picgolf_handle h)
 {
     if (!h->poly) adapt_sort_interval(h);
-    else if (h->sort_auto && !h->force_sort && h->poly_quiet) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
+    else if (h->sort_auto && !h->force_sort && h->poly_quiet && !(h->fs_enabled && h->sset_n == 0)) h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
     h->force_sort = false;
     const int sp = h->timer.begin(ST_SORT, h->stream);
     SortArgs a;
@@ -1129,6 +1169,13 @@ static FPArgs fp_args(picgolf_handle h)
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.k = 0;
     a.slow_count = h->slow_count; a.K = h->K; a.G = h->Gpoly; a.Mg = h->Mg;
     a.dN = (double)c.N * (CP_NSUB / 2); // polynomial passes: y = (x+X)*dN = c*N*CP_NSUB
+    a.fs_hist = nullptr; a.fs_cursor = nullptr; a.fs_vout = nullptr; a.fs_pid_in = nullptr; a.fs_pid_out = nullptr;
+    a.fs_scale = (double)((int64_t)c.N << h->sublg); a.fs_hs = c.dt / 2 * a.fs_scale;
+    a.fs_magic = CP_MAGIC + (double)(1 << h->sublg) / 2 - 0.5; a.fs_sublg = h->sublg;
+    if (h->fs_now) {
+        a.fs_hist = h->bin_count; a.fs_cursor = h->bin_cursor; a.fs_vout = h->vspare;
+        a.fs_pid_in = h->pid[h->pidpar]; a.fs_pid_out = h->pid[1 - h->pidpar];
+    }
     return a;
 }
 
@@ -1175,6 +1222,14 @@ static int enqueue_sweep(picgolf_handle h, int k, cudaGraphConditionalHandle con
         g.E = h->E; g.G = h->Gpoly; g.Mg = h->Mg; g.ctrl = h->ctrl; g.N = N; g.k = k; g.det = h->det ? 1 : 0;
         const int sp = h->timer.begin(ST_SOLVE, h->stream);
         gpoly_kernel<<<dim3((N + 127) / 128, CP_NSUB), 128, 0, h->stream>>>(g);
+        h->timer.end(sp, h->stream);
+        h->launches++;
+    }
+    if (poly && h->fs_now) { // fused re-sort: the bin counts of the previous pass -> slot cursors if this sweep is final, else cleared
+        FsScanArgs f;
+        f.hist = h->bin_count; f.cursor = h->bin_cursor; f.sync = h->fs_sync; f.ctrl = h->ctrl; f.nbins = h->nbins; f.k = k;
+        const int sp = h->timer.begin(ST_SORT, h->stream);
+        cp_fs_scan_kernel<<<(h->nbins + FS_CHUNK - 1) / FS_CHUNK, 1024, 0, h->stream>>>(f);
         h->timer.end(sp, h->stream);
         h->launches++;
     }
@@ -1331,14 +1386,21 @@ static int step_fixedpoint(picgolf_handle h)
     // e2e arm) then never pays for a from-scratch sort + unsort that a single step cannot amortise.
     h->use_sorted_now = h->sorted && (h->pid_valid || h->steps > 0);
     if (h->use_sorted_now && h->poly && h->pid_valid) probe_poly_flushes(h);
-    if (h->use_sorted_now && (!h->pid_valid || h->since_sort >= h->sort_every || h->force_sort)) PG_TRY(sort_particles_1d(h));
+    // polynomial passes on arrays that have been sorted once: the re-sort rides along with the passes of the LAST step the
+    // current order is allowed to serve (pg_kernels_poly.cuh) -- the stand-alone sort runs before the first step of a new order
+    const bool can_fuse = h->use_sorted_now && h->poly && h->pid_valid && h->fs_enabled && h->sset_n == 0 && !h->simpson;
+    const bool due = h->use_sorted_now && (!h->pid_valid || h->force_sort || h->since_sort >= h->sort_every - (can_fuse ? 1 : 0));
+    h->fs_now = due && can_fuse;
+    if (due && !h->fs_now) PG_TRY(sort_particles_1d(h));
     if (h->simpson) return step_simpson(h);
     h->pass_blocks = poly_now(h) ? h->nblocks_poly : h->use_sorted_now ? h->nblocks_sorted : h->nblocks;
     if (!h->have_deposit) PG_TRY(enqueue_first_pass(h));
     const bool loop = !h->loop_off && !h->loop_failed && !h->timer.enabled && (!h->comm || h->peer_ok);
     bool done = false;
     if (loop) {
-        const int slot = h->par + 2 * (h->rho_fx == h->rho_base[1] ? 1 : 0) + 4 * (h->use_sorted_now ? 1 : 0) + 8 * h->sset_cur;
+        const std::array<uintptr_t, 8> slot = {(uintptr_t)h->xb[h->par], (uintptr_t)h->vb[h->par], (uintptr_t)h->vb[1 - h->par], (uintptr_t)h->xb[1 - h->par],
+                                               h->fs_now ? (uintptr_t)h->vspare : 0, (uintptr_t)h->rho_fx,
+                                               (uintptr_t)((h->use_sorted_now ? 1 : 0) + (h->fs_now ? 2 + 4 * h->pidpar : 0)), 0};
         cudaGraphExec_t &exec = h->loop_graph[slot];
         if (!exec && build_loop_graph(h, &exec) != 0) { // no conditional nodes on this driver: fixed schedule for good
             cudaGetLastError();
@@ -1359,6 +1421,12 @@ static int step_fixedpoint(picgolf_handle h)
         }
     }
     if (!done) PG_TRY(enqueue_fixed_schedule(h));
+    if (h->fs_now) { // the final pass wrote x, v and the ids to their slots: v sits in the third buffer, the work buffer becomes the spare
+        std::swap(h->vb[1 - h->par], h->vspare);
+        h->pidpar ^= 1; h->sorts++; h->fused_sorts++; h->force_sort = false;
+        h->since_sort = -1;
+        h->fs_now = false;
+    }
     h->par ^= 1;
     h->since_sort++;
     // the final pass deposited the next step's first rho (atomic / sorted kernels: into rho_next; polynomial: the moment grid)
@@ -1863,6 +1931,13 @@ PG_API int picgolf_sort_stats(picgolf_handle h, int64_t *sorts, int64_t *slow_pa
         }
         *slow_particles = (int64_t)n;
     }
+    return 0;
+}
+
+PG_API int picgolf_fused_sorts(picgolf_handle h, int64_t *n)
+{
+    if (!h || !n) return fail(PICGOLF_ERR_ARG, "null argument");
+    *n = h->fused_sorts;
     return 0;
 }
 

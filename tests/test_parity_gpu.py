@@ -601,7 +601,8 @@ def test_poly_mode_c2_golden(pg, oracle):
     assert relnorm(D[:, :3], g["D"][:, :3]) < TOL
     x, v = sim.particles()
     assert relnorm(x, g["x"]) < TOL and relnorm(v, g["v"]) < TOL
-    assert sim.sort_stats()[0] == 5
+    # the stand-alone sort before step 1 (0-based), then fused into the passes of steps 3, 6, 9, 12, 15: an order serves three steps
+    assert sim.sort_stats()[0] == 6 and sim.fused_sorts == 5
 
 
 @pytest.mark.parametrize("start", ["uniform", "quiet"])
@@ -650,12 +651,68 @@ def test_poly_mode_matches_atomic_mode(pg, oracle, start, N, P):
         assert np.array_equal(swa, sws)
     assert relnorm(Ds[:, 1:3], Da[:, 1:3]) < TOL
     sorts, flushes = s.sort_stats()
-    assert sorts == 3  # before steps 1, 5, 9 (0-based)
+    assert sorts == 3 and s.fused_sorts == 2  # before step 1 (0-based), then inside the passes of steps 4 and 8
     if P // N >= 4096:
         # (cell, sign v) bins drift as a whole: each lane of the warp that streams a bin flushes once per polynomial interval
         # (8 per cell and beam: 32 * 16 * N / P = 0.03 flushes per particle and pass here, plus one per warp range);
         # lanes alternating between intervals would flush on a large share of their particles
         assert flushes / (P * float(sws[1:].sum())) < 0.1
+
+
+@pytest.mark.parametrize("det", [0, 1])
+@pytest.mark.parametrize("max_sweeps", [10, 2, 1])
+def test_fused_resort_matches_standalone_sort(pg, monkeypatch, max_sweeps, det):
+    """The re-sort fused into the passes of a step (pg_kernels_poly.cuh: bins counted by pass k-1, slots reserved and written by
+    the final pass k) against the same run with the stand-alone counting sort (PICGOLF_FUSED_SORT=0) and against the any-order
+    kernels: warm beams, an order that serves ONE step (sort_every=1), ragged tail, and the short steps -- max_sweeps = 2 (the
+    counting pass is pass 1, which starts from v = V) and max_sweeps = 1 (no counting pass: the final pass writes unpermuted to
+    the same buffers).  Particles come back in the caller's order through the ids the final pass carries along."""
+    N, P, steps = 256, (1 << 22) + 77, 9
+    rng = np.random.default_rng(31)
+    x0 = rng.random(P)
+    v0 = np.where(np.arange(P) >= P // 2, 1.0, -1.0) + 0.3 * rng.standard_normal(P)
+    runs = []
+    for fused, mode in ((1, pg.DEPOSIT_POLY), (0, pg.DEPOSIT_POLY), (0, pg.DEPOSIT_ATOMIC)):
+        monkeypatch.setenv("PICGOLF_FUSED_SORT", str(fused))
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, deposit_mode=mode, sort_every=1, max_sweeps=max_sweeps,
+                                      deterministic=det if mode == pg.DEPOSIT_POLY else 0)
+        sim.set_particles(x0, v0)
+        sim.step(steps)
+        runs.append((sim, sim.particles(), sim.fields(), sim.diagnostics()))
+    (f, pf, ff, df), (s, ps, fs_, ds), (a, pa, fa, da) = runs
+    assert f.deposit_path == pg.DEPOSIT_POLY and f.fused_sorts == steps - 2 and s.fused_sorts == 0  # step 0: any-order kernel, step 1: stand-alone sort
+    assert f.sort_stats()[0] == steps - 1 and s.sort_stats()[0] == steps - 1
+    for got, ref in ((pf, ps), (pf, pa)):
+        for g, r in zip(got, ref):
+            assert relnorm(g, r) < TOL
+    for got, ref in ((ff, fs_), (ff, fa)):  # fields of a warm plasma after 9 steps of differently ordered sums (3e-12 measured)
+        for g, r in zip(got, ref):
+            assert relnorm(g, r) < 2e-11
+    assert np.array_equal(df[1], da[1]) and np.array_equal(ds[1], da[1])
+    assert relnorm(df[0][:steps, 1:3], da[0][:steps, 1:3]) < TOL
+    if max_sweeps == 1:
+        assert set(df[1][:steps]) == {1}
+    # the fused order is the order of the next step's mid-points: a lane changes interval when the stream does, not because of the spread in v
+    if not det and max_sweeps == 10:
+        assert f.sort_stats()[1] < 0.1 * P * float(df[1][:steps].sum())
+    for sim in (f, s, a):
+        sim.close()
+
+
+def test_fused_resort_reproducible_in_deterministic_mode(pg):
+    """deterministic = 1 with a fused re-sort every step: the order inside a bin changes from run to run (atomic slot
+    reservation), the integer moment sums do not care -- bit-identical rho, E, x, v, D."""
+    N, P = 256, 1 << 22
+    out = []
+    for _ in range(2):
+        sim = pg.gaussian_fixed_point(N=N, P=P, T=16, W=400.0, deposit_mode=pg.DEPOSIT_POLY, sort_every=1, deterministic=1)
+        sim.init_synthetic(seed=5, vth=0.2)
+        sim.step(8)
+        assert sim.fused_sorts == 6
+        out.append(sim.particles() + sim.fields() + (sim.diagnostics()[0][:8],))
+        sim.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
 
 
 def test_poly_mode_warm_beams_force_resort(pg):
