@@ -13,12 +13,10 @@
 // form (degree 16) that round 1 shipped; that moves the pass from the FP64 pipe to HBM.
 //
 // fp_pass_poly: every warp streams ONE contiguous range of the (cell, sign v, sub-cell position)-sorted particle arrays
-// with 128-bit loads (2 particles per lane and row).  Deposit: each lane keeps ONE moment set in registers, that of the
-// interval it is currently in, and keeps adding to it while |u| <= 1 relative to that interval's centre (the polynomials
-// are fitted that far: hysteresis of half an interval on either side), so a sorted bin that straddles an interval edge
-// never makes a lane alternate; the set is flushed with 11 integer REDs into the fixed-point moment grid Mg only when a
-// particle lies a whole interval away -- ~20 times per pass in sorted order -- so there are no shared-memory atomics and
-// no per-particle atomics at all.
+// with 128-bit loads (2 particles per lane and row).  Deposit: the warp shares ONE current interval; each lane sums u^n of its
+// particles in registers, the 32 lane sets are added up and flushed with 11 integer REDs into the fixed-point moment grid Mg
+// when the stream has moved on to the next interval (cp_deposit_row) -- no shared-memory atomics and no per-particle atomics
+// at all.  (Deterministic mode: one set per lane with a spare, see below.)
 // Gather: the G rows of the CP_WG intervals around the warp's position are staged in shared memory; a particle reads the
 // 11 coefficients of its own interval (lanes in the same interval broadcast).  Any particle order is handled correctly
 // (window reloads, global-memory gather, early flushes); order only decides the speed, and the flushes are counted so
@@ -61,6 +59,8 @@ constexpr int CP_NM = CP_NC - 1; // moments kept as doubles (n = 1..10); n = 0 i
 constexpr int CP_WG = 16;        // intervals in a warp's gather window (two cells)
 constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned
 constexpr double CP_UMAX = 1.0;  // a lane stays with its interval while |u| <= CP_UMAX (the range the polynomials are fitted on)
+constexpr double CP_UMOVE = 0.75; // default mode: the warp moves to the next interval when most of a row has |u| > CP_UMOVE (after the move those
+                                  // particles sit at |u| < 1/4 and the rest of the row within 3/4 of the new centre: the warp never moves straight back)
 constexpr double CP_MAGIC = 6755399441055744.0; // 1.5 * 2^52: y + CP_MAGIC rounds y to the nearest integer (ties to even), |y| < 2^51
 
 #ifndef PG_CP_THREADS
@@ -229,6 +229,10 @@ __device__ __forceinline__ void cp_flush(CPSet<DET> &s, fx_t *Mg, double fx_scal
             atomicAdd(p, to_fx((double)s.cnt, fx_scale));
 #pragma unroll
             for (int n = 0; n < CP_NM; ++n) atomicAdd(p + 1 + n, to_fx((double)s.m[n], fx_scale));
+#ifdef PG_EXP_DOUBLEFLUSH // measurement builds only: every flush issues its REDs twice (the second time adding zero) -- what the REDs cost
+#pragma unroll
+            for (int n = 0; n < CP_NC; ++n) atomicAdd(p + n, (fx_t)(s.cnt >> 30));
+#endif
         }
         s.clear();
     }
@@ -301,6 +305,85 @@ __device__ __forceinline__ void cp_deposit1(double y, CPSet<DET> &P, CPSpare &sp
             P.m[n] += pa; P.m[n + 1] += pb;
         }
         if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
+    }
+}
+
+// ---- default (not deterministic) deposit: the WARP shares one interval --------------------------------------------------
+// Every lane sums u^n of its particles relative to the warp's current interval (centre, idx: warp-uniform) in registers.  When
+// most of a row lies more than 3/4 of an interval from the centre the stream has moved on: the 32 lane sets are added up through
+// shared memory (lane n sums moment n) and go to the moment grid with ONE set of 11 REDs, and the warp re-centres on the
+// interval of the first such particle.  With every lane flushing for itself (the form this replaces) the same event cost
+// 32 x 11 REDs to the same 11 addresses -- 0.35 ms of a 5 ms step at 2^28 particles (measured by issuing them twice).
+// The 3/4 is hysteresis: a bin that straddles an interval edge does not make the warp alternate.  A particle
+// more than a whole interval from the centre (|u| > 1: outside the range the polynomials are fitted on -- disordered input)
+// is deposited on its own (11 REDs).
+__device__ __noinline__ void cp_deposit_single(double y, fx_t *Mg, double fx_scale, int Mmask)
+{
+    int idx;
+    double centre;
+    cp_interval(y, idx, centre);
+    const double u = y - centre, u2 = u * u;
+    fx_t *p = Mg + (size_t)(idx & Mmask) * CP_NC;
+    atomicAdd(p, to_fx(1.0, fx_scale));
+    double pa = u, pb = u2;
+#pragma unroll
+    for (int n = 0; n < CP_NM; n += 2) {
+        atomicAdd(p + 1 + n, to_fx(pa, fx_scale));
+        atomicAdd(p + 2 + n, to_fx(pb, fx_scale));
+        pa *= u2; pb *= u2;
+    }
+}
+
+// colw: the warp's [CP_NM][32] slice of the lane-column area (row stride cstride doubles).
+__device__ __forceinline__ void cp_flush_warp(CPSet<false> &s, double *colw, int lane, int cstride, fx_t *Mg, double fx_scale, int Mmask)
+{
+    const int total = __reduce_add_sync(0xffffffffu, s.cnt);
+    if (total) {
+#pragma unroll
+        for (int n = 0; n < CP_NM; ++n) colw[n * cstride + lane] = s.m[n];
+        __syncwarp();
+        fx_t *p = Mg + (size_t)(s.idx & Mmask) * CP_NC;
+        if (lane < CP_NM) {
+            const double *r = colw + lane * cstride;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; i += 2) { t0 += r[(i + lane) & 31]; t1 += r[(i + 1 + lane) & 31]; } // rotated: no bank conflicts
+            atomicAdd(p + 1 + lane, to_fx(t0 + t1, fx_scale));
+        } else if (lane == CP_NM) {
+            atomicAdd(p, to_fx((double)total, fx_scale));
+        }
+        __syncwarp();
+        s.clear();
+    }
+}
+
+__device__ __forceinline__ void cp_deposit_row(const double (&y)[2], CPSet<false> &P, double *colw, int lane, int cstride, fx_t *Mg,
+                                               double fx_scale, int Mmask, unsigned int &nflush)
+{
+    double u[2] = {y[0] - P.centre, y[1] - P.centre};
+    const unsigned int f0 = __ballot_sync(0xffffffffu, !(fabs(u[0]) <= CP_UMOVE)), f1 = __ballot_sync(0xffffffffu, !(fabs(u[1]) <= CP_UMOVE));
+    if (__popc(f0) + __popc(f1) > 32) { // most of the row has left the interval (or there is none yet)
+        nflush += P.cnt > 0;
+        cp_flush_warp(P, colw, lane, cstride, Mg, fx_scale, Mmask);
+        const double yr = __shfl_sync(0xffffffffu, f0 ? y[0] : y[1], __ffs(f0 ? f0 : f1) - 1);
+        cp_interval(yr, P.idx, P.centre);
+        u[0] = y[0] - P.centre; u[1] = y[1] - P.centre;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (fabs(u[q]) <= CP_UMAX) {
+            P.cnt++;
+            const double u2 = u[q] * u[q];
+            double pa = u[q], pb = u2;
+#pragma unroll
+            for (int n = 0; n < CP_NM; n += 2) {
+                P.m[n] += pa; P.m[n + 1] += pb;
+                if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
+            }
+        } else {
+            ++nflush;
+            cp_deposit_single(y[q], Mg, fx_scale, Mmask);
+        }
     }
 }
 
@@ -560,6 +643,10 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
     const double y = (xj + Xj) * dNs;
     cp_interval(y, idx, centre);
     const double u = y - centre;
+    if constexpr (!DET) {
+        cp_deposit_single(y, a.Mg, a.fx_scale, Mmask);
+        return;
+    }
     CPSet<DET> one; // the streaming loop's own arithmetic (same powers, same rounding) for a set of one particle
     one.clear(); one.centre = 1e300;
     unsigned int nf = 0;
@@ -637,7 +724,9 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             uint2 ids = make_uint2(0u, 0u);
             CPFsRes res;
             if (fs_final) { // fused re-sort: reserve this row's slots early, the atomics return while the gather is evaluated
+#ifndef PG_EXP_NOPID
                 ids = __ldcs(reinterpret_cast<const uint2 *>(a.fs_pid_in) + j2);
+#endif
                 if (fs_scatter) cp_fs_reserve(a, xj, vj, lane, res);
             }
             int idx[2];
@@ -690,11 +779,16 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
                 if (fs) { // to the slots of the re-sorted arrays (runs of a row are contiguous)
                     long long dst[2] = {2 * j2, 2 * j2 + 1};
                     if (fs_scatter) cp_fs_slots(res, lane, dst);
+#ifdef PG_EXP_NOSCATTER // measurement builds only: slots reserved, results written in stream order -- what the scattered stores cost
+                    if (dst[0] != -1) { dst[0] = 2 * j2; dst[1] = 2 * j2 + 1; }
+#endif
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         a.xout[dst[q]] = Xj[q];
                         a.fs_vout[dst[q]] = vj[q];
+#ifndef PG_EXP_NOPID // measurement builds only (particles come back in sorted order): what carrying the ids costs
                         a.fs_pid_out[dst[q]] = q ? ids.y : ids.x;
+#endif
                     }
                 } else {
                     __stcs(xo2 + j2, make_double2(Xj[0], Xj[1]));
@@ -704,11 +798,17 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             for (int q = 0; q < 2; ++q) xj[q] = Xj[q] + (vj[q] + Vj[q]) * hdt;
             if (fs_count) cp_fs_count(a, xj, vj, lane); // the bins this row is written to if the next sweep is the final one
         }
+        if constexpr (DET) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) cp_deposit1<DET>((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, a.fx_scale, Mmask, nflush);
+            for (int q = 0; q < 2; ++q) cp_deposit1<DET>((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, a.fx_scale, Mmask, nflush);
+        } else {
+            const double yd[2] = {(xj[0] + Xj[0]) * dNs, (xj[1] + Xj[1]) * dNs};
+            cp_deposit_row(yd, A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask, nflush);
+        }
     }
     cp_async_wait<0>();
-    cp_flush<DET>(A, a.Mg, a.fx_scale, Mmask);
+    if constexpr (DET) cp_flush<DET>(A, a.Mg, a.fx_scale, Mmask);
+    else cp_flush_warp(A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask);
     if (DET) cp_flush_spare(spare, col, cstride, a.Mg, Mmask);
     // ragged tail of the shard: fewer than 64 particles, first warp of the last block
     if (blockIdx.x == gridDim.x - 1 && warp == 0) {

@@ -972,9 +972,9 @@ def test_deterministic_fast_path_bit_reproducible(pg, N, P):
         sim = pg.gaussian_fixed_point(N=N, P=P, T=8, W=400.0, deterministic=det, sort_every=3)
         assert sim.deposit_path == pg.DEPOSIT_POLY
         sim.set_particles(xs, vs)
-        sim.step(7)  # step 1 any-order, sorts before steps 2 and 5, five polynomial steps
+        sim.step(7)  # step 1 any-order, stand-alone sort before step 2, re-sorts fused into the passes of steps 4 and 7, six polynomial steps
         res.append(sim.fields() + sim.particles() + (sim.raw_diagnostics(), sim.diagnostics()[1]))
-        assert sim.sort_stats()[0] == 2
+        assert sim.sort_stats()[0] == 3 and sim.fused_sorts == 2
         sim.close()
     a, b, c, d = res
     for u, w in zip(a, b):

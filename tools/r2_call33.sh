@@ -1,0 +1,13 @@
+set -x
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r2_33_gpu_tests.txt 2>&1; tail -4 gpurun_out/r2_33_gpu_tests.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_33_smoke.txt 2>&1; tail -3 gpurun_out/r2_33_smoke.txt
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_33_bench.json 2> gpurun_out/r2_33_bench.err; tail -3 gpurun_out/r2_33_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_33_bench.json').read().strip().splitlines()[-1])
+print('ms/step', d['ms_per_step'], 'launches', d['gpu_launches'], 'roof', d['roofline']['frac'], d['roofline']['launch_ms'], d['hbm_roofline_frac_step'], d['roofline']['stage_ms_per_step'])
+print('e2e', d['e2e']['ms_per_step'], d['e2e']['serial_set_step_get']['ms_per_step'])
+print('warm', {k:(v['ms_per_step'], v['resorts'], v['resorts_fused_into_the_passes']) for k,v in d['warm_regime'].items() if isinstance(v,dict)})
+print('others', {k:(v['ms_per_step'], v['hbm_roofline_frac_step']) for k,v in d['other_workloads'].items()})
+print('clocks', d['clocks'])
+PY
