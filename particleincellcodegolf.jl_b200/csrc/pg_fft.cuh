@@ -183,6 +183,112 @@ __device__ __forceinline__ void fft_smem4(double *re, double *im, int n, int bat
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-blocked Stockham FFT for the 1D solve (N >= 512, a power of two, N/8 threads): every thread holds 8 points, a pass is
+// one radix-8 butterfly per thread (a closing radix-4 / radix-2 pass when log2 N is not a multiple of 3), so N = 4096 takes 4
+// passes with 2 barriers each instead of the 6 radix-2^2 passes of fft_smem4, with 128-bit shared-memory accesses (interleaved
+// re/im) and natural-order output (no bit reversal between the two transforms of a solve).  Reads of a pass are contiguous
+// (x[i + r N/R]); its writes go to ((i - k) R + k) + r p, k = i mod p -- stride R on the first pass, which the padding
+// (one 16-byte slot after every 8 points) spreads over all banks.  N = 8192: 16 points (two butterflies) per thread, so that the block
+// stays at 512 threads and the butterflies in registers.  Forward transform only: the solve's inverse is
+// real(ifft(xi)) = real(fft(conj xi)) / N.  tw[m] = exp(-2 pi i m / N), m < N/2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int st_phys(int i) { return i + (i >> 3); }
+__host__ __device__ inline size_t st_points(int N) { return (size_t)N + (size_t)(N >> 3); }
+
+__device__ __forceinline__ double2 st_cmul(double2 a, double2 w) { return make_double2(fma(a.x, w.x, -(a.y * w.y)), fma(a.x, w.y, a.y * w.x)); }
+__device__ __forceinline__ double2 st_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 st_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 st_mulmi(double2 a) { return make_double2(a.y, -a.x); } // a * (-i)
+__device__ __forceinline__ double2 st_tw(const double2 *__restrict__ tw, int m, int N)
+{
+    const int h = N >> 1;
+    double2 w = __ldg(&tw[m & (h - 1)]);
+    if (m & h) { w.x = -w.x; w.y = -w.y; }
+    return w;
+}
+
+// In-register DFT of R points, natural order in and out (e^{-i theta} convention).
+template <int R>
+__device__ __forceinline__ void st_dft(double2 (&u)[R])
+{
+    if constexpr (R == 2) {
+        const double2 a = st_add(u[0], u[1]), b = st_sub(u[0], u[1]);
+        u[0] = a; u[1] = b;
+    } else if constexpr (R == 4) {
+        const double2 p0 = st_add(u[0], u[2]), p1 = st_add(u[1], u[3]);
+        const double2 q0 = st_sub(u[0], u[2]), q1 = st_mulmi(st_sub(u[1], u[3]));
+        u[0] = st_add(p0, p1); u[2] = st_sub(p0, p1);
+        u[1] = st_add(q0, q1); u[3] = st_sub(q0, q1);
+    } else {
+        constexpr double H = 0.70710678118654752440; // 1/sqrt(2)
+        double2 s[4], t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[j] = st_add(u[j], u[j + 4]); t[j] = st_sub(u[j], u[j + 4]); }
+        // t_j *= w8^j, w8 = (1 - i)/sqrt(2)
+        t[1] = make_double2((t[1].x + t[1].y) * H, (t[1].y - t[1].x) * H);
+        t[2] = st_mulmi(t[2]);
+        t[3] = make_double2((t[3].y - t[3].x) * H, -(t[3].x + t[3].y) * H);
+        st_dft<4>(s);
+        st_dft<4>(t);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { u[2 * m] = s[m]; u[2 * m + 1] = t[m]; }
+    }
+}
+
+// One pass: p = product of the radices of the passes before it.  blockDim.x == N/PT.
+template <int R, int PT>
+__device__ __forceinline__ void st_pass(double2 *buf, int N, int p, const double2 *__restrict__ tw)
+{
+    constexpr int M = PT / R; // butterflies per thread
+    const int T = N / R;
+    double2 u[M][R];
+    int jb[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int i = threadIdx.x + m * blockDim.x;
+        const int k = i & (p - 1);
+        jb[m] = (i - k) * R + k;
+        double2 w[R];
+        if (p > 1) { // the table reads go first: they are the long-latency ones.  w^1, w^2, w^4 from the table, the others one product away
+            const int tws = N / (p * R);
+#pragma unroll
+            for (int r = 1; r < R; r <<= 1) w[r] = st_tw(tw, k * r * tws, N);
+            if constexpr (R >= 4) w[3] = st_cmul(w[1], w[2]);
+            if constexpr (R == 8) { w[5] = st_cmul(w[1], w[4]); w[6] = st_cmul(w[2], w[4]); w[7] = st_cmul(w[3], w[4]); }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[m][r] = buf[st_phys(i + r * T)];
+        if (p > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[m][r] = st_cmul(u[m][r], w[r]);
+        }
+        st_dft<R>(u[m]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[st_phys(jb[m] + r * p)] = u[m][r];
+    __syncthreads();
+}
+
+template <int PT>
+__device__ __forceinline__ void fft_stockham8(double2 *buf, int N, int lg, const double2 *__restrict__ tw)
+{
+    int p = 1;
+    for (int done = 0; done + 3 <= lg; done += 3, p <<= 3) st_pass<8, PT>(buf, N, p, tw);
+    if (lg % 3 == 2) st_pass<4, PT>(buf, N, p, tw);
+    else if (lg % 3 == 1) st_pass<2, PT>(buf, N, p, tw);
+}
+
+// Launch shape of solve1d_kernel: N >= 512 runs the register-blocked transform (N/8 threads, padded interleaved points),
+// smaller grids the radix-2^2 one (N/2 threads, separate planes).  32 doubles of reduction scratch follow the points.
+__host__ __device__ inline bool solve1d_stockham(int N) { return N >= 512 && N <= 8192; }
+__host__ __device__ inline int solve1d_points(int N) { return N > 4096 ? 16 : 8; } // grid points per thread of the register-blocked transform
+__host__ __device__ inline int solve1d_threads(int N) { return solve1d_stockham(N) ? N / solve1d_points(N) : (N / 2 < 32 ? 32 : (N / 2 > 1024 ? 1024 : N / 2)); }
+__host__ __device__ inline size_t solve1d_smem_bytes(int N) { return (solve1d_stockham(N) ? st_points(N) * 16 : (size_t)N * 16) + 32 * 8; }
+
 __device__ __forceinline__ int bitrev(int v, int lg) { return (int)(__brev((unsigned)v) >> (32 - lg)); }
 
 struct Solve1DArgs {
@@ -209,10 +315,12 @@ __device__ long long g_solve_prof[8];
 #define PG_PROF(i) do { } while (0)
 #endif
 
-// One block.  Dynamic shared memory: 2*N doubles + 32.
+__device__ __forceinline__ void solve1d_decide(const Solve1DArgs &a, double d2, double f2, double e2, double *scratch, int k, bool peer_failed);
+
+// One block.  Dynamic shared memory: 2*N doubles + 32.  (N >= 512: solve1d_stock_kernel below.)
 __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double *re = smem, *im = smem + a.N, *scratch = smem + 2 * a.N;
     if (a.fixedpoint && a.ctrl->final_k >= 0) { // step already converged: predicated no-op
         if (a.cond && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);
@@ -270,6 +378,12 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
         d2 = fma(d, d, d2); f2 = fma(f, f, f2); e2 = fma(e, e, e2);
     }
     PG_PROF(5);
+    solve1d_decide(a, d2, f2, e2, scratch, k, peer_failed);
+}
+
+// Norms of the solve and the convergence decision of the fixed point (thread 0 writes Ctrl and steers the WHILE node).
+__device__ __forceinline__ void solve1d_decide(const Solve1DArgs &a, double d2, double f2, double e2, double *scratch, int k, bool peer_failed)
+{
     d2 = block_sum(d2, scratch);
     f2 = block_sum(f2, scratch);
     e2 = block_sum(e2, scratch);
@@ -289,6 +403,99 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
             if (a.cond) cudaGraphSetConditional(a.cond, last ? 0u : 1u); // the rest of this iteration still runs (pass k finalises)
         }
     }
+}
+
+// The solve for N >= 512 (solve1d_stockham): the same steps as solve1d_kernel around the register-blocked transform; every thread owns
+// PT grid points in every phase, with all its global loads issued before anything depends on them.  Dynamic shared memory: solve1d_smem_bytes(N).
+template <int PT>
+__global__ void __launch_bounds__(512) solve1d_stock_kernel(Solve1DArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    double2 *buf = reinterpret_cast<double2 *>(smem);
+    double *scratch = smem + 2 * st_points(a.N);
+    if (a.fixedpoint && a.ctrl->final_k >= 0) { // step already converged: predicated no-op
+        if (a.cond && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);
+        return;
+    }
+    const int N = a.N;
+    PG_PROF(0);
+    const int k = a.k >= 0 ? a.k : a.ctrl->sweeps + 1; // read by every thread before thread 0 records it below
+    const bool peers = a.peer.nranks > 1 && !a.rho_in;
+    unsigned long long pseq = 0ULL;
+    if (peers) {
+        pseq = peer_gather_begin(a.peer);
+        if (threadIdx.x == 0) a.ctrl->flush_global = peer_flush_sum(a.peer);
+    }
+    {
+        double r[PT];
+        if (a.rho_in) {
+#pragma unroll
+            for (int q = 0; q < PT; ++q) r[q] = a.rho_in[threadIdx.x + q * blockDim.x];
+        } else if (peers) {
+#pragma unroll
+            for (int q = 0; q < PT; ++q) r[q] = (double)peer_sum(a.peer, pseq, threadIdx.x + q * blockDim.x) * a.fx_inv * a.w; // the publish kernel cleared rho_fx
+        } else {
+            unsigned long long raw[PT];
+#pragma unroll
+            for (int q = 0; q < PT; ++q) raw[q] = a.rho_fx[threadIdx.x + q * blockDim.x];
+#pragma unroll
+            for (int q = 0; q < PT; ++q) r[q] = (double)(long long)raw[q] * a.fx_inv * a.w;
+        }
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const int n = threadIdx.x + q * blockDim.x;
+            if (!a.rho_in && !peers) a.rho_fx[n] = 0ULL;
+            a.rho_last[n] = r[q];
+            buf[st_phys(n)] = make_double2(r[q], 0.0);
+        }
+    }
+    __syncthreads();
+    if (peers) peer_gather_end(a.peer, pseq);
+    const bool peer_failed = peers && *a.peer.error != 0; // a peer never published (pg_peer.cuh): poison the field, end the step
+    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
+    PG_PROF(1);
+    fft_stockham8<PT>(buf, N, a.lg, a.tw);
+    PG_PROF(2);
+    // xi = fft(rho)./ik ; xi[1] *= 0, stored CONJUGATED: real(ifft(xi)) = real(fft(conj xi))/N.  z/(i b) = (Im z)/b - i (Re z)/b,  b = 2pi*kk
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+        const int s = threadIdx.x + q * blockDim.x;
+        double2 z = buf[st_phys(s)];
+        if (s == 0) z = make_double2(0.0, 0.0);
+        else {
+            const double kk = (s <= N / 2) ? (double)s : (double)(s - N);
+            const double ib = 1.0 / (TWO_PI * kk); // one division per grid point
+            z = make_double2(z.y * ib, z.x * ib);
+        }
+        buf[st_phys(s)] = z;
+    }
+    __syncthreads();
+    PG_PROF(3);
+    fft_stockham8<PT>(buf, N, a.lg, a.tw);
+    PG_PROF(4);
+    double d2 = 0.0, f2 = 0.0, e2 = 0.0;
+    const double iN = 1.0 / (double)N; // exact: N is a power of two
+    {
+        double f[PT], hst[PT];
+#pragma unroll
+        for (int q = 0; q < PT; ++q) f[q] = a.E[threadIdx.x + q * blockDim.x];
+        if (a.hist) {
+#pragma unroll
+            for (int q = 0; q < PT; ++q) hst[q] = a.hist[threadIdx.x + q * blockDim.x];
+        }
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const int n = threadIdx.x + q * blockDim.x;
+            double e = buf[st_phys(n)].x * iN;
+            if (peer_failed) e = __longlong_as_double(0x7ff8000000000000LL);
+            a.E[n] = e;
+            if (a.hist) a.hist[n] = hst[q] + e;
+            const double d = f[q] - e;
+            d2 = fma(d, d, d2); f2 = fma(f[q], f[q], f2); e2 = fma(e, e, e2);
+        }
+    }
+    PG_PROF(5);
+    solve1d_decide(a, d2, f2, e2, scratch, k, peer_failed);
 }
 
 // ---------------------------------------------------------------------------------------------

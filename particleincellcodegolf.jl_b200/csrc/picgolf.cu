@@ -317,6 +317,21 @@ static int set_smem(K kernel, size_t bytes)
     return 0;
 }
 
+// N >= 512: register-blocked Stockham transform (8 or 16 grid points per thread), else the radix-2^2 one.
+static void launch_solve1d_kernel(const Solve1DArgs &a, cudaStream_t stream)
+{
+    const int N = a.N;
+    if (!solve1d_stockham(N)) solve1d_kernel<<<1, solve1d_threads(N), solve1d_smem_bytes(N), stream>>>(a);
+    else if (solve1d_points(N) == 16) solve1d_stock_kernel<16><<<1, solve1d_threads(N), solve1d_smem_bytes(N), stream>>>(a);
+    else solve1d_stock_kernel<8><<<1, solve1d_threads(N), solve1d_smem_bytes(N), stream>>>(a);
+}
+static int set_smem_solve1d(int N)
+{
+    const size_t smem = solve1d_smem_bytes(N);
+    if (!solve1d_stockham(N)) return set_smem(solve1d_kernel, smem);
+    return solve1d_points(N) == 16 ? set_smem(solve1d_stock_kernel<16>, smem) : set_smem(solve1d_stock_kernel<8>, smem);
+}
+
 // instantiated variants of the slice-streaming 2D kernel: field replicas G, deposit replicas D, threads of the one block per SM
 typedef void (*p2d_kernel_t)(P2DArgs);
 static p2d_kernel_t stream_kernel(int G, int D, int threads)
@@ -515,7 +530,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
         PG_TRY(make_twiddles(&h->tw, N));
         h->smem_pass = (size_t)(2 * N + 32) * sizeof(double);
         h->npart = 2;
-        PG_TRY(set_smem(solve1d_kernel, h->smem_pass));
+        PG_TRY(set_smem_solve1d((int)N));
         h->dft = !is_pow2(N); // NGP leapfrog on a grid that is not 2^k (validated in picgolf_create): direct transforms
         if (h->dft) {
             PG_TRY(dalloc(&h->dft_spec, (size_t)N)); PG_TRY(dalloc(&h->dft_part, (size_t)dft_blocks((int)N))); PG_TRY(dalloc(&h->dft_arrive, 1));
@@ -1006,9 +1021,8 @@ static int launch_solve1d(picgolf_handle h, int k, bool simpson_e1 = false, cuda
         int64_t ti = h->steps / c.diag_every;
         if (ti < h->T) a.hist = h->hist + (size_t)ti * c.N;
     }
-    int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, c.N / 2));
     const int sp2_ = h->timer.begin(ST_SOLVE, h->stream);
-    solve1d_kernel<<<1, threads, h->smem_pass, h->stream>>>(a);
+    launch_solve1d_kernel(a, h->stream);
     h->timer.end(sp2_, h->stream);
     h->launches++;
     return 0;
@@ -2203,10 +2217,9 @@ PG_API int picgolf_stage_solve1d(const double *rho, int64_t N, double *E)
     a.rho_in = dr.as<double>(); a.rho_fx = nullptr; a.rho_last = dl.as<double>(); a.E = dE.as<double>(); a.tw = tw;
     a.ctrl = dctrl.as<Ctrl>(); a.w = 1.0; a.fx_inv = 1.0; a.rtol = 0; a.atol = 0; a.N = (int)N; a.lg = ilog2(N);
     a.fixedpoint = 0; a.k = 1; a.max_sweeps = 1; a.store_normE1 = 0; a.hist = nullptr;
-    size_t smem = (size_t)(2 * N + 32) * 8;
-    int rc = set_smem(solve1d_kernel, smem);
+    int rc = set_smem_solve1d((int)N);
     if (rc == 0) {
-        solve1d_kernel<<<1, (int)std::min<int64_t>(1024, std::max<int64_t>(32, N / 2)), smem>>>(a);
+        launch_solve1d_kernel(a, 0);
         rc = finish();
     }
     if (rc == 0) rc = dE.download(E, N * 8);

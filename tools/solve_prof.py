@@ -12,7 +12,7 @@ import particleincellcodegolf.jl_b200 as pg
 
 lib = pg.load()
 names = ["entry->rho loaded", "forward FFT", "divide by ik", "inverse FFT", "E out + norms", "block sums"]
-for N in (128, 1024, 4096, 8192):
+for N in (128, 512, 1024, 2048, 4096, 8192):
     sim = pg.ngp_fourier(N=N, P=1 << 20, NT=64)
     sim.init_synthetic(seed=1)
     sim.step(8)
