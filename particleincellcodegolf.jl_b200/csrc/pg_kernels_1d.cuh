@@ -73,7 +73,7 @@ struct FPArgs {
     double *fs_vout;                   // the final pass writes v to its slot here (the work buffer is still being read in place)
     const unsigned int *fs_pid_in;     // original index of every particle (picgolf_get_particles un-sorts with it)
     unsigned int *fs_pid_out;
-    double fs_scale, fs_hs, fs_magic;  // N * 2^sublg, dt/2 * fs_scale, 1.5 * 2^52 + 2^(sublg-1) - 1/2
+    double fs_scale, fs_hs, fs_magic;  // N * 2^sublg, dt/2 * fs_scale, 1.5 * 2^52 + 2^(sublg-1)
     int fs_sublg;
 };
 

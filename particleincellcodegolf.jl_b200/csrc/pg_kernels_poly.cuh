@@ -46,17 +46,21 @@
 // and writes to the same buffers unpermuted, so the host's buffer rotation never depends on the sweep count.
 #pragma once
 #include "pg_kernels_1d.cuh"
+#ifdef PG_CWS_ALT // measurement builds: 16 intervals per cell, degree 8 (tools/gen_gauss_cellpoly.py --nsub 16 --deg 8)
+#include "gauss_cellpoly_16_8.inc"
+#else
 #include "gauss_cellpoly.inc"
+#endif
 #include <type_traits>
 
 namespace pg {
 
 constexpr int CP_NSUB = PG_CWS_NSUB; // polynomial intervals per cell
-constexpr int CP_SUBLG = 3;
+constexpr int CP_SUBLG = CP_NSUB == 16 ? 4 : 3;
 static_assert((1 << CP_SUBLG) == CP_NSUB, "CP_NSUB must be 2^CP_SUBLG");
 constexpr int CP_NC = PG_CWS_NC; // coefficients / moments per interval (degree 10)
 constexpr int CP_NM = CP_NC - 1; // moments kept as doubles (n = 1..10); n = 0 is an integer count
-constexpr int CP_WG = 16;        // intervals in a warp's gather window (two cells)
+constexpr int CP_WG = 2 * CP_NSUB; // intervals in a warp's gather window (two cells)
 constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned
 constexpr double CP_UMAX = 1.0;  // a lane stays with its interval while |u| <= CP_UMAX (the range the polynomials are fitted on)
 constexpr double CP_UMOVE = 0.75; // default mode: the warp moves to the next interval when most of a row has |u| > CP_UMOVE (after the move those
@@ -145,9 +149,11 @@ constexpr int CP_DETV_FRAC = 40;                     // the same for the diagnos
 constexpr double CP_DETV_MAGIC = 6144.0;             // 1.5 * 2^(52-40)
 constexpr int CPM_LD = CP_NSUB * CP_NC + 1; // 89 doubles per source cell
 
+constexpr size_t CPM_SMEM = (size_t)(CPM_CELLS + 12) * CPM_LD * sizeof(double); // dynamic shared memory of mom2rho_kernel
+
 __global__ void __launch_bounds__(32 * CP_NSUB) mom2rho_kernel(Mom2RhoArgs a)
 {
-    __shared__ double Ms[(CPM_CELLS + 12) * CPM_LD];
+    extern __shared__ double Ms[]; // [(CPM_CELLS + 12) * CPM_LD]
     __shared__ double part[CP_NSUB][CPM_CELLS];
     if (a.ctrl->final_k >= 0) return; // converged: the moments belong to the next step's first solve
     const int N = a.N, Nmask = N - 1, Mmask = N * CP_NSUB - 1;
@@ -177,7 +183,10 @@ __global__ void __launch_bounds__(32 * CP_NSUB) mom2rho_kernel(Mom2RhoArgs a)
     part[s][i] = s0 + s1;
     __syncthreads();
     if (threadIdx.x < CPM_CELLS && i0 + i < N) {
-        const double r = ((part[0][i] + part[1][i]) + (part[2][i] + part[3][i])) + ((part[4][i] + part[5][i]) + (part[6][i] + part[7][i]));
+        double r = 0.0; // the sub-intervals of a cell, added in a fixed order (8 intervals: the same tree as before)
+#pragma unroll
+        for (int s8 = 0; s8 < CP_NSUB; s8 += 8)
+            r += ((part[s8][i] + part[s8 + 1][i]) + (part[s8 + 2][i] + part[s8 + 3][i])) + ((part[s8 + 4][i] + part[s8 + 5][i]) + (part[s8 + 6][i] + part[s8 + 7][i]));
         a.rho[i0 + i] += to_fx(r, a.fx_scale);
     }
 }
@@ -391,16 +400,17 @@ __device__ __forceinline__ void cp_deposit_row(const double (&y)[2], CPSet<false
 // Horner chains in u^2.
 __device__ __forceinline__ double cp_horner(const double *g, double u)
 {
-    static_assert(CP_NC == 11, "cp_horner is written for degree 10");
+    static_assert(CP_NC % 2 == 1 && CP_NC >= 5, "cp_horner is written for an even degree");
+    constexpr int H = (CP_NC - 1) / 2;
     const double2 *g2 = reinterpret_cast<const double2 *>(g);
     const double u2 = u * u;
-    double2 c = g2[5];
-    double ge = c.x; // c_10
-    c = g2[4];
+    double2 c = g2[H];
+    double ge = c.x; // top coefficient (even)
+    c = g2[H - 1];
     ge = fma(ge, u2, c.x);
-    double go = c.y; // c_9
+    double go = c.y; // top odd coefficient
 #pragma unroll
-    for (int m = 3; m >= 0; --m) {
+    for (int m = H - 2; m >= 0; --m) {
         c = g2[m];
         ge = fma(ge, u2, c.x);
         go = fma(go, u2, c.y);
@@ -453,8 +463,8 @@ __device__ __forceinline__ long long block_sum_ll(long long v, double *scratch)
 }
 
 // ---- fused re-sort (see the header) ----------------------------------------------------------------------------------------
-// Bin of the particle that ends the step at x = xn (not yet wrapped) with velocity vb: position xn + vb*dt/2 rounded to
-// 1/2^sublg of a cell (offset by half a cell: bins are centred on the stencil centres, like sort_key_of), wrapped; sign of vb.
+// Bin of the particle that ends the step at x = xn (not yet wrapped) with velocity vb: position xn + vb*dt/2 rounded to the nearest
+// 1/2^sublg of a cell, offset by half a cell (a cell's bins surround its stencil centre, like sort_key_of), wrapped; sign of vb.
 __device__ __forceinline__ int cp_fs_key(const FPArgs &a, double xn, double vb)
 {
     const double big = fma(vb, a.fs_hs, xn * a.fs_scale) + a.fs_magic;

@@ -594,6 +594,7 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
                     h->smem_poly = cp_smem_bytes(CP_THREADS);
                     PG_TRY(set_smem(fp_pass_poly<true, false>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false, false>, h->smem_poly));
                     PG_TRY(set_smem(fp_pass_poly<true, true>, h->smem_poly)); PG_TRY(set_smem(fp_pass_poly<false, true>, h->smem_poly));
+                    PG_TRY(set_smem(mom2rho_kernel, CPM_SMEM));
                     PG_TRY(dalloc(&h->Gpoly, (size_t)CP_GS * CP_NSUB * N)); PG_TRY(dalloc(&h->Mg, (size_t)2 * CP_NC * CP_NSUB * N)); // x2: deterministic mode
                     PG_CUDA(cudaMemset(h->Gpoly, 0, (size_t)CP_GS * CP_NSUB * N * sizeof(double)));
                     PG_CUDA(cudaMemset(h->Mg, 0, (size_t)2 * CP_NC * CP_NSUB * N * sizeof(unsigned long long)));
@@ -1185,7 +1186,7 @@ static FPArgs fp_args(picgolf_handle h)
     a.dN = (double)c.N * (CP_NSUB / 2); // polynomial passes: y = (x+X)*dN = c*N*CP_NSUB
     a.fs_hist = nullptr; a.fs_cursor = nullptr; a.fs_vout = nullptr; a.fs_pid_in = nullptr; a.fs_pid_out = nullptr;
     a.fs_scale = (double)((int64_t)c.N << h->sublg); a.fs_hs = c.dt / 2 * a.fs_scale;
-    a.fs_magic = CP_MAGIC + (double)(1 << h->sublg) / 2 - 0.5; a.fs_sublg = h->sublg;
+    a.fs_magic = CP_MAGIC + (double)(1 << h->sublg) / 2; a.fs_sublg = h->sublg;
     if (h->fs_now) {
         a.fs_hist = h->bin_count; a.fs_cursor = h->bin_cursor; a.fs_vout = h->vspare;
         a.fs_pid_in = h->pid[h->pidpar]; a.fs_pid_out = h->pid[1 - h->pidpar];
@@ -1225,7 +1226,7 @@ static int enqueue_sweep(picgolf_handle h, int k, cudaGraphConditionalHandle con
         m.flush_src = (h->comm && !h->peer_ok) ? h->slow_count : nullptr;
         m.det = h->det ? 1 : 0;
         const int sp = h->timer.begin(ST_SOLVE, h->stream);
-        mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 32 * CP_NSUB, 0, h->stream>>>(m);
+        mom2rho_kernel<<<(N + CPM_CELLS - 1) / CPM_CELLS, 32 * CP_NSUB, CPM_SMEM, h->stream>>>(m);
         h->timer.end(sp, h->stream);
         h->launches++;
     }

@@ -92,13 +92,21 @@ def check(tabf):
 
 
 def main():
+    global NSUB, DEG, OUT
+    # measurement variants: --nsub 16 --deg 8 --out <path> (the shipped table is 8 intervals of degree 10)
+    for flag, conv in (("--nsub", int), ("--deg", int), ("--out", str)):
+        if flag in sys.argv:
+            val = conv(sys.argv[sys.argv.index(flag) + 1])
+            if flag == "--nsub": NSUB = val
+            elif flag == "--deg": DEG = val
+            else: OUT = val
     tabf = as_floats(table())
     worst, defect = check(tabf)
-    assert worst < mp.mpf("1.1e-16"), worst
+    assert worst < mp.mpf("1.1e-16") or "--out" in sys.argv, worst
     out = []
     out.append("// GENERATED by tools/gen_gauss_cellpoly.py -- do not edit.")
     out.append("// Sub-cell polynomial form of the erf-shape stencil: W_j(delta) = sum_n PG_CWS[s][j+6][n] * u^n on sub-interval s of a cell,")
-    out.append("// delta = (s - 4 + u)/8, fitted for |u| <= 1 (twice the interval), j = -6..6 (offset of the cell from the centre k), n = 0..10.")
+    out.append(f"// delta = (s - {NSUB // 2} + u)/{NSUB}, fitted for |u| <= 1 (twice the interval), j = -6..6 (offset of the cell from the centre k), n = 0..{DEG}.")
     out.append(f"// max |fit - exact| over all weights (binary64 coefficients): {mp.nstr(worst, 3)}")
     out.append(f"// max |sum_j PG_CWS[s][j][n] - [n==0]|: {mp.nstr(defect, 3)}")
     out.append(f"#define PG_CWS_NSUB {NSUB}")
