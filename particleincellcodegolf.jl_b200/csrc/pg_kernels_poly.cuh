@@ -222,27 +222,16 @@ __device__ __forceinline__ void cp_det_red(fx_t *p2, long long val)
     atomicAdd(p2 + 1, (fx_t)(val >> 32));
 }
 
-// Add the set to the fixed-point moment grid (11 integer REDs; DET: 22) and clear it.
-template <bool DET>
-__device__ __forceinline__ void cp_flush(CPSet<DET> &s, fx_t *Mg, double fx_scale, int Mmask)
+// Deterministic mode: add a lane's set to the two-word moment grid (22 integer REDs) and clear it.  (The default mode flushes
+// per warp: cp_flush_warp below.)
+__device__ __forceinline__ void cp_flush(CPSet<true> &s, fx_t *Mg, int Mmask)
 {
     if (s.cnt) {
-        if (DET) {
-            fx_t *p = Mg + (size_t)(s.idx & Mmask) * (2 * CP_NC);
-            cp_det_red(p, (long long)s.cnt << CP_DET_FRAC);
-            const unsigned long long off = (unsigned long long)s.cnt * (unsigned long long)__double_as_longlong(CP_DET_MAGIC);
+        fx_t *p = Mg + (size_t)(s.idx & Mmask) * (2 * CP_NC);
+        cp_det_red(p, (long long)s.cnt << CP_DET_FRAC);
+        const unsigned long long off = (unsigned long long)s.cnt * (unsigned long long)__double_as_longlong(CP_DET_MAGIC);
 #pragma unroll
-            for (int n = 0; n < CP_NM; ++n) cp_det_red(p + 2 * (1 + n), (long long)((unsigned long long)s.m[n] - off));
-        } else {
-            fx_t *p = Mg + (size_t)(s.idx & Mmask) * CP_NC;
-            atomicAdd(p, to_fx((double)s.cnt, fx_scale));
-#pragma unroll
-            for (int n = 0; n < CP_NM; ++n) atomicAdd(p + 1 + n, to_fx((double)s.m[n], fx_scale));
-#ifdef PG_EXP_DOUBLEFLUSH // measurement builds only: every flush issues its REDs twice (the second time adding zero) -- what the REDs cost
-#pragma unroll
-            for (int n = 0; n < CP_NC; ++n) atomicAdd(p + n, (fx_t)(s.cnt >> 30));
-#endif
-        }
+        for (int n = 0; n < CP_NM; ++n) cp_det_red(p + 2 * (1 + n), (long long)((unsigned long long)s.m[n] - off));
         s.clear();
     }
 }
@@ -262,44 +251,32 @@ __device__ __forceinline__ void cp_flush_spare(CPSpare &sp, unsigned long long *
     }
 }
 
-// M[m][n] += u^n for the particle at y.  Default: the lane stays with its interval while |u| <= CP_UMAX (see the header).
-// DET: the interval is round(y) whatever the lane did before; `col` / `sp` hold the other interval of an alternating lane.
-template <bool DET>
-__device__ __forceinline__ void cp_deposit1(double y, CPSet<DET> &P, CPSpare &sp, unsigned long long *col, int stride, fx_t *Mg,
-                                            double fx_scale, int Mmask, unsigned int &nflush)
+// Deterministic mode: M[m][n] += u^n for the particle at y, m = round(y) whatever the lane did before; `col` / `sp` hold the
+// other interval of an alternating lane.
+__device__ __forceinline__ void cp_deposit1(double y, CPSet<true> &P, CPSpare &sp, unsigned long long *col, int stride, fx_t *Mg,
+                                            int Mmask, unsigned int &nflush)
 {
-    double u;
-    if (DET) {
-        int idx;
-        double centre;
-        cp_interval(y, idx, centre);
-        u = y - centre;
-        if (idx != P.idx || P.cnt >= CP_DET_MAXCNT) {
-            if (idx == sp.idx && idx != P.idx) { // change over to the other interval: exchange the two sets
+    int idx;
+    double centre;
+    cp_interval(y, idx, centre);
+    const double u = y - centre;
+    if (idx != P.idx || P.cnt >= CP_DET_MAXCNT) {
+        if (idx == sp.idx && idx != P.idx) { // change over to the other interval: exchange the two sets
 #pragma unroll
-                for (int n = 0; n < CP_NM; ++n) { const unsigned long long m = col[n * stride]; col[n * stride] = (unsigned long long)P.m[n]; P.m[n] = m; }
-                const int c = sp.cnt; sp.cnt = P.cnt; P.cnt = c;
-                sp.idx = P.idx; P.idx = idx;
-                ++nflush;
-                if (P.cnt >= CP_DET_MAXCNT) cp_flush<DET>(P, Mg, fx_scale, Mmask);
-            } else if (idx == P.idx) {           // full set
-                cp_flush<DET>(P, Mg, fx_scale, Mmask);
-            } else {                             // a third interval: retire the spare, park the current set
-                nflush += sp.cnt > 0;
-                cp_flush_spare(sp, col, stride, Mg, Mmask);
+            for (int n = 0; n < CP_NM; ++n) { const unsigned long long m = col[n * stride]; col[n * stride] = P.m[n]; P.m[n] = m; }
+            const int c = sp.cnt; sp.cnt = P.cnt; P.cnt = c;
+            sp.idx = P.idx; P.idx = idx;
+            ++nflush;
+            if (P.cnt >= CP_DET_MAXCNT) cp_flush(P, Mg, Mmask);
+        } else if (idx == P.idx) {           // full set
+            cp_flush(P, Mg, Mmask);
+        } else {                             // a third interval: retire the spare, park the current set
+            nflush += sp.cnt > 0;
+            cp_flush_spare(sp, col, stride, Mg, Mmask);
 #pragma unroll
-                for (int n = 0; n < CP_NM; ++n) { col[n * stride] = (unsigned long long)P.m[n]; P.m[n] = 0; }
-                sp.cnt = P.cnt; sp.idx = P.idx;
-                P.cnt = 0; P.idx = idx;
-            }
-        }
-    } else {
-        u = y - P.centre;
-        if (!(fabs(u) <= CP_UMAX)) { // ~20 times per pass in sorted order (and for the lane's first particle)
-            nflush += P.cnt > 0;
-            cp_flush<DET>(P, Mg, fx_scale, Mmask);
-            cp_interval(y, P.idx, P.centre);
-            u = y - P.centre;
+            for (int n = 0; n < CP_NM; ++n) { col[n * stride] = P.m[n]; P.m[n] = 0; }
+            sp.cnt = P.cnt; sp.idx = P.idx;
+            P.cnt = 0; P.idx = idx;
         }
     }
     P.cnt++;
@@ -307,12 +284,8 @@ __device__ __forceinline__ void cp_deposit1(double y, CPSet<DET> &P, CPSpare &sp
     double pa = u, pb = u2;
 #pragma unroll
     for (int n = 0; n < CP_NM; n += 2) {
-        if (DET) {
-            P.m[n] += (unsigned long long)__double_as_longlong(pa + CP_DET_MAGIC);
-            P.m[n + 1] += (unsigned long long)__double_as_longlong(pb + CP_DET_MAGIC);
-        } else {
-            P.m[n] += pa; P.m[n + 1] += pb;
-        }
+        P.m[n] += (unsigned long long)__double_as_longlong(pa + CP_DET_MAGIC);
+        P.m[n + 1] += (unsigned long long)__double_as_longlong(pb + CP_DET_MAGIC);
         if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
     }
 }
@@ -651,21 +624,17 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
         if (fs && !final && cp_fs_counts(k, a.ctrl)) atomicAdd(&a.fs_hist[cp_fs_key(a, xj, vj)], 1u);
     }
     const double y = (xj + Xj) * dNs;
-    cp_interval(y, idx, centre);
-    const double u = y - centre;
     if constexpr (!DET) {
         cp_deposit_single(y, a.Mg, a.fx_scale, Mmask);
-        return;
+    } else { // the streaming loop's own arithmetic (same powers, same rounding) for a set of one particle
+        CPSet<true> one;
+        one.clear(); one.centre = 1e300; one.idx = 0x40000000; // not an interval any particle can be in
+        unsigned int nf = 0;
+        CPSpare nosp; nosp.cnt = 0; nosp.idx = 0x40000001;
+        unsigned long long dummy[CP_NM];
+        cp_deposit1(y, one, nosp, dummy, 1, a.Mg, Mmask, nf);
+        cp_flush(one, a.Mg, Mmask);
     }
-    CPSet<DET> one; // the streaming loop's own arithmetic (same powers, same rounding) for a set of one particle
-    one.clear(); one.centre = 1e300;
-    unsigned int nf = 0;
-    CPSpare nosp; nosp.cnt = 0; nosp.idx = 0x40000001;
-    one.idx = 0x40000000; // DET: not an interval any particle can be in
-    unsigned long long dummy[CP_NM];
-    cp_deposit1<DET>(y, one, nosp, dummy, 1, a.Mg, a.fx_scale, Mmask, nf);
-    cp_flush<DET>(one, a.Mg, a.fx_scale, Mmask);
-    (void)u;
 }
 
 // Pass k of a step (same contract as fp_pass_sorted / fp_pass_atomic; FPArgs.G / FPArgs.Mg carry the polynomial
@@ -810,14 +779,14 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
         }
         if constexpr (DET) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) cp_deposit1<DET>((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, a.fx_scale, Mmask, nflush);
+            for (int q = 0; q < 2; ++q) cp_deposit1((xj[q] + Xj[q]) * dNs, A, spare, col, cstride, a.Mg, Mmask, nflush);
         } else {
             const double yd[2] = {(xj[0] + Xj[0]) * dNs, (xj[1] + Xj[1]) * dNs};
             cp_deposit_row(yd, A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask, nflush);
         }
     }
     cp_async_wait<0>();
-    if constexpr (DET) cp_flush<DET>(A, a.Mg, a.fx_scale, Mmask);
+    if constexpr (DET) cp_flush(A, a.Mg, Mmask);
     else cp_flush_warp(A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask);
     if (DET) cp_flush_spare(spare, col, cstride, a.Mg, Mmask);
     // ragged tail of the shard: fewer than 64 particles, first warp of the last block
