@@ -10,7 +10,9 @@
 //     deposit  r[k[1]] += k[2]             : M[m][n] += u^n,        rho[i] = sum_j sum_s sum_n CWS[s][j][n] M[m(i-j,s)][n]   mom2rho_kernel
 // A particle-sweep then costs one Horner evaluation (10 DFMA) and 10 power accumulations -- 47 FP64 instructions instead
 // of the ~255 of the two 13-weight stencil evaluations in fp_pass_sorted, and of the 66 of the one-polynomial-per-cell
-// form (degree 16) that round 1 shipped; that moves the pass from the FP64 pipe to HBM.
+// form (degree 16) that round 1 shipped; that moves the pass from the FP64 pipe to HBM.  (16 intervals of degree 8 fitted on
+// |u| <= 7/8 -- 41 instructions, -DPG_CWS_ALT -- are 2.7 % faster per step on cold beams and 10 - 28 % slower on warm ones,
+// where the narrower intervals turn more deposits into outliers; the constants below follow the table.)
 //
 // fp_pass_poly: every warp streams ONE contiguous range of the (cell, sign v, sub-cell position)-sorted particle arrays
 // with 128-bit loads (2 particles per lane and row).  Deposit: the warp shares ONE current interval; each lane sums u^n of its
@@ -46,7 +48,7 @@
 // and writes to the same buffers unpermuted, so the host's buffer rotation never depends on the sweep count.
 #pragma once
 #include "pg_kernels_1d.cuh"
-#ifdef PG_CWS_ALT // measurement builds: 16 intervals per cell, degree 8 (tools/gen_gauss_cellpoly.py --nsub 16 --deg 8)
+#ifdef PG_CWS_ALT // A/B builds: 16 intervals per cell, degree 8, fitted on |u| <= 7/8 (tools/gen_gauss_cellpoly.py --nsub 16 --deg 8 --range 0.875)
 #include "gauss_cellpoly_16_8.inc"
 #else
 #include "gauss_cellpoly.inc"
@@ -62,9 +64,9 @@ constexpr int CP_NC = PG_CWS_NC; // coefficients / moments per interval (degree 
 constexpr int CP_NM = CP_NC - 1; // moments kept as doubles (n = 1..10); n = 0 is an integer count
 constexpr int CP_WG = 2 * CP_NSUB; // intervals in a warp's gather window (two cells)
 constexpr int CP_GS = CP_NC + 1; // row stride of the gather tables: coefficient pairs (c_2m, c_2m+1) are 16-byte aligned
-constexpr double CP_UMAX = 1.0;  // a lane stays with its interval while |u| <= CP_UMAX (the range the polynomials are fitted on)
-constexpr double CP_UMOVE = 0.75; // default mode: the warp moves to the next interval when most of a row has |u| > CP_UMOVE (after the move those
-                                  // particles sit at |u| < 1/4 and the rest of the row within 3/4 of the new centre: the warp never moves straight back)
+constexpr double CP_UMAX = PG_CWS_UMAX; // the polynomials are fitted on |u| <= CP_UMAX: a particle stays with the warp's interval that far from its centre
+constexpr double CP_UMOVE = CP_UMAX - 0.25; // default mode: the warp moves on when most of a row has |u| > CP_UMOVE (after the move those particles sit
+                                            // within 1/4 of the new centre and the rest of the row within CP_UMOVE: the warp never moves straight back)
 constexpr double CP_MAGIC = 6755399441055744.0; // 1.5 * 2^52: y + CP_MAGIC rounds y to the nearest integer (ties to even), |y| < 2^51
 
 #ifndef PG_CP_THREADS
@@ -292,12 +294,12 @@ __device__ __forceinline__ void cp_deposit1(double y, CPSet<true> &P, CPSpare &s
 
 // ---- default (not deterministic) deposit: the WARP shares one interval --------------------------------------------------
 // Every lane sums u^n of its particles relative to the warp's current interval (centre, idx: warp-uniform) in registers.  When
-// most of a row lies more than 3/4 of an interval from the centre the stream has moved on: the 32 lane sets are added up through
+// most of a row lies more than CP_UMOVE = 3/4 of an interval from the centre the stream has moved on: the 32 lane sets are added up through
 // shared memory (lane n sums moment n) and go to the moment grid with ONE set of 11 REDs, and the warp re-centres on the
 // interval of the first such particle.  With every lane flushing for itself (the form this replaces) the same event cost
 // 32 x 11 REDs to the same 11 addresses -- 0.35 ms of a 5 ms step at 2^28 particles (measured by issuing them twice).
 // The 3/4 is hysteresis: a bin that straddles an interval edge does not make the warp alternate.  A particle
-// more than a whole interval from the centre (|u| > 1: outside the range the polynomials are fitted on -- disordered input)
+// more than CP_UMAX = 1 interval from the centre (outside the range the polynomials are fitted on -- disordered input)
 // is deposited on its own (11 REDs).
 __device__ __noinline__ void cp_deposit_single(double y, fx_t *Mg, double fx_scale, int Mmask)
 {

@@ -25,10 +25,10 @@
 using namespace pg;
 
 #ifndef PG_POLY_SUBLG
-#define PG_POLY_SUBLG 5
+#define PG_POLY_SUBLG (CP_SUBLG + 2)
 #endif
-constexpr int POLY_MAXBINS = 1 << 18;
-constexpr int POLY_SUBLG = PG_POLY_SUBLG; // polynomial mode: up to 2^5 position sub-bins per (cell, sign v) bin
+constexpr int POLY_MAXBINS = 1 << (16 + CP_SUBLG);
+constexpr int POLY_SUBLG = PG_POLY_SUBLG; // polynomial mode: up to four position sub-bins per polynomial interval in every (cell, sign v) bin
 
 #define PG_API extern "C" __attribute__((visibility("default")))
 

@@ -12,12 +12,16 @@ from scipy.special import erf
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INC = os.path.join(ROOT, "particleincellcodegolf.jl_b200", "csrc", "gauss_cellpoly.inc")
-NSUB, NC = 8, 11
+_text = open(INC).read()
+NSUB = int(re.search(r"#define PG_CWS_NSUB (\d+)", _text).group(1))   # 8 intervals per cell
+NC = int(re.search(r"#define PG_CWS_NC (\d+)", _text).group(1))       # degree 10
+UMAX = float(re.search(r"#define PG_CWS_UMAX ([0-9.eE+-]+)", _text).group(1))  # fitted on |u| <= 1
+SUBLG = NSUB.bit_length() - 1
 
 
 def load_table():
-    text = open(INC).read()
-    body = text[text.index("PG_CWS[8][13][11]"):]
+    text = _text
+    body = text[text.index(f"PG_CWS[{NSUB}][13][{NC}]"):]
     rows = re.findall(r"\{([^{}]+)\},", body)
     tab = np.array([[float(v) for v in r.split(",")] for r in rows]).reshape(NSUB, 13, NC)
     return tab
@@ -32,7 +36,7 @@ def intervals(c, N):
     """Interval m, centre k (Julia index), sub-interval s and u of stencil centres c -- the kernel's arithmetic."""
     y = c * N * NSUB  # exact for power-of-two N
     m = np.rint(y).astype(np.int64)
-    return m, (m + NSUB // 2) >> 3, (m + NSUB // 2) & (NSUB - 1), y - m
+    return m, (m + NSUB // 2) >> SUBLG, (m + NSUB // 2) & (NSUB - 1), y - m
 
 
 def test_weights_match_reference_expression():
@@ -65,13 +69,13 @@ def test_weights_match_reference_expression():
 
 
 def test_hysteresis_range_is_covered():
-    """A lane keeps using interval m while |u| <= 1: the polynomials must hold there, and what the shifted stencil leaves out
+    """A warp keeps using interval m while |u| <= UMAX: the polynomials must hold there, and what the shifted stencil leaves out
     (the reference's 13th cell at the far end) must be below binary64 resolution."""
     CWS = load_table()
-    u = np.linspace(-1, 1, 401)
+    u = np.linspace(-UMAX, UMAX, 401)
     worst = 0.0
     for s in range(NSUB):
-        delta = (s - NSUB // 2 + u) / NSUB  # down to -0.625, up to 0.5
+        delta = (s - NSUB // 2 + u) / NSUB  # down to -1/2 - UMAX/NSUB
         for jj in range(13):
             j = jj - 6
             ref = (erf(j + 0.5 - delta) - erf(j - 0.5 - delta)) / 2
@@ -80,7 +84,7 @@ def test_hysteresis_range_is_covered():
             worst = max(worst, np.abs(np.polynomial.polynomial.polyval(u, CWS[s, jj]) - ref).max())
     assert worst < 4e-16
     # weight of the cell the reference's own 13-cell stencil would hold instead, at the far edge of the range
-    assert (erf(6.5 + 0.625) - erf(5.5 + 0.625)) / 2 < 3e-17
+    assert (erf(6.5 + 0.5 + UMAX / NSUB) - erf(5.5 + 0.5 + UMAX / NSUB)) / 2 < 3e-17
 
 
 def test_moment_deposit_and_poly_gather_are_the_stencil():
@@ -102,7 +106,7 @@ def test_moment_deposit_and_poly_gather_are_the_stencil():
     # moment form; half of the particles deposit into a NEIGHBOURING interval (|u| up to 1), as a lane with hysteresis does
     m, _, _, u = intervals(c, N)
     shift = rng.integers(-1, 2, P) * (rng.random(P) < 0.5)
-    shift = np.where(np.abs(u - shift) <= 1.0, shift, 0)
+    shift = np.where(np.abs(u - shift) <= UMAX, shift, 0)
     m2, u2 = m + shift, u - shift
     M = np.zeros((N * NSUB, NC))
     row = m2 % (N * NSUB)

@@ -35,6 +35,7 @@ HALF = mp.mpf(1) / 2
 DEG = 10
 HW = 6
 NSUB = 8
+RANGE = mp.mpf(1)  # the fit covers |u| <= RANGE (PG_CWS_UMAX): twice the interval
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "particleincellcodegolf.jl_b200", "csrc", "gauss_cellpoly.inc")
 
 
@@ -47,8 +48,8 @@ def delta(s, u):
 
 
 def cheb_monomial(f, n):
-    """Degree-n Chebyshev interpolant of f on [-1,1] as monomial coefficients."""
-    nodes = [mp.cos(mp.pi * (2 * k + 1) / (2 * (n + 1))) for k in range(n + 1)]
+    """Degree-n Chebyshev interpolant of f on [-RANGE, RANGE] as monomial coefficients."""
+    nodes = [RANGE * mp.cos(mp.pi * (2 * k + 1) / (2 * (n + 1))) for k in range(n + 1)]
     V = mp.matrix(n + 1, n + 1)
     y = mp.matrix(n + 1, 1)
     for i, x in enumerate(nodes):
@@ -80,7 +81,7 @@ def check(tabf):
     worst = mp.mpf(0)
     for s, sub in enumerate(tabf):
         for i in range(129):
-            u = mp.mpf(2 * i) / 128 - 1
+            u = (mp.mpf(2 * i) / 128 - 1) * RANGE
             d = delta(s, u)
             for jj, row in enumerate(sub):
                 j = jj - HW
@@ -92,13 +93,16 @@ def check(tabf):
 
 
 def main():
-    global NSUB, DEG, OUT
-    # measurement variants: --nsub 16 --deg 8 --out <path> (the shipped table is 8 intervals of degree 10)
-    for flag, conv in (("--nsub", int), ("--deg", int), ("--out", str)):
+    global NSUB, DEG, OUT, RANGE
+    # other tables for A/B builds: --nsub 16 --deg 8 --range 0.875 --out <path> (-DPG_CWS_ALT: 2.7 % faster on cold beams at 2^28
+    # particles -- 41 instead of 47 FP64 instructions per particle-sweep -- but 10 / 28 % slower at thermal spreads of 0.3 / 1.0 of the
+    # beam speed, where the narrower intervals turn more deposits into outliers; measured on B200, profiles/r2_s_*)
+    for flag, conv in (("--nsub", int), ("--deg", int), ("--range", mp.mpf), ("--out", str)):
         if flag in sys.argv:
             val = conv(sys.argv[sys.argv.index(flag) + 1])
             if flag == "--nsub": NSUB = val
             elif flag == "--deg": DEG = val
+            elif flag == "--range": RANGE = val
             else: OUT = val
     tabf = as_floats(table())
     worst, defect = check(tabf)
@@ -106,11 +110,12 @@ def main():
     out = []
     out.append("// GENERATED by tools/gen_gauss_cellpoly.py -- do not edit.")
     out.append("// Sub-cell polynomial form of the erf-shape stencil: W_j(delta) = sum_n PG_CWS[s][j+6][n] * u^n on sub-interval s of a cell,")
-    out.append(f"// delta = (s - {NSUB // 2} + u)/{NSUB}, fitted for |u| <= 1 (twice the interval), j = -6..6 (offset of the cell from the centre k), n = 0..{DEG}.")
+    out.append(f"// delta = (s - {NSUB // 2} + u)/{NSUB}, fitted for |u| <= {mp.nstr(RANGE, 4)} (the interval is |u| <= 1/2), j = -6..6 (offset of the cell from the centre k), n = 0..{DEG}.")
     out.append(f"// max |fit - exact| over all weights (binary64 coefficients): {mp.nstr(worst, 3)}")
     out.append(f"// max |sum_j PG_CWS[s][j][n] - [n==0]|: {mp.nstr(defect, 3)}")
     out.append(f"#define PG_CWS_NSUB {NSUB}")
     out.append(f"#define PG_CWS_NC {DEG + 1}")
+    out.append(f"#define PG_CWS_UMAX {mp.nstr(RANGE, 17)}")
     out.append(f"__constant__ double PG_CWS[{NSUB}][{2 * HW + 1}][{DEG + 1}] = {{")
     for sub in tabf:
         out.append("  {")
