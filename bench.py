@@ -271,7 +271,7 @@ def run_gpu(args):
                   "fp_pass_sorted<FIRST,NP=2> (gather + implicit-midpoint update + deposit; 3 variants: first/middle/final pass)")
         tkey = "gauss_fp_poly" if poly else "gauss_fp"
     elif args.workload == "ngp":
-        passes = float(nroof + 1)
+        passes = float(nroof)  # the warm-up call left the first step's charge deposited: K steps are K passes
         alg_bytes_launch = 32.0 * per_gpu
         kernel = "lf_pass_ngp_tma (TMA-staged tiles: drift + kick + drift + NGP deposit)"
         tkey = "ngp"

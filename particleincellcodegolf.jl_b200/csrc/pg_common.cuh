@@ -18,6 +18,8 @@ namespace pg {
 // exactly 1.0); else r.   src/NGPFourier.jl:2, src/GaussianFixedPoint.jl:9.
 __device__ __forceinline__ double jl_mod1(double a)
 {
+    if (a > 0.0 && a < 1.0) return a; // nothing to wrap (nearly every call): the same bits as below without the FRND of trunc(), which
+                                      // runs on the quarter-rate XU pipe -- 3 % of the TMA-staged NGP pass (same-box A/B, profiles/r2_t_*)
     double r = a - trunc(a); // == fmod(a, 1.0), exact
     if (r == 0.0) return 0.0;
     if (r < 0.0) return r + 1.0;

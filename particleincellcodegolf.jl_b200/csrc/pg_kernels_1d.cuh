@@ -370,17 +370,22 @@ struct LFArgs {
     double *partials;            // [2*gridDim.x]
     long long P;
     double dt, fx_scale;
-    int N, do_kick, do_deposit;
+    int N, do_kick, do_deposit;  // do_deposit = 2: deposit at the half-drifted position but store the full-step x (last step of a call)
     int pow2;                    // N is a power of two: the cell index is a mask instead of Julia's mod1 division
+    int do_predrift;             // the stored x is a full-step position whose half drift u() was only deposited (do_deposit = 2 of the
+                                 // previous call): redo it first -- the same operands, the same bits
 };
 
-// One particle of a leapfrog pass (shared by the vectorised and the scalar loops).
-template <int SHAPE>
+// One particle of a leapfrog pass (shared by the vectorised and the scalar loops).  EDGE: the first / last pass of a picgolf_step call
+// (do_predrift, do_deposit = 2) -- a separate instantiation, so that the passes in between carry none of it (at run time the extra
+// mod and select cost the TMA-staged NGP pass 5 %).
+template <int SHAPE, bool EDGE>
 __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, fx_t *rs, unsigned int *cs, double &xj, double &vj,
                                             double &sv2, double &sv)
 {
     const int N = a.N, Nmask = N - 1;
     const double dN = (double)N, dt = a.dt;
+    if (EDGE && a.do_predrift) xj = jl_mod1(xj + vj / 2 * dt);
     if (a.do_kick) {
         xj = jl_mod1(xj + vj / 2 * dt);
         double e;
@@ -395,13 +400,14 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
         sv += vj;
     }
     if (a.do_deposit) {
-        xj = jl_mod1(xj + vj / 2 * dt);
-        if (SHAPE == 0) atomicAdd(&cs[a.pow2 ? ngp_cell0_pow2(xj, N) : ngp_cell0(xj, N)], 1u);
+        const double xd = jl_mod1(xj + vj / 2 * dt);
+        if (SHAPE == 0) atomicAdd(&cs[a.pow2 ? ngp_cell0_pow2(xd, N) : ngp_cell0(xd, N)], 1u);
         else {
             int ibase; double W[GAUSS_NW];
-            gauss_weights(xj, dN, ibase, W);
+            gauss_weights(xd, dN, ibase, W);
             gauss_deposit_atomic(rs, ibase, W, a.fx_scale, Nmask);
         }
+        if (!EDGE || a.do_deposit == 1) xj = xd;
     }
 }
 
@@ -410,7 +416,7 @@ __device__ __forceinline__ void lf_particle(const LFArgs &a, const double *Es, f
 // loads/stores, two pairs (4 particles) in flight per thread.
 __host__ __device__ inline size_t lf_smem_bytes(int shape, int N) { return (size_t)N * 8 + (size_t)N * (shape == 0 ? 4 : 8) + 256; }
 
-template <int SHAPE> // 0 = NGP, 1 = Gaussian
+template <int SHAPE, bool EDGE> // 0 = NGP, 1 = Gaussian
 __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
 {
     extern __shared__ double smem[];
@@ -433,27 +439,27 @@ __global__ void __launch_bounds__(PG_THREADS) lf_pass(LFArgs a)
         long long p = tid;
         for (; p + stride < npair; p += 2 * stride) { // two 128-bit loads per array in flight
             double2 xa = __ldcs(x2 + p), va = __ldcs(v2 + p), xb = __ldcs(x2 + p + stride), vb = __ldcs(v2 + p + stride);
-            lf_particle<SHAPE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
-            lf_particle<SHAPE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
-            lf_particle<SHAPE>(a, Es, rs, cs, xb.x, vb.x, sv2, sv);
-            lf_particle<SHAPE>(a, Es, rs, cs, xb.y, vb.y, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xb.x, vb.x, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xb.y, vb.y, sv2, sv);
             __stcs(x2 + p, xa); __stcs(v2 + p, va); __stcs(x2 + p + stride, xb); __stcs(v2 + p + stride, vb);
         }
         for (; p < npair; p += stride) {
             double2 xa = __ldcs(x2 + p), va = __ldcs(v2 + p);
-            lf_particle<SHAPE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
-            lf_particle<SHAPE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xa.x, va.x, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xa.y, va.y, sv2, sv);
             __stcs(x2 + p, xa); __stcs(v2 + p, va);
         }
         if ((a.P & 1) && tid == 0) { // odd tail
             double xj = a.x[a.P - 1], vj = a.v[a.P - 1];
-            lf_particle<SHAPE>(a, Es, rs, cs, xj, vj, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xj, vj, sv2, sv);
             a.x[a.P - 1] = xj; a.v[a.P - 1] = vj;
         }
     } else {
         for (long long j = tid; j < a.P; j += stride) {
             double xj = ld_stream(a.x + j), vj = ld_stream(a.v + j);
-            lf_particle<SHAPE>(a, Es, rs, cs, xj, vj, sv2, sv);
+            lf_particle<SHAPE, EDGE>(a, Es, rs, cs, xj, vj, sv2, sv);
             st_stream(a.x + j, xj);
             st_stream(a.v + j, vj);
         }
@@ -491,6 +497,7 @@ __host__ __device__ inline size_t lf_tma_smem_bytes(int N)
 }
 
 constexpr int LF_TMA_THREADS = 512;
+template <bool EDGE>
 __global__ void __launch_bounds__(LF_TMA_THREADS, 1) lf_pass_ngp_tma(LFArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -531,8 +538,8 @@ __global__ void __launch_bounds__(LF_TMA_THREADS, 1) lf_pass_ngp_tma(LFArgs a)
         for (int i = 0; i < LF_TILE / LF_TMA_THREADS; i += 2) { // pairs via 128-bit shared accesses
             const int p = (i / 2) * LF_TMA_THREADS + threadIdx.x;
             double2 xa = reinterpret_cast<double2 *>(xs)[p], va = reinterpret_cast<double2 *>(vs)[p];
-            lf_particle<0>(a, Es, nullptr, cs, xa.x, va.x, sv2, sv);
-            lf_particle<0>(a, Es, nullptr, cs, xa.y, va.y, sv2, sv);
+            lf_particle<0, EDGE>(a, Es, nullptr, cs, xa.x, va.x, sv2, sv);
+            lf_particle<0, EDGE>(a, Es, nullptr, cs, xa.y, va.y, sv2, sv);
             reinterpret_cast<double2 *>(xs)[p] = xa; reinterpret_cast<double2 *>(vs)[p] = va;
         }
         fence_proxy_async(); // the updated tile must be visible to the copy engine
@@ -555,7 +562,7 @@ __global__ void __launch_bounds__(LF_TMA_THREADS, 1) lf_pass_ngp_tma(LFArgs a)
         const long long t0 = ntiles * LF_TILE;
         for (long long j = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < a.P; j += (long long)gridDim.x * blockDim.x) {
             double xj = a.x[j], vj = a.v[j];
-            lf_particle<0>(a, Es, nullptr, cs, xj, vj, sv2, sv);
+            lf_particle<0, EDGE>(a, Es, nullptr, cs, xj, vj, sv2, sv);
             a.x[j] = xj; a.v[j] = vj;
         }
     }

@@ -623,19 +623,19 @@ static int create_impl(const picgolf_config *cfg, picgolf_handle h)
             }
         } else if (h->ngp) {
             h->smem_lf = lf_smem_bytes(0, N);
-            PG_TRY(set_smem(lf_pass<0>, h->smem_lf));
-            PG_TRY(occupancy_blocks(lf_pass<0>, PG_THREADS, h->smem_lf, h->sms, (h->count + 3) / 4, &h->nblocks));
+            PG_TRY(set_smem(lf_pass<0, false>, h->smem_lf)); PG_TRY(set_smem(lf_pass<0, true>, h->smem_lf));
+            PG_TRY(occupancy_blocks(lf_pass<0, true>, PG_THREADS, h->smem_lf, h->sms, (h->count + 3) / 4, &h->nblocks));
             // large shards stream their particle tiles with TMA bulk copies (one persistent block per SM)
             h->ngp_tma = c.deposit_mode != PICGOLF_DEPOSIT_ATOMIC && h->count >= (1 << 20) && lf_tma_smem_bytes(N) <= 200 * 1024;
             if (h->ngp_tma) {
                 h->smem_lf = lf_tma_smem_bytes(N);
-                PG_TRY(set_smem(lf_pass_ngp_tma, h->smem_lf));
+                PG_TRY(set_smem(lf_pass_ngp_tma<false>, h->smem_lf)); PG_TRY(set_smem(lf_pass_ngp_tma<true>, h->smem_lf));
                 h->nblocks = h->sms;
             }
         } else {
             h->smem_lf = lf_smem_bytes(1, N);
-            PG_TRY(set_smem(lf_pass<1>, h->smem_lf));
-            PG_TRY(occupancy_blocks(lf_pass<1>, PG_THREADS, h->smem_lf, h->sms, h->count, &h->nblocks));
+            PG_TRY(set_smem(lf_pass<1, false>, h->smem_lf)); PG_TRY(set_smem(lf_pass<1, true>, h->smem_lf));
+            PG_TRY(occupancy_blocks(lf_pass<1, true>, PG_THREADS, h->smem_lf, h->sms, h->count, &h->nblocks));
         }
     } else {
         const int NX = (int)c.N, NY = (int)c.NY;
@@ -1455,17 +1455,26 @@ static int step_fixedpoint(picgolf_handle h)
     return 0;
 }
 
-static int lf_launch(picgolf_handle h, int do_kick, int do_deposit)
+static int lf_launch(picgolf_handle h, int do_kick, int do_deposit, int do_predrift = 0)
 {
     const picgolf_config &c = h->cfg;
     LFArgs a;
+    a.do_predrift = do_predrift;
     a.x = h->xb[0]; a.v = h->vb[0]; a.E = h->E; a.rho = h->rho_fx; a.partials = h->partials;
     a.P = h->count; a.dt = c.dt; a.fx_scale = h->fx_scale; a.N = (int)c.N; a.do_kick = do_kick; a.do_deposit = do_deposit;
     a.pow2 = h->dft ? 0 : 1;
     const int sp5_ = h->timer.begin(ST_PARTICLES, h->stream);
-    if (h->ngp_tma) lf_pass_ngp_tma<<<h->nblocks, LF_TMA_THREADS, h->smem_lf, h->stream>>>(a);
-    else if (h->ngp) lf_pass<0><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
-    else lf_pass<1><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+    const bool edge = do_predrift || do_deposit == 2; // first / last pass of a call: its own instantiation (lf_particle)
+    if (h->ngp_tma) {
+        if (edge) lf_pass_ngp_tma<true><<<h->nblocks, LF_TMA_THREADS, h->smem_lf, h->stream>>>(a);
+        else lf_pass_ngp_tma<false><<<h->nblocks, LF_TMA_THREADS, h->smem_lf, h->stream>>>(a);
+    } else if (h->ngp) {
+        if (edge) lf_pass<0, true><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+        else lf_pass<0, false><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+    } else {
+        if (edge) lf_pass<1, true><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+        else lf_pass<1, false><<<h->nblocks, PG_THREADS, h->smem_lf, h->stream>>>(a);
+    }
     h->timer.end(sp5_, h->stream);
     h->launches++;
     return 0;
@@ -1595,14 +1604,20 @@ PG_API int picgolf_step(picgolf_handle h, int64_t nsteps)
         }
         h->have_deposit = true;
     } else {
-        rc = lf_launch(h, 0, 1); // u(); deposit of the first step
+        // A call ends on full-step positions (what picgolf_get_particles hands out), but its last pass has already deposited the
+        // charge of the NEXT step at the half-drifted positions (do_deposit = 2); the next call redoes that half drift in its first
+        // pass (do_predrift) instead of spending a pass of its own on u() + deposit: K steps cost K passes, not K + 1 -- a driver
+        // that records something after every step (picgolf_step(h, 1) in a loop) runs twice as fast.
+        const bool pending = h->have_deposit;
+        if (!pending) rc = lf_launch(h, 0, 1); // first step after the particles were set: u(); deposit
         for (int64_t s = 0; s < nsteps && rc == 0; ++s) {
             rc = allreduce_grid(h);
             if (rc == 0) rc = launch_solve1d(h, 1);
-            if (rc == 0) rc = lf_launch(h, 1, s + 1 < nsteps ? 1 : 0); // u(); kick [; u(); deposit of the next step]
+            if (rc == 0) rc = lf_launch(h, 1, s + 1 < nsteps ? 1 : 2, (s == 0 && pending) ? 1 : 0); // u(); kick; u(); deposit of the next step
             if (rc == 0) rc = launch_step_end(h, true);
             h->steps++;
         }
+        if (rc == 0) h->have_deposit = true;
     }
     h->timer.end(sp8_, h->stream);
     if (rc != 0) return rc;
@@ -2138,13 +2153,13 @@ PG_API int picgolf_stage_ngp_deposit(const double *x, int64_t count, int64_t N, 
     PG_TRY(dx.upload(x, count * 8)); PG_TRY(dv.upload(zeros.data(), count * 8));
     PG_TRY(dcnt.zero(N * 8)); PG_TRY(dpart.zero(2 * 1024 * 8));
     size_t smem = lf_smem_bytes(0, (int)N);
-    PG_TRY(set_smem(lf_pass<0>, smem));
+    PG_TRY(set_smem(lf_pass<0, false>, smem));
     LFArgs a;
     a.x = dx.as<double>(); a.v = dv.as<double>(); a.E = nullptr; a.rho = dcnt.as<unsigned long long>();
     a.partials = dpart.as<double>(); a.P = count; a.dt = 0.0; a.fx_scale = 1.0; a.N = (int)N; a.do_kick = 0; a.do_deposit = 1;
     a.pow2 = is_pow2(N) ? 1 : 0;
     // with v = 0 and dt = 0 the half drift is x = mod(x + 0, 1): positions in [0,1) are unchanged
-    lf_pass<0><<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(a);
+    lf_pass<0, false><<<(unsigned)std::min<int64_t>(grid1(count), 1024), PG_THREADS, smem>>>(a);
     PG_TRY(finish());
     std::vector<unsigned long long> cnt((size_t)N);
     PG_TRY(dcnt.download(cnt.data(), N * 8));

@@ -222,6 +222,27 @@ def test_c1_ngp_steps(pg, oracle):
     assert relnorm(x2, g["x"]) < TOL and relnorm(v2, g["v"]) < TOL
 
 
+@pytest.mark.parametrize("P", [1 << 21, 8192])
+def test_leapfrog_split_calls_cost_no_extra_pass(pg, P):
+    """A call of picgolf_step ends on full-step positions but leaves the NEXT step's charge deposited (the last pass deposits at the
+    half-drifted positions without storing them); the next call redoes that half drift in its first pass.  3 + 1 + 4 steps must give
+    the bits of 8 steps at once, and cost 8 particle passes + the one after set_particles, not 11 (TMA-staged and plain kernels)."""
+    N = 4096 if P > 8192 else 128
+    sims = []
+    for split in ((8,), (3, 1, 4)):
+        sim = pg.ngp_fourier(N=N, P=P, NT=16, W=256.0)
+        sim.init_synthetic(seed=11)
+        l0 = sim.launches
+        for k in split:
+            sim.step(k)
+            x, v = sim.particles()  # a read-back between the calls must see full-step positions and must not disturb the pending deposit
+            assert 0 <= x.min() and x.max() <= 1
+        sims.append((sim.particles(), sim.fields(), sim.raw_diagnostics(), sim.launches - l0))
+    (pa, fa, Ra, la), (pb, fb, Rb, lb) = sims
+    assert all(np.array_equal(a, b) for a, b in zip(pa + fa, pb + fb)) and np.array_equal(Ra, Rb)
+    assert la == lb == 1 + 3 * 8  # first deposit pass, then (solve, pass, step_end) per step
+
+
 def test_explicit_gaussian_steps(pg, oracle):
     """src/Gaussian.jl: leapfrog with the erf shape."""
     g = golden("gauss_explicit")
