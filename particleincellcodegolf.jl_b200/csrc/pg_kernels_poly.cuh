@@ -341,14 +341,34 @@ __device__ __forceinline__ void cp_flush_warp(CPSet<false> &s, double *colw, int
     }
 }
 
+// M += u^n, n = 1..CP_NM, and the count, for one particle of the lane.
+__device__ __forceinline__ void cp_accumulate(CPSet<false> &P, double u)
+{
+    P.cnt++;
+    const double u2 = u * u;
+    double pa = u, pb = u2;
+#pragma unroll
+    for (int n = 0; n < CP_NM; n += 2) {
+        P.m[n] += pa; P.m[n + 1] += pb;
+        if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
+    }
+}
+
 __device__ __forceinline__ void cp_deposit_row(const double (&y)[2], CPSet<false> &P, double *colw, int lane, int cstride, fx_t *Mg,
                                                double fx_scale, int Mmask, unsigned int &nflush)
 {
     double u[2] = {y[0] - P.centre, y[1] - P.centre};
-    const unsigned int f0 = __ballot_sync(0xffffffffu, !(fabs(u[0]) <= CP_UMOVE)), f1 = __ballot_sync(0xffffffffu, !(fabs(u[1]) <= CP_UMOVE));
-    if (__popc(f0) + __popc(f1) > 32) { // most of the row has left the interval (or there is none yet)
+    const int far = (fabs(u[0]) <= CP_UMOVE ? 0 : 1) + (fabs(u[1]) <= CP_UMOVE ? 0 : 1);
+    const int nfar = __reduce_add_sync(0xffffffffu, far); // one REDUX; most rows of a sorted stream: 0
+    if (nfar == 0) {
+        cp_accumulate(P, u[0]);
+        cp_accumulate(P, u[1]);
+        return;
+    }
+    if (nfar > 32) { // most of the row has left the interval (or there is none yet)
         nflush += P.cnt > 0;
         cp_flush_warp(P, colw, lane, cstride, Mg, fx_scale, Mmask);
+        const unsigned int f0 = __ballot_sync(0xffffffffu, !(fabs(u[0]) <= CP_UMOVE)), f1 = __ballot_sync(0xffffffffu, !(fabs(u[1]) <= CP_UMOVE));
         const double yr = __shfl_sync(0xffffffffu, f0 ? y[0] : y[1], __ffs(f0 ? f0 : f1) - 1);
         cp_interval(yr, P.idx, P.centre);
         u[0] = y[0] - P.centre; u[1] = y[1] - P.centre;
@@ -356,14 +376,7 @@ __device__ __forceinline__ void cp_deposit_row(const double (&y)[2], CPSet<false
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         if (fabs(u[q]) <= CP_UMAX) {
-            P.cnt++;
-            const double u2 = u[q] * u[q];
-            double pa = u[q], pb = u2;
-#pragma unroll
-            for (int n = 0; n < CP_NM; n += 2) {
-                P.m[n] += pa; P.m[n + 1] += pb;
-                if (n + 2 < CP_NM) { pa *= u2; pb *= u2; }
-            }
+            cp_accumulate(P, u[q]);
         } else {
             ++nflush;
             cp_deposit_single(y[q], Mg, fx_scale, Mmask);
@@ -639,6 +652,14 @@ __device__ __forceinline__ void cp_tail_particle(const FPArgs &a, long long j, b
     }
 }
 
+// Which of the run-time properties of a pass the streaming loop of fp_pass_poly is compiled for (-1: read at run time).  The kernel
+// nodes of the device-driven loop are the same for every sweep, so the pass learns on the device whether it is the first sweep
+// (v = V: no work-buffer stream), a middle one or the final one, and whether the step re-sorts; the loop body is instantiated for the
+// three plain cases with these as constants (fewer uniform branches, selects and live values in a loop that is bound by
+// instruction issue) and once generically for everything else.
+template <int F, int V, int S>
+struct CPSpec { static constexpr int final_ = F, v0 = V, fs = S; };
+
 // Pass k of a step (same contract as fp_pass_sorted / fp_pass_atomic; FPArgs.G / FPArgs.Mg carry the polynomial
 // tables, FPArgs.dN = N*CP_NSUB/2 so that y = (x+X)*dN).  Row = 64 consecutive particles; lane l owns particles 2l and 2l+1.
 template <bool FIRST, bool DET>
@@ -648,10 +669,10 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     __shared__ double scratch[32];
     const int fk = a.ctrl->final_k, k = FIRST ? 0 : sweep_index(a.k, a.ctrl);
     if (!FIRST && fk >= 0 && k > fk) return;
-    const bool final = !FIRST && fk == k;
-    const bool v0_is_V = FIRST || k == 1; // sweep 1 starts from v = V: the work buffer is stale until pass 1 writes it
-    const bool fs = !FIRST && a.fs_hist != nullptr; // re-sort fused into this step's passes
-    const bool fs_final = fs && final, fs_scatter = fs_final && k >= 2 && cp_fs_counts(k - 1, a.ctrl), fs_count = fs && !final && cp_fs_counts(k, a.ctrl);
+    const bool final_rt = !FIRST && fk == k;
+    const bool v0_rt = FIRST || k == 1; // sweep 1 starts from v = V: the work buffer is stale until pass 1 writes it
+    const bool fs_rt = !FIRST && a.fs_hist != nullptr; // re-sort fused into this step's passes
+    const bool fs_scatter_rt = fs_rt && final_rt && k >= 2 && cp_fs_counts(k - 1, a.ctrl), fs_count_rt = fs_rt && !final_rt && cp_fs_counts(k, a.ctrl);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double *Gw = smem + warp * (CP_GS * CP_WG); // [CP_WG][CP_GS]
     const int Mmask = a.N * CP_NSUB - 1;
@@ -678,6 +699,12 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
     unsigned int nflush = 0;
     // particle rows arrive through a per-warp cp.async ring: no registers are held while a row is in flight
     double2 *ring = reinterpret_cast<double2 *>(smem + wpb * (CP_GS * CP_WG)) + warp * (CP_STAGES * CP_STAGE_D2) + lane;
+    auto stream = [&](auto spec) {
+    using Spec = decltype(spec);
+    const bool final = Spec::final_ < 0 ? final_rt : Spec::final_ != 0;
+    const bool v0_is_V = Spec::v0 < 0 ? v0_rt : Spec::v0 != 0;
+    const bool fs = Spec::fs < 0 ? fs_rt : false;
+    const bool fs_final = fs && final, fs_scatter = Spec::fs < 0 ? fs_scatter_rt : false, fs_count = Spec::fs < 0 ? fs_count_rt : false;
     long long j2 = ((long long)r0 << 5) + lane; // double2 index of this lane's pair
     auto issue = [&](int r, long long jj) {     // row r -> stage r % CP_STAGES (always commits: uniform group count)
         if (r < r1) {
@@ -787,6 +814,16 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
             cp_deposit_row(yd, A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask, nflush);
         }
     }
+    }; // stream
+    if constexpr (FIRST) {
+        stream(CPSpec<0, 1, 0>{});
+    } else {
+        if (fs_rt || (final_rt && v0_rt)) stream(CPSpec<-1, -1, -1>{}); // a re-sorting step; a step that ends at sweep 1
+        else if (final_rt) stream(CPSpec<1, 0, 0>{});
+        else if (v0_rt) stream(CPSpec<0, 1, 0>{});
+        else stream(CPSpec<0, 0, 0>{});
+    }
+    const bool final = final_rt, v0_is_V = v0_rt;
     cp_async_wait<0>();
     if constexpr (DET) cp_flush(A, a.Mg, Mmask);
     else cp_flush_warp(A, reinterpret_cast<double *>(col) - lane, lane, cstride, a.Mg, a.fx_scale, Mmask);
