@@ -20,6 +20,7 @@
 #include "pg_kernels_2d.cuh"
 #include "pg_kernels_poly.cuh"
 #include "pg_sort.cuh"
+#include "pg_sort_policy.h"
 #include "pg_kernels_simpson.cuh"
 
 using namespace pg;
@@ -1106,24 +1107,16 @@ static void probe_poly_flushes(picgolf_handle h)
                 const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during step s - RUNAHEAD - 1
                 const int age = h->probe_age[(s - POLY_RUNAHEAD - 1) & 7];
                 const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
-                double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
-                if (h->det) expect += std::min(1.0, (double)CP_NSUB / (double)(1 << h->sublg));
-                h->poly_quiet = frac < 5e-5 + 1.5 * expect;
-                if (frac > 1e-3 + 3.0 * expect) {
-                    if (age < h->sort_every) { h->sort_every = std::max(1, age); h->grow_hold = 32; }
-                } else if (h->poly_quiet && age + 1 >= h->sort_every && h->grow_hold == 0) {
-                    h->sort_every = std::min(64, h->sort_every + std::max(1, h->sort_every / 2));
-                }
-                if (h->grow_hold > 0) --h->grow_hold;
+                const double expect = poly_expected_flushes((double)h->cfg.N, CP_NSUB, h->nranks, warps, (double)h->cfg.P, h->det, h->sublg);
+                PolySortPolicy pol{h->sort_every, h->grow_hold, h->poly_quiet};
+                poly_sort_policy_probe(pol, frac, age, expect); // pg_sort_policy.h
+                h->sort_every = pol.sort_every; h->grow_hold = pol.grow_hold; h->poly_quiet = pol.quiet;
             } else if (h->probe_have_prev) {
                 const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during one step
                 // expected in sorted order: the warp that streams a (cell, sign v) group walks through its CP_NSUB polynomial
                 // intervals, and each of its 32 lanes flushes once per interval (plus once per warp range); ~4 passes per step
                 const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
-                double expect = 4.0 * 32.0 * (2.0 * CP_NSUB * (double)h->cfg.N + warps) / (double)h->cfg.P;
-                // deterministic mode has no hysteresis: in the sub-bin that an interval edge cuts through (one in 2^sublg / CP_NSUB)
-                // a lane changes over between its two sets on up to every other particle, and the change-overs are counted too
-                if (h->det) expect += std::min(1.0, (double)CP_NSUB / (double)(1 << h->sublg));
+                const double expect = poly_expected_flushes((double)h->cfg.N, CP_NSUB, h->nranks, warps, (double)h->cfg.P, h->det, h->sublg);
                 h->poly_quiet = frac < 5e-5 + 1.5 * expect;
                 if (frac > 1e-3 + 3.0 * expect && h->since_sort >= 2 + POLY_RUNAHEAD) {
                     h->force_sort = true;
