@@ -69,6 +69,23 @@ __device__ __forceinline__ fx_t to_fx_small(double v, double fx_scale)
     return (fx_t)(__double_as_longlong(v * fx_scale + M) - __double_as_longlong(M));
 }
 
+// 64-bit integer add into SHARED memory as two native 32-bit atomics.  atomicAdd on a 64-bit shared word compiles to a compare-and-swap
+// loop on sm_100a (ATOMS.CAST.SPIN.64); 32-bit adds are native (ATOMS.ADD).  The low-word add returns the old value, which tells whether
+// THIS add carried; the carry rides along with the high-word add.  Every add propagates its own carry exactly once, so when all adds have
+// landed the two words hold the same 64-bit sum (mod 2^64, two's complement included) the 64-bit atomic would have produced -- bit for bit,
+// in any order.  (Readers must wait for a barrier, as with any shared-memory accumulation: between the two halves of an add the word is torn.)
+// Measured on B200 (tools/f_rows_timing.py, 2^24 particles, N = 4096): the Simpson-1/3 passes, which deposit into two or three grids per
+// particle, 8.5 -> 5.7 ms/step (Gaussian) and 3.1 -> 2.5 (area); the single-grid 1D2V pass is FASTER with the compare-and-swap form
+// (0.72 vs 1.03 ms), so gauss_deposit_atomic keeps it.
+__device__ __forceinline__ void smem_add64(fx_t *cell, fx_t v)
+{
+    unsigned int *w = reinterpret_cast<unsigned int *>(cell); // little endian: w[0] low, w[1] high
+    const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    const unsigned int old = atomicAdd(w, lo);
+    const unsigned int carry = old > ~lo ? 1u : 0u; // old + lo wrapped
+    atomicAdd(w + 1, hi + carry); // unconditionally: skipping it when there is nothing to add costs more (a divergent branch) than it saves
+}
+
 // ---- reductions -------------------------------------------------------------------------
 
 __device__ __forceinline__ double warp_sum(double v)

@@ -30,7 +30,7 @@ __device__ __forceinline__ void gauss_deposit_atomic(fx_t *rs, int ibase, const 
 {
     // r[k[1]] += k[2]*w      src/GaussianFixedPoint.jl:6   (the factor w is applied by the solve)
 #pragma unroll
-    for (int k = 0; k < GAUSS_NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale));
+    for (int k = 0; k < GAUSS_NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale)); // CAS loop in shared memory; see smem_add64
 }
 
 __device__ __forceinline__ void flush_grid(const fx_t *rs, fx_t *rho, int N)

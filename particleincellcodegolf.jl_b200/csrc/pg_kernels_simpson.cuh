@@ -51,7 +51,7 @@ template <int NW>
 __device__ __forceinline__ void sp_deposit(fx_t *rs, int ibase, const double (&W)[NW], double fx_scale, int Nmask)
 {
 #pragma unroll
-    for (int k = 0; k < NW; ++k) atomicAdd(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale));
+    for (int k = 0; k < NW; ++k) smem_add64(&rs[(ibase + k - 1) & Nmask], to_fx(W[k], fx_scale)); // rs is a shared-memory grid
 }
 
 struct SPArgs {
