@@ -30,6 +30,7 @@ struct Ctrl {
     int fs_pred;     // fused re-sort (pg_kernels_poly.cuh): the passes k with k + 1 >= fs_pred count their bins; min of the last two steps' sweeps
     unsigned long long flush_global; // multi-GPU polynomial mode: sum over the ranks of the flush counters (pg_peer.cuh)
     unsigned long long loop_sweeps;  // sweeps executed inside the device-driven loop since the particles were set (launch accounting)
+    unsigned long long loop_fs_sweeps; // ... of which sweeps of a re-sorting step, which launch cp_fs_scan_kernel as well
 };
 
 // Sweep index of a launch.  The fixed schedule (stage timers on, NCCL reduction) passes it as a kernel argument; inside the

@@ -533,7 +533,7 @@ __device__ __forceinline__ void cp_fs_slots(const CPFsRes &r, int lane, long lon
 struct FsScanArgs {
     unsigned int *hist, *cursor;
     unsigned long long *sync; // [FS_MAXBLOCKS]
-    const Ctrl *ctrl;
+    Ctrl *ctrl;
     int nbins, k;
 };
 constexpr int FS_CHUNK = 1024 * 16;
@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(1024) cp_fs_scan_kernel(FsScanArgs a)
 {
     __shared__ unsigned int wsum[32];
     __shared__ unsigned int carry_s;
+    if (a.k < 0 && blockIdx.x == 0 && threadIdx.x == 0) a.ctrl->loop_fs_sweeps += 1ULL; // launch accounting of the device-driven loop
     const int fk = a.ctrl->final_k, k = sweep_index(a.k, a.ctrl);
     if (k < 2 || (fk >= 0 && k > fk)) return; // pass 0 does not count: at sweep 1 the counts are still zero
     if (!cp_fs_counts(k - 1, a.ctrl)) return; // neither did pass k-1 (the step was expected to take more sweeps)

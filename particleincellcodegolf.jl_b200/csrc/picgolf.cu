@@ -773,7 +773,7 @@ static int bank_loop_launches(picgolf_handle h)
     PG_CUDA(cudaStreamSynchronize(h->stream));
     Ctrl c;
     PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
-    h->launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep;
+    h->launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep + (int64_t)c.loop_fs_sweeps;
     h->loop_steps = 0;
     return 0;
 }
@@ -1284,7 +1284,7 @@ static int build_loop_graph(picgolf_handle h, cudaGraphExec_t *exec)
     int rc = enqueue_sweep(h, -1, cond);
     h->stream = run;
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, nullptr);
-    h->loop_launches_per_sweep = (int)(h->launches - l0);
+    h->loop_launches_per_sweep = (int)(h->launches - l0) - (h->fs_now ? 1 : 0); // the bin scan of a re-sorting step is counted on the device (Ctrl.loop_fs_sweeps)
     h->launches = l0;
     if (rc != 0) return rc;
     PG_CUDA(e);
@@ -1936,7 +1936,7 @@ PG_API int picgolf_launch_count(picgolf_handle h, int64_t *launches)
         PG_CUDA(cudaStreamSynchronize(h->stream));
         Ctrl c;
         PG_CUDA(cudaMemcpy(&c, h->ctrl, sizeof(c), cudaMemcpyDeviceToHost));
-        *launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep;
+        *launches += (int64_t)c.loop_sweeps * h->loop_launches_per_sweep + (int64_t)c.loop_fs_sweeps;
     }
     return 0;
 }

@@ -713,6 +713,9 @@ def test_fused_resort_matches_standalone_sort(pg, monkeypatch, max_sweeps, det):
     assert relnorm(df[0][:steps, 1:3], da[0][:steps, 1:3]) < TOL
     if max_sweeps == 1:
         assert set(df[1][:steps]) == {1}
+    # launch accounting (sweeps are counted on the device): a re-sorting step launches the bin scan once per sweep, the other run
+    # launched the three kernels of the stand-alone sort before each of those steps instead
+    assert f.launches - s.launches == int(df[1][2:steps].sum()) - 3 * (steps - 2)
     # the fused order is the order of the next step's mid-points: a lane changes interval when the stream does, not because of the spread in v
     if not det and max_sweeps == 10:
         assert f.sort_stats()[1] < 0.1 * P * float(df[1][:steps].sum())
