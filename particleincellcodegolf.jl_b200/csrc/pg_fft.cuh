@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(512) solve1d_stock_kernel(Solve1DArgs a)
     unsigned long long pseq = 0ULL;
     if (peers) {
         pseq = peer_gather_begin(a.peer);
-        if (threadIdx.x == 0) a.ctrl->flush_global = peer_flush_sum(a.peer);
+        if (threadIdx.x < 32) { // PEER_MAX <= 32 ranks: one lane each
+            const unsigned long long fsum = peer_flush_sum_warp(a.peer);
+            if (threadIdx.x == 0) a.ctrl->flush_global = fsum;
+        }
     }
     {
         double r[PT];
@@ -433,8 +436,10 @@ __global__ void __launch_bounds__(512) solve1d_stock_kernel(Solve1DArgs a)
 #pragma unroll
             for (int q = 0; q < PT; ++q) r[q] = a.rho_in[threadIdx.x + q * blockDim.x];
         } else if (peers) {
+            long long raw[PT];
+            peer_sum_many<PT>(a.peer, pseq, threadIdx.x, blockDim.x, raw); // the publish kernel cleared rho_fx
 #pragma unroll
-            for (int q = 0; q < PT; ++q) r[q] = (double)peer_sum(a.peer, pseq, threadIdx.x + q * blockDim.x) * a.fx_inv * a.w; // the publish kernel cleared rho_fx
+            for (int q = 0; q < PT; ++q) r[q] = (double)raw[q] * a.fx_inv * a.w;
         } else {
             unsigned long long raw[PT];
 #pragma unroll

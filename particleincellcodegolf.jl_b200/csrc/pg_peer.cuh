@@ -105,6 +105,36 @@ __device__ __forceinline__ long long peer_sum(const PeerArgs &p, unsigned long l
     for (int q = 0; q < p.nranks; ++q) s += ld_relaxed_sys(peer_data(p.peer[q], slot, p.ncell) + n);
     return (long long)s;
 }
+// The same sum for PT grid cells of one thread (n0, n0 + stride, ...), with the PT loads from a rank all in flight before the first is
+// used: peer_sum() alone walks rank by rank with one dependent NVLink round trip each -- 64 in a row for 8 points on 8 GPUs, which cost
+// the 8-GPU step 0.2 ms (3 solves); this way a solve waits for nranks round trips.
+template <int PT>
+__device__ __forceinline__ void peer_sum_many(const PeerArgs &p, unsigned long long seq, int n0, int stride, long long (&out)[PT])
+{
+    const int slot = (int)(seq & 1ULL);
+    unsigned long long acc[PT];
+#pragma unroll
+    for (int i = 0; i < PT; ++i) acc[i] = 0ULL;
+    for (int q = 0; q < p.nranks; ++q) {
+        const fx_t *src = peer_data(p.peer[q], slot, p.ncell) + n0;
+        unsigned long long v[PT];
+#pragma unroll
+        for (int i = 0; i < PT; ++i) v[i] = ld_relaxed_sys(src + (long long)i * stride);
+#pragma unroll
+        for (int i = 0; i < PT; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < PT; ++i) out[i] = (long long)acc[i];
+}
+// Sum of the ranks' flush counters; the first warp calls it (after peer_gather_begin), lane 0 holds the result.
+__device__ __forceinline__ unsigned long long peer_flush_sum_warp(const PeerArgs &p)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long s = lane < p.nranks ? ld_relaxed_sys(&p.peer[lane]->flushes) : 0ULL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
 __device__ __forceinline__ unsigned long long peer_flush_sum(const PeerArgs &p) // after peer_gather_begin
 {
     unsigned long long s = 0ULL;
