@@ -79,6 +79,10 @@ constexpr int CP_THREADS = PG_CP_THREADS; // threads per block of fp_pass_poly
 #ifndef PG_CP_STAGES
 #define PG_CP_STAGES 4
 #endif
+#ifndef PG_CP_UNROLL
+#define PG_CP_UNROLL 1 // rows per trip of the streaming loop (A/B builds)
+#endif
+constexpr int CP_UNROLL = PG_CP_UNROLL;
 constexpr int CP_STAGES = PG_CP_STAGES; // rows of particle data in flight per warp (cp.async ring, 1.5 KB per stage)
 constexpr int CP_STAGE_D2 = 96;  // double2 slots per stage: X, V, v pairs of the 32 lanes
 
@@ -719,6 +723,7 @@ __global__ void __launch_bounds__(CP_THREADS, PG_CP_MINBLOCKS) fp_pass_poly(FPAr
 #pragma unroll
     for (int s = 0; s < CP_STAGES - 1; ++s) issue(r0 + s, j2 + 32 * s);
     int stage = 0;
+#pragma unroll CP_UNROLL
     for (int r = r0; r < r1; ++r, j2 += 32) {
         issue(r + CP_STAGES - 1, j2 + 32 * (CP_STAGES - 1));
         cp_async_wait<CP_STAGES - 1>(); // row r has landed
