@@ -164,6 +164,15 @@ function diagnostics(s::Sim)
     return D[1:rows[], :], sw[1:rows[]]
 end
 
+# (sorts so far, flushes / window misses, sorts that were fused into the particle passes): the library re-sorts on its own (the
+# reference's sortparticles!, Electrostatic2D3V.jl:57-62, has no counterpart a driver must call); this is for curiosity and tuning
+function sort_stats(s::Sim)
+    a, b, c = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:picgolf_sort_stats, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), s.h, a, b))
+    check(ccall((:picgolf_fused_sorts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), s.h, c))
+    return a[], b[], c[]
+end
+
 # ------------------------------------------------------------------------------------------------
 # PIC2D3V.jl electrostatic path (include/picgolf_es.h): Species / shapes / ElectrostaticField / ElectrostaticDiagnostics.
 #
