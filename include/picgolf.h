@@ -164,7 +164,11 @@ int picgolf_get_particles_2d3v(picgolf_handle h, double *x, double *y, double *v
  *   CIC_BORIS_2D3V   Electrostatic2D3V.jl:121-157
  *   GAUSS_SIMPSON13  GaussianFixedPointQuietSimpson13.jl:8-17 (fields: rho = rho(x,x), E = E[end,:])
  * and append one diagnostics row per recorded step.  Asynchronous: returns after enqueueing;
- * any getter or picgolf_synchronize() waits. */
+ * any getter or picgolf_synchronize() waits.
+ * A call ends on the scripts' end-of-step state (x, v as the reference holds them after `for t`'s body; rho, E of the last solve),
+ * whatever nsteps is: calling picgolf_step(h, 1) K times gives the bits of picgolf_step(h, K).  The charge of the NEXT step's first
+ * solve is already deposited when a call returns (leapfrog schemes: at the half-drifted positions u() will produce; fixed point:
+ * at the first mid-points), so K steps cost K particle passes however the calls are split. */
 int picgolf_step(picgolf_handle h, int64_t nsteps);
 int picgolf_synchronize(picgolf_handle h);
 /* Streaming form of  picgolf_set_particles(x_in, v_in) -> picgolf_step(1) -> picgolf_get_particles(x_out, v_out)  for a driver
