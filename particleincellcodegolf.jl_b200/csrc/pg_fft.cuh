@@ -29,6 +29,7 @@ struct Ctrl {
     unsigned int sp_arrive;
     int fs_pred;     // fused re-sort (pg_kernels_poly.cuh): the passes k with k + 1 >= fs_pred count their bins; min of the last two steps' sweeps
     unsigned long long flush_global; // multi-GPU polynomial mode: sum over the ranks of the flush counters (pg_peer.cuh)
+    unsigned long long flush_step;   // ... as the FIRST solve of a step sees it: everything up to the end of the previous step (the host's per-step probe)
     unsigned long long loop_sweeps;  // sweeps executed inside the device-driven loop since the particles were set (launch accounting)
     unsigned long long loop_fs_sweeps; // ... of which sweeps of a re-sorting step, which launch cp_fs_scan_kernel as well
 };
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     unsigned long long pseq = 0ULL;
     if (peers) {
         pseq = peer_gather_begin(a.peer);
-        if (threadIdx.x == 0) a.ctrl->flush_global = peer_flush_sum(a.peer);
+        if (threadIdx.x == 0) { const unsigned long long fsum = peer_flush_sum(a.peer); a.ctrl->flush_global = fsum; if (k == 1) a.ctrl->flush_step = fsum; }
     }
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double r;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(1024) solve1d_kernel(Solve1DArgs a)
     __syncthreads();
     if (peers) peer_gather_end(a.peer, pseq);
     const bool peer_failed = peers && *a.peer.error != 0; // a peer never published (pg_peer.cuh): poison the field, end the step
-    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
+    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; if (k == 1) a.ctrl->flush_step = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
     PG_PROF(1);
     fft_smem4<false>(re, im, N, 1, 1, 0, a.tw, N);
     PG_PROF(2);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(512) solve1d_stock_kernel(Solve1DArgs a)
         pseq = peer_gather_begin(a.peer);
         if (threadIdx.x < 32) { // PEER_MAX <= 32 ranks: one lane each
             const unsigned long long fsum = peer_flush_sum_warp(a.peer);
-            if (threadIdx.x == 0) a.ctrl->flush_global = fsum;
+            if (threadIdx.x == 0) { a.ctrl->flush_global = fsum; if (k == 1) a.ctrl->flush_step = fsum; }
         }
     }
     {
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(512) solve1d_stock_kernel(Solve1DArgs a)
     __syncthreads();
     if (peers) peer_gather_end(a.peer, pseq);
     const bool peer_failed = peers && *a.peer.error != 0; // a peer never published (pg_peer.cuh): poison the field, end the step
-    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
+    if (a.flush_slot && threadIdx.x == 0) { a.ctrl->flush_global = a.rho_fx[N]; if (k == 1) a.ctrl->flush_step = a.rho_fx[N]; a.rho_fx[N] = 0ULL; }
     PG_PROF(1);
     fft_stockham8<PT>(buf, N, a.lg, a.tw);
     PG_PROF(2);

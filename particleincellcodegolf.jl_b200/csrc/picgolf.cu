@@ -1105,7 +1105,7 @@ static void probe_poly_flushes(picgolf_handle h)
                 // every step: never let the order get as old again as it was in a step that flushed a lot; grow (by half, up to
                 // 64) only when the oldest order the interval allows was still quiet, and not for 32 steps after a cut
                 const double frac = (double)(now - h->slow_seen) / (double)h->cfg.P; // flushes per particle during step s - RUNAHEAD - 1
-                const int age = h->probe_age[(s - POLY_RUNAHEAD - 1) & 7];
+                const int age = h->probe_age[(s - POLY_RUNAHEAD - (h->comm ? 2 : 1)) & 7];
                 const double warps = (double)h->nblocks_poly * (CP_THREADS / 32) * (double)h->nranks;
                 const double expect = poly_expected_flushes((double)h->cfg.N, CP_NSUB, h->nranks, warps, (double)h->cfg.P, h->det, h->sublg);
                 PolySortPolicy pol{h->sort_every, h->grow_hold, h->poly_quiet};
@@ -1129,7 +1129,10 @@ static void probe_poly_flushes(picgolf_handle h)
             h->probe_have_prev = false;
         }
     }
-    const void *src = h->comm ? (const void *)&h->ctrl->flush_global : (const void *)h->slow_count;
+    // several GPUs: the sum over the ranks as the first solve of the PREVIOUS step saw it, i.e. everything up to the end of the step before
+    // that one -- whole steps, like the single-GPU counter, one step later (the running sum flush_global is cut off in the middle of a step:
+    // a step's final pass, where a stale order shows, would be billed to the step after it)
+    const void *src = h->comm ? (const void *)&h->ctrl->flush_step : (const void *)h->slow_count;
     cudaMemcpyAsync(&h->slow_host[s & 7], src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
     h->probe_step[s & 7] = s;
     h->probe_age[s & 7] = (int)std::min<int64_t>(h->since_sort, 1 << 20);
